@@ -1,0 +1,343 @@
+// common.cuh -- shared device/host helpers for libzdw_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/zdw_b200.h"
+
+namespace zdwb {
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;
+  std::string err;
+  unsigned long long launches = 0;
+  int sm_count = 148;
+  // tuning knobs
+  long long small_sort_max = 16384;  // dictionaries up to this many entries take the single-CTA sort
+  long long ht_initial_log2 = 20;    // first-try size of the string hash set (grown x8 on overflow)
+  long long dec_tile_bytes = 8192;   // row-stream bytes per CTA in the decoder's row-boundary discovery
+  unsigned long long last_out_per_row = 0;  // decoded bytes per row of the previous block (sizes the next output)
+  unsigned long long last_unique = 0;  // dictionary size of the previous block (seeds the next hash set)
+  // outputs owned by the context (valid until the next call)
+  void* out_dev = nullptr;     // device output buffer
+  void* out_dev2 = nullptr;    // second device output (row offsets)
+  void* out_host = nullptr;    // pinned host output
+  size_t out_host_cap = 0;
+  void* out_host2 = nullptr;
+  size_t out_host2_cap = 0;
+  void* in_stage = nullptr;    // pinned staging for pageable host inputs (unused when caller memory is pinned)
+  // small pinned scratch for device->host readbacks of metadata
+  void* meta_host = nullptr;
+};
+
+struct Status {
+  int code;
+};
+
+#define ZDWB_CUDA_TRY(ctx, expr)                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof(_b), "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+               cudaGetErrorString(_e));                                                            \
+      (ctx)->err = _b;                                                                             \
+      (void)cudaGetLastError();                                                                    \
+      return (_e == cudaErrorMemoryAllocation) ? ZDWB_ERR_OOM : ZDWB_ERR_CUDA;                      \
+    }                                                                                              \
+  } while (0)
+
+#define ZDWB_TRY(expr)                    \
+  do {                                    \
+    int _rc = (expr);                     \
+    if (_rc != ZDWB_OK) return _rc;       \
+  } while (0)
+
+// count a launch and check for launch-configuration errors
+#define ZDWB_LAUNCH_CHECK(ctx)                                                                     \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    ZDWB_CUDA_TRY(ctx, cudaGetLastError());                                                        \
+  } while (0)
+
+// Scoped device allocation from the context's stream-ordered pool.
+struct DevBuf {
+  Ctx* ctx = nullptr;
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(Ctx* c, size_t n) {
+    release();
+    ctx = c;
+    bytes = n ? n : 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      char b[256];
+      snprintf(b, sizeof(b), "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      c->err = b;
+      (void)cudaGetLastError();
+      return e == cudaErrorMemoryAllocation ? ZDWB_ERR_OOM : ZDWB_ERR_CUDA;
+    }
+    return ZDWB_OK;
+  }
+  void release() {
+    if (p) {
+      cudaFreeAsync(p, ctx->stream);
+      p = nullptr;
+    }
+  }
+  void* detach() {
+    void* q = p;
+    p = nullptr;
+    return q;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// column types
+// ---------------------------------------------------------------------------------------------
+// "dictionary" types: ConvertToZDW.cpp:345-352
+__host__ __device__ __forceinline__ bool is_text_like(uint8_t t) {
+  return t == ZDWB_DECIMAL || t == ZDWB_VARCHAR || t == ZDWB_TEXT || t == ZDWB_TINYTEXT ||
+         t == ZDWB_MEDIUMTEXT || t == ZDWB_LONGTEXT || t == ZDWB_DATETIME || t == ZDWB_CHAR_2;
+}
+__host__ __device__ __forceinline__ bool is_int_type(uint8_t t) {
+  return (t >= ZDWB_TINY && t <= ZDWB_LONGLONG) || (t >= ZDWB_TINY_SIGNED && t <= ZDWB_LONGLONG_SIGNED);
+}
+__host__ __device__ __forceinline__ bool is_signed_int_type(uint8_t t) {
+  return t >= ZDWB_TINY_SIGNED && t <= ZDWB_LONGLONG_SIGNED;
+}
+__host__ __device__ __forceinline__ bool is_known_type(uint8_t t) {
+  return is_text_like(t) || is_int_type(t) || t == ZDWB_CHAR;
+}
+
+// ---------------------------------------------------------------------------------------------
+// numeric semantics shared by kernels and host-side unit tests
+// ---------------------------------------------------------------------------------------------
+
+// strtoull(f, NULL, 10) over a bounded field (ConvertToZDW.cpp:385,564): skip
+// isspace() bytes, optional sign, digits; overflow saturates to 2^64-1 regardless of sign; a '-'
+// negates modulo 2^64.  Bytes past `len` read as NUL (the reference NUL-terminates every field).
+__host__ __device__ __forceinline__ uint64_t parse_u64_field(const uint8_t* p, uint32_t len) {
+  uint32_t i = 0;
+  while (i < len) {
+    uint8_t ch = p[i];
+    if (ch == ' ' || (ch >= 9 && ch <= 13)) ++i;
+    else break;
+  }
+  bool neg = false;
+  if (i < len && (p[i] == '+' || p[i] == '-')) {
+    neg = p[i] == '-';
+    ++i;
+  }
+  uint64_t v = 0;
+  bool ovf = false;
+  while (i < len) {
+    uint32_t d = (uint32_t)p[i] - (uint32_t)'0';
+    if (d > 9) break;
+    // v*10 + d > 2^64-1 ?
+    if (v > 1844674407370955161ULL || (v == 1844674407370955161ULL && d > 5)) ovf = true;
+    v = v * 10 + d;
+    ++i;
+  }
+  if (ovf) return ~0ULL;
+  return neg ? (0 - v) : v;
+}
+
+// CHAR column value: sign-extended first byte (+ second byte * 256).  `second_always` selects the
+// pass-2 rule (ConvertToZDW.cpp:543-547: add f[1]*256 whenever f[0] != 0) over the pass-1 rule
+// (:359-361: only when f[0] == '\\').  f[1] reads as NUL for a 1-byte field.
+__host__ __device__ __forceinline__ uint64_t char_tuple(const uint8_t* p, uint32_t len, bool second_always) {
+  if (len == 0) return 0;
+  int64_t v = (int64_t)(int8_t)p[0];
+  if (second_always || p[0] == '\\') {
+    int32_t b1 = len > 1 ? (int32_t)(int8_t)p[1] : 0;
+    v += (int64_t)(b1 * 256);
+  }
+  return (uint64_t)v;
+}
+
+// bytes needed to store v (1..8): ConvertToZDW.cpp:458-465, dictionary.cpp:62-73
+__host__ __device__ __forceinline__ uint32_t bytes_needed(uint64_t v) {
+  uint32_t k = 1;
+  while (v >= 256) {
+    ++k;
+    v >>= 8;
+  }
+  return k;
+}
+
+// llutoa (UnconvertFromZDW.cpp:318-330): writes digits ending at `end` (exclusive), returns length.
+__host__ __device__ __forceinline__ uint32_t fmt_u64(uint64_t v, uint8_t* end) {
+  uint8_t* p = end;
+  do {
+    *--p = (uint8_t)('0' + (v % 10));
+    v /= 10;
+  } while (v);
+  return (uint32_t)(end - p);
+}
+
+// lltoa (UnconvertFromZDW.cpp:333-356) including its INT64_MIN behaviour: the
+// negation overflows, every `value % 10` is then <= 0 and the digit byte is 0x30 + rem.
+__host__ __device__ __forceinline__ uint32_t fmt_i64(int64_t sv, uint8_t* end) {
+  uint8_t* p = end;
+  bool minus = false;
+  if (sv < 0) {
+    minus = true;
+    sv = (int64_t)(0 - (uint64_t)sv);
+  }
+  do {
+    int64_t rem = sv % 10;
+    sv /= 10;
+    *--p = (uint8_t)(rem + 0x30);
+  } while (sv != 0);
+  if (minus) *--p = '-';
+  return (uint32_t)(end - p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// streaming 16-byte load that does not allocate in L1 (each TSV byte is consumed once per pass)
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// per-byte equality mask of a 32-bit word against a replicated byte: bit 7 of each byte lane set
+__device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t rep) {
+  uint32_t x = w ^ rep;
+  // zero-byte detect, exact variant (no false positives across byte lanes)
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+// gather the four bit-7 flags of a word into the low 4 bits
+__device__ __forceinline__ uint32_t movemask4(uint32_t m) {
+  return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+}
+// 16-bit mask of bytes equal to `ch` within a 16-byte chunk
+__device__ __forceinline__ uint32_t chunk_mask(const uint4& v, uint8_t ch) {
+  const uint32_t rep = 0x01010101u * ch;
+  return movemask4(bytes_eq(v.x, rep)) | (movemask4(bytes_eq(v.y, rep)) << 4) |
+         (movemask4(bytes_eq(v.z, rep)) << 8) | (movemask4(bytes_eq(v.w, rep)) << 12);
+}
+
+// block-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024).
+// `warp_sums` is shared scratch of >= 33 words.  Returns the exclusive prefix; *total gets the block sum.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < nwarps ? warp_sums[lane] : 0;
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= (unsigned)o) wi += t;
+    }
+    if (lane < nwarps) warp_sums[lane] = wi - w;  // exclusive warp offsets
+    if (lane == 31) warp_sums[32] = wi;           // block total
+  }
+  __syncthreads();
+  uint32_t r = warp_sums[warp] + inc - v;
+  if (total) *total = warp_sums[32];
+  __syncthreads();  // scratch may be reused by the caller right away
+  return r;
+}
+
+__device__ __forceinline__ uint64_t block_exclusive_scan64(uint64_t v, uint64_t* warp_sums, uint64_t* total) {
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < nwarps ? warp_sums[lane] : 0;
+    uint64_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= (unsigned)o) wi += t;
+    }
+    if (lane < nwarps) warp_sums[lane] = wi - w;
+    if (lane == 31) warp_sums[32] = wi;
+  }
+  __syncthreads();
+  uint64_t r = warp_sums[warp] + inc - v;
+  if (total) *total = warp_sums[32];
+  __syncthreads();
+  return r;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// generic device-wide primitives (scan.cu / sort.cu)
+// ---------------------------------------------------------------------------------------------
+// out[i] = sum(in[0..i)), i in [0,n); total (device pointer, may be null) = sum(in[0..n)).  in == out allowed.
+int exclusive_scan_u32(Ctx* ctx, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev);
+int exclusive_scan_u64(Ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, uint64_t* total_dev);
+
+// Sorts the unique strings of a block into strcmp (unsigned byte, prefix-first) order.
+//   base       : device pointer the (start,len) pairs refer to (the TSV buffer)
+//   starts/lens: n entries describing each distinct string (no two equal, none containing NUL)
+//   order_out  : n entries; order_out[i] = index of the i-th smallest string
+int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const uint32_t* lens, uint32_t n,
+                 uint32_t max_len, uint32_t* order_out);
+
+}  // namespace zdwb

@@ -1,0 +1,138 @@
+// ctx.cu -- C ABI entry points of libzdw_b200 (see include/zdw_b200.h).
+#include <new>
+
+#include "common.cuh"
+
+struct zdwb_ctx : zdwb::Ctx {};
+
+namespace zdwb {
+int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
+                      zdwb_block_out* out);
+int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size_t avail, const zdwb_decode_opts* opts,
+                      zdwb_rows_out* out);
+}  // namespace zdwb
+
+using zdwb::Ctx;
+
+extern "C" {
+
+int zdwb_abi_version(void) { return ZDWB_ABI_VERSION; }
+
+int zdwb_ctx_create(int device, size_t workspace_hint, zdwb_ctx** out) {
+  if (!out) return ZDWB_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    (void)cudaGetLastError();
+    return ZDWB_ERR_NO_DEVICE;  // no CPU fallback
+  }
+  if (device < 0 || device >= count) return ZDWB_ERR_BAD_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ZDWB_ERR_NO_DEVICE;
+  zdwb_ctx* c = new (std::nothrow) zdwb_ctx();
+  if (!c) return ZDWB_ERR_OOM;
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return ZDWB_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  if (cudaDeviceGetDefaultMemPool(&c->pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;  // keep freed blocks cached in the pool between calls
+    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  if (cudaHostAlloc(&c->meta_host, 4096, cudaHostAllocDefault) != cudaSuccess) {
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return ZDWB_ERR_OOM;
+  }
+  if (workspace_hint) {
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, workspace_hint, c->stream) == cudaSuccess) cudaFreeAsync(p, c->stream);
+    cudaStreamSynchronize(c->stream);
+    (void)cudaGetLastError();
+  }
+  *out = c;
+  return ZDWB_OK;
+}
+
+void zdwb_ctx_destroy(zdwb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->out_dev) cudaFreeAsync(c->out_dev, c->stream);
+  if (c->out_dev2) cudaFreeAsync(c->out_dev2, c->stream);
+  cudaStreamSynchronize(c->stream);
+  if (c->out_host) cudaFreeHost(c->out_host);
+  if (c->out_host2) cudaFreeHost(c->out_host2);
+  if (c->meta_host) cudaFreeHost(c->meta_host);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* zdwb_last_error(const zdwb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int zdwb_ctx_set_stream(zdwb_ctx* c, void* cuda_stream) {
+  if (!c) return ZDWB_ERR_BAD_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return ZDWB_OK;
+}
+
+int zdwb_ctx_set_tuning(zdwb_ctx* c, const char* name, long long value) {
+  if (!c || !name) return ZDWB_ERR_BAD_ARG;
+  if (!strcmp(name, "small_sort_max")) c->small_sort_max = value;
+  else if (!strcmp(name, "ht_initial_log2")) c->ht_initial_log2 = value;
+  else if (!strcmp(name, "dec_tile_bytes")) c->dec_tile_bytes = value;
+  else return ZDWB_ERR_BAD_ARG;
+  return ZDWB_OK;
+}
+
+unsigned long long zdwb_ctx_kernel_launches(const zdwb_ctx* c) { return c ? c->launches : 0ull; }
+
+int zdwb_encode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
+                      zdwb_block_out* out) {
+  if (!c) return ZDWB_ERR_BAD_ARG;
+  c->err.clear();
+  if (!schema || !out || !opts || (!tsv && n)) {
+    c->err = "zdwb_encode_block: null argument";
+    return ZDWB_ERR_BAD_ARG;
+  }
+  if (cudaSetDevice(c->device) != cudaSuccess) {
+    c->err = "cudaSetDevice failed";
+    return ZDWB_ERR_NO_DEVICE;
+  }
+  return zdwb::encode_block_impl(c, schema, tsv, n, opts, out);
+}
+
+int zdwb_decode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* zdw, size_t avail, const zdwb_decode_opts* opts,
+                      zdwb_rows_out* out) {
+  if (!c) return ZDWB_ERR_BAD_ARG;
+  c->err.clear();
+  if (!schema || !out || !opts || !zdw) {
+    c->err = "zdwb_decode_block: null argument";
+    return ZDWB_ERR_BAD_ARG;
+  }
+  if (cudaSetDevice(c->device) != cudaSuccess) {
+    c->err = "cudaSetDevice failed";
+    return ZDWB_ERR_NO_DEVICE;
+  }
+  return zdwb::decode_block_impl(c, schema, zdw, avail, opts, out);
+}
+
+void* zdwb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void zdwb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,396 @@
+// sort.cu -- orders the unique strings of a block dictionary by strcmp (unsigned bytes, prefix first).
+//
+// Replaces the red-black tree of the reference (std::map<const char*, ULONG, strcmp-less>,
+// dictionary.h:30-35) whose in-order walk defines the on-disk dictionary order (dictionary.cpp:99-108).
+//
+// Two paths, same result:
+//   * small dictionaries (n <= Ctx::small_sort_max, typical for analytics-shaped data): one CTA,
+//     bitonic network in shared memory over (8-byte big-endian prefix key, id), ties broken by a
+//     byte-wise compare of the remaining bytes;
+//   * large dictionaries: LSD radix sort on the 8-byte prefix, then iterative refinement - strings that
+//     still tie are re-sorted by (tie-group id, next 8 bytes) until every group is a singleton.  Because
+//     the strings are distinct and contain no NUL, zero padding makes "shorter prefix sorts first" fall
+//     out of the integer compare.
+#include "common.cuh"
+
+namespace zdwb {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// keys
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t prefix_key(const uint8_t* s, uint32_t len, uint32_t off) {
+  uint64_t k = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t p = off + i;
+    uint64_t b = p < len ? (uint64_t)__ldg(s + p) : 0ull;
+    k = (k << 8) | b;
+  }
+  return k;
+}
+
+// ids == nullptr -> identity
+__global__ void k_make_keys(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts,
+                            const uint32_t* __restrict__ lens, const uint32_t* __restrict__ ids, uint32_t n,
+                            uint32_t off, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals_out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t id = ids ? ids[i] : i;
+  keys[i] = prefix_key(base + starts[id], lens[id], off);
+  if (vals_out) vals_out[i] = id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort of (key u64, seg u32, val u32) records, 8 bits per pass
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;  // per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARP_ITEMS = RS_ITEMS * 32;
+
+__device__ __forceinline__ uint32_t rs_digit(const uint64_t* keys, const uint32_t* segs, uint32_t i, int pass) {
+  return pass < 8 ? (uint32_t)((keys[i] >> (8 * pass)) & 255u) : ((segs[i] >> (8 * (pass - 8))) & 255u);
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+    k_radix_hist(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs, uint32_t n, int pass,
+                 uint32_t* __restrict__ hist, uint32_t ntiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    uint32_t i = base + k * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[rs_digit(keys, segs, i, pass)], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// Stable scatter.  Warp w of the CTA owns the contiguous sub-range [tile + w*512, +512) and walks it in
+// 16 steps of 32 consecutive items, so the order (warp, step, lane) is the input order.
+__global__ void __launch_bounds__(RS_THREADS)
+    k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs,
+                    const uint32_t* __restrict__ vals, uint32_t n, int pass, const uint32_t* __restrict__ hist_scanned,
+                    uint32_t ntiles, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ segs_out,
+                    uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t wc[RS_WARPS][256];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) wc[warp][d] = 0;
+  __syncwarp();
+  const uint32_t wbase = blockIdx.x * RS_TILE + warp * RS_WARP_ITEMS;
+  // sweep 1: per-warp digit counts
+  for (int s = 0; s < RS_ITEMS; ++s) {
+    uint32_t i = wbase + s * 32 + lane;
+    bool valid = i < n;
+    unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      uint32_t d = rs_digit(keys, segs, i, pass);
+      unsigned peers = __match_any_sync(act, d);
+      if (lane == (unsigned)(__ffs(peers) - 1)) wc[warp][d] += __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: global base of this tile, then exclusive over the warps of the CTA
+  {
+    const uint32_t d = threadIdx.x;
+    uint32_t run = hist_scanned[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      uint32_t t = wc[w][d];
+      wc[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  // sweep 2: ranks and scatter
+  for (int s = 0; s < RS_ITEMS; ++s) {
+    uint32_t i = wbase + s * 32 + lane;
+    bool valid = i < n;
+    unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      uint32_t d = rs_digit(keys, segs, i, pass);
+      unsigned peers = __match_any_sync(act, d);
+      uint32_t dst = wc[warp][d] + __popc(peers & lanemask_lt());
+      __syncwarp(act);
+      if (lane == (unsigned)(__ffs(peers) - 1)) wc[warp][d] += __popc(peers);
+      keys_out[dst] = keys[i];
+      if (segs_out) segs_out[dst] = segs[i];
+      vals_out[dst] = vals[i];
+    }
+    __syncwarp();
+  }
+}
+
+struct SortBufs {
+  uint64_t* key[2];
+  uint32_t* seg[2];  // may be null (round 0)
+  uint32_t* val[2];
+  int cur = 0;
+};
+
+// Sorts records [0,n) by digits `pass_list`; result ends up in b.{key,seg,val}[b.cur].
+int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, uint32_t* hist, uint32_t ntiles) {
+  for (int q = 0; q < npass; ++q) {
+    const int pass = pass_list[q];
+    const int s = b.cur, d = b.cur ^ 1;
+    k_radix_hist<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
+    ZDWB_LAUNCH_CHECK(ctx);
+    ZDWB_TRY(exclusive_scan_u32(ctx, hist, hist, (size_t)ntiles * 256, nullptr));
+    k_radix_scatter<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
+                                                           b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
+    ZDWB_LAUNCH_CHECK(ctx);
+    b.cur = d;
+  }
+  return ZDWB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// refinement bookkeeping
+// ---------------------------------------------------------------------------------------------
+// head[i] = record i starts a new tie group; unres[i] = record i is in a group of >= 2 records.
+__global__ void k_mark_groups(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs, uint32_t n,
+                              uint32_t* __restrict__ head, uint32_t* __restrict__ unres) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto is_head = [&](uint32_t j) -> bool {
+    if (j == 0) return true;
+    if (keys[j] != keys[j - 1]) return true;
+    if (segs && segs[j] != segs[j - 1]) return true;
+    return false;
+  };
+  const bool h = is_head(i);
+  const bool next_h = (i + 1 == n) ? true : is_head(i + 1);
+  head[i] = h ? 1u : 0u;
+  unres[i] = (h && next_h) ? 0u : 1u;
+}
+
+// Compacts unresolved records.  pos_in == nullptr -> identity (round 0).
+__global__ void k_compact_unresolved(const uint32_t* __restrict__ unres, const uint32_t* __restrict__ unres_scan,
+                                     const uint32_t* __restrict__ head_scan, const uint32_t* __restrict__ vals,
+                                     const uint32_t* __restrict__ pos_in, uint32_t n, uint32_t* __restrict__ ids_out,
+                                     uint32_t* __restrict__ seg_out, uint32_t* __restrict__ pos_out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !unres[i]) return;
+  const uint32_t j = unres_scan[i];
+  ids_out[j] = vals[i];
+  seg_out[j] = head_scan[i];  // group id = (#heads in [0..i]) - 1, prepared by k_group_ids
+  pos_out[j] = pos_in ? pos_in[i] : i;
+}
+
+// group id of record i = (#heads in [0..i]) - 1, from the exclusive scan of head[]
+__global__ void k_group_ids(const uint32_t* __restrict__ head, uint32_t* __restrict__ head_scan, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  head_scan[i] = head_scan[i] + head[i] - 1u;
+}
+
+__global__ void k_scatter_order(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ vals, uint32_t n,
+                                uint32_t* __restrict__ order) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[pos[i]] = vals[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// small path: one CTA, bitonic network in shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int SS_THREADS = 1024;
+
+__device__ __forceinline__ bool str_less_from(const uint8_t* base, uint32_t sa, uint32_t la, uint32_t sb, uint32_t lb,
+                                              uint32_t from) {
+  const uint32_t m = la < lb ? la : lb;
+  for (uint32_t i = from; i < m; ++i) {
+    uint8_t a = __ldg(base + sa + i), b = __ldg(base + sb + i);
+    if (a != b) return a < b;
+  }
+  return la < lb;
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+    k_small_sort(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
+                 uint32_t n, uint32_t npow2, uint32_t* __restrict__ order) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* id = reinterpret_cast<uint32_t*>(smem_raw + (size_t)npow2 * 8);
+  for (uint32_t i = threadIdx.x; i < npow2; i += SS_THREADS) {
+    if (i < n) {
+      key[i] = prefix_key(base + starts[i], lens[i], 0);
+      id[i] = i;
+    } else {
+      key[i] = ~0ull;
+      id[i] = 0xffffffffu;  // sentinel: greater than every real string
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = 2; k <= npow2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (npow2 >> 1); t += SS_THREADS) {
+        // t-th compare-exchange pair of this stage: insert a zero bit at position log2(j)
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t l = i | j;
+        const bool asc = (i & k) == 0;
+        const uint64_t ka = key[i], kb = key[l];
+        const uint32_t ia = id[i], ib = id[l];
+        bool a_less_b;  // strict
+        if (ia == 0xffffffffu) a_less_b = false;
+        else if (ib == 0xffffffffu) a_less_b = true;
+        else if (ka != kb) a_less_b = ka < kb;
+        else a_less_b = str_less_from(base, starts[ia], lens[ia], starts[ib], lens[ib], 8);
+        bool b_less_a;
+        if (ib == 0xffffffffu) b_less_a = false;
+        else if (ia == 0xffffffffu) b_less_a = true;
+        else if (ka != kb) b_less_a = kb < ka;
+        else b_less_a = !a_less_b && ia != ib;  // distinct strings: exactly one is smaller
+        const bool swap = asc ? b_less_a : a_less_b;
+        if (swap) {
+          key[i] = kb;
+          key[l] = ka;
+          id[i] = ib;
+          id[l] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += SS_THREADS) order[i] = id[i];
+}
+
+}  // namespace
+
+int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const uint32_t* lens, uint32_t n,
+                 uint32_t max_len, uint32_t* order_out) {
+  if (n == 0) return ZDWB_OK;
+  cudaStream_t st = ctx->stream;
+
+  // ---- small path
+  long long small_max = ctx->small_sort_max;
+  if (small_max > 16384) small_max = 16384;
+  if ((long long)n <= small_max) {
+    uint32_t np2 = 2;
+    while (np2 < n) np2 <<= 1;
+    const size_t smem = (size_t)np2 * 12;
+    ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_small_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
+    k_small_sort<<<1, SS_THREADS, smem, st>>>(base, starts, lens, n, np2, order_out);
+    ZDWB_LAUNCH_CHECK(ctx);
+    return ZDWB_OK;
+  }
+
+  // ---- large path
+  const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  DevBuf keyA, keyB, segA, segB, valA, valB, hist, head, unres, unres_scan, ids, pos, pos2, total;
+  ZDWB_TRY(keyA.alloc(ctx, (size_t)n * 8));
+  ZDWB_TRY(keyB.alloc(ctx, (size_t)n * 8));
+  ZDWB_TRY(valA.alloc(ctx, (size_t)n * 4));
+  ZDWB_TRY(valB.alloc(ctx, (size_t)n * 4));
+  ZDWB_TRY(hist.alloc(ctx, (size_t)ntiles * 256 * 4));
+  ZDWB_TRY(head.alloc(ctx, (size_t)n * 4));
+  ZDWB_TRY(unres.alloc(ctx, (size_t)n * 4));
+  ZDWB_TRY(unres_scan.alloc(ctx, (size_t)n * 4));
+  ZDWB_TRY(total.alloc(ctx, 16));
+
+  const unsigned g256 = (n + 255) / 256;
+  SortBufs b;
+  b.key[0] = keyA.as<uint64_t>();
+  b.key[1] = keyB.as<uint64_t>();
+  b.seg[0] = b.seg[1] = nullptr;
+  b.val[0] = valA.as<uint32_t>();
+  b.val[1] = valB.as<uint32_t>();
+  b.cur = 0;
+
+  // round 0: sort everything by the first 8 bytes
+  k_make_keys<<<g256, 256, 0, st>>>(base, starts, lens, nullptr, n, 0, b.key[0], b.val[0]);
+  ZDWB_LAUNCH_CHECK(ctx);
+  {
+    const int passes[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    ZDWB_TRY(radix_passes(ctx, b, n, passes, 8, hist.as<uint32_t>(), ntiles));
+  }
+  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(order_out, b.val[b.cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+
+  // tie groups of round 0
+  k_mark_groups<<<g256, 256, 0, st>>>(b.key[b.cur], nullptr, n, head.as<uint32_t>(), unres.as<uint32_t>());
+  ZDWB_LAUNCH_CHECK(ctx);
+  ZDWB_TRY(exclusive_scan_u32(ctx, unres.as<uint32_t>(), unres_scan.as<uint32_t>(), n, total.as<uint32_t>()));
+  uint32_t m = 0;
+  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->meta_host, total.p, 4, cudaMemcpyDeviceToHost, st));
+  ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  m = *reinterpret_cast<uint32_t*>(ctx->meta_host);
+  if (m == 0) return ZDWB_OK;
+
+  // unresolved records: ids, group ids, target positions
+  ZDWB_TRY(segA.alloc(ctx, (size_t)m * 4));
+  ZDWB_TRY(segB.alloc(ctx, (size_t)m * 4));
+  ZDWB_TRY(ids.alloc(ctx, (size_t)m * 4));
+  ZDWB_TRY(pos.alloc(ctx, (size_t)m * 4));
+  ZDWB_TRY(pos2.alloc(ctx, (size_t)m * 4));
+  {
+    DevBuf head_scan;
+    ZDWB_TRY(head_scan.alloc(ctx, (size_t)n * 4));
+    ZDWB_TRY(exclusive_scan_u32(ctx, head.as<uint32_t>(), head_scan.as<uint32_t>(), n, nullptr));
+    k_group_ids<<<g256, 256, 0, st>>>(head.as<uint32_t>(), head_scan.as<uint32_t>(), n);
+    ZDWB_LAUNCH_CHECK(ctx);
+    k_compact_unresolved<<<g256, 256, 0, st>>>(unres.as<uint32_t>(), unres_scan.as<uint32_t>(), head_scan.as<uint32_t>(),
+                                               b.val[b.cur], nullptr, n, ids.as<uint32_t>(), segA.as<uint32_t>(),
+                                               pos.as<uint32_t>());
+    ZDWB_LAUNCH_CHECK(ctx);
+  }
+  uint32_t* pos_cur = pos.as<uint32_t>();
+  uint32_t* pos_nxt = pos2.as<uint32_t>();
+
+  for (uint32_t round = 1;; ++round) {
+    const uint32_t off = round * 8;
+    if (off > max_len + 8) {
+      ctx->err = "sort_strings: tie groups did not resolve (duplicate strings in the unique set?)";
+      return ZDWB_ERR_CUDA;
+    }
+    const unsigned gm = (m + 255) / 256;
+    const uint32_t mt = (m + RS_TILE - 1) / RS_TILE;
+    // records: key = next 8 bytes, seg = group id, val = string id
+    b.seg[0] = segA.as<uint32_t>();
+    b.seg[1] = segB.as<uint32_t>();
+    // the current group ids live in segA; make sure the record set starts in slot 0
+    b.cur = 0;
+    k_make_keys<<<gm, 256, 0, st>>>(base, starts, lens, ids.as<uint32_t>(), m, off, b.key[0], b.val[0]);
+    ZDWB_LAUNCH_CHECK(ctx);
+    int passes[12];
+    int np = 0;
+    for (int p = 0; p < 8; ++p) passes[np++] = p;
+    const uint32_t seg_bytes = bytes_needed((uint64_t)(m ? m - 1 : 0));
+    for (uint32_t p = 0; p < seg_bytes; ++p) passes[np++] = 8 + (int)p;
+    ZDWB_TRY(radix_passes(ctx, b, m, passes, np, hist.as<uint32_t>(), mt));
+    // write the refined order back to the positions these records occupy
+    k_scatter_order<<<gm, 256, 0, st>>>(pos_cur, b.val[b.cur], m, order_out);
+    ZDWB_LAUNCH_CHECK(ctx);
+    // new tie groups
+    k_mark_groups<<<gm, 256, 0, st>>>(b.key[b.cur], b.seg[b.cur], m, head.as<uint32_t>(), unres.as<uint32_t>());
+    ZDWB_LAUNCH_CHECK(ctx);
+    ZDWB_TRY(exclusive_scan_u32(ctx, unres.as<uint32_t>(), unres_scan.as<uint32_t>(), m, total.as<uint32_t>()));
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->meta_host, total.p, 4, cudaMemcpyDeviceToHost, st));
+    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    const uint32_t m2 = *reinterpret_cast<uint32_t*>(ctx->meta_host);
+    if (m2 == 0) break;
+    {
+      DevBuf head_scan;
+      ZDWB_TRY(head_scan.alloc(ctx, (size_t)m * 4));
+      ZDWB_TRY(exclusive_scan_u32(ctx, head.as<uint32_t>(), head_scan.as<uint32_t>(), m, nullptr));
+      k_group_ids<<<gm, 256, 0, st>>>(head.as<uint32_t>(), head_scan.as<uint32_t>(), m);
+      ZDWB_LAUNCH_CHECK(ctx);
+      // compact into (ids, segA, pos_nxt).  The kernel reads none of the seg arrays (k_mark_groups, the last
+      // reader of the sorted segs, is already ordered before it), so the new group ids go straight to segA.
+      k_compact_unresolved<<<gm, 256, 0, st>>>(unres.as<uint32_t>(), unres_scan.as<uint32_t>(), head_scan.as<uint32_t>(),
+                                               b.val[b.cur], pos_cur, m, ids.as<uint32_t>(), segA.as<uint32_t>(), pos_nxt);
+      ZDWB_LAUNCH_CHECK(ctx);
+    }
+    uint32_t* t = pos_cur;
+    pos_cur = pos_nxt;
+    pos_nxt = t;
+    m = m2;
+  }
+  return ZDWB_OK;
+}
+
+}  // namespace zdwb
