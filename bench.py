@@ -1,0 +1,591 @@
+#!/usr/bin/env python
+"""bench.py -- TSV->ZDW encode / ZDW->TSV decode throughput of the B200 hot path (BASELINE config C4).
+
+  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle/_ref)
+
+Workload (config C4): synthetic analytics-hits-shaped TSV, 2 086 columns (256 populated),
+64 blocks of 131 072 rows (about 32 GB) generated from the reference's own analytics-hits fixture with
+seed 20190901.  ZDW blocks are independent, so the file is sharded by whole blocks over the N ranks
+(strong scaling: the total work is the same at every N) and there is no data-path collective; the host
+concatenates blocks in order.  A "step" encodes every block of the rank's shard and decodes it again.
+
+`value`   = encode GB/s, TSV bytes / device time, inputs resident in HBM, outputs left in HBM.
+`decode`  = the same for the decoder (ZDW blocks resident in HBM, TSV left in HBM).
+`e2e`     = the same metric through the C ABI with HOST buffers: pinned TSV in, host ZDW out (copies timed).
+`roofline`= dominant kernel, algorithmic bytes (TSV + ZDW of a block) / its mean launch time,
+            measured with CUDA events in one instrumented step after the timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import lzma
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+SEED = 20190901
+ROWS_PER_BLOCK = 131072
+TOTAL_BLOCKS = 64
+METRIC = "TSV->ZDW encode GB/s (decode GB/s alongside) on synthetic analytics-hits-shaped TSV"
+
+
+# --------------------------------------------------------------------------------------- generator
+def _build_synth() -> Path:
+    so = ROOT / "tools" / "libsynth_gen.so"
+    src = ROOT / "tools" / "synth_gen.c"
+    if not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-o", str(so), str(src)], check=True)
+    return so
+
+
+class Synth:
+    def __init__(self):
+        self.L = C.CDLL(str(_build_synth()))
+        self.L.synth_profile_create.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
+        self.L.synth_profile_create.restype = C.c_void_p
+        self.L.synth_block.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t]
+        self.L.synth_block.restype = C.c_size_t
+        self.L.synth_max_row_bytes.argtypes = [C.c_void_p]
+        self.L.synth_max_row_bytes.restype = C.c_uint32
+        fixture = lzma.decompress((ROOT / "tests" / "golden" / "analytics-hits.sql.xz").read_bytes())
+        self.desc = (ROOT / "tests" / "golden" / "analytics-hits.desc.sql").read_bytes()
+        import oracle as O  # desc parsing only (the reference's ReadDescFile rules)
+        self.schema = O.parse_desc(self.desc)
+        self.h = self.L.synth_profile_create(fixture, len(fixture), self.schema.ncols)
+        if not self.h:
+            raise RuntimeError("fixture does not parse")
+        self.max_row = self.L.synth_max_row_bytes(self.h)
+
+    def cap_for(self, rows: int) -> int:
+        return rows * 4600 + self.max_row + (1 << 20)
+
+    def block_into(self, block: int, rows: int, ptr: int, cap: int) -> int:
+        n = self.L.synth_block(self.h, SEED, block, rows, C.c_void_p(ptr), cap)
+        if n == 0:
+            raise RuntimeError("synthetic block did not fit its buffer")
+        return n
+
+
+# --------------------------------------------------------------------------------------- helpers
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[2 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def _ref_env():
+    ref = ROOT / "oracle" / "_ref"
+    env = dict(os.environ)
+    env["PATH"] = f"{ref / 'nocomp'}:{env.get('PATH', '')}"
+    return env
+
+
+def _ref_roundtrip(workdir: Path, tsv_path: Path, desc: bytes):
+    """One reference process: convertDWfile then unconvertDWfile on a shard. Returns (t_enc, t_dec, tsv_bytes)."""
+    ref = ROOT / "oracle" / "_ref"
+    (workdir / "x.desc.sql").write_bytes(desc)
+    if tsv_path != workdir / "x.sql":
+        os.symlink(tsv_path, workdir / "x.sql")
+    env = _ref_env()
+    t0 = time.perf_counter()
+    subprocess.run([str(ref / "convertDWfile"), "-q", "x.sql"], cwd=workdir, env=env, check=True, capture_output=True)
+    t1 = time.perf_counter()
+    os.rename(workdir / "x.zdw.gz", workdir / "y.zdw")
+    (workdir / "out").mkdir(exist_ok=True)
+    subprocess.run([str(ref / "unconvertDWfile"), "-q", "-d", "out", "y.zdw"], cwd=workdir, env=env, check=True, capture_output=True)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, tsv_path.stat().st_size
+
+
+def have_ref() -> bool:
+    ref = ROOT / "oracle" / "_ref"
+    return (ref / "convertDWfile").exists() and (ref / "unconvertDWfile").exists() and (ref / "nocomp" / "gzip").exists()
+
+
+def ref_parallel_step(synth: Synth, shard_rows: int, nproc: int, scratch: Path, inputs: list):
+    """nproc independent reference processes, one shard each (the reference is single-threaded).
+    Returns (enc_wall, dec_wall, total_tsv_bytes) with wall = slowest process."""
+    res = [None] * nproc
+
+    def work(i):
+        wd = scratch / f"p{i}"
+        if wd.exists():
+            shutil.rmtree(wd)
+        wd.mkdir(parents=True)
+        res[i] = _ref_roundtrip(wd, inputs[i], synth.desc)
+
+    with ThreadPoolExecutor(max_workers=nproc) as ex:
+        list(ex.map(work, range(nproc)))
+    return max(r[0] for r in res), max(r[1] for r in res), sum(r[2] for r in res)
+
+
+def make_ref_inputs(synth: Synth, rows: int, nproc: int, scratch: Path):
+    inputs = []
+    cap = synth.cap_for(rows)
+    buf = (C.c_uint8 * cap)()
+    for i in range(nproc):
+        n = synth.block_into(1000 + i, rows, C.addressof(buf), cap)
+        p = scratch / f"shard{i}.sql"
+        with open(p, "wb") as f:
+            f.write(memoryview(buf)[:n])
+        inputs.append(p)
+    return inputs
+
+
+def scratch_dir() -> Path:
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    return Path(tempfile.mkdtemp(prefix="zdwbench_", dir=base))
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    if not have_ref():
+        # the oracle always exists: fall back to the C port when the compiled reference did not travel
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref binaries missing on this box"}))
+        return 0
+    synth = Synth()
+    nproc = max(1, min(os.cpu_count() or 1, args.ref_procs))
+    rows = args.ref_rows
+    scratch = scratch_dir()
+    try:
+        inputs = make_ref_inputs(synth, rows, nproc, scratch)
+        for _ in range(args.warmup):
+            ref_parallel_step(synth, rows, nproc, scratch, inputs)
+        te, td, tot = [], [], 0
+        t_all0 = time.perf_counter()
+        for _ in range(args.steps):
+            e, d, b = ref_parallel_step(synth, rows, nproc, scratch, inputs)
+            te.append(e)
+            td.append(d)
+            tot = b
+        t_all = time.perf_counter() - t_all0
+        enc = tot * args.steps / sum(te) / 1e9
+        dec = tot * args.steps / sum(td) / 1e9
+        sample = (f"{nproc} independent convertDWfile/unconvertDWfile processes (reference is single-threaded), one "
+                  f"{rows}-row C4-shaped shard each ({tot / nproc / 1e6:.0f} MB), tmpfs, compressor stage replaced by cat")
+        line = {
+            "impl": "reference", "metric": METRIC, "value": enc, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, note="bounded sample per step, see cpu_baseline.sample"),
+            "decode": {"value": dec, "unit": "GB/s"},
+            "cpu_baseline": {"value": enc, "decode_value": dec, "unit": "GB/s", "cores": nproc, "kind": "reference", "sample": sample},
+            "e2e": {"value": enc, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "decode_value": dec},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+    return 0
+
+
+def workload_config(args, note=None):
+    cfg = {"workload": (f"C4 synthetic analytics-hits-shaped TSV: 2086 columns (256 populated), {args.blocks} blocks x "
+                        f"{args.rows_per_block} rows, seed {SEED}, block-sharded over {args.gpus} GPU(s)"),
+           "blocks": args.blocks, "rows_per_block": args.rows_per_block, "parallelism": f"block-shard x{args.gpus}",
+           "l2": "inputs larger than L2 (every block is ~0.5 GB and is read once per pass)"}
+    if note:
+        cfg["note"] = note
+    if getattr(args, "reduced_from", None):
+        cfg["reduced"] = f"host RAM too small for {args.reduced_from} blocks; ran {args.blocks}"
+    return cfg
+
+
+# --------------------------------------------------------------------------------------- CUDA arm
+def cpu_baseline_sample(synth: Synth, rows: int):
+    """Reference (oracle/_ref) on ONE core over one bounded shard; rank 0, N=1 only."""
+    if not have_ref():
+        return None
+    scratch = scratch_dir()
+    try:
+        inputs = make_ref_inputs(synth, rows, 1, scratch)
+        e, d, b = ref_parallel_step(synth, rows, 1, scratch, inputs)
+        return {"value": b / e / 1e9, "decode_value": b / d / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference",
+                "sample": f"one {rows}-row C4-shaped shard ({b / 1e6:.0f} MB): convertDWfile {e:.2f} s, unconvertDWfile {d:.2f} s, "
+                          "single process (the reference has no threads), tmpfs, compressor stage replaced by cat"}
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
+def run_cuda(args):
+    import torch
+
+    from zdw_b200 import Context
+    from zdw_b200.capi import load_library
+
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = load_library()
+    synth = Synth()
+    types = synth.schema.types
+
+    # ---- shard: whole blocks, contiguous ranges, in file order
+    nb = args.blocks
+    avail = _mem_available()
+    need = 2.3 * nb / world * synth.cap_for(args.rows_per_block)
+    if avail and need > avail:  # not enough host RAM for the named workload: shrink it and say so
+        nb = max(world, int(nb * avail / need))
+        args.reduced_from = args.blocks
+        args.blocks = nb
+    lo, hi = rank * nb // world, (rank + 1) * nb // world
+    my_blocks = list(range(lo, hi))
+    rows = args.rows_per_block
+
+    # ---- host (pinned) inputs
+    cap = synth.cap_for(rows)
+    host_ptrs, host_lens = [], []
+    pinned = True
+    for _ in my_blocks:
+        p = L.zdwb_host_alloc(cap)
+        if not p:
+            pinned = False
+            break
+        host_ptrs.append(p)
+    if not pinned:  # fall back to pageable memory (e2e gets slower; recorded in the JSON line)
+        for p in host_ptrs:
+            L.zdwb_host_free(p)
+        keep = [(C.c_uint8 * cap)() for _ in my_blocks]
+        host_ptrs = [C.addressof(k) for k in keep]
+    with ThreadPoolExecutor(max_workers=max(1, min(len(my_blocks), (os.cpu_count() or 2) // max(1, world), 16))) as ex:
+        host_lens = list(ex.map(lambda ib: synth.block_into(ib[1], rows, host_ptrs[ib[0]], cap), list(enumerate(my_blocks))))
+    tsv_bytes = sum(host_lens)
+
+    ctx = Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- device-resident inputs
+    dev_tsv = []
+    for p, n in zip(host_ptrs, host_lens):
+        t = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+        arr = (C.c_uint8 * n).from_address(p)
+        t[:n].copy_(torch.frombuffer(arr, dtype=torch.uint8), non_blocking=False)
+        dev_tsv.append(t)
+    torch.cuda.synchronize(dev)
+
+    # ---- one untimed pass: produce the ZDW blocks the decoder will read, and keep host copies for e2e decode
+    dev_zdw, zdw_lens, host_zdw = [], [], []
+    for t, n in zip(dev_tsv, host_lens):
+        blk = ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
+        z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)
+        _d2d(torch, z, blk.dev_ptr, blk.length)
+        dev_zdw.append(z)
+        zdw_lens.append(blk.length)
+    torch.cuda.synchronize(dev)
+    zdw_bytes = sum(zdw_lens)
+    for z, n in zip(dev_zdw, zdw_lens):
+        host_zdw.append(z[:n].cpu().numpy().tobytes())
+
+    def encode_pass():
+        for t, n in zip(dev_tsv, host_lens):
+            ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
+
+    def decode_pass():
+        for z, n in zip(dev_zdw, zdw_lens):
+            ctx.decode_block(types, z.data_ptr(), n, input_on_device=True, output_on_device=True)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- parity gate: the first block must round-trip bit-exactly (every timing counts only if parity holds)
+    rt = ctx.decode_block(types, dev_zdw[0].data_ptr(), zdw_lens[0], input_on_device=True, output_on_device=True)
+    back = torch.empty(rt.length, dtype=torch.uint8, device=dev)
+    _d2d(torch, back, rt.dev_ptr, rt.length)
+    if rt.length != host_lens[0] or not torch.equal(back, dev_tsv[0][:host_lens[0]]):
+        raise SystemExit("parity gate failed: decode(encode(block 0)) != block 0")
+
+    for _ in range(args.warmup):
+        encode_pass()
+        decode_pass()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    enc_ms, dec_ms = [], []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev[0].record(stream)
+        encode_pass()
+        ev[1].record(stream)
+        decode_pass()
+        ev[2].record(stream)
+        ev[2].synchronize()
+        enc_ms.append(ev[0].elapsed_time(ev[1]))
+        dec_ms.append(ev[1].elapsed_time(ev[2]))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop()
+
+    # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H inside the timed region)
+    def e2e_encode_pass():
+        tot = 0
+        for p, n in zip(host_ptrs, host_lens):
+            blk = L_encode_host(ctx, types, p, n)
+            tot += blk
+        return tot
+
+    def e2e_decode_pass():
+        tot = 0
+        for zb in host_zdw:
+            r = ctx.decode_block(types, zb)
+            tot += r.length
+        return tot
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_encode_pass()
+    barrier()
+    t0 = time.perf_counter()
+    d2h_enc = 0
+    for _ in range(e2e_steps):
+        d2h_enc = e2e_encode_pass()
+    torch.cuda.synchronize(dev)
+    t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
+    e2e_dec_blocks = host_zdw[:max(1, args.e2e_decode_blocks)]
+    t0 = time.perf_counter()
+    d2h_dec = 0
+    for zb in e2e_dec_blocks:
+        d2h_dec += ctx.decode_block(types, zb).length
+    torch.cuda.synchronize(dev)
+    t_e2e_dec = time.perf_counter() - t0
+
+    # ---- instrumented step: per-kernel CUDA-event times for the roofline
+    ctx.set_tuning("kernel_timing", 1)
+    ctx.kernel_times()
+    encode_pass()
+    kt_enc = ctx.kernel_times()
+    decode_pass()
+    kt_dec = ctx.kernel_times()
+    ctx.set_tuning("kernel_timing", 0)
+
+    # ---- reduce over ranks: time = max, bytes = sum
+    enc_t = sum(enc_ms) / 1e3
+    dec_t = sum(dec_ms) / 1e3
+    vals = torch.tensor([enc_t, dec_t, t_e2e_enc, t_e2e_dec, t_wall], dtype=torch.float64, device=dev)
+    sums = torch.tensor([tsv_bytes, zdw_bytes, float(d2h_enc), float(d2h_dec), float(launches),
+                         float(sum(host_lens[:len(e2e_dec_blocks)]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    enc_t, dec_t, t_e2e_enc, t_e2e_dec, t_wall = [float(x) for x in vals.tolist()]
+    tot_tsv, tot_zdw, d2h_enc_all, d2h_dec_all, launches_all, e2e_dec_tsv = [float(x) for x in sums.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        enc_gbs = tot_tsv * args.steps / enc_t / 1e9
+        dec_gbs = tot_tsv * args.steps / dec_t / 1e9
+        nblk = len(my_blocks)
+        alg_bytes_block = (tsv_bytes + zdw_bytes) / nblk  # B_enc = B_dec = TSV + ZDW bytes of a block
+
+        def roof(kt, traffic_key):
+            if not kt:
+                return None
+            name, (cnt, ms) = max(kt.items(), key=lambda kv: kv[1][1])
+            per_launch_s = ms / 1e3 / nblk  # this kernel's time per block (it is launched once per block)
+            ach = alg_bytes_block / per_launch_s / 1e9
+            total_ms = sum(v[1] for v in kt.values())
+            return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "peak_source": peak_src, "traffic": _traffic(name),
+                    "algorithmic_bytes_per_launch": alg_bytes_block, "launch_ms": per_launch_s * 1e3,
+                    "launches_per_block": cnt / nblk,
+                    "share_of_step": ms / total_ms if total_ms else None,
+                    "kernels_ms_per_block": {k: round(v[1] / nblk, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][1])},
+                    "timed": "instrumented step (CUDA events around every launch) right after the timed steps"}
+
+        line = {
+            "metric": METRIC, "value": enc_gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (enc_t + dec_t) / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+            "encode": {"value": enc_gbs, "unit": "GB/s", "ms_per_step": 1e3 * enc_t / args.steps,
+                       "pipeline_frac_of_hbm_peak": (tot_tsv + tot_zdw) * args.steps / enc_t / 1e9 / (peak * world)},
+            "decode": {"value": dec_gbs, "unit": "GB/s", "ms_per_step": 1e3 * dec_t / args.steps,
+                       "pipeline_frac_of_hbm_peak": (tot_tsv + tot_zdw) * args.steps / dec_t / 1e9 / (peak * world),
+                       "roofline": roof(kt_dec, "decode")},
+            "roofline": roof(kt_enc, "encode"),
+            "e2e": {"value": tot_tsv / t_e2e_enc / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(tot_tsv),
+                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned,
+                    "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks),
+                    "decode_d2h_bytes": int(d2h_dec_all)},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "tsv_bytes": int(tot_tsv), "zdw_bytes": int(tot_zdw),
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline_sample(synth, args.cpu_rows)
+            line["cpu_baseline"] = cb if cb else {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
+                                                  "sample": "oracle/_ref missing on this box"}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _mem_available():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024 // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except OSError:
+        pass
+    return None
+
+
+def _traffic(kernel: str):
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def _d2d(torch, dst_tensor, src_ptr: int, n: int):
+    """device->device copy from a raw pointer into a torch tensor (plain cudaMemcpyAsync on torch's stream)."""
+    cudart = _cudart()
+    rc = cudart.cudaMemcpyAsync(C.c_void_p(dst_tensor.data_ptr()), C.c_void_p(src_ptr), C.c_size_t(n), 3,
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"cudaMemcpyAsync failed: {rc}")
+    torch.cuda.current_stream().synchronize()
+
+
+_CUDART = None
+
+
+def _cudart():
+    global _CUDART
+    if _CUDART is None:
+        for name in ("libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                _CUDART = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        _CUDART.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    return _CUDART
+
+
+def L_encode_host(ctx, types, ptr: int, n: int) -> int:
+    """Host pointer in, host bytes out, without copying the input through Python."""
+    from zdw_b200 import capi
+    tarr = (C.c_uint8 * len(types))(*types)
+    sch = capi._Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
+    o = capi._EncOpts(0, 0, 0, 0, 0, 0, 0)
+    out = capi._BlockOut()
+    rc = ctx._L.zdwb_encode_block(ctx._h, C.byref(sch), C.c_void_p(ptr), n, C.byref(o), C.byref(out))
+    if rc:
+        raise RuntimeError(ctx.last_error())
+    return int(out.len)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--blocks", type=int, default=TOTAL_BLOCKS)
+    ap.add_argument("--rows-per-block", type=int, default=ROWS_PER_BLOCK)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-decode-blocks", type=int, default=8)
+    ap.add_argument("--cpu-rows", type=int, default=131072, help="rows of the bounded cpu_baseline sample")
+    ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")
+    ap.add_argument("--ref-procs", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -74,12 +74,18 @@ const char* zdwb_last_error(const zdwb_ctx* ctx);
 int zdwb_ctx_set_stream(zdwb_ctx* ctx, void* cuda_stream);
 
 /* Tuning / test knobs (name = value).  Known names: "small_sort_max" (largest dictionary sorted by the
- * single-CTA path), "ht_load_shift" (hash table slots = 2^shift * upper bound).  Returns ZDWB_ERR_BAD_ARG
+ * single-CTA path), "ht_initial_log2" (first-try size of the string hash set), "dec_tile_bytes" (row-stream bytes
+ * per CTA in the decoder's row-boundary discovery), "kernel_timing" (0/1).  Returns ZDWB_ERR_BAD_ARG
  * for unknown names. */
 int zdwb_ctx_set_tuning(zdwb_ctx* ctx, const char* name, long long value);
 
 /* Number of kernels this context has launched so far (bench.py reports the delta as gpu_launches). */
 unsigned long long zdwb_ctx_kernel_launches(const zdwb_ctx* ctx);
+
+/* With the tuning knob "kernel_timing" = 1 every kernel launch is bracketed by CUDA events on the launching
+ * stream.  This call synchronises, writes one line "name<TAB>launches<TAB>total_ms" per kernel into buf
+ * (NUL-terminated, truncated to cap), clears the record and returns the untruncated length. */
+size_t zdwb_ctx_kernel_times(zdwb_ctx* ctx, char* buf, size_t cap);
 
 int zdwb_abi_version(void);
 

@@ -16,7 +16,7 @@ STATUS_NAMES = {0: "OK", 1: "ERR_CUDA", 2: "ERR_OOM", 3: "ERR_WRONG_COLUMNS", 4:
 
 EXPORTED_SYMBOLS = [
     "zdwb_abi_version", "zdwb_ctx_create", "zdwb_ctx_destroy", "zdwb_last_error", "zdwb_ctx_set_stream",
-    "zdwb_ctx_set_tuning", "zdwb_ctx_kernel_launches", "zdwb_encode_block", "zdwb_decode_block", "zdwb_host_alloc",
+    "zdwb_ctx_set_tuning", "zdwb_ctx_kernel_launches", "zdwb_ctx_kernel_times", "zdwb_encode_block", "zdwb_decode_block", "zdwb_host_alloc",
     "zdwb_host_free",
 ]
 
@@ -85,6 +85,8 @@ def load_library():
     L.zdwb_ctx_set_tuning.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     L.zdwb_ctx_kernel_launches.argtypes = [C.c_void_p]
     L.zdwb_ctx_kernel_launches.restype = C.c_ulonglong
+    L.zdwb_ctx_kernel_times.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.zdwb_ctx_kernel_times.restype = C.c_size_t
     L.zdwb_encode_block.argtypes = [C.c_void_p, C.POINTER(_Schema), C.c_void_p, C.c_size_t, C.POINTER(_EncOpts),
                                     C.POINTER(_BlockOut)]
     L.zdwb_decode_block.argtypes = [C.c_void_p, C.POINTER(_Schema), C.c_void_p, C.c_size_t, C.POINTER(_DecOpts),
@@ -169,6 +171,16 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self._L.zdwb_ctx_kernel_launches(self._h))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (launches, total_ms)} since the last call (needs set_tuning("kernel_timing", 1))."""
+        buf = C.create_string_buffer(1 << 16)
+        self._L.zdwb_ctx_kernel_times(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split("\t")
+            out[name] = (int(cnt), float(ms))
+        return out
 
     # ------------------------------------------------------------------ encode
     def encode_block(self, types, tsv, n: int | None = None, *, trim=False, input_on_device=False,

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/zdw_b200.h"
 
@@ -39,6 +40,33 @@ struct Ctx {
   void* in_stage = nullptr;    // pinned staging for pageable host inputs (unused when caller memory is pinned)
   // small pinned scratch for device->host readbacks of metadata
   void* meta_host = nullptr;
+  // optional per-kernel timing (CUDA events on the launching stream), for the roofline report
+  bool timing = false;
+  struct Timed {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Timed> timed;
+};
+
+// Brackets one kernel launch with events when Ctx::timing is on (zero cost otherwise).
+struct KernelScope {
+  Ctx* c;
+  const char* name;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelScope(Ctx* ctx, const char* n) : c(ctx), name(n) {
+    if (c->timing) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c->stream);
+    }
+  }
+  ~KernelScope() {
+    if (e0) {
+      cudaEventRecord(e1, c->stream);
+      c->timed.push_back(Ctx::Timed{name, e0, e1});
+    }
+  }
 };
 
 struct Status {

@@ -1,4 +1,5 @@
 // ctx.cu -- C ABI entry points of libzdw_b200 (see include/zdw_b200.h).
+#include <map>
 #include <new>
 
 #include "common.cuh"
@@ -86,11 +87,43 @@ int zdwb_ctx_set_tuning(zdwb_ctx* c, const char* name, long long value) {
   if (!strcmp(name, "small_sort_max")) c->small_sort_max = value;
   else if (!strcmp(name, "ht_initial_log2")) c->ht_initial_log2 = value;
   else if (!strcmp(name, "dec_tile_bytes")) c->dec_tile_bytes = value;
+  else if (!strcmp(name, "kernel_timing")) c->timing = value != 0;
   else return ZDWB_ERR_BAD_ARG;
   return ZDWB_OK;
 }
 
 unsigned long long zdwb_ctx_kernel_launches(const zdwb_ctx* c) { return c ? c->launches : 0ull; }
+
+size_t zdwb_ctx_kernel_times(zdwb_ctx* c, char* buf, size_t cap) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  std::map<std::string, std::pair<unsigned long long, double>> agg;
+  for (auto& t : c->timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+      auto& a = agg[t.name];
+      a.first += 1;
+      a.second += ms;
+    }
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  c->timed.clear();
+  (void)cudaGetLastError();
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap) {
+    const size_t k = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), k);
+    buf[k] = 0;
+  }
+  return out.size();
+}
 
 int zdwb_encode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
                       zdwb_block_out* out) {

@@ -752,7 +752,10 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
       return ZDWB_ERR_UNSUPPORTED;
     }
     ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_tile_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_dec_tile_maps<<<ntiles, DEC_THREADS, smem_maps, st>>>(P, win, T, maps0.as<uint64_t>());
+    {
+      KernelScope _ks(ctx, "k_dec_tile_maps");
+      k_dec_tile_maps<<<ntiles, DEC_THREADS, smem_maps, st>>>(P, win, T, maps0.as<uint64_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     // up-sweep: compose groups of G maps until one remains
     const uint32_t G = 32;
@@ -774,7 +777,10 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
         cleanup();
         return rc;
       }
-      k_dec_compose<<<n_out, DEC_THREADS, 0, st>>>(levels.back()->as<uint64_t>(), n_in, M, G, nb->as<uint64_t>());
+      {
+        KernelScope _ks(ctx, "k_dec_compose");
+        k_dec_compose<<<n_out, DEC_THREADS, 0, st>>>(levels.back()->as<uint64_t>(), n_in, M, G, nb->as<uint64_t>());
+      }
       ctx->launches++;
       levels.push_back(nb);
       counts.push_back(n_out);
@@ -799,14 +805,20 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
         cleanup();
         return rc;
       }
-      k_dec_descend<<<(n_parent + 127) / 128, 128, 0, st>>>(levels[lv]->as<uint64_t>(), n_in, M, G, ent_parent->as<uint64_t>(),
+      {
+        KernelScope _ks(ctx, "k_dec_descend");
+        k_dec_descend<<<(n_parent + 127) / 128, 128, 0, st>>>(levels[lv]->as<uint64_t>(), n_in, M, G, ent_parent->as<uint64_t>(),
                                                           n_parent, ec->as<uint64_t>());
+      }
       ctx->launches++;
       ent_parent = ec;
     }
     // with a single tile the root entry is the tile entry
-    k_dec_row_starts<<<(ntiles + DEC_WARPS - 1) / DEC_WARPS, DEC_THREADS, 0, st>>>(P, T, ntiles, ent_parent->as<uint64_t>(),
+    {
+      KernelScope _ks(ctx, "k_dec_row_starts");
+      k_dec_row_starts<<<(ntiles + DEC_WARPS - 1) / DEC_WARPS, DEC_THREADS, 0, st>>>(P, T, ntiles, ent_parent->as<uint64_t>(),
                                                                                   row_off.as<uint32_t>());
+    }
     ctx->launches++;
     cudaError_t le = cudaGetLastError();
     uint32_t h_end = 0;
@@ -855,21 +867,33 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     ZDWB_TRY(shas.alloc(ctx, (size_t)nstrips * U));
     const size_t smem_sum = (size_t)U * 4 + lut_smem + 16;
     ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_strip_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R, lut_in_smem,
+    {
+      KernelScope _ks(ctx, "k_dec_strip_summary");
+      k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R, lut_in_smem,
                                                                sval.as<unsigned long long>(), shas.as<uint8_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     const uint32_t S = (nstrips + 255) / 256;
     const uint32_t nseg = (nstrips + S - 1) / S;
     ZDWB_TRY(seg_val.alloc(ctx, (size_t)nseg * U * 8));
     ZDWB_TRY(seg_has.alloc(ctx, (size_t)nseg * U));
     dim3 g2((U + 127) / 128, nseg);
-    k_carry_reduce<<<g2, 128, 0, st>>>(sval.as<unsigned long long>(), shas.as<uint8_t>(), nstrips, U, S,
+    {
+      KernelScope _ks(ctx, "k_carry_reduce");
+      k_carry_reduce<<<g2, 128, 0, st>>>(sval.as<unsigned long long>(), shas.as<uint8_t>(), nstrips, U, S,
                                        seg_val.as<unsigned long long>(), seg_has.as<uint8_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
-    k_carry_scan<<<(U + 127) / 128, 128, 0, st>>>(seg_val.as<unsigned long long>(), seg_has.as<uint8_t>(), nseg, U);
+    {
+      KernelScope _ks(ctx, "k_carry_scan");
+      k_carry_scan<<<(U + 127) / 128, 128, 0, st>>>(seg_val.as<unsigned long long>(), seg_has.as<uint8_t>(), nseg, U);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
-    k_carry_apply<<<g2, 128, 0, st>>>(sval.as<unsigned long long>(), shas.as<uint8_t>(), seg_val.as<unsigned long long>(), nstrips,
+    {
+      KernelScope _ks(ctx, "k_carry_apply");
+      k_carry_apply<<<g2, 128, 0, st>>>(sval.as<unsigned long long>(), shas.as<uint8_t>(), seg_val.as<unsigned long long>(), nstrips,
                                       U, S, cin.as<unsigned long long>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
   }
 
@@ -905,10 +929,13 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     }
     ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, (size_t)nstrips * 8, st));
     ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(d_meta.p, 0, sizeof(DecMeta), st));
-    k_dec_format<<<nstrips, DEC_THREADS, smem_fmt, st>>>(P, FT, row_off.as<uint32_t>(), R, lut_in_smem,
+    {
+      KernelScope _ks(ctx, "k_dec_format");
+      k_dec_format<<<nstrips, DEC_THREADS, smem_fmt, st>>>(P, FT, row_off.as<uint32_t>(), R, lut_in_smem,
                                                         cin.as<unsigned long long>(), status.as<uint64_t>(),
                                                         static_cast<uint8_t*>(ctx->out_dev), out_cap,
                                                         static_cast<uint64_t*>(ctx->out_dev2), meta);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hm, meta, sizeof(DecMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));

@@ -694,7 +694,10 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   DevBuf tile_cnt, total_d;
   ZDWB_TRY(tile_cnt.alloc(ctx, (size_t)idx_tiles * 8));
   ZDWB_TRY(total_d.alloc(ctx, 8));
-  k_rows_count<<<idx_tiles, ENC_THREADS, 0, st>>>(buf, n, lo, tile_cnt.as<uint64_t>());
+  {
+    KernelScope _ks(ctx, "k_rows_count");
+    k_rows_count<<<idx_tiles, ENC_THREADS, 0, st>>>(buf, n, lo, tile_cnt.as<uint64_t>());
+  }
   ZDWB_LAUNCH_CHECK(ctx);
   ZDWB_TRY(exclusive_scan_u64(ctx, tile_cnt.as<uint64_t>(), tile_cnt.as<uint64_t>(), idx_tiles, total_d.as<uint64_t>()));
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->meta_host, total_d.p, 8, cudaMemcpyDeviceToHost, st));
@@ -709,8 +712,11 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   DevBuf row_start, row_end;
   ZDWB_TRY(row_start.alloc(ctx, (size_t)(rows_total + 1) * 4));
   ZDWB_TRY(row_end.alloc(ctx, (size_t)rows_total * 4));
-  k_rows_write<<<idx_tiles, ENC_THREADS, 0, st>>>(buf, n, lo, tile_cnt.as<uint64_t>(), ncols, row_start.as<uint32_t>(),
+  {
+    KernelScope _ks(ctx, "k_rows_write");
+    k_rows_write<<<idx_tiles, ENC_THREADS, 0, st>>>(buf, n, lo, tile_cnt.as<uint64_t>(), ncols, row_start.as<uint32_t>(),
                                                   row_end.as<uint32_t>(), meta);
+  }
   ZDWB_LAUNCH_CHECK(ctx);
 
   const uint64_t nrows64 = (opts->max_rows && opts->max_rows < rows_total) ? opts->max_rows : rows_total;
@@ -745,8 +751,11 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   }
   out->nrows = nrows;
 
-  k_row_longest<<<std::min<uint32_t>((nrows + 255) / 256, 1024u), 256, 0, st>>>(row_start.as<uint32_t>(), row_end.as<uint32_t>(),
+  {
+    KernelScope _ks(ctx, "k_row_longest");
+    k_row_longest<<<std::min<uint32_t>((nrows + 255) / 256, 1024u), 256, 0, st>>>(row_start.as<uint32_t>(), row_end.as<uint32_t>(),
                                                                               nrows, tail_bytes, meta);
+  }
   ZDWB_LAUNCH_CHECK(ctx);
 
   // ---- pass 1 (retry with a larger hash set when it fills up)
@@ -774,12 +783,18 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(slots.p, 0, cap * 8, st));
     ht.slots = slots.as<unsigned long long>();
     ht.mask = (uint32_t)(cap - 1);
-    k_init_minmax<<<(ncols + 255) / 256, 256, 0, st>>>(colmin.as<unsigned long long>(), colmax.as<unsigned long long>(),
+    {
+      KernelScope _ks(ctx, "k_init_minmax");
+      k_init_minmax<<<(ncols + 255) / 256, 256, 0, st>>>(colmin.as<unsigned long long>(), colmax.as<unsigned long long>(),
                                                        colset.as<uint32_t>(), ncols);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
-    k_pass1<<<tiles1, ENC_THREADS, 0, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc1, ncols,
+    {
+      KernelScope _ks(ctx, "k_pass1");
+      k_pass1<<<tiles1, ENC_THREADS, 0, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc1, ncols,
                                             types_d.as<uint8_t>(), opts->trim_trailing_spaces, ht, colset.as<uint32_t>(),
                                             colmin.as<unsigned long long>(), colmax.as<unsigned long long>(), meta);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -814,9 +829,12 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   ZDWB_TRY(cbase.alloc(ctx, (size_t)ncols * 8));
   ZDWB_TRY(used_idx.alloc(ctx, (size_t)ncols * 4));
   ZDWB_TRY(used_cols.alloc(ctx, (size_t)ncols * 4));
-  k_col_stats<<<1, ENC_THREADS, 0, st>>>(types_d.as<uint8_t>(), ncols, colset.as<uint32_t>(), colmin.as<unsigned long long>(),
+  {
+    KernelScope _ks(ctx, "k_col_stats");
+    k_col_stats<<<1, ENC_THREADS, 0, st>>>(types_d.as<uint8_t>(), ncols, colset.as<uint32_t>(), colmin.as<unsigned long long>(),
                                          colmax.as<unsigned long long>(), csize.as<uint8_t>(), cbase.as<unsigned long long>(),
                                          used_idx.as<int32_t>(), used_cols.as<uint32_t>(), meta);
+  }
   ZDWB_LAUNCH_CHECK(ctx);
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
   ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -835,9 +853,12 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ctx->out_dev = ob.detach();
   }
   uint8_t* outp = static_cast<uint8_t*>(ctx->out_dev);
-  k_block_header<<<std::max(1u, std::min((ncols + 255) / 256, 64u)), 256, 0, st>>>(
+  {
+    KernelScope _ks(ctx, "k_block_header");
+    k_block_header<<<std::max(1u, std::min((ncols + 255) / 256, 64u)), 256, 0, st>>>(
       outp, meta, nrows, longest_field, is_last ? 1u : 0u, ncols, csize.as<uint8_t>(), cbase.as<unsigned long long>(),
       used_cols.as<uint32_t>());
+  }
   ZDWB_LAUNCH_CHECK(ctx);
 
   // ---- dictionary: compact, sort, offsets, emit
@@ -852,17 +873,26 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ZDWB_TRY(order.alloc(ctx, (size_t)nu * 4));
     ZDWB_TRY(offs.alloc(ctx, (size_t)nu * 4));
     const uint32_t cap = ht.mask + 1;
-    k_ht_compact<<<(cap + ENC_THREADS - 1) / ENC_THREADS, ENC_THREADS, 0, st>>>(ht.slots, cap, ustart.as<uint32_t>(),
+    {
+      KernelScope _ks(ctx, "k_ht_compact");
+      k_ht_compact<<<(cap + ENC_THREADS - 1) / ENC_THREADS, ENC_THREADS, 0, st>>>(ht.slots, cap, ustart.as<uint32_t>(),
                                                                                ulen.as<uint32_t>(), uslot.as<uint32_t>(), meta);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(sort_strings(ctx, buf, ustart.as<uint32_t>(), ulen.as<uint32_t>(), nu, hmeta->max_str_len, order.as<uint32_t>()));
-    k_sorted_lens<<<(nu + 255) / 256, 256, 0, st>>>(order.as<uint32_t>(), ulen.as<uint32_t>(), nu, offs.as<uint32_t>());
+    {
+      KernelScope _ks(ctx, "k_sorted_lens");
+      k_sorted_lens<<<(nu + 255) / 256, 256, 0, st>>>(order.as<uint32_t>(), ulen.as<uint32_t>(), nu, offs.as<uint32_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u32(ctx, offs.as<uint32_t>(), offs.as<uint32_t>(), nu, nullptr));
     const uint64_t threads = (uint64_t)nu * 8;
-    k_dict_emit<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(buf, order.as<uint32_t>(), ustart.as<uint32_t>(),
+    {
+      KernelScope _ks(ctx, "k_dict_emit");
+      k_dict_emit<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(buf, order.as<uint32_t>(), ustart.as<uint32_t>(),
                                                                   ulen.as<uint32_t>(), uslot.as<uint32_t>(), offs.as<uint32_t>(),
                                                                   nu, outp + hmeta->dict_base, slot_off.as<uint32_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
   }
 
@@ -888,11 +918,14 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     DevBuf status;
     ZDWB_TRY(status.alloc(ctx, (size_t)tiles2 * 8));
     ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, (size_t)tiles2 * 8, st));
-    k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc2, ncols,
+    {
+      KernelScope _ks(ctx, "k_pass2");
+      k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc2, ncols,
                                                types_d.as<uint8_t>(), opts->trim_trailing_spaces, ht, slot_off.as<uint32_t>(),
                                                used_idx.as<int32_t>(), used_cols.as<uint32_t>(), csize.as<uint8_t>(),
                                                cbase.as<unsigned long long>(), U, nflag, status.as<uint64_t>(), outp + rows_base,
                                                meta);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));

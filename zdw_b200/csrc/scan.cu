@@ -89,16 +89,25 @@ int exclusive_scan_impl(Ctx* ctx, const T* in, T* out, size_t n, T* total_dev) {
   }
   const size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (nb == 1) {
-    k_scan_down<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, nullptr, total_dev);
+    {
+      KernelScope _ks(ctx, "k_scan_down");
+      k_scan_down<T><<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, nullptr, total_dev);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     return ZDWB_OK;
   }
   DevBuf sums;
   ZDWB_TRY(sums.alloc(ctx, nb * sizeof(T)));
-  k_scan_reduce<T><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.as<T>());
+  {
+    KernelScope _ks(ctx, "k_scan_reduce");
+    k_scan_reduce<T><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.as<T>());
+  }
   ZDWB_LAUNCH_CHECK(ctx);
   ZDWB_TRY(exclusive_scan_impl<T>(ctx, sums.as<T>(), sums.as<T>(), nb, nullptr));
-  k_scan_down<T><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, sums.as<T>(), total_dev);
+  {
+    KernelScope _ks(ctx, "k_scan_down");
+    k_scan_down<T><<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, sums.as<T>(), total_dev);
+  }
   ZDWB_LAUNCH_CHECK(ctx);
   return ZDWB_OK;
 }

@@ -139,11 +139,17 @@ int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int np
   for (int q = 0; q < npass; ++q) {
     const int pass = pass_list[q];
     const int s = b.cur, d = b.cur ^ 1;
-    k_radix_hist<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
+    {
+      KernelScope _ks(ctx, "k_radix_hist");
+      k_radix_hist<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u32(ctx, hist, hist, (size_t)ntiles * 256, nullptr));
-    k_radix_scatter<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
+    {
+      KernelScope _ks(ctx, "k_radix_scatter");
+      k_radix_scatter<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
                                                            b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     b.cur = d;
   }
@@ -275,7 +281,10 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
     while (np2 < n) np2 <<= 1;
     const size_t smem = (size_t)np2 * 12;
     ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_small_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
-    k_small_sort<<<1, SS_THREADS, smem, st>>>(base, starts, lens, n, np2, order_out);
+    {
+      KernelScope _ks(ctx, "k_small_sort");
+      k_small_sort<<<1, SS_THREADS, smem, st>>>(base, starts, lens, n, np2, order_out);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     return ZDWB_OK;
   }
@@ -303,7 +312,10 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   b.cur = 0;
 
   // round 0: sort everything by the first 8 bytes
-  k_make_keys<<<g256, 256, 0, st>>>(base, starts, lens, nullptr, n, 0, b.key[0], b.val[0]);
+  {
+    KernelScope _ks(ctx, "k_make_keys");
+    k_make_keys<<<g256, 256, 0, st>>>(base, starts, lens, nullptr, n, 0, b.key[0], b.val[0]);
+  }
   ZDWB_LAUNCH_CHECK(ctx);
   {
     const int passes[8] = {0, 1, 2, 3, 4, 5, 6, 7};
@@ -312,7 +324,10 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(order_out, b.val[b.cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
 
   // tie groups of round 0
-  k_mark_groups<<<g256, 256, 0, st>>>(b.key[b.cur], nullptr, n, head.as<uint32_t>(), unres.as<uint32_t>());
+  {
+    KernelScope _ks(ctx, "k_mark_groups");
+    k_mark_groups<<<g256, 256, 0, st>>>(b.key[b.cur], nullptr, n, head.as<uint32_t>(), unres.as<uint32_t>());
+  }
   ZDWB_LAUNCH_CHECK(ctx);
   ZDWB_TRY(exclusive_scan_u32(ctx, unres.as<uint32_t>(), unres_scan.as<uint32_t>(), n, total.as<uint32_t>()));
   uint32_t m = 0;
@@ -331,15 +346,24 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
     DevBuf head_scan;
     ZDWB_TRY(head_scan.alloc(ctx, (size_t)n * 4));
     ZDWB_TRY(exclusive_scan_u32(ctx, head.as<uint32_t>(), head_scan.as<uint32_t>(), n, nullptr));
-    k_group_ids<<<g256, 256, 0, st>>>(head.as<uint32_t>(), head_scan.as<uint32_t>(), n);
+    {
+      KernelScope _ks(ctx, "k_group_ids");
+      k_group_ids<<<g256, 256, 0, st>>>(head.as<uint32_t>(), head_scan.as<uint32_t>(), n);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
-    k_compact_unresolved<<<g256, 256, 0, st>>>(unres.as<uint32_t>(), unres_scan.as<uint32_t>(), head_scan.as<uint32_t>(),
+    {
+      KernelScope _ks(ctx, "k_compact_unresolved");
+      k_compact_unresolved<<<g256, 256, 0, st>>>(unres.as<uint32_t>(), unres_scan.as<uint32_t>(), head_scan.as<uint32_t>(),
                                                b.val[b.cur], nullptr, n, ids.as<uint32_t>(), segA.as<uint32_t>(),
                                                pos.as<uint32_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
   }
   uint32_t* pos_cur = pos.as<uint32_t>();
   uint32_t* pos_nxt = pos2.as<uint32_t>();
+  // group ids are numbered over the record set they were computed on: all n records after round 0,
+  // the previous round's m records afterwards
+  uint32_t seg_max = n - 1;
 
   for (uint32_t round = 1;; ++round) {
     const uint32_t off = round * 8;
@@ -354,19 +378,28 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
     b.seg[1] = segB.as<uint32_t>();
     // the current group ids live in segA; make sure the record set starts in slot 0
     b.cur = 0;
-    k_make_keys<<<gm, 256, 0, st>>>(base, starts, lens, ids.as<uint32_t>(), m, off, b.key[0], b.val[0]);
+    {
+      KernelScope _ks(ctx, "k_make_keys");
+      k_make_keys<<<gm, 256, 0, st>>>(base, starts, lens, ids.as<uint32_t>(), m, off, b.key[0], b.val[0]);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     int passes[12];
     int np = 0;
     for (int p = 0; p < 8; ++p) passes[np++] = p;
-    const uint32_t seg_bytes = bytes_needed((uint64_t)(m ? m - 1 : 0));
+    const uint32_t seg_bytes = bytes_needed((uint64_t)seg_max);
     for (uint32_t p = 0; p < seg_bytes; ++p) passes[np++] = 8 + (int)p;
     ZDWB_TRY(radix_passes(ctx, b, m, passes, np, hist.as<uint32_t>(), mt));
     // write the refined order back to the positions these records occupy
-    k_scatter_order<<<gm, 256, 0, st>>>(pos_cur, b.val[b.cur], m, order_out);
+    {
+      KernelScope _ks(ctx, "k_scatter_order");
+      k_scatter_order<<<gm, 256, 0, st>>>(pos_cur, b.val[b.cur], m, order_out);
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     // new tie groups
-    k_mark_groups<<<gm, 256, 0, st>>>(b.key[b.cur], b.seg[b.cur], m, head.as<uint32_t>(), unres.as<uint32_t>());
+    {
+      KernelScope _ks(ctx, "k_mark_groups");
+      k_mark_groups<<<gm, 256, 0, st>>>(b.key[b.cur], b.seg[b.cur], m, head.as<uint32_t>(), unres.as<uint32_t>());
+    }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u32(ctx, unres.as<uint32_t>(), unres_scan.as<uint32_t>(), m, total.as<uint32_t>()));
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->meta_host, total.p, 4, cudaMemcpyDeviceToHost, st));
@@ -377,17 +410,24 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
       DevBuf head_scan;
       ZDWB_TRY(head_scan.alloc(ctx, (size_t)m * 4));
       ZDWB_TRY(exclusive_scan_u32(ctx, head.as<uint32_t>(), head_scan.as<uint32_t>(), m, nullptr));
-      k_group_ids<<<gm, 256, 0, st>>>(head.as<uint32_t>(), head_scan.as<uint32_t>(), m);
+      {
+        KernelScope _ks(ctx, "k_group_ids");
+        k_group_ids<<<gm, 256, 0, st>>>(head.as<uint32_t>(), head_scan.as<uint32_t>(), m);
+      }
       ZDWB_LAUNCH_CHECK(ctx);
       // compact into (ids, segA, pos_nxt).  The kernel reads none of the seg arrays (k_mark_groups, the last
       // reader of the sorted segs, is already ordered before it), so the new group ids go straight to segA.
-      k_compact_unresolved<<<gm, 256, 0, st>>>(unres.as<uint32_t>(), unres_scan.as<uint32_t>(), head_scan.as<uint32_t>(),
+      {
+        KernelScope _ks(ctx, "k_compact_unresolved");
+        k_compact_unresolved<<<gm, 256, 0, st>>>(unres.as<uint32_t>(), unres_scan.as<uint32_t>(), head_scan.as<uint32_t>(),
                                                b.val[b.cur], pos_cur, m, ids.as<uint32_t>(), segA.as<uint32_t>(), pos_nxt);
+      }
       ZDWB_LAUNCH_CHECK(ctx);
     }
     uint32_t* t = pos_cur;
     pos_cur = pos_nxt;
     pos_nxt = t;
+    seg_max = m - 1;
     m = m2;
   }
   return ZDWB_OK;
