@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""profile_one.py -- one device-resident encode + decode of a synthetic C4-shaped block, for use under ncu.
+
+  ncu ... python tools/profile_one.py [--rows N] [--reps K] [--mode both|encode|decode]
+
+Prints the per-kernel CUDA-event times of the last repetition (never a bench value: this runs under a profiler).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=131072)
+    ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--mode", default="both", choices=["both", "encode", "decode"])
+    ap.add_argument("--timing", type=int, default=0)
+    args = ap.parse_args()
+
+    import torch
+
+    import bench
+    from zdw_b200 import Context
+
+    synth = bench.Synth()
+    types = synth.schema.types
+    cap = synth.cap_for(args.rows)
+    buf = (C.c_uint8 * cap)()
+    n = synth.block_into(0, args.rows, C.addressof(buf), cap)
+    dev = torch.device("cuda", 0)
+    t = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    t[:n].copy_(torch.frombuffer((C.c_uint8 * n).from_address(C.addressof(buf)), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    ctx = Context(0)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    if args.timing:
+        ctx.set_tuning("kernel_timing", 1)
+    blk = ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
+    z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)
+    bench._d2d(torch, z, blk.dev_ptr, blk.length)
+    for _ in range(args.reps):
+        if args.mode in ("both", "encode"):
+            ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
+            if args.timing:
+                print("encode", sorted(ctx.kernel_times().items(), key=lambda kv: -kv[1][1]))
+        if args.mode in ("both", "decode"):
+            ctx.decode_block(types, z.data_ptr(), blk.length, input_on_device=True, output_on_device=True)
+            if args.timing:
+                print("decode", sorted(ctx.kernel_times().items(), key=lambda kv: -kv[1][1]))
+    torch.cuda.synchronize()
+    print(f"rows={args.rows} tsv={n} zdw={blk.length} launches={ctx.kernel_launches()}")
+
+
+if __name__ == "__main__":
+    main()
