@@ -283,15 +283,22 @@ __device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t rep) {
   // zero-byte detect, exact variant (no false positives across byte lanes)
   return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
-// gather the four bit-7 flags of a word into the low 4 bits
-__device__ __forceinline__ uint32_t movemask4(uint32_t m) {
-  return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
-}
+// gather the four bit-7 flags of a word into the low 4 bits: (m >> 7) has bits 0/8/16/24; the multiplier
+// 2^21 + 2^14 + 2^7 + 1 moves them to bits 21..24 and no two partial products share a bit (no carries)
+__device__ __forceinline__ uint32_t movemask4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
 // 16-bit mask of bytes equal to `ch` within a 16-byte chunk
 __device__ __forceinline__ uint32_t chunk_mask(const uint4& v, uint8_t ch) {
   const uint32_t rep = 0x01010101u * ch;
   return movemask4(bytes_eq(v.x, rep)) | (movemask4(bytes_eq(v.y, rep)) << 4) |
          (movemask4(bytes_eq(v.z, rep)) << 8) | (movemask4(bytes_eq(v.w, rep)) << 12);
+}
+// does the 16-byte chunk hold any byte equal to `ch`?  ((x - 0x01..) & ~x & 0x80..) is exact as an any-test
+__device__ __forceinline__ bool chunk_has(const uint4& v, uint8_t ch) {
+  const uint32_t rep = 0x01010101u * ch;
+  const uint32_t a = v.x ^ rep, b = v.y ^ rep, c = v.z ^ rep, d = v.w ^ rep;
+  const uint32_t z = ((a - 0x01010101u) & ~a) | ((b - 0x01010101u) & ~b) | ((c - 0x01010101u) & ~c) |
+                     ((d - 0x01010101u) & ~d);
+  return (z & 0x80808080u) != 0u;
 }
 
 // block-wide exclusive scan of one uint32 per thread (blockDim.x multiple of 32, <= 1024).

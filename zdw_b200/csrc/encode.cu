@@ -42,7 +42,7 @@ struct EncMeta {
   uint32_t idx_size;
   uint32_t nflag;
   uint32_t max_row_bytes;
-  uint32_t tile_ticket;
+  uint32_t pad0;
   uint64_t dict_total;   // Dictionary::getSize()
   uint64_t dict_base;    // offset of the dictionary origin byte inside the block
   uint64_t stats_base;
@@ -142,14 +142,25 @@ __global__ void k_row_longest(const uint32_t* __restrict__ row_start, const uint
 
 // ---------------------------------------------------------------------------------------------
 // field walker: calls f(row, col, start, len) for every NON-EMPTY field of rows [row0, row0+k) whose
-// bytes are [b0, b1).  One thread owns one 16-byte chunk per iteration; a delimiter's (row, col) comes
-// from a block-wide prefix count of delimiters, its field start from the previous boundary.
+// bytes are [b0, b1).
+//
+// Phase A (delimiter-parallel): one thread owns 32 bytes per iteration (two aligned 16-byte loads), builds the
+// tab / terminator / blank-line bit masks and - with bit arithmetic only - the mask of delimiters that close a
+// non-empty field (in analytics-shaped data most delimiters close empty fields and cost nothing further).  A
+// block-wide prefix count of delimiters gives every delimiter its (row, col).
+// Phase B (field-parallel): the non-empty fields of the iteration are queued in shared memory and handed out
+// one per thread, so the expensive per-field work (hashing, probing, number parsing) runs with full warps no
+// matter how the fields were distributed over the bytes.
 // ---------------------------------------------------------------------------------------------
+constexpr int WALK_SPAN = 32;                          // bytes per thread per iteration
+constexpr int QCAP = 1024;                             // queued fields per round
+
 struct WalkScratch {
   uint32_t scan_ws[34];
   int32_t last[ENC_THREADS];
   int32_t wmax[ENC_THREADS / 32];
   int32_t carry;
+  uint4 queue[QCAP];  // (row, col, start, len)
 };
 
 constexpr int32_t NO_BOUNDARY = INT32_MIN;
@@ -160,63 +171,91 @@ __device__ __forceinline__ void walk_tile_fields(const uint8_t* __restrict__ buf
                                                  F&& f) {
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t pc0 = lo + ((((int64_t)b0 - lo) >> 4) << 4);
-  const uint32_t nch = (uint32_t)(((int64_t)b1 - pc0 + 15) >> 4);
+  const uint32_t nsp = (uint32_t)(((int64_t)b1 - pc0 + WALK_SPAN - 1) / WALK_SPAN);
   if (tid == 0) ts.carry = (int32_t)((int64_t)b0 - 1 - pc0);  // the byte before a row start is a boundary
   uint32_t kbase = 0;
   __syncthreads();
-  for (uint32_t it0 = 0; it0 < nch; it0 += ENC_THREADS) {
+  for (uint32_t it0 = 0; it0 < nsp; it0 += ENC_THREADS) {
     const uint32_t j = it0 + tid;
-    const int64_t p0 = pc0 + (int64_t)j * 16;
-    ChunkMasks m{0u, 0u, 0u};
-    if (j < nch) m = classify_chunk(buf, n, p0, (int64_t)b0, (int64_t)b1);
-    const uint32_t bound = m.tab | m.term | m.skip;
-    const uint32_t delims = m.tab | m.term;
-    const int32_t mylast = bound ? (int32_t)(j * 16 + (31 - __clz(bound))) : NO_BOUNDARY;
+    const int64_t p0 = pc0 + (int64_t)j * WALK_SPAN;
+    uint32_t tab = 0, term = 0, skip = 0;
+    if (j < nsp) {
+      const ChunkMasks m0 = classify_chunk(buf, n, p0, (int64_t)b0, (int64_t)b1);
+      const ChunkMasks m1 = classify_chunk(buf, n, p0 + 16, (int64_t)b0, (int64_t)b1);
+      tab = m0.tab | (m1.tab << 16);
+      term = m0.term | (m1.term << 16);
+      skip = m0.skip | (m1.skip << 16);
+    }
+    const uint32_t bound = tab | term | skip;
+    const uint32_t delims = tab | term;
+    const int32_t rel0 = (int32_t)(j * WALK_SPAN);
+    const int32_t mylast = bound ? rel0 + (31 - __clz(bound)) : NO_BOUNDARY;
     ts.last[tid] = mylast;
     const int32_t wm = __reduce_max_sync(0xffffffffu, mylast);
     if (lane == 0) ts.wmax[warp] = wm;
-    uint32_t total;
-    const uint32_t excl = block_exclusive_scan((uint32_t)__popc(delims), ts.scan_ws, &total);
+    __syncthreads();
+    // last boundary before this thread's span
+    int32_t pb = NO_BOUNDARY;
     if (delims) {
-      const uint32_t k = kbase + excl;
-      uint32_t row = row0 + k / ncols;
-      uint32_t col = k % ncols;
-      uint32_t d = delims;
-      while (d) {
-        const int i = __ffs(d) - 1;
-        d &= d - 1;
-        const uint32_t lowb = bound & ((1u << i) - 1u);
-        int32_t srel;
-        if (lowb) {
-          srel = (int32_t)(j * 16 + (31 - __clz(lowb))) + 1;
-        } else {
-          int t = (int)tid - 1;
-          int32_t lp = NO_BOUNDARY;
-          while (t >= 0 && (lp = ts.last[t]) == NO_BOUNDARY) --t;
-          srel = (t >= 0 ? lp : ts.carry) + 1;
-        }
-        const uint32_t start = (uint32_t)(pc0 + srel);
-        uint32_t end = (uint32_t)(p0 + i);
-        if (trim) {  // -t: ConvertToZDW.cpp:295-313
-          while (end > start && __ldg(buf + end - 1) == (uint8_t)' ') --end;
-        }
-        if (end > start) f(row, col, start, end - start);
-        if ((m.term >> i) & 1u) {
-          ++row;
-          col = 0;
-        } else {
-          ++col;
+      int t = (int)tid - 1;
+      while (t >= 0 && (pb = ts.last[t]) == NO_BOUNDARY) --t;
+      if (t < 0) pb = ts.carry;
+    }
+    // delimiters whose preceding byte is not a boundary close a non-empty field
+    const uint32_t ne = delims & ~((bound << 1) | (pb == rel0 - 1 ? 1u : 0u));
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan(((uint32_t)__popc(ne) << 16) | (uint32_t)__popc(delims), ts.scan_ws, &total);
+    const uint32_t total_ne = total >> 16;
+    uint32_t row_f = 0, col_f = 0;
+    if (ne) {
+      const uint32_t k0 = kbase + (excl & 0xffffu);
+      const uint32_t q = k0 / ncols;
+      row_f = row0 + q;
+      col_f = k0 - q * ncols;
+    }
+    for (uint32_t base = 0; base < total_ne; base += QCAP) {
+      if (ne) {
+        uint32_t qi = excl >> 16;
+        uint32_t d = ne;
+        while (d) {
+          const int i = __ffs(d) - 1;
+          d &= d - 1;
+          if (qi >= base && qi < base + QCAP) {
+            const uint32_t below = (1u << i) - 1u;
+            uint32_t col = col_f + (uint32_t)__popc(delims & below);
+            uint32_t row = row_f;
+            while (col >= ncols) {
+              col -= ncols;
+              ++row;
+            }
+            const uint32_t lowb = bound & below;
+            const int32_t srel = (lowb ? rel0 + (31 - __clz(lowb)) : pb) + 1;
+            const uint32_t start = (uint32_t)(pc0 + srel);
+            const uint32_t end = (uint32_t)(p0 + i);
+            ts.queue[qi - base] = make_uint4(row, col, start, end - start);
+          }
+          ++qi;
         }
       }
+      __syncthreads();
+      const uint32_t cnt = min((uint32_t)QCAP, total_ne - base);
+      for (uint32_t t = tid; t < cnt; t += ENC_THREADS) {
+        const uint4 rec = ts.queue[t];
+        uint32_t len = rec.w;
+        if (trim) {  // -t: ConvertToZDW.cpp:295-313
+          while (len && __ldg(buf + rec.z + len - 1) == (uint8_t)' ') --len;
+        }
+        if (len) f(rec.x, rec.y, rec.z, len);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (tid == 0) {
       int32_t mx = NO_BOUNDARY;
 #pragma unroll
       for (int w = 0; w < ENC_THREADS / 32; ++w) mx = ts.wmax[w] > mx ? ts.wmax[w] : mx;
       if (mx != NO_BOUNDARY) ts.carry = mx;
     }
-    kbase += total;
+    kbase += total & 0xffffu;
     __syncthreads();
   }
 }
@@ -224,25 +263,70 @@ __device__ __forceinline__ void walk_tile_fields(const uint8_t* __restrict__ buf
 // ---------------------------------------------------------------------------------------------
 // string hash set (open addressing, 64-bit slots: (start+1) << 32 | len, 0 = empty)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t hash_bytes(const uint8_t* __restrict__ p, uint32_t len) {
-  uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)len * 0xD6E8FEB86659FD93ull);
-  uint32_t i = 0;
-  while (i < len) {
-    uint64_t w = 0;
-    const uint32_t m = len - i < 8 ? len - i : 8;
-    for (uint32_t k = 0; k < m; ++k) w |= (uint64_t)__ldg(p + i + k) << (8 * k);
-    h = (h ^ w) * 0xff51afd7ed558ccdull;
-    h ^= h >> 32;
-    i += m;
+// Little-endian 32-bit words of the byte string that starts at an arbitrary address: aligned loads + funnel shift.
+// Reads at most one aligned word past the word holding the last requested byte.
+struct WordStream {
+  const uint32_t* w;
+  uint32_t sh, cur;
+  __device__ __forceinline__ explicit WordStream(const uint8_t* a) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(a);
+    w = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
+    sh = (uint32_t)(u & 3u) * 8u;
+    cur = __ldg(w);
   }
-  h *= 0xc4ceb9fe1a85ec53ull;
-  h ^= h >> 29;
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t nx = __ldg(++w);
+    const uint32_t r = __funnelshift_r(cur, nx, sh);
+    cur = nx;
+    return r;
+  }
+  // the next `rem` (1..3) bytes, zero-extended
+  __device__ __forceinline__ uint32_t tail(uint32_t rem) {
+    uint32_t r;
+    if (sh + rem * 8u <= 32u) r = cur >> sh;
+    else r = __funnelshift_r(cur, __ldg(w + 1), sh);
+    return r & ((1u << (rem * 8u)) - 1u);
+  }
+};
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+// MurmurHash3 (x86_32) over the field bytes
+__device__ __forceinline__ uint32_t hash_bytes(const uint8_t* __restrict__ p, uint32_t len) {
+  WordStream ws(p);
+  uint32_t h = 0x9747b28cu;
+  uint32_t i = 0;
+  for (; i + 4 <= len; i += 4) {
+    uint32_t k = ws.next();
+    k *= 0xcc9e2d51u;
+    k = rotl32(k, 15);
+    k *= 0x1b873593u;
+    h ^= k;
+    h = rotl32(h, 13);
+    h = h * 5u + 0xe6546b64u;
+  }
+  if (len - i) {
+    uint32_t k = ws.tail(len - i);
+    k *= 0xcc9e2d51u;
+    k = rotl32(k, 15);
+    k *= 0x1b873593u;
+    h ^= k;
+  }
+  h ^= len;
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
   return h;
 }
 
 __device__ __forceinline__ bool bytes_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len) {
-  for (uint32_t i = 0; i < len; ++i)
-    if (__ldg(a + i) != __ldg(b + i)) return false;
+  WordStream sa(a), sb(b);
+  uint32_t i = 0;
+  for (; i + 4 <= len; i += 4)
+    if (sa.next() != sb.next()) return false;
+  if (len - i) return sa.tail(len - i) == sb.tail(len - i);
   return true;
 }
 
@@ -255,7 +339,7 @@ struct HashTable {
 __device__ __forceinline__ bool ht_insert(const HashTable ht, const uint8_t* __restrict__ buf, uint32_t start, uint32_t len,
                                           EncMeta* __restrict__ meta) {
   if (*reinterpret_cast<volatile uint32_t*>(&meta->ht_overflow)) return false;
-  uint32_t i = (uint32_t)hash_bytes(buf + start, len) & ht.mask;
+  uint32_t i = hash_bytes(buf + start, len) & ht.mask;
   const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
   for (uint32_t probe = 0; probe < HT_MAX_PROBE; ++probe) {
     unsigned long long cur = ht.slots[i];
@@ -276,7 +360,7 @@ __device__ __forceinline__ bool ht_insert(const HashTable ht, const uint8_t* __r
 // returns the slot holding the string or 0xffffffff
 __device__ __forceinline__ uint32_t ht_find(const HashTable ht, const uint8_t* __restrict__ buf, uint32_t start,
                                             uint32_t len) {
-  uint32_t i = (uint32_t)hash_bytes(buf + start, len) & ht.mask;
+  uint32_t i = hash_bytes(buf + start, len) & ht.mask;
   for (uint32_t probe = 0; probe <= ht.mask; ++probe) {
     const unsigned long long cur = ht.slots[i];
     if (cur == 0ull) return 0xffffffffu;
@@ -365,23 +449,27 @@ __global__ void k_sorted_lens(const uint32_t* __restrict__ order, const uint32_t
   if (i < n) out[i] = ulen[order[i]] + 1u;
 }
 
-// 8 lanes copy one dictionary entry; offs[i] = sum of (len+1) of the entries sorted before i.
+// dictionary offset of every hash-set slot: offs[i] = sum of (len+1) of the entries sorted before i; offset 0 is the
+// origin byte (dictionary.cpp:96-98)
+__global__ void k_dict_slots(const uint32_t* __restrict__ order, const uint32_t* __restrict__ uslot,
+                             const uint32_t* __restrict__ offs, uint32_t n, uint32_t* __restrict__ slot_off) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) slot_off[uslot[order[g]]] = 1u + offs[g];
+}
+
+// 8 lanes copy one dictionary entry
 __global__ void k_dict_emit(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ order,
                             const uint32_t* __restrict__ ustart, const uint32_t* __restrict__ ulen,
-                            const uint32_t* __restrict__ uslot, const uint32_t* __restrict__ offs, uint32_t n,
-                            uint8_t* __restrict__ dict_origin, uint32_t* __restrict__ slot_off) {
+                            const uint32_t* __restrict__ offs, uint32_t n, uint8_t* __restrict__ dict_origin) {
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
   if (g >= n) return;
   const uint32_t id = order[g];
-  const uint32_t off = 1u + offs[g];  // offset 0 is the origin byte: dictionary.cpp:96-98
+  const uint32_t off = 1u + offs[g];
   const uint32_t len = ulen[id];
   const uint8_t* src = buf + ustart[id];
   uint8_t* dst = dict_origin + off;
   for (uint32_t k = sub; k < len; k += 8) dst[k] = __ldg(src + k);
-  if (sub == 0) {
-    dst[len] = 0;
-    slot_off[uslot[id]] = off;
-  }
+  if (sub == 0) dst[len] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -474,30 +562,28 @@ __global__ void k_block_header(uint8_t* __restrict__ out, const EncMeta* __restr
 // ---------------------------------------------------------------------------------------------
 // pass 2
 // ---------------------------------------------------------------------------------------------
-// status word of the decoupled look-back: bits 63..62 = state (0 none, 1 aggregate, 2 inclusive prefix)
-constexpr uint64_t LB_AGG = 1ull << 62, LB_PFX = 2ull << 62, LB_MASK = (1ull << 62) - 1ull;
-
+// One CTA encodes R consecutive rows.  The values of the rows (and of the row before the first one, which the
+// repeat flags of the first row compare against) are gathered into a shared-memory matrix by the field walker;
+// flags and value bytes are then produced row by row, one warp per row.  The tile's bytes go to its own slot of
+// a staging buffer (tile * tile_cap); k_gather_tiles packs the tiles once every tile length is known, which keeps
+// the row stream free of any cross-CTA dependency while it is being produced.
 __global__ void __launch_bounds__(ENC_THREADS)
     k_pass2(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, const uint32_t* __restrict__ row_start,
             const uint32_t* __restrict__ row_end, uint32_t nrows, uint32_t rows_per_cta, uint32_t ncols,
             const uint8_t* __restrict__ types, int trim, HashTable ht, const uint32_t* __restrict__ slot_off,
             const int32_t* __restrict__ used_idx, const uint32_t* __restrict__ used_cols,
             const uint8_t* __restrict__ csize, const unsigned long long* __restrict__ cbase, uint32_t U,
-            uint32_t nflag, uint64_t* __restrict__ tile_status, uint8_t* __restrict__ out_rows,
+            uint32_t nflag, uint64_t tile_cap, uint8_t* __restrict__ staging, uint64_t* __restrict__ tile_bytes,
             EncMeta* __restrict__ meta) {
   extern __shared__ __align__(16) uint8_t dsm[];
   __shared__ WalkScratch ts;
-  __shared__ uint32_t s_tile;
-  __shared__ unsigned long long s_base;
   // dynamic smem: nval[(R+1)*U] u64 | rowoff[R+1] u32 | usz[U] u8
   unsigned long long* nval = reinterpret_cast<unsigned long long*>(dsm);
   uint32_t* rowoff = reinterpret_cast<uint32_t*>(dsm + (size_t)(rows_per_cta + 1) * U * 8);
   uint8_t* usz = reinterpret_cast<uint8_t*>(rowoff + rows_per_cta + 1);
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0) s_tile = atomicAdd(&meta->tile_ticket, 1u);  // tiles start in ticket order: look-back cannot deadlock
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  const uint32_t tile = blockIdx.x;
   const uint32_t r0 = tile * rows_per_cta;
   const uint32_t r1 = min(nrows, r0 + rows_per_cta);
   const uint32_t R = r1 - r0;
@@ -559,35 +645,13 @@ __global__ void __launch_bounds__(ENC_THREADS)
       if (j < R) rowoff[j] = run + inc - v;
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) rowoff[R] = run;
-  }
-  __syncthreads();
-
-  // ---- decoupled look-back over tiles for the byte offset of this tile's first row
-  if (tid == 0) {
-    const uint64_t total = rowoff[R];
-    uint64_t run = 0;
-    if (tile == 0) {
-      st_release_u64(&tile_status[0], LB_PFX | total);
-    } else {
-      st_release_u64(&tile_status[tile], LB_AGG | total);
-      int64_t j = (int64_t)tile - 1;
-      for (;;) {
-        uint64_t s;
-        do {
-          s = ld_acquire_u64(&tile_status[j]);
-        } while ((s >> 62) == 0ull);
-        run += s & LB_MASK;
-        if ((s >> 62) == 2ull) break;
-        --j;
-      }
-      st_release_u64(&tile_status[tile], LB_PFX | (run + total));
+    if (lane == 0) {
+      rowoff[R] = run;
+      tile_bytes[tile] = run;
     }
-    s_base = run;
-    if (r1 == nrows) meta->rows_bytes = run + total;
   }
   __syncthreads();
-  uint8_t* tile_out = out_rows + s_base;
+  uint8_t* tile_out = staging + (uint64_t)tile * tile_cap;
 
   // ---- emit: flag bytes, then the low columnSize bytes of every changed value (little-endian)
   for (uint32_t j = warp; j < R; j += ENC_THREADS / 32) {
@@ -620,6 +684,31 @@ __global__ void __launch_bounds__(ENC_THREADS)
       voff += tot;
     }
   }
+}
+
+// packs the staged tiles into the row stream: tile t's bytes go to out_rows + tile_off[t]
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_gather_tiles(const uint8_t* __restrict__ staging, uint64_t tile_cap, const uint64_t* __restrict__ tile_off,
+                   const uint64_t* __restrict__ tile_bytes, uint8_t* __restrict__ out_rows) {
+  const uint32_t tile = blockIdx.x;
+  const uint8_t* src = staging + (uint64_t)tile * tile_cap;
+  uint8_t* dst = out_rows + tile_off[tile];
+  const uint32_t nb = (uint32_t)tile_bytes[tile];
+  // head bytes up to a 16-byte aligned destination, 16-byte body through a funnel of source words, byte tail
+  const uint32_t head = min(nb, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+  for (uint32_t k = threadIdx.x; k < head; k += ENC_THREADS) dst[k] = src[k];
+  const uint32_t body = (nb - head) >> 4;
+  for (uint32_t q = threadIdx.x; q < body; q += ENC_THREADS) {
+    const uint8_t* s = src + head + (size_t)q * 16;
+    WordStream ws(s);
+    uint4 v;
+    v.x = ws.next();
+    v.y = ws.next();
+    v.z = ws.next();
+    v.w = ws.next();
+    *reinterpret_cast<uint4*>(dst + head + (size_t)q * 16) = v;
+  }
+  for (uint32_t k = head + body * 16 + threadIdx.x; k < nb; k += ENC_THREADS) dst[k] = src[k];
 }
 
 __global__ void k_init_minmax(unsigned long long* colmin, unsigned long long* colmax, uint32_t* colset, uint32_t ncols) {
@@ -761,7 +850,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   // ---- pass 1 (retry with a larger hash set when it fills up)
   const uint64_t block_bytes = (uint64_t)h_last[0] + 1;
   const uint64_t avg_row = std::max<uint64_t>(1, block_bytes / nrows);
-  uint32_t rpc1 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 32768 / avg_row), 4096);
+  uint32_t rpc1 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 65536 / avg_row), 4096);
   const uint32_t tiles1 = (nrows + rpc1 - 1) / rpc1;
 
   DevBuf colset, colmin, colmax, slots;
@@ -840,33 +929,12 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   const uint32_t U = hmeta->n_used, nflag = hmeta->nflag;
   const uint64_t rows_base = hmeta->rows_base;
-  const uint64_t out_cap = rows_base + (uint64_t)nrows * hmeta->max_row_bytes + 16;
 
-  // ---- output buffer
-  if (ctx->out_dev) {
-    cudaFreeAsync(ctx->out_dev, st);
-    ctx->out_dev = nullptr;
-  }
-  {
-    DevBuf ob;
-    ZDWB_TRY(ob.alloc(ctx, out_cap));
-    ctx->out_dev = ob.detach();
-  }
-  uint8_t* outp = static_cast<uint8_t*>(ctx->out_dev);
-  {
-    KernelScope _ks(ctx, "k_block_header");
-    k_block_header<<<std::max(1u, std::min((ncols + 255) / 256, 64u)), 256, 0, st>>>(
-      outp, meta, nrows, longest_field, is_last ? 1u : 0u, ncols, csize.as<uint8_t>(), cbase.as<unsigned long long>(),
-      used_cols.as<uint32_t>());
-  }
-  ZDWB_LAUNCH_CHECK(ctx);
-
-  // ---- dictionary: compact, sort, offsets, emit
-  DevBuf slot_off;
+  // ---- dictionary order: compact the hash set, sort, offsets of the sorted entries, offset per slot
+  DevBuf slot_off, ustart, ulen, uslot, order, offs;
   ZDWB_TRY(slot_off.alloc(ctx, ((size_t)ht.mask + 1) * 4));
-  if (n_unique) {
-    const uint32_t nu = (uint32_t)n_unique;
-    DevBuf ustart, ulen, uslot, order, offs;
+  const uint32_t nu = (uint32_t)n_unique;
+  if (nu) {
     ZDWB_TRY(ustart.alloc(ctx, (size_t)nu * 4));
     ZDWB_TRY(ulen.alloc(ctx, (size_t)nu * 4));
     ZDWB_TRY(uslot.alloc(ctx, (size_t)nu * 4));
@@ -886,55 +954,93 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u32(ctx, offs.as<uint32_t>(), offs.as<uint32_t>(), nu, nullptr));
-    const uint64_t threads = (uint64_t)nu * 8;
     {
-      KernelScope _ks(ctx, "k_dict_emit");
-      k_dict_emit<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(buf, order.as<uint32_t>(), ustart.as<uint32_t>(),
-                                                                  ulen.as<uint32_t>(), uslot.as<uint32_t>(), offs.as<uint32_t>(),
-                                                                  nu, outp + hmeta->dict_base, slot_off.as<uint32_t>());
+      KernelScope _ks(ctx, "k_dict_slots");
+      k_dict_slots<<<(nu + 255) / 256, 256, 0, st>>>(order.as<uint32_t>(), uslot.as<uint32_t>(), offs.as<uint32_t>(), nu,
+                                                   slot_off.as<uint32_t>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
   }
 
-  // ---- pass 2
+  // ---- pass 2 into the staging buffer
   uint64_t rows_bytes = 0;
+  DevBuf staging, tile_bytes, tile_off, rows_total_d;
+  uint32_t tiles2 = 0;
+  uint64_t tile_cap = 0;
   if (U > 0) {
     // rows per CTA: bounded by the shared-memory value matrix ((R+1) * U * 8 bytes) and a byte target
-    const size_t smem_budget = 96 * 1024;
+    const size_t smem_budget = 64 * 1024;
     const uint64_t by_smem = smem_budget / ((uint64_t)U * 8);
     if (by_smem < 2) {
       // even one row + its predecessor do not fit the default budget: allow the full 200 KiB
-      if ((uint64_t)U * 8 * 2 + 1024 > 200 * 1024) {
-        ctx->err = "encode: more than 12700 used columns in one block are not supported";
+      if ((uint64_t)U * 8 * 2 + 1024 > 180 * 1024) {
+        ctx->err = "encode: more than 11400 used columns in one block are not supported";
         return ZDWB_ERR_UNSUPPORTED;
       }
     }
-    uint32_t rpc2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 32768 / avg_row), 1024);
+    uint32_t rpc2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 65536 / avg_row), 1024);
     if (by_smem >= 2) rpc2 = (uint32_t)std::min<uint64_t>(rpc2, by_smem - 1);
     else rpc2 = 1;
     const size_t smem = (size_t)(rpc2 + 1) * U * 8 + (size_t)(rpc2 + 1) * 4 + U + 16;
-    ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    const uint32_t tiles2 = (nrows + rpc2 - 1) / rpc2;
-    DevBuf status;
-    ZDWB_TRY(status.alloc(ctx, (size_t)tiles2 * 8));
-    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, (size_t)tiles2 * 8, st));
+    ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    tiles2 = (nrows + rpc2 - 1) / rpc2;
+    tile_cap = (((uint64_t)rpc2 * hmeta->max_row_bytes) + 15) & ~15ull;
+    ZDWB_TRY(staging.alloc(ctx, (size_t)tiles2 * tile_cap + 64));
+    ZDWB_TRY(tile_bytes.alloc(ctx, (size_t)tiles2 * 8));
+    ZDWB_TRY(tile_off.alloc(ctx, (size_t)tiles2 * 8));
+    ZDWB_TRY(rows_total_d.alloc(ctx, 8));
     {
       KernelScope _ks(ctx, "k_pass2");
       k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc2, ncols,
                                                types_d.as<uint8_t>(), opts->trim_trailing_spaces, ht, slot_off.as<uint32_t>(),
                                                used_idx.as<int32_t>(), used_cols.as<uint32_t>(), csize.as<uint8_t>(),
-                                               cbase.as<unsigned long long>(), U, nflag, status.as<uint64_t>(), outp + rows_base,
-                                               meta);
+                                               cbase.as<unsigned long long>(), U, nflag, tile_cap, staging.as<uint8_t>(),
+                                               tile_bytes.as<uint64_t>(), meta);
     }
     ZDWB_LAUNCH_CHECK(ctx);
+    ZDWB_TRY(exclusive_scan_u64(ctx, tile_bytes.as<uint64_t>(), tile_off.as<uint64_t>(), tiles2, rows_total_d.as<uint64_t>()));
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, rows_total_d.p, 8, cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (hmeta->lookup_miss) {
       ctx->err = "encode: internal error, " + std::to_string(hmeta->lookup_miss) + " dictionary lookups missed in pass 2";
       return ZDWB_ERR_CUDA;
     }
-    rows_bytes = hmeta->rows_bytes;
+    memcpy(&rows_bytes, reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, 8);
   }
+
+  // ---- output buffer of the exact size: header + dictionary + column stats, then the packed rows
+  if (ctx->out_dev) {
+    cudaFreeAsync(ctx->out_dev, st);
+    ctx->out_dev = nullptr;
+  }
+  {
+    DevBuf ob;
+    ZDWB_TRY(ob.alloc(ctx, rows_base + rows_bytes + 64));
+    ctx->out_dev = ob.detach();
+  }
+  uint8_t* outp = static_cast<uint8_t*>(ctx->out_dev);
+  {
+    KernelScope _ks(ctx, "k_block_header");
+    k_block_header<<<std::max(1u, std::min((ncols + 255) / 256, 64u)), 256, 0, st>>>(
+      outp, meta, nrows, longest_field, is_last ? 1u : 0u, ncols, csize.as<uint8_t>(), cbase.as<unsigned long long>(),
+      used_cols.as<uint32_t>());
+  }
+  ZDWB_LAUNCH_CHECK(ctx);
+  if (nu) {
+    const uint64_t threads = (uint64_t)nu * 8;
+    KernelScope _ks(ctx, "k_dict_emit");
+    k_dict_emit<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(buf, order.as<uint32_t>(), ustart.as<uint32_t>(),
+                                                                ulen.as<uint32_t>(), offs.as<uint32_t>(), nu,
+                                                                outp + hmeta->dict_base);
+  }
+  if (nu) ZDWB_LAUNCH_CHECK(ctx);
+  if (tiles2) {
+    KernelScope _ks(ctx, "k_gather_tiles");
+    k_gather_tiles<<<tiles2, ENC_THREADS, 0, st>>>(staging.as<uint8_t>(), tile_cap, tile_off.as<uint64_t>(),
+                                                 tile_bytes.as<uint64_t>(), outp + rows_base);
+  }
+  if (tiles2) ZDWB_LAUNCH_CHECK(ctx);
 
   const size_t total_len = (size_t)(rows_base + rows_bytes);
   out->len = total_len;

@@ -54,11 +54,10 @@ __device__ __forceinline__ ChunkMasks classify_chunk(const uint8_t* __restrict__
   const int64_t ib = (p0 + 16 > (int64_t)n) ? (int64_t)n - p0 : 16;
   const uint32_t inbuf = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
   uint32_t tab = chunk_mask(v, '\t') & inbuf;
-  uint32_t nl = chunk_mask(v, '\n') & inbuf;
+  uint32_t nl = chunk_has(v, '\n') ? (chunk_mask(v, '\n') & inbuf) : 0u;  // newlines are rare: 1 per row
   if ((tab | nl) == 0u) return r;
-  const uint32_t bs = chunk_mask(v, '\\') & inbuf;
-  uint32_t prevbs = bs << 1;
-  if (p0 > 0 && __ldg(buf + p0 - 1) == (uint8_t)'\\') prevbs |= 1u;
+  uint32_t prevbs = chunk_has(v, '\\') ? (chunk_mask(v, '\\') & inbuf) << 1 : 0u;
+  if (((tab | nl) & 1u) && p0 > 0 && __ldg(buf + p0 - 1) == (uint8_t)'\\') prevbs |= 1u;
   uint32_t sus = (tab | nl) & prevbs;
   while (sus) {
     const int i = __ffs(sus) - 1;
