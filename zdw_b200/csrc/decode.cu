@@ -48,7 +48,6 @@ struct DecParams {
   const uint8_t* usz;          // [U] value width of every used column
   const unsigned long long* ubase;  // [U]
   const uint8_t* utype;        // [U]
-  const uint8_t* lut;          // [F][256] bytes of values selected by a flag byte
   const uint32_t* planes;      // [4][W] bit k of the width of used column u, as flag-word masks
 };
 
@@ -175,10 +174,12 @@ __global__ void __launch_bounds__(DEC_THREADS)
 
 // ---------------------------------------------------------------------------------------------
 // row parser: one warp walks the flag bytes of a row and calls cb(u, value offset inside the row)
-// for every flagged used column, lanes working on different flag bytes.
+// for every flagged used column, lanes working on different flag bytes.  `planes` = the 4 bit planes of the
+// column widths (shared or global memory): the value bytes selected by flag byte j are
+// sum_k 2^k * popc(flags & plane_k byte j).
 // ---------------------------------------------------------------------------------------------
 template <class CB>
-__device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint8_t* __restrict__ lut,
+__device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint32_t* __restrict__ planes,
                                                const uint8_t* __restrict__ rp, CB&& cb) {
   const unsigned lane = lane_id();
   uint32_t run = P.F;
@@ -187,7 +188,11 @@ __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint8_t
     uint32_t fb = 0, bl = 0;
     if (j < P.F) {
       fb = __ldg(rp + j);
-      bl = lut[j * 256 + fb];
+      if (fb) {
+        const uint32_t sh = (j & 3u) * 8u, w = j >> 2;
+        bl = __popc(fb & (planes[w] >> sh)) + 2u * __popc(fb & (planes[P.W + w] >> sh)) +
+             4u * __popc(fb & (planes[2 * P.W + w] >> sh)) + 8u * __popc(fb & (planes[3 * P.W + w] >> sh));
+      }
     }
     uint32_t inc = bl;
 #pragma unroll
@@ -210,26 +215,23 @@ __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint8_t
   }
 }
 
+// little-endian value of sz (1..8) bytes at an arbitrary address: two aligned 64-bit loads
 __device__ __forceinline__ unsigned long long load_le(const uint8_t* __restrict__ p, uint32_t sz) {
-  unsigned long long v = 0;
-  for (uint32_t b = 0; b < sz; ++b) v |= (unsigned long long)__ldg(p + b) << (8 * b);
-  return v;
-}
-
-__device__ __forceinline__ const uint8_t* stage_lut(const DecParams& P, uint8_t* s_lut, bool lut_in_smem) {
-  if (!lut_in_smem) return P.lut;
-  for (uint32_t i = threadIdx.x; i < P.F * 256; i += blockDim.x) s_lut[i] = P.lut[i];
-  return s_lut;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+  unsigned long long v = __ldg(w) >> sh;
+  if (sh + sz * 8u > 64u) v |= __ldg(w + 1) << (64u - sh);
+  return sz >= 8 ? v : (v & ((1ull << (sz * 8u)) - 1ull));
 }
 
 // last explicit value of every used column inside a strip of R rows
 __global__ void __launch_bounds__(DEC_THREADS)
-    k_dec_strip_summary(const DecParams P, const uint32_t* __restrict__ row_off, uint32_t R, int lut_in_smem,
+    k_dec_strip_summary(const DecParams P, const uint32_t* __restrict__ row_off, uint32_t R,
                         unsigned long long* __restrict__ sval, uint8_t* __restrict__ shas) {
   extern __shared__ __align__(16) uint8_t dsm[];
   int32_t* last_row = reinterpret_cast<int32_t*>(dsm);
-  uint8_t* s_lut = dsm + (size_t)P.U * 4;
-  const uint8_t* lut = stage_lut(P, s_lut, lut_in_smem != 0);
+  const uint32_t* lut = P.planes;
   for (uint32_t u = threadIdx.x; u < P.U; u += DEC_THREADS) last_row[u] = -1;
   __syncthreads();
   const uint32_t r0 = blockIdx.x * R, r1 = min(P.nrows, r0 + R);
@@ -298,126 +300,299 @@ __global__ void k_carry_apply(const unsigned long long* __restrict__ sval, const
 // ---------------------------------------------------------------------------------------------
 // formatting
 // ---------------------------------------------------------------------------------------------
+// An output row is a fixed template - separators, the defaults of unused columns, the terminator - with the text of
+// the used columns ("items", in output order) spliced in.  Static segment i precedes item i; segment n_items closes
+// the row.  Static byte k of the template therefore lands at k + (dynamic bytes of the items before its segment).
 struct FmtTables {
   uint32_t n_items;             // dynamic items (used columns that are output), in output order
   const uint32_t* item_u;       // [n_items] used-column index
-  const uint32_t* seg_off;      // [n_items + 1] static segment i precedes item i; the last one ends the row
-  const uint32_t* seg_len;      // [n_items + 1]
-  const uint32_t* seg_cum;      // [n_items + 1] static bytes before segment i
-  const uint8_t* blob;          // static bytes (separators, defaults of unused columns, terminator)
+  const uint32_t* item_pos;     // [n_items] static bytes in front of the text of item i
+  const uint2* sgrp;            // [ceil(static_total/4)] .x = 4 template bytes, .y = segment of the first byte
+                                //   | (bit 28+b set: byte b >= 1 of the group opens the next segment)
   uint32_t static_total;
 };
 
-// Length of the text of used column u holding stored value v; *dict_ptr gets the dictionary string for
-// text-like columns.  Mirrors the switch in readNextRow (UnconvertFromZDW.cpp:1349-1453).
-__device__ __forceinline__ uint32_t value_text(const DecParams& P, uint32_t u, unsigned long long v, uint8_t* tmp24,
-                                               const uint8_t** src, DecMeta* meta) {
-  const uint8_t t = P.utype[u];
-  if (is_text_like(t)) {
-    if (v == 0) {
-      if (t == ZDWB_DECIMAL) {  // outputDefault(DECIMAL)
-        *src = reinterpret_cast<const uint8_t*>("0.000000000000");
-        return 14;
-      }
-      *src = tmp24;
-      return 0;
+// strlen of the dictionary entry at s, at most `room` bytes: aligned 32-bit loads + zero-byte detect
+// (GetWord + strlen, UnconvertFromZDW.cpp:359-371,1380)
+__device__ __forceinline__ uint32_t dict_strlen(const uint8_t* __restrict__ s, uint64_t room) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t lead = (uint32_t)(a & 3u);
+  uint32_t x = __ldg(w) | ((1u << (lead * 8u)) - 1u);  // bytes in front of s never terminate
+  int64_t done = -(int64_t)lead;                       // bytes of the string covered so far
+  for (;;) {
+    const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;
+    if (z) {
+      const uint64_t l = (uint64_t)(done + ((__ffs(z) - 1) >> 3));
+      return (uint32_t)(l < room ? l : room);
     }
+    done += 4;
+    if ((uint64_t)done >= room) return (uint32_t)room;
+    x = __ldg(++w);
+  }
+}
+
+__device__ __forceinline__ uint32_t digits_u64(unsigned long long v) {
+  if (v < 10ull) return 1;
+  if (v <= 0xffffffffull) {
+    const uint32_t x = (uint32_t)v;
+    return x < 100u ? 2u : x < 1000u ? 3u : x < 10000u ? 4u : x < 100000u ? 5u : x < 1000000u ? 6u : x < 10000000u ? 7u
+           : x < 100000000u ? 8u : x < 1000000000u ? 9u : 10u;
+  }
+  uint32_t n = 10;
+  v /= 10000000000ull;
+  while (v) {
+    ++n;
+    v /= 10;
+  }
+  return n;
+}
+
+// Length of the text of used column u holding stored value v.  Mirrors the switch in readNextRow
+// (UnconvertFromZDW.cpp:1349-1453).
+__device__ __forceinline__ uint32_t value_len(const DecParams& P, uint32_t u, uint8_t t, unsigned long long v, DecMeta* meta) {
+  if (is_text_like(t)) {
+    if (v == 0) return t == ZDWB_DECIMAL ? 14u : 0u;  // outputDefault(DECIMAL) = "0.000000000000"
     const uint32_t index = (uint32_t)(v + P.ubase[u]);  // ULONG index: :1363
     if ((uint64_t)index > P.dict_total) {                // :1364 (the reference allows index == dictionarySize)
       meta->err = 1;
-      *src = tmp24;
       return 0;
     }
-    const uint8_t* s = P.blk + P.dict_base + index;
-    const uint64_t room = P.dict_total > index ? P.dict_total - index : 0;
-    uint32_t l = 0;
-    while (l < room && __ldg(s + l) != 0) ++l;
-    *src = s;
-    return l;
+    return dict_strlen(P.blk + P.dict_base + index, P.dict_total - index);
   }
   if (t == ZDWB_CHAR) {  // :1396-1420
-    *src = tmp24;
     if (v == 0) return 0;
-    const unsigned long long tu = v + P.ubase[u];
-    tmp24[0] = (uint8_t)tu;
-    if (tmp24[0] != (uint8_t)'\\') return tmp24[0] ? 1u : 0u;
-    tmp24[1] = (uint8_t)(tu >> 8);
-    return 2;
+    const uint8_t b0 = (uint8_t)(v + P.ubase[u]);
+    return b0 == (uint8_t)'\\' ? 2u : (b0 ? 1u : 0u);
   }
   const unsigned long long full = v ? v + P.ubase[u] : 0ull;
-  uint32_t l;
-  if (is_signed_int_type(t)) l = fmt_i64((int64_t)full, tmp24 + 24);
-  else l = fmt_u64(full, tmp24 + 24);
-  *src = tmp24 + 24 - l;
-  return l;
+  if (is_signed_int_type(t) && (long long)full < 0) {
+    // lltoa (:333-356): '-' then one character per division step of the negated value (INT64_MIN stays negative
+    // and still takes 19 steps)
+    const unsigned long long mag = 0ull - full;
+    return 1u + digits_u64(mag);
+  }
+  return digits_u64(full);
 }
 
+// Writes the text of used column u (len bytes, len > 0) to d (shared or global memory).
+__device__ __forceinline__ void value_write(const DecParams& P, uint32_t u, uint8_t t, unsigned long long v, uint32_t len,
+                                            uint8_t* __restrict__ d) {
+  if (is_text_like(t)) {
+    if (v == 0) {
+      const char* z = "0.000000000000";
+      for (uint32_t k = 0; k < len; ++k) d[k] = (uint8_t)z[k];
+      return;
+    }
+    const uint8_t* s = P.blk + P.dict_base + (uint32_t)(v + P.ubase[u]);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    uint32_t cur = __ldg(w);
+    uint32_t k = 0;
+    for (; k + 4 <= len; k += 4) {
+      const uint32_t nx = __ldg(++w);
+      const uint32_t x = __funnelshift_r(cur, nx, sh);
+      cur = nx;
+      d[k] = (uint8_t)x;
+      d[k + 1] = (uint8_t)(x >> 8);
+      d[k + 2] = (uint8_t)(x >> 16);
+      d[k + 3] = (uint8_t)(x >> 24);
+    }
+    if (k < len) {
+      uint32_t x = cur >> sh;
+      if (sh + (len - k) * 8u > 32u) x = __funnelshift_r(cur, __ldg(w + 1), sh);
+      for (; k < len; ++k, x >>= 8) d[k] = (uint8_t)x;
+    }
+    return;
+  }
+  if (t == ZDWB_CHAR) {
+    const unsigned long long tu = v + P.ubase[u];
+    d[0] = (uint8_t)tu;
+    if (len > 1) d[1] = (uint8_t)(tu >> 8);
+    return;
+  }
+  unsigned long long full = v ? v + P.ubase[u] : 0ull;
+  if (is_signed_int_type(t) && (long long)full < 0) {
+    // lltoa: value = -value (overflows for INT64_MIN), then signed % 10 and / 10; digit byte = rem + '0'
+    long long sv = (long long)(0ull - full);
+    d[0] = (uint8_t)'-';
+    uint32_t p = len;
+    do {
+      const long long rem = sv % 10;
+      sv /= 10;
+      d[--p] = (uint8_t)(rem + 0x30);
+    } while (sv != 0 && p > 1);
+    return;
+  }
+  uint32_t p = len;
+  if (full <= 0xffffffffull) {
+    uint32_t x = (uint32_t)full;
+    do {
+      const uint32_t q = x / 10u;
+      d[--p] = (uint8_t)('0' + (x - q * 10u));
+      x = q;
+    } while (p);
+    return;
+  }
+  do {
+    const unsigned long long q = full / 10ull;
+    d[--p] = (uint8_t)('0' + (uint32_t)(full - q * 10ull));
+    full = q;
+  } while (p);
+}
+
+// all 32 lanes copy n bytes (dictionary -> row)
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n) {
+  for (uint32_t k = lane_id(); k < n; k += 32) d[k] = __ldg(s + k);
+}
+
+constexpr uint32_t FMT_SHORT = 20;   // texts up to this length go through a thread's 24-byte text cache
+constexpr uint32_t FMT_TEXTC = 24;
+
+// One warp writes the template bytes of a row, 4 bytes per lane per step.
+__device__ __forceinline__ void warp_write_template(const FmtTables& FT, const uint32_t* __restrict__ ioffj,
+                                                    uint8_t* __restrict__ row) {
+  const uint32_t ngrp = (FT.static_total + 3) >> 2;
+  for (uint32_t g = lane_id(); g < ngrp; g += 32) {
+    const uint2 sg = __ldg(FT.sgrp + g);
+    const uint32_t k0 = g << 2;
+    const uint32_t nb = min(4u, FT.static_total - k0);
+    uint32_t seg = sg.y & 0x0fffffffu;
+    uint32_t shift = ioffj[seg];
+    const uint32_t opens = sg.y >> 28;
+    uint32_t bytes = sg.x;
+#pragma unroll
+    for (uint32_t b = 0; b < 4; ++b) {
+      if (b < nb) {
+        if (b && ((opens >> b) & 1u)) shift = ioffj[++seg];
+        row[k0 + b + shift] = (uint8_t)bytes;
+        bytes >>= 8;
+      }
+    }
+  }
+}
+
+// Shared-memory carve-up of k_dec_format (host and device must agree).
+struct FmtSmem {
+  size_t val, lenu, ioff, rowoff, sflag, planes, cinv, cinl, textc, obuf, total;
+  __host__ __device__ FmtSmem(uint32_t R, uint32_t U, uint32_t NI, uint32_t F, uint32_t W, uint32_t out_cap) {
+    size_t o = 0;
+    val = o;    o += (size_t)R * U * 8;
+    cinv = o;   o += (size_t)U * 8;
+    lenu = o;   o += (size_t)R * U * 4;
+    ioff = o;   o += (size_t)R * (NI + 1) * 4;
+    rowoff = o; o += (size_t)(R + 1) * 4;
+    planes = o; o += (size_t)4 * W * 4;
+    cinl = o;   o += (size_t)U * 4;
+    sflag = o;  o += (size_t)R * F;
+    o = (o + 15) & ~(size_t)15;
+    textc = o;  o += (size_t)DEC_THREADS * FMT_TEXTC;
+    obuf = o;   o += (size_t)out_cap + 16;
+    total = o;
+  }
+};
+
+// One strip of R rows: explicit values -> fill forward -> text lengths -> row offsets (decoupled look-back over
+// strips) -> rows assembled in shared memory -> coalesced stores.
 __global__ void __launch_bounds__(DEC_THREADS)
-    k_dec_format(const DecParams P, const FmtTables FT, const uint32_t* __restrict__ row_off, uint32_t R, int lut_in_smem,
+    k_dec_format(const DecParams P, const FmtTables FT, const uint32_t* __restrict__ row_off, uint32_t R, uint32_t out_smem_cap,
                  const unsigned long long* __restrict__ cin, uint64_t* __restrict__ strip_status, uint8_t* __restrict__ out,
                  uint64_t out_cap, uint64_t* __restrict__ out_row_off, DecMeta* __restrict__ meta) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  __shared__ uint32_t s_strip;
+  __shared__ uint32_t s_strip, s_nexp, s_nlong;
   __shared__ unsigned long long s_base;
-  // layout: val[R*U] u64 | ilen[R*NI] u32 | ioff[R*NI] u32 | rowoff[R+1] u32 | sflag[R*F] u8 | lut[F*256]
   const uint32_t U = P.U, F = P.F, NI = FT.n_items;
-  unsigned long long* val = reinterpret_cast<unsigned long long*>(dsm);
-  uint32_t* ilen = reinterpret_cast<uint32_t*>(val + (size_t)R * U);
-  uint32_t* ioff = ilen + (size_t)R * NI;
-  uint32_t* rowoff = ioff + (size_t)R * NI;
-  uint8_t* sflag = reinterpret_cast<uint8_t*>(rowoff + R + 1);
-  uint8_t* s_lut = sflag + (size_t)R * F;
+  const FmtSmem L(R, U, NI, F, P.W, out_smem_cap);
+  unsigned long long* val = reinterpret_cast<unsigned long long*>(dsm + L.val);
+  unsigned long long* cinv = reinterpret_cast<unsigned long long*>(dsm + L.cinv);
+  uint32_t* lenu = reinterpret_cast<uint32_t*>(dsm + L.lenu);
+  uint32_t* ioff = reinterpret_cast<uint32_t*>(dsm + L.ioff);
+  uint32_t* rowoff = reinterpret_cast<uint32_t*>(dsm + L.rowoff);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(dsm + L.planes);
+  uint32_t* cinl = reinterpret_cast<uint32_t*>(dsm + L.cinl);
+  uint8_t* sflag = dsm + L.sflag;
+  uint8_t* textc = dsm + L.textc + (size_t)threadIdx.x * FMT_TEXTC;
+  uint8_t* obuf = dsm + L.obuf;
+  unsigned long long* elist = reinterpret_cast<unsigned long long*>(obuf);  // explicit values; dead before obuf is used
+  uint32_t* llist = lenu;                                                   // long items; lenu is dead by then
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0) s_strip = atomicAdd(&meta->tile_ticket, 1u);
-  const uint8_t* lut = stage_lut(P, s_lut, lut_in_smem != 0);
+  if (tid == 0) {
+    s_strip = atomicAdd(&meta->tile_ticket, 1u);
+    s_nexp = 0;
+    s_nlong = 0;
+  }
+  for (uint32_t i = tid; i < 4 * P.W; i += DEC_THREADS) planes[i] = P.planes[i];
   __syncthreads();
   const uint32_t strip = s_strip;
   const uint32_t r0 = strip * R, r1 = min(P.nrows, r0 + R), Rn = r1 - r0;
   const uint8_t* rows = P.blk + P.rows_base;
 
-  // ---- explicit values of this strip
+  // ---- 1. where the explicit values of this strip are
   for (uint32_t j = warp; j < Rn; j += DEC_WARPS) {
-    const uint8_t* rp = rows + row_off[r0 + j];
+    const uint32_t ro = row_off[r0 + j];
+    const uint8_t* rp = rows + ro;
     for (uint32_t k = lane; k < F; k += 32) sflag[j * F + k] = __ldg(rp + k);
-    warp_parse_row(P, lut, rp, [&](uint32_t u, uint32_t voff) { val[(size_t)j * U + u] = load_le(rp + voff, P.usz[u]); });
+    warp_parse_row(P, planes, rp, [&](uint32_t u, uint32_t voff) {
+      const uint32_t e = atomicAdd(&s_nexp, 1u);
+      elist[e] = ((unsigned long long)(ro + voff) << 32) | (unsigned long long)((j << 24) | u);
+    });
   }
   __syncthreads();
-  // ---- fill forward: a column keeps its value until a row flags it again (:1339-1345)
-  for (uint32_t u = tid; u < U; u += DEC_THREADS) {
-    unsigned long long v = cin[(size_t)strip * U + u];
-    const uint32_t fb = u >> 3, bit = u & 7u;
-    for (uint32_t j = 0; j < Rn; ++j) {
-      if ((sflag[j * F + fb] >> bit) & 1u) v = val[(size_t)j * U + u];
-      else val[(size_t)j * U + u] = v;
+  // ---- 2. load them and measure their text, all at once; same for the values carried into the strip
+  {
+    const uint32_t nexp = s_nexp;
+    for (uint32_t e = tid; e < nexp; e += DEC_THREADS) {
+      const unsigned long long ent = elist[e];
+      const uint32_t u = (uint32_t)ent & 0xffffffu, j = ((uint32_t)ent >> 24) & 0xffu;
+      const unsigned long long v = load_le(rows + (uint32_t)(ent >> 32), P.usz[u]);
+      val[(size_t)j * U + u] = v;
+      lenu[(size_t)j * U + u] = value_len(P, u, P.utype[u], v, meta);
+    }
+    for (uint32_t u = tid; u < U; u += DEC_THREADS) {
+      const unsigned long long v = cin[(size_t)strip * U + u];
+      cinv[u] = v;
+      cinl[u] = value_len(P, u, P.utype[u], v, meta);
     }
   }
   __syncthreads();
-  // ---- field lengths and their prefix inside each row
-  uint8_t tmp[24];
+  // ---- 3. fill forward: a column keeps its value - and its text length - until a row flags it again (:1339-1345)
+  for (uint32_t u = tid; u < U; u += DEC_THREADS) {
+    unsigned long long v = cinv[u];
+    uint32_t len = cinl[u];
+    const uint32_t fb = u >> 3, bit = u & 7u;
+    for (uint32_t j = 0; j < Rn; ++j) {
+      if ((sflag[j * F + fb] >> bit) & 1u) {
+        v = val[(size_t)j * U + u];
+        len = lenu[(size_t)j * U + u];
+      } else {
+        val[(size_t)j * U + u] = v;
+        lenu[(size_t)j * U + u] = len;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 4. offset of every item's text among the dynamic bytes of its row; row lengths; strip total
   for (uint32_t j = warp; j < Rn; j += DEC_WARPS) {
     uint32_t run = 0;
+    uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
     for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
       const uint32_t i = i0 + lane;
-      uint32_t l = 0;
-      if (i < NI) {
-        const uint32_t u = FT.item_u[i];
-        const uint8_t* src;
-        l = value_text(P, u, val[(size_t)j * U + u], tmp, &src, meta);
-      }
+      const uint32_t l = i < NI ? lenu[(size_t)j * U + __ldg(FT.item_u + i)] : 0u;
       uint32_t inc = l;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= (unsigned)o) inc += t;
       }
-      if (i < NI) {
-        ilen[(size_t)j * NI + i] = l;
-        ioff[(size_t)j * NI + i] = run + inc - l;
-      }
+      if (i < NI) ioffj[i] = run + inc - l;
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) rowoff[j] = FT.static_total + run;
+    if (lane == 0) {
+      ioffj[NI] = run;
+      rowoff[j] = FT.static_total + run;
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -434,65 +609,147 @@ __global__ void __launch_bounds__(DEC_THREADS)
       if (j < Rn) rowoff[j] = run + inc - v;
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) rowoff[Rn] = run;
+    if (lane == 0) {
+      rowoff[Rn] = run;
+      // publish this strip's byte count right away; the look-back itself happens after the rows are assembled
+      st_release_u64(&strip_status[strip], (strip == 0 ? LB_PFX : LB_AGG) | (uint64_t)run);
+    }
   }
   __syncthreads();
-  // ---- decoupled look-back over strips
-  if (tid == 0) {
-    const uint64_t total = rowoff[Rn];
+  const uint32_t strip_bytes = rowoff[Rn];
+
+  // warp 0: exclusive prefix of the strip totals (32 predecessors per step)
+  auto look_back = [&]() {
+    if (warp != 0) return;
     uint64_t run = 0;
-    if (strip == 0) {
-      st_release_u64(&strip_status[0], LB_PFX | total);
-    } else {
-      st_release_u64(&strip_status[strip], LB_AGG | total);
+    if (strip != 0) {
       int64_t q = (int64_t)strip - 1;
       for (;;) {
-        uint64_t s;
-        do {
-          s = ld_acquire_u64(&strip_status[q]);
-        } while ((s >> 62) == 0ull);
-        run += s & LB_MASK;
-        if ((s >> 62) == 2ull) break;
-        --q;
+        const int64_t idx = q - (int64_t)lane;
+        uint64_t sv = LB_PFX;  // in front of strip 0: an empty inclusive prefix
+        if (idx >= 0) {
+          do {
+            sv = ld_acquire_u64(&strip_status[idx]);
+          } while ((sv >> 62) == 0ull);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
+        const unsigned take = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : 0xffffffffu;  // lanes up to the nearest prefix
+        uint64_t c = ((take >> lane) & 1u) ? (sv & LB_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        run += c;
+        if (pm) break;
+        q -= 32;
       }
-      st_release_u64(&strip_status[strip], LB_PFX | (run + total));
+      if (lane == 0) st_release_u64(&strip_status[strip], LB_PFX | (run + strip_bytes));
     }
-    s_base = run;
-    if (r1 == P.nrows) {
-      meta->out_bytes = run + total;
-      if (out_row_off) out_row_off[P.nrows] = run + total;
+    if (lane == 0) {
+      s_base = run;
+      if (r1 == P.nrows) {
+        meta->out_bytes = run + strip_bytes;
+        if (out_row_off) out_row_off[P.nrows] = run + strip_bytes;
+      }
     }
+  };
+  const bool single_batch = strip_bytes <= out_smem_cap;
+  if (!single_batch) {
+    look_back();
+    __syncthreads();
   }
-  __syncthreads();
+
+  // ---- 5. rows are assembled in shared memory, batch by batch.  A row that does not fit the shared buffer at all
+  // is assembled in global memory.
+  uint32_t jb = 0;
+  while (jb < Rn) {
+    uint32_t je = jb;
+    while (je < Rn && rowoff[je + 1] - rowoff[jb] <= out_smem_cap) ++je;
+    const bool direct = je == jb;
+    if (direct) je = jb + 1;
+    const uint32_t nbytes = rowoff[je] - rowoff[jb];
+    uint8_t* stage = direct ? out + s_base + rowoff[jb] : obuf;
+    const uint32_t nbr = je - jb;
+    if (direct && s_base + rowoff[je] > out_cap) break;  // host reruns with the exact size
+    // 5a. template
+    for (uint32_t j = jb + warp; j < je; j += DEC_WARPS)
+      warp_write_template(FT, ioff + (size_t)j * (NI + 1), stage + (rowoff[j] - rowoff[jb]));
+    // 5b. short texts: a thread owns an item for a run of consecutive rows and re-renders its text only when the
+    // value changes
+    {
+      const uint32_t nch = NI ? max(1u, min(DEC_THREADS / NI, nbr)) : 1u;
+      const uint32_t Lr = (nbr + nch - 1) / nch;
+      for (uint32_t w = tid; w < NI * nch; w += DEC_THREADS) {
+        const uint32_t i = w % NI, c = w / NI;
+        const uint32_t u = __ldg(FT.item_u + i), pos0 = __ldg(FT.item_pos + i);
+        const uint8_t t = P.utype[u];
+        const bool textual = is_text_like(t);
+        bool have = false;
+        unsigned long long vprev = 0;
+        const uint32_t ja = jb + c * Lr, jz = min(je, ja + Lr);
+        for (uint32_t j = ja; j < jz; ++j) {
+          const uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
+          const uint32_t o = ioffj[i], l = ioffj[i + 1] - o;
+          if (!l) continue;
+          const unsigned long long v = val[(size_t)j * U + u];
+          if (textual && v != 0 && l > FMT_SHORT) {
+            llist[atomicAdd(&s_nlong, 1u)] = (j << 24) | i;  // NI < 2^24 checked by the host
+            continue;
+          }
+          if (!have || v != vprev) {
+            value_write(P, u, t, v, l, textc);
+            have = true;
+            vprev = v;
+          }
+          uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + pos0 + o;
+          for (uint32_t k = 0; k < l; ++k) d[k] = textc[k];
+        }
+      }
+    }
+    __syncthreads();
+    // 5c. long texts: one warp per text, straight from the dictionary
+    {
+      const uint32_t nlong = s_nlong;
+      for (uint32_t e = warp; e < nlong; e += DEC_WARPS) {
+        const uint32_t ent = llist[e];
+        const uint32_t i = ent & 0xffffffu, j = ent >> 24;
+        const uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
+        const uint32_t o = ioffj[i], l = ioffj[i + 1] - o;
+        const uint32_t u = __ldg(FT.item_u + i);
+        const uint8_t* src = P.blk + P.dict_base + (uint32_t)(val[(size_t)j * U + u] + P.ubase[u]);
+        warp_copy_bytes(stage + (rowoff[j] - rowoff[jb]) + __ldg(FT.item_pos + i) + o, src, l);
+      }
+    }
+    if (single_batch) look_back();
+    __syncthreads();
+    if (tid == 0) s_nlong = 0;
+    const uint64_t base = s_base;
+    if (!direct) {
+      if (base + rowoff[Rn] > out_cap) break;  // the host's size estimate was too small: it reruns with the exact size
+      // 5d. flush: 4-byte stores, the shared-memory side re-aligned by a funnel shift
+      uint8_t* gdst = out + base + rowoff[jb];
+      const uint32_t head = min(nbytes, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 3u)) & 3u));
+      if (tid < head) gdst[tid] = stage[tid];
+      const uint32_t nw = (nbytes - head) >> 2;
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
+      uint32_t* gw = reinterpret_cast<uint32_t*>(gdst + head);
+      const uint32_t sh = head * 8u;
+      if (sh == 0) {
+        for (uint32_t m = tid; m < nw; m += DEC_THREADS) gw[m] = sw[m];
+      } else {
+        for (uint32_t m = tid; m < nw; m += DEC_THREADS) gw[m] = __funnelshift_r(sw[m], sw[m + 1], sh);
+      }
+      const uint32_t done = head + (nw << 2);
+      if (tid < nbytes - done) gdst[done + tid] = stage[done + tid];
+    }
+    __syncthreads();
+    jb = je;
+  }
   const uint64_t base = s_base;
-  if (out_row_off)
-    for (uint32_t j = tid; j < Rn; j += DEC_THREADS) out_row_off[r0 + j] = base + rowoff[j];
-  if (base + rowoff[Rn] > out_cap) {  // the host's size estimate was too small: it reruns with the exact size
+  if (base + strip_bytes > out_cap) {
     if (tid == 0) meta->overflow = 1;
     return;
   }
-
-  // ---- write: static segment i, then the text of item i; the last segment closes the row
-  for (uint32_t j = warp; j < Rn; j += DEC_WARPS) {
-    uint8_t* orow = out + base + rowoff[j];
-    const uint32_t dyn_total = (j + 1 <= Rn ? rowoff[j + 1] - rowoff[j] : 0u) - FT.static_total;
-    for (uint32_t i0 = 0; i0 <= NI; i0 += 32) {
-      const uint32_t i = i0 + lane;
-      if (i > NI) continue;
-      const uint32_t doff = i < NI ? ioff[(size_t)j * NI + i] : dyn_total;
-      uint8_t* d = orow + FT.seg_cum[i] + doff;
-      const uint8_t* sb = FT.blob + FT.seg_off[i];
-      const uint32_t sl = FT.seg_len[i];
-      for (uint32_t k = 0; k < sl; ++k) d[k] = __ldg(sb + k);
-      if (i < NI) {
-        d += sl;
-        const uint32_t u = FT.item_u[i];
-        const uint8_t* src;
-        const uint32_t l = value_text(P, u, val[(size_t)j * U + u], tmp, &src, meta);
-        for (uint32_t k = 0; k < l; ++k) d[k] = src[k];
-      }
-    }
-  }
+  if (out_row_off)
+    for (uint32_t j = tid; j < Rn; j += DEC_THREADS) out_row_off[r0 + j] = base + rowoff[j];
 }
 
 struct HostBlockHeader {
@@ -628,20 +885,15 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   const uint64_t dev_avail = in_dev ? avail : rows_base + win;
 
   // ---- tables
-  std::vector<uint8_t> lut((size_t)(F ? F : 1) * 256, 0);
   std::vector<uint32_t> planes((size_t)4 * (W ? W : 1), 0);
   for (uint32_t u = 0; u < U; ++u) {
-    const uint32_t j = u / 8, b = u % 8;
-    for (uint32_t v = 0; v < 256; ++v)
-      if (v & (1u << b)) lut[(size_t)j * 256 + v] += usz[u];
     for (uint32_t k = 0; k < 4; ++k)
       if (usz[u] & (1u << k)) planes[(size_t)k * W + u / 32] |= 1u << (u % 32);
   }
-  DevBuf d_usz, d_ubase, d_utype, d_lut, d_planes, d_meta;
+  DevBuf d_usz, d_ubase, d_utype, d_planes, d_meta;
   ZDWB_TRY(upload(ctx, d_usz, usz));
   ZDWB_TRY(upload(ctx, d_ubase, ubase));
   ZDWB_TRY(upload(ctx, d_utype, utype));
-  ZDWB_TRY(upload(ctx, d_lut, lut));
   ZDWB_TRY(upload(ctx, d_planes, planes));
   ZDWB_TRY(d_meta.alloc(ctx, sizeof(DecMeta)));
   ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(d_meta.p, 0, sizeof(DecMeta), st));
@@ -661,7 +913,6 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   P.usz = d_usz.as<uint8_t>();
   P.ubase = d_ubase.as<unsigned long long>();
   P.utype = d_utype.as<uint8_t>();
-  P.lut = d_lut.as<uint8_t>();
   P.planes = d_planes.as<uint32_t>();
 
   // ---- output plan: static segments and dynamic items in output order
@@ -686,46 +937,57 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     for (uint32_t c = 0; c < nc; ++c) pos_src[c] = (int32_t)c;
   }
   std::string blob;
-  std::vector<uint32_t> seg_off, seg_len, seg_cum, item_u;
+  std::vector<uint32_t> item_u, item_pos, seg_of;  // seg_of[k] = static segment of template byte k
   {
-    size_t seg_start = 0;
-    uint32_t cum = 0;
+    uint32_t seg = 0;
     for (size_t k = 0; k < pos_src.size(); ++k) {
-      if (k) blob.push_back((char)sep);
+      if (k) {
+        blob.push_back((char)sep);
+        seg_of.push_back(seg);
+      }
       const int32_t c = pos_src[k];
       if (c < 0) continue;
       if (used_idx[c] < 0) {
+        const size_t before = blob.size();
         append_default(blob, schema->types[c]);
+        seg_of.resize(blob.size(), seg);
+        (void)before;
       } else {
-        seg_off.push_back((uint32_t)seg_start);
-        seg_len.push_back((uint32_t)(blob.size() - seg_start));
-        seg_cum.push_back(cum);
-        cum += (uint32_t)(blob.size() - seg_start);
         item_u.push_back((uint32_t)used_idx[c]);
-        seg_start = blob.size();
+        item_pos.push_back((uint32_t)blob.size());
+        ++seg;
       }
     }
     blob.push_back((char)term);
-    seg_off.push_back((uint32_t)seg_start);
-    seg_len.push_back((uint32_t)(blob.size() - seg_start));
-    seg_cum.push_back(cum);
+    seg_of.push_back(seg);
   }
   const uint32_t NI = (uint32_t)item_u.size();
-  std::vector<uint8_t> blobv(blob.begin(), blob.end());
-  DevBuf d_item_u, d_seg_off, d_seg_len, d_seg_cum, d_blob;
+  const uint32_t static_total = (uint32_t)blob.size();
+  std::vector<uint2> sgrp((static_total + 3) / 4);
+  for (uint32_t g = 0; g < sgrp.size(); ++g) {
+    uint32_t bytes = 0, opens = 0;
+    for (uint32_t b2 = 0; b2 < 4; ++b2) {
+      const uint32_t k = g * 4 + b2;
+      if (k >= static_total) break;
+      bytes |= (uint32_t)(uint8_t)blob[k] << (8 * b2);
+      if (b2 && seg_of[k] != seg_of[k - 1]) opens |= 1u << b2;
+    }
+    sgrp[g] = make_uint2(bytes, seg_of[g * 4] | (opens << 28));
+  }
+  if (NI >= (1u << 28)) {
+    ctx->err = "decode: too many output columns";
+    return ZDWB_ERR_UNSUPPORTED;
+  }
+  DevBuf d_item_u, d_item_pos, d_sgrp;
   ZDWB_TRY(upload(ctx, d_item_u, item_u));
-  ZDWB_TRY(upload(ctx, d_seg_off, seg_off));
-  ZDWB_TRY(upload(ctx, d_seg_len, seg_len));
-  ZDWB_TRY(upload(ctx, d_seg_cum, seg_cum));
-  ZDWB_TRY(upload(ctx, d_blob, blobv));
+  ZDWB_TRY(upload(ctx, d_item_pos, item_pos));
+  ZDWB_TRY(upload(ctx, d_sgrp, sgrp));
   FmtTables FT;
   FT.n_items = NI;
   FT.item_u = d_item_u.as<uint32_t>();
-  FT.seg_off = d_seg_off.as<uint32_t>();
-  FT.seg_len = d_seg_len.as<uint32_t>();
-  FT.seg_cum = d_seg_cum.as<uint32_t>();
-  FT.blob = d_blob.as<uint8_t>();
-  FT.static_total = (uint32_t)blob.size();
+  FT.item_pos = d_item_pos.as<uint32_t>();
+  FT.sgrp = d_sgrp.as<uint2>();
+  FT.static_total = static_total;
 
   if (nrows == 0) {
     out->consumed = rows_base;
@@ -839,24 +1101,26 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   out->consumed = rows_base + consumed_stream;
 
   // ---- strips
-  const int lut_in_smem = (size_t)F * 256 <= 48 * 1024 ? 1 : 0;
-  const size_t lut_smem = lut_in_smem ? (size_t)F * 256 : 0;
-  // rows per strip: shared memory of k_dec_format is R * (8U + 8NI + F) + lut
-  const size_t per_row = (size_t)8 * U + (size_t)8 * NI + F + 4;
-  const size_t budget = 64 * 1024;
-  uint32_t R = (uint32_t)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_row, 1), 512));
-  {
-    // keep the TSV bytes per strip moderate (about 32 KiB)
-    const uint64_t approx_row = (uint64_t)FT.static_total + (uint64_t)NI * 8;
-    const uint32_t by_bytes = (uint32_t)std::max<uint64_t>(8, 32768 / std::max<uint64_t>(approx_row, 1));
-    R = std::min(R, std::max(by_bytes, 8u));
-    if (R == 0) R = 1;
-  }
-  const size_t smem_fmt = (size_t)R * per_row + 64 + lut_smem + (size_t)(R + 1) * 4;
-  if (smem_fmt > 200 * 1024) {
-    ctx->err = "decode: too many used columns for the format kernel";
+  // rows per strip: about 32 KiB of TSV, bounded by the per-row tables of k_dec_format (val, lenu, ioff, flags)
+  if (U >= (1u << 24)) {
+    ctx->err = "decode: more than 2^24 used columns";
     return ZDWB_ERR_UNSUPPORTED;
   }
+  const size_t per_row = (size_t)12 * U + (size_t)4 * (NI + 1) + F + 4;
+  uint64_t est_row = (uint64_t)FT.static_total + (uint64_t)NI * 8;
+  if (ctx->last_out_per_row > est_row) est_row = ctx->last_out_per_row;
+  uint32_t R = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(32768 / std::max<uint64_t>(est_row, 1), 256));
+  R = (uint32_t)std::max<size_t>(1, std::min<size_t>(R, (40 * 1024) / per_row));
+  uint32_t out_smem_cap = (uint32_t)((std::max<size_t>({(size_t)32 * 1024, (size_t)2 * est_row, (size_t)R * U * 8}) + 15) & ~(size_t)15);
+  {
+    const size_t fixed = FmtSmem(R, U, NI, F, W, 0).total;
+    if (fixed + (size_t)R * U * 8 + 64 > 200 * 1024) {
+      ctx->err = "decode: too many used columns for the format kernel";
+      return ZDWB_ERR_UNSUPPORTED;
+    }
+    if (fixed + out_smem_cap > 200 * 1024) out_smem_cap = (uint32_t)((200 * 1024 - fixed) & ~(size_t)15);
+  }
+  const size_t smem_fmt = FmtSmem(R, U, NI, F, W, out_smem_cap).total;
   const uint32_t nstrips = (nrows + R - 1) / R;
 
   DevBuf cin;
@@ -865,11 +1129,11 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     DevBuf sval, shas, seg_val, seg_has;
     ZDWB_TRY(sval.alloc(ctx, (size_t)nstrips * U * 8));
     ZDWB_TRY(shas.alloc(ctx, (size_t)nstrips * U));
-    const size_t smem_sum = (size_t)U * 4 + lut_smem + 16;
+    const size_t smem_sum = (size_t)U * 4 + 16;
     ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_strip_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
       KernelScope _ks(ctx, "k_dec_strip_summary");
-      k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R, lut_in_smem,
+      k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R,
                                                                sval.as<unsigned long long>(), shas.as<uint8_t>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
@@ -900,10 +1164,10 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   // ---- output buffers.  The exact TSV size is only known once every field has been measured, which the
   // format kernel does anyway; so size the buffer by an estimate, let strips that would not fit skip their
   // writes (the look-back still yields the exact total) and rerun once with the exact size if needed.
-  uint64_t est_row = FT.static_total;
-  for (uint32_t i = 0; i < NI; ++i) est_row += is_text_like(utype[item_u[i]]) ? 16 : 8;
-  if (ctx->last_out_per_row > est_row) est_row = ctx->last_out_per_row;
-  uint64_t out_cap = (uint64_t)nrows * est_row + 4096;
+  uint64_t est_out_row = FT.static_total;
+  for (uint32_t i = 0; i < NI; ++i) est_out_row += is_text_like(utype[item_u[i]]) ? 16 : 8;
+  if (ctx->last_out_per_row > est_out_row) est_out_row = ctx->last_out_per_row;
+  uint64_t out_cap = (uint64_t)nrows * est_out_row + 4096;
   if (ctx->out_dev2) {
     cudaFreeAsync(ctx->out_dev2, st);
     ctx->out_dev2 = nullptr;
@@ -915,7 +1179,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   }
   DevBuf status;
   ZDWB_TRY(status.alloc(ctx, (size_t)nstrips * 8));
-  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_format, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_format, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
   DecMeta* hm = static_cast<DecMeta*>(ctx->meta_host);
   for (int attempt = 0;; ++attempt) {
     if (ctx->out_dev) {
@@ -931,7 +1195,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(d_meta.p, 0, sizeof(DecMeta), st));
     {
       KernelScope _ks(ctx, "k_dec_format");
-      k_dec_format<<<nstrips, DEC_THREADS, smem_fmt, st>>>(P, FT, row_off.as<uint32_t>(), R, lut_in_smem,
+      k_dec_format<<<nstrips, DEC_THREADS, smem_fmt, st>>>(P, FT, row_off.as<uint32_t>(), R, out_smem_cap,
                                                         cin.as<unsigned long long>(), status.as<uint64_t>(),
                                                         static_cast<uint8_t*>(ctx->out_dev), out_cap,
                                                         static_cast<uint64_t*>(ctx->out_dev2), meta);
