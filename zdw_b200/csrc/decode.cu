@@ -307,8 +307,9 @@ struct FmtTables {
   uint32_t n_items;             // dynamic items (used columns that are output), in output order
   const uint32_t* item_u;       // [n_items] used-column index
   const uint32_t* item_pos;     // [n_items] static bytes in front of the text of item i
-  const uint2* sgrp;            // [ceil(static_total/4)] .x = 4 template bytes, .y = segment of the first byte
-                                //   | (bit 28+b set: byte b >= 1 of the group opens the next segment)
+  const uint4* sgrp;            // [n_groups] template bytes in groups of 1..4 that never straddle a segment:
+                                //   .x = the bytes, .y = segment, .z = offset of the first byte in the template, .w = count
+  uint32_t n_groups;
   uint32_t static_total;
 };
 
@@ -442,34 +443,54 @@ __device__ __forceinline__ void value_write(const DecParams& P, uint32_t u, uint
   } while (p);
 }
 
+constexpr uint32_t FMT_SHORT = 16;   // texts up to this length go through a thread's text cache
+constexpr uint32_t FMT_TEXTC = 24;   // bytes of text cache per thread (20 digits fit)
+
+// Renders the text (len <= FMT_TEXTC; dictionary strings: len <= FMT_SHORT) of used column u into the thread's
+// word-aligned text cache.  The dictionary path is straight-line so that lanes with different lengths stay converged.
+__device__ __forceinline__ void render_short(const DecParams& P, uint32_t u, uint8_t t, unsigned long long v, uint32_t len,
+                                             uint32_t* __restrict__ tc) {
+  if (is_text_like(t)) {
+    if (v == 0) {  // outputDefault(DECIMAL): "0.000000000000"
+      tc[0] = 0x30302e30u;
+      tc[1] = 0x30303030u;
+      tc[2] = 0x30303030u;
+      tc[3] = 0x00003030u;
+      return;
+    }
+    const uint8_t* s = P.blk + P.dict_base + (uint32_t)(v + P.ubase[u]);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t* wend = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.blk + P.avail - 1) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    const uint32_t room = (uint32_t)min((ptrdiff_t)4, wend - w);  // whole words readable after *w (block end)
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, room)), w2 = __ldg(w + min(2u, room)), w3 = __ldg(w + min(3u, room)),
+                   w4 = __ldg(w + min(4u, room));
+    tc[0] = __funnelshift_r(w0, w1, sh);
+    tc[1] = __funnelshift_r(w1, w2, sh);
+    tc[2] = __funnelshift_r(w2, w3, sh);
+    tc[3] = __funnelshift_r(w3, w4, sh);
+    return;
+  }
+  value_write(P, u, t, v, len, reinterpret_cast<uint8_t*>(tc));
+}
+
 // all 32 lanes copy n bytes (dictionary -> row)
 __device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n) {
   for (uint32_t k = lane_id(); k < n; k += 32) d[k] = __ldg(s + k);
 }
 
-constexpr uint32_t FMT_SHORT = 20;   // texts up to this length go through a thread's 24-byte text cache
-constexpr uint32_t FMT_TEXTC = 24;
 
-// One warp writes the template bytes of a row, 4 bytes per lane per step.
+// One warp writes the template bytes of a row, one group (up to 4 bytes of one segment) per lane per step.
 __device__ __forceinline__ void warp_write_template(const FmtTables& FT, const uint32_t* __restrict__ ioffj,
                                                     uint8_t* __restrict__ row) {
-  const uint32_t ngrp = (FT.static_total + 3) >> 2;
-  for (uint32_t g = lane_id(); g < ngrp; g += 32) {
-    const uint2 sg = __ldg(FT.sgrp + g);
-    const uint32_t k0 = g << 2;
-    const uint32_t nb = min(4u, FT.static_total - k0);
-    uint32_t seg = sg.y & 0x0fffffffu;
-    uint32_t shift = ioffj[seg];
-    const uint32_t opens = sg.y >> 28;
-    uint32_t bytes = sg.x;
-#pragma unroll
-    for (uint32_t b = 0; b < 4; ++b) {
-      if (b < nb) {
-        if (b && ((opens >> b) & 1u)) shift = ioffj[++seg];
-        row[k0 + b + shift] = (uint8_t)bytes;
-        bytes >>= 8;
-      }
-    }
+  for (uint32_t g = lane_id(); g < FT.n_groups; g += 32) {
+    const uint4 sg = __ldg(FT.sgrp + g);
+    uint8_t* d = row + sg.z + ioffj[sg.y];
+    d[0] = (uint8_t)sg.x;
+    if (sg.w > 1) d[1] = (uint8_t)(sg.x >> 8);
+    if (sg.w > 2) d[2] = (uint8_t)(sg.x >> 16);
+    if (sg.w > 3) d[3] = (uint8_t)(sg.x >> 24);
   }
 }
 
@@ -695,27 +716,48 @@ __global__ void __launch_bounds__(DEC_THREADS)
             continue;
           }
           if (!have || v != vprev) {
-            value_write(P, u, t, v, l, textc);
+            render_short(P, u, t, v, l, reinterpret_cast<uint32_t*>(textc));
             have = true;
             vprev = v;
           }
           uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + pos0 + o;
-          for (uint32_t k = 0; k < l; ++k) d[k] = textc[k];
+          const uint32_t* tw = reinterpret_cast<const uint32_t*>(textc);
+          for (uint32_t k = 0; k < l; k += 4) {
+            const uint32_t x = tw[k >> 2], nb = l - k;
+            d[k] = (uint8_t)x;
+            if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
+            if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
+            if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
+          }
         }
       }
     }
     __syncthreads();
-    // 5c. long texts: one warp per text, straight from the dictionary
+    // 5c. long texts straight from the dictionary: 8 lanes per text, 4 bytes per lane per step
     {
       const uint32_t nlong = s_nlong;
-      for (uint32_t e = warp; e < nlong; e += DEC_WARPS) {
+      const uint32_t grp = lane >> 3, gl = lane & 7u;
+      for (uint32_t e = warp * 4 + grp; e < nlong; e += DEC_WARPS * 4) {
         const uint32_t ent = llist[e];
         const uint32_t i = ent & 0xffffffu, j = ent >> 24;
         const uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
         const uint32_t o = ioffj[i], l = ioffj[i + 1] - o;
         const uint32_t u = __ldg(FT.item_u + i);
         const uint8_t* src = P.blk + P.dict_base + (uint32_t)(val[(size_t)j * U + u] + P.ubase[u]);
-        warp_copy_bytes(stage + (rowoff[j] - rowoff[jb]) + __ldg(FT.item_pos + i) + o, src, l);
+        uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + __ldg(FT.item_pos + i) + o;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+        for (uint32_t k = gl * 4; k < l; k += 32) {
+          const uint32_t nb = l - k;
+          const uint32_t lo = __ldg(w + (k >> 2));
+          const uint32_t hi = (sh + min(nb, 4u) * 8u > 32u) ? __ldg(w + (k >> 2) + 1) : 0u;
+          const uint32_t x = __funnelshift_r(lo, hi, sh);
+          d[k] = (uint8_t)x;
+          if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
+          if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
+          if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
+        }
       }
     }
     if (single_batch) look_back();
@@ -963,18 +1005,16 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   }
   const uint32_t NI = (uint32_t)item_u.size();
   const uint32_t static_total = (uint32_t)blob.size();
-  std::vector<uint2> sgrp((static_total + 3) / 4);
-  for (uint32_t g = 0; g < sgrp.size(); ++g) {
-    uint32_t bytes = 0, opens = 0;
-    for (uint32_t b2 = 0; b2 < 4; ++b2) {
-      const uint32_t k = g * 4 + b2;
-      if (k >= static_total) break;
-      bytes |= (uint32_t)(uint8_t)blob[k] << (8 * b2);
-      if (b2 && seg_of[k] != seg_of[k - 1]) opens |= 1u << b2;
-    }
-    sgrp[g] = make_uint2(bytes, seg_of[g * 4] | (opens << 28));
+  std::vector<uint4> sgrp;
+  for (uint32_t k = 0; k < static_total;) {
+    uint32_t n = 1;
+    while (n < 4 && k + n < static_total && seg_of[k + n] == seg_of[k]) ++n;
+    uint32_t bytes = 0;
+    for (uint32_t b2 = 0; b2 < n; ++b2) bytes |= (uint32_t)(uint8_t)blob[k + b2] << (8 * b2);
+    sgrp.push_back(make_uint4(bytes, seg_of[k], k, n));
+    k += n;
   }
-  if (NI >= (1u << 28)) {
+  if (NI >= (1u << 24)) {
     ctx->err = "decode: too many output columns";
     return ZDWB_ERR_UNSUPPORTED;
   }
@@ -986,7 +1026,8 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   FT.n_items = NI;
   FT.item_u = d_item_u.as<uint32_t>();
   FT.item_pos = d_item_pos.as<uint32_t>();
-  FT.sgrp = d_sgrp.as<uint2>();
+  FT.sgrp = d_sgrp.as<uint4>();
+  FT.n_groups = (uint32_t)sgrp.size();
   FT.static_total = static_total;
 
   if (nrows == 0) {
