@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ZDWB_ABI_VERSION 1
+#define ZDWB_ABI_VERSION 2
 
 /* status codes (mapped to the reference's ERR_CODE enums by the host classes) */
 enum {
@@ -102,7 +102,9 @@ typedef struct {
   int32_t trim_trailing_spaces; /* -t : ConvertToZDW.cpp:295-313 */
   int32_t input_on_device;      /* `tsv` is a device pointer (already resident in HBM) */
   int32_t output_on_device;     /* leave the encoded block in HBM: out->bytes is then a device pointer */
-  int32_t reserved0;
+  int32_t more_input_follows;   /* the buffer is a window of a larger input: an unterminated last line is NOT the dropped
+                                   final line of getnextrow.cpp:67-69 but the head of a row that continues in the next
+                                   window; it is left unconsumed (tsv_consumed points at it) and isLast is written as 0 */
   uint32_t prev_longest_line;   /* m_LongestLine carried in from earlier blocks of the file (0 = 16384 start value,
                                    ConvertToZDW.cpp:965; the field is cumulative, getnextrow.cpp:57-65) */
   uint32_t reserved1;
@@ -134,6 +136,13 @@ int zdwb_encode_block(zdwb_ctx* ctx, const zdwb_schema* schema, const void* tsv,
 
 /* ---- decode ---------------------------------------------------------------------------------- */
 
+/* constant text for an output position (virtual_export_basename, UnconvertFromZDW.cpp:1253-1255) */
+typedef struct {
+  uint32_t pos;              /* output position */
+  uint32_t len;
+  const char* text;          /* host memory, no separators inside */
+} zdwb_fill;
+
 typedef struct {
   int32_t input_on_device;   /* `zdw` is a device pointer */
   int32_t output_on_device;  /* leave the TSV (and row offsets) in HBM */
@@ -148,7 +157,14 @@ typedef struct {
    * PROVIDE_EMPTY_MISSING_COLUMNS case). */
   const int32_t* out_col;
   uint32_t n_out;
-  uint32_t reserved2;
+  uint32_t n_fills;          /* constant texts for positions no file column maps to */
+  const zdwb_fill* fills;
+  int32_t rownum_pos;        /* output position of the running row number (virtual_export_row, :1256-1261), -1 = none;
+                                only honoured when out_col != NULL */
+  int32_t validate_only;     /* -t: walk every row, bounds-check dictionary offsets, produce no text (:1488-1572) */
+  uint64_t first_row_number; /* number of the block's first row (1-based, runs on across blocks) */
+  int32_t want_flag_counts;  /* -s: also return out->flag_counts[ncols_used] = rows in which the column's bit is set */
+  int32_t reserved3;
 } zdwb_decode_opts;
 
 typedef struct {
@@ -163,6 +179,7 @@ typedef struct {
   uint64_t dict_bytes;
   uint32_t ncols_used;
   uint32_t reserved2;
+  const uint64_t* flag_counts; /* host memory, ncols_used entries (only if want_flag_counts) */
 } zdwb_rows_out;
 
 /* Decodes the block that starts at zdw[0] (the numRows field) given `avail` bytes. `version` is the file's

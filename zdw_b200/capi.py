@@ -38,7 +38,7 @@ class _Schema(C.Structure):
 
 class _EncOpts(C.Structure):
     _fields_ = [("trim", C.c_int32), ("input_on_device", C.c_int32), ("output_on_device", C.c_int32),
-                ("reserved0", C.c_int32), ("prev_longest_line", C.c_uint32), ("reserved1", C.c_uint32),
+                ("more_input_follows", C.c_int32), ("prev_longest_line", C.c_uint32), ("reserved1", C.c_uint32),
                 ("max_rows", C.c_uint64)]
 
 
@@ -49,17 +49,23 @@ class _BlockOut(C.Structure):
                 ("dict_index_size", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class _Fill(C.Structure):
+    _fields_ = [("pos", C.c_uint32), ("len", C.c_uint32), ("text", C.c_char_p)]
+
+
 class _DecOpts(C.Structure):
     _fields_ = [("input_on_device", C.c_int32), ("output_on_device", C.c_int32), ("want_row_offsets", C.c_int32),
                 ("at_end_of_file", C.c_int32), ("separator", C.c_uint8), ("reserved", C.c_uint8 * 7),
-                ("out_col", C.POINTER(C.c_int32)), ("n_out", C.c_uint32), ("reserved2", C.c_uint32)]
+                ("out_col", C.POINTER(C.c_int32)), ("n_out", C.c_uint32), ("n_fills", C.c_uint32),
+                ("fills", C.POINTER(_Fill)), ("rownum_pos", C.c_int32), ("validate_only", C.c_int32),
+                ("first_row_number", C.c_uint64), ("want_flag_counts", C.c_int32), ("reserved3", C.c_int32)]
 
 
 class _RowsOut(C.Structure):
     _fields_ = [("tsv", C.c_void_p), ("len", C.c_size_t), ("row_off", C.c_void_p), ("nrows", C.c_uint32),
                 ("line_length", C.c_uint32), ("is_last", C.c_uint8), ("reserved", C.c_uint8 * 7),
                 ("consumed", C.c_uint64), ("dict_bytes", C.c_uint64), ("ncols_used", C.c_uint32),
-                ("reserved2", C.c_uint32)]
+                ("reserved2", C.c_uint32), ("flag_counts", C.c_void_p)]
 
 
 _lib = None
@@ -126,6 +132,7 @@ class DecodedBlock:
     consumed: int
     dict_bytes: int
     ncols_used: int
+    flag_counts: list | None = None
 
 
 class Context:
@@ -184,7 +191,7 @@ class Context:
 
     # ------------------------------------------------------------------ encode
     def encode_block(self, types, tsv, n: int | None = None, *, trim=False, input_on_device=False,
-                     output_on_device=False, prev_longest_line=0, max_rows=0) -> EncodedBlock:
+                     output_on_device=False, prev_longest_line=0, max_rows=0, more_input_follows=False) -> EncodedBlock:
         """tsv: bytes-like (host) or an int device pointer (input_on_device=True, n required)."""
         tarr = (C.c_uint8 * max(len(types), 1))(*types)
         sch = _Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
@@ -195,7 +202,8 @@ class Context:
             keep = tsv if isinstance(tsv, (bytes, bytearray)) else bytes(tsv)
             n = len(keep) if n is None else n
             ptr = C.cast(C.c_char_p(bytes(keep)), C.c_void_p) if not isinstance(keep, bytes) else C.cast(C.c_char_p(keep), C.c_void_p)
-        o = _EncOpts(int(trim), int(input_on_device), int(output_on_device), 0, prev_longest_line, 0, max_rows)
+        o = _EncOpts(int(trim), int(input_on_device), int(output_on_device), int(more_input_follows), prev_longest_line, 0,
+                     max_rows)
         out = _BlockOut()
         rc = self._L.zdwb_encode_block(self._h, C.byref(sch), ptr, n, C.byref(o), C.byref(out))
         if rc:
@@ -210,7 +218,9 @@ class Context:
 
     # ------------------------------------------------------------------ decode
     def decode_block(self, types, zdw, avail: int | None = None, *, input_on_device=False, output_on_device=False,
-                     want_row_offsets=False, at_end_of_file=True, separator=b"\t", out_col=None, n_out=0) -> DecodedBlock:
+                     want_row_offsets=False, at_end_of_file=True, separator=b"\t", out_col=None, n_out=0, fills=None,
+                     rownum_pos=-1, first_row_number=1, validate_only=False, want_flag_counts=False) -> DecodedBlock:
+        """fills: {output position: bytes} constant texts for positions no file column maps to."""
         tarr = (C.c_uint8 * max(len(types), 1))(*types)
         sch = _Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
         if input_on_device:
@@ -223,9 +233,13 @@ class Context:
         oc = None
         if out_col is not None:
             oc = (C.c_int32 * len(out_col))(*out_col)
+        fl = None
+        if fills:
+            fl = (_Fill * len(fills))(*[_Fill(int(k), len(v), v) for k, v in fills.items()])
         o = _DecOpts(int(input_on_device), int(output_on_device), int(want_row_offsets), int(at_end_of_file),
                      separator[0], (C.c_uint8 * 7)(), C.cast(oc, C.POINTER(C.c_int32)) if oc is not None else None,
-                     n_out, 0)
+                     n_out, len(fills) if fills else 0, C.cast(fl, C.POINTER(_Fill)) if fl is not None else None,
+                     rownum_pos, int(validate_only), first_row_number, int(want_flag_counts), 0)
         out = _RowsOut()
         rc = self._L.zdwb_decode_block(self._h, C.byref(sch), ptr, avail, C.byref(o), C.byref(out))
         if rc:
@@ -237,5 +251,8 @@ class Context:
             if want_row_offsets and out.row_off:
                 arr = (C.c_uint64 * (out.nrows + 1)).from_address(out.row_off)
                 offs = list(arr)
+        counts = None
+        if want_flag_counts and out.flag_counts:
+            counts = list((C.c_uint64 * out.ncols_used).from_address(out.flag_counts))
         return DecodedBlock(tsv, int(out.tsv or 0), out.len, offs, out.nrows, out.line_length, bool(out.is_last),
-                            out.consumed, out.dict_bytes, out.ncols_used)
+                            out.consumed, out.dict_bytes, out.ncols_used, counts)

@@ -37,6 +37,7 @@ struct Ctx {
   size_t out_host_cap = 0;
   void* out_host2 = nullptr;
   size_t out_host2_cap = 0;
+  std::vector<unsigned long long> flag_counts;  // -s statistics of the last decoded block
   void* in_stage = nullptr;    // pinned staging for pageable host inputs (unused when caller memory is pinned)
   // small pinned scratch for device->host readbacks of metadata
   void* meta_host = nullptr;

@@ -225,13 +225,15 @@ __device__ __forceinline__ unsigned long long load_le(const uint8_t* __restrict_
   return sz >= 8 ? v : (v & ((1ull << (sz * 8u)) - 1ull));
 }
 
-// last explicit value of every used column inside a strip of R rows
+// last explicit value of every used column inside a strip of R rows; optionally (-t / -s) bounds-checks the
+// dictionary offset of every explicit value (UnconvertFromZDW.cpp:1527-1560) and counts the set flag bits per column
 __global__ void __launch_bounds__(DEC_THREADS)
-    k_dec_strip_summary(const DecParams P, const uint32_t* __restrict__ row_off, uint32_t R,
-                        unsigned long long* __restrict__ sval, uint8_t* __restrict__ shas) {
+    k_dec_strip_summary(const DecParams P, const uint32_t* __restrict__ row_off, uint32_t R, int validate,
+                        unsigned long long* __restrict__ flag_counts, unsigned long long* __restrict__ sval,
+                        uint8_t* __restrict__ shas, DecMeta* __restrict__ meta) {
   extern __shared__ __align__(16) uint8_t dsm[];
   int32_t* last_row = reinterpret_cast<int32_t*>(dsm);
-  const uint32_t* lut = P.planes;
+  const uint32_t* planes = P.planes;
   for (uint32_t u = threadIdx.x; u < P.U; u += DEC_THREADS) last_row[u] = -1;
   __syncthreads();
   const uint32_t r0 = blockIdx.x * R, r1 = min(P.nrows, r0 + R);
@@ -239,13 +241,21 @@ __global__ void __launch_bounds__(DEC_THREADS)
   const uint8_t* rows = P.blk + P.rows_base;
   for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
     const int32_t rl = (int32_t)(r - r0);
-    warp_parse_row(P, lut, rows + row_off[r], [&](uint32_t u, uint32_t) { atomicMax(&last_row[u], rl); });
+    const uint8_t* rp = rows + row_off[r];
+    warp_parse_row(P, planes, rp, [&](uint32_t u, uint32_t voff) {
+      atomicMax(&last_row[u], rl);
+      if (flag_counts) atomicAdd(&flag_counts[u], 1ull);
+      if (validate && is_text_like(P.utype[u])) {
+        const unsigned long long v = load_le(rp + voff, P.usz[u]);
+        if (v != 0 && (uint64_t)(uint32_t)(v + P.ubase[u]) > P.dict_total) meta->err = 1;
+      }
+    });
   }
   __syncthreads();
   for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row(P, lut, rp, [&](uint32_t u, uint32_t voff) {
+    warp_parse_row(P, planes, rp, [&](uint32_t u, uint32_t voff) {
       if (last_row[u] == rl) sval[(size_t)blockIdx.x * P.U + u] = load_le(rp + voff, P.usz[u]);
     });
   }
@@ -311,7 +321,9 @@ struct FmtTables {
                                 //   .x = the bytes, .y = segment, .z = offset of the first byte in the template, .w = count
   uint32_t n_groups;
   uint32_t static_total;
+  unsigned long long first_row;  // number of the block's first row, for the virtual row-number item
 };
+constexpr uint32_t ITEM_ROWNUM = 0xffffffffu;  // item_u marker: the item is the running row number, not a used column
 
 // strlen of the dictionary entry at s, at most `room` bytes: aligned 32-bit loads + zero-byte detect
 // (GetWord + strlen, UnconvertFromZDW.cpp:359-371,1380)
@@ -600,7 +612,11 @@ __global__ void __launch_bounds__(DEC_THREADS)
     uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
     for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
       const uint32_t i = i0 + lane;
-      const uint32_t l = i < NI ? lenu[(size_t)j * U + __ldg(FT.item_u + i)] : 0u;
+      uint32_t l = 0;
+      if (i < NI) {
+        const uint32_t iu = __ldg(FT.item_u + i);
+        l = iu == ITEM_ROWNUM ? digits_u64(FT.first_row + r0 + j) : lenu[(size_t)j * U + iu];
+      }
       uint32_t inc = l;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -701,7 +717,8 @@ __global__ void __launch_bounds__(DEC_THREADS)
       for (uint32_t w = tid; w < NI * nch; w += DEC_THREADS) {
         const uint32_t i = w % NI, c = w / NI;
         const uint32_t u = __ldg(FT.item_u + i), pos0 = __ldg(FT.item_pos + i);
-        const uint8_t t = P.utype[u];
+        const bool rownum = u == ITEM_ROWNUM;
+        const uint8_t t = rownum ? (uint8_t)ZDWB_LONGLONG : P.utype[u];
         const bool textual = is_text_like(t);
         bool have = false;
         unsigned long long vprev = 0;
@@ -710,6 +727,12 @@ __global__ void __launch_bounds__(DEC_THREADS)
           const uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
           const uint32_t o = ioffj[i], l = ioffj[i + 1] - o;
           if (!l) continue;
+          if (rownum) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261)
+            unsigned long long x = FT.first_row + r0 + j;
+            uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + pos0 + o;
+            for (uint32_t p = l; p > 0; x /= 10ull) d[--p] = (uint8_t)('0' + (uint32_t)(x % 10ull));
+            continue;
+          }
           const unsigned long long v = val[(size_t)j * U + u];
           if (textual && v != 0 && l > FMT_SHORT) {
             llist[atomicAdd(&s_nlong, 1u)] = (j << 24) | i;  // NI < 2^24 checked by the host
@@ -988,12 +1011,24 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
         seg_of.push_back(seg);
       }
       const int32_t c = pos_src[k];
-      if (c < 0) continue;
+      if (c < 0) {
+        if (opts->out_col && opts->rownum_pos >= 0 && (size_t)opts->rownum_pos == k) {
+          item_u.push_back(ITEM_ROWNUM);
+          item_pos.push_back((uint32_t)blob.size());
+          ++seg;
+        } else {
+          for (uint32_t f = 0; f < opts->n_fills; ++f) {
+            if (opts->fills[f].pos == k && opts->fills[f].len) {
+              blob.append(opts->fills[f].text, opts->fills[f].len);
+              seg_of.resize(blob.size(), seg);
+            }
+          }
+        }
+        continue;
+      }
       if (used_idx[c] < 0) {
-        const size_t before = blob.size();
         append_default(blob, schema->types[c]);
         seg_of.resize(blob.size(), seg);
-        (void)before;
       } else {
         item_u.push_back((uint32_t)used_idx[c]);
         item_pos.push_back((uint32_t)blob.size());
@@ -1029,6 +1064,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   FT.sgrp = d_sgrp.as<uint4>();
   FT.n_groups = (uint32_t)sgrp.size();
   FT.static_total = static_total;
+  FT.first_row = opts->first_row_number;
 
   if (nrows == 0) {
     out->consumed = rows_base;
@@ -1164,8 +1200,13 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   const size_t smem_fmt = FmtSmem(R, U, NI, F, W, out_smem_cap).total;
   const uint32_t nstrips = (nrows + R - 1) / R;
 
-  DevBuf cin;
+  DevBuf cin, d_counts;
   ZDWB_TRY(cin.alloc(ctx, (size_t)nstrips * std::max(U, 1u) * 8));
+  if (opts->want_flag_counts && U) {
+    ZDWB_TRY(d_counts.alloc(ctx, (size_t)U * 8));
+    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(d_counts.p, 0, (size_t)U * 8, st));
+  }
+  if (U == 0 && opts->validate_only) return ZDWB_OK;
   if (U) {
     DevBuf sval, shas, seg_val, seg_has;
     ZDWB_TRY(sval.alloc(ctx, (size_t)nstrips * U * 8));
@@ -1174,10 +1215,28 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_strip_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
       KernelScope _ks(ctx, "k_dec_strip_summary");
-      k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R,
-                                                               sval.as<unsigned long long>(), shas.as<uint8_t>());
+      k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R, opts->validate_only,
+                                                               d_counts.as<unsigned long long>(), sval.as<unsigned long long>(),
+                                                               shas.as<uint8_t>(), meta);
     }
     ZDWB_LAUNCH_CHECK(ctx);
+    if (opts->validate_only || opts->want_flag_counts) {
+      DecMeta* hm0 = static_cast<DecMeta*>(ctx->meta_host);
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hm0, meta, sizeof(DecMeta), cudaMemcpyDeviceToHost, st));
+      if (opts->want_flag_counts) {
+        ctx->flag_counts.resize(U);
+        ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->flag_counts.data(), d_counts.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+      }
+      ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (opts->want_flag_counts) out->flag_counts = reinterpret_cast<const uint64_t*>(ctx->flag_counts.data());
+      if (opts->validate_only) {
+        if (hm0->err) {
+          ctx->err = "decode: dictionary offset out of range";
+          return ZDWB_ERR_CORRUPT;  // CORRUPTED_DATA_ERROR, UnconvertFromZDW.cpp:1532-1534
+        }
+        return ZDWB_OK;
+      }
+    }
     const uint32_t S = (nstrips + 255) / 256;
     const uint32_t nseg = (nstrips + S - 1) / S;
     ZDWB_TRY(seg_val.alloc(ctx, (size_t)nseg * U * 8));
@@ -1206,7 +1265,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   // format kernel does anyway; so size the buffer by an estimate, let strips that would not fit skip their
   // writes (the look-back still yields the exact total) and rerun once with the exact size if needed.
   uint64_t est_out_row = FT.static_total;
-  for (uint32_t i = 0; i < NI; ++i) est_out_row += is_text_like(utype[item_u[i]]) ? 16 : 8;
+  for (uint32_t i = 0; i < NI; ++i) est_out_row += (item_u[i] != ITEM_ROWNUM && is_text_like(utype[item_u[i]])) ? 16 : 8;
   if (ctx->last_out_per_row > est_out_row) est_out_row = ctx->last_out_per_row;
   uint64_t out_cap = (uint64_t)nrows * est_out_row + 4096;
   if (ctx->out_dev2) {

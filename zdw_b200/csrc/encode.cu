@@ -795,7 +795,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   const uint64_t rows_total = packed >> 32;
   out->rows_in_buffer = rows_total;
   if (rows_total == 0) {
-    out->tsv_consumed = n;
+    out->tsv_consumed = opts->more_input_follows ? 0 : n;  // a window without a complete row: the caller widens it
     return ZDWB_OK;  // "Empty data file -- nothing to process", ConvertToZDW.cpp:824-835
   }
   DevBuf row_start, row_end;
@@ -810,7 +810,8 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
 
   const uint64_t nrows64 = (opts->max_rows && opts->max_rows < rows_total) ? opts->max_rows : rows_total;
   const uint32_t nrows = (uint32_t)nrows64;
-  const bool is_last = nrows64 == rows_total;
+  const bool took_all = nrows64 == rows_total;
+  const bool is_last = took_all && !opts->more_input_follows;
 
   // block extent + validation result
   uint32_t h_last[2] = {0, 0};  // row_end[nrows-1], row_start[rows_total]
@@ -830,6 +831,8 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   if (is_last) {
     out->tsv_consumed = n;
     tail_bytes = (uint32_t)(n - h_last[1]);
+  } else if (took_all) {
+    out->tsv_consumed = h_last[1];  // the unterminated tail belongs to the next window
   } else {
     // the next block starts at the first byte of row `nrows`
     uint32_t nxt;

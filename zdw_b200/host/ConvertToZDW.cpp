@@ -1,0 +1,446 @@
+// ConvertToZDW.cpp -- see ConvertToZDW.h.  Reference behaviour cited as cplusplus/ConvertToZDW.cpp:<line>.
+#include "ConvertToZDW.h"
+
+#include <string.h>
+#include <strings.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <fstream>
+#include <new>
+
+using std::map;
+using std::string;
+using std::vector;
+
+namespace adobe {
+namespace zdw {
+
+const int ConvertToZDW::CONVERT_ZDW_CURRENT_VERSION = 11;
+const char ConvertToZDW::CONVERT_ZDW_VERSION_TAIL[3] = "b";
+
+const char ConvertToZDW::ERR_CODE_TEXTS[ERR_CODE_COUNT][30] = {
+  "OK", "NO_ARGS", "CONVERSION_FAILED", "UNTAR_FAILED", "MISSING_DESC_FILE", "MISSING_SQL_FILE", "FILE_CREATION_ERR",
+  "OUT_OF_MEMORY", "UNCONVERT_FAILED", "FILE_SIZES_DIFFER", "FILES_DIFFER", "MISSING_ARGUMENT", "GZIP_FAILED",
+  "BZIP2_FAILED", "DESC_FILE_MISSING_TYPE_INFO", "WRONG_NUM_OF_COLUMNS_ON_A_ROW", "BAD_PARAMETER",
+  "TOO_MANY_INPUT_FILES", "NO_INPUT_FILES", "CANT_OPEN_TEMP_FILE", "Unknown error", "BAD_METADATA_PARAMETER",
+  "BAD_METADATA_FILE"};
+
+namespace {
+
+const size_t DEFAULT_BLOCK_BYTES = (size_t)1 << 30;   // TSV bytes per block window
+const size_t MAX_WINDOW_BYTES = 0xff000000ull;         // zdwb_encode_block takes < 4 GiB per call
+
+bool startsWith(const char* s, const char* prefix) { return strncmp(s, prefix, strlen(prefix)) == 0; }
+
+// Pinned host window over the input stream: [data, data + len) always starts at a row boundary.
+class InputWindow {
+ public:
+  InputWindow() : buf(NULL), cap(0), len(0), eof(false) {}
+  ~InputWindow() { zdwb_host_free(buf); }
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    char* nb = static_cast<char*>(zdwb_host_alloc(want + 64));
+    if (!nb) return false;
+    if (len) memcpy(nb, buf, len);
+    zdwb_host_free(buf);
+    buf = nb;
+    cap = want;
+    return true;
+  }
+  // tops the window up from `in`; `tee` (may be NULL) receives a copy of everything read
+  void fill(FILE* in, FILE* tee) {
+    while (!eof && len < cap) {
+      const size_t got = fread(buf + len, 1, cap - len, in);
+      if (got && tee) fwrite(buf + len, 1, got, tee);
+      len += got;
+      if (got == 0) eof = true;
+    }
+  }
+  void consume(size_t n) {
+    if (n >= len) {
+      len = 0;
+    } else {
+      memmove(buf, buf + n, len - n);
+      len -= n;
+    }
+  }
+  char* buf;
+  size_t cap, len;
+  bool eof;
+};
+
+}  // namespace
+
+ConvertToZDW::ConvertToZDW(const bool quiet, const bool streamingInput)
+    : compressor(GZIP), statusOutput(defaultStatusOutputCallback), bQuiet(quiet), bTrimTrailingSpaces(false),
+      bStreamingInput(streamingInput), rowsPerBlock(0), blockBytes(DEFAULT_BLOCK_BYTES), gpuDevice(-1) {}
+
+ConvertToZDW::~ConvertToZDW() {}
+
+const char* ConvertToZDW::compressorExtension() const {
+  switch (compressor) {
+    case GZIP: return ".gz";
+    case BZIP2: return ".bz2";
+    case XZ: case FXZ: return ".xz";
+    case ZSTD: return ".zst";
+  }
+  return "";
+}
+
+const char* ConvertToZDW::compressorCommand() const {
+  switch (compressor) {
+    case GZIP: return "gzip";
+    case BZIP2: return "bzip2";
+    case XZ: return "xz";
+    case FXZ: return "fxz";
+    case ZSTD: return "zstd";
+  }
+  return "";
+}
+
+// .desc.sql -> column names, type ids, char sizes.  The matching is prefix based and order matters
+// (ConvertToZDW.cpp:91-162): varchar(N); char(1) -> CHAR, char(2) -> CHAR_2, any other char(N) ->
+// VARCHAR; text; tinytext; mediumtext; longtext; datetime; decimal (also one character in); everything else is an
+// integer, signed unless the line mentions "unsigned": tinyint / smallint / bigint, and LONG for the rest (int,
+// mediumint, float, double, timestamp, ...).  Lines starting with "Field" (any case) are skipped; a line without
+// a tab is an error.  Lines are cut at 1023 bytes like the reference's fgets buffer.
+bool ConvertToZDW::readDescFile(FILE* f, DescSchema& out) {
+  char line[1024];
+  while (fgets(line, sizeof(line), f)) {
+    if (!strncasecmp(line, "Field", 5)) continue;
+    char* tab = strchr(line, '\t');
+    if (!tab) return false;
+    *tab = 0;
+    const char* type = tab + 1;
+    out.names.push_back(line);
+    int charSize = 0;
+    unsigned char id;
+    if (startsWith(type, "varchar")) {
+      id = ZT_VARCHAR;
+      charSize = atoi(type + 8);
+    } else if (startsWith(type, "char")) {
+      charSize = atoi(type + 5);
+      id = charSize == 1 ? ZT_CHAR : charSize == 2 ? ZT_CHAR_2 : ZT_VARCHAR;
+    } else if (startsWith(type, "text")) {
+      id = ZT_TEXT;
+    } else if (startsWith(type, "tinytext")) {
+      id = ZT_TINYTEXT;
+    } else if (startsWith(type, "mediumtext")) {
+      id = ZT_MEDIUMTEXT;
+    } else if (startsWith(type, "longtext")) {
+      id = ZT_LONGTEXT;
+    } else if (startsWith(type, "datetime")) {
+      id = ZT_DATETIME;
+    } else if (startsWith(type, "decimal") || (type[0] && startsWith(type + 1, "decimal"))) {
+      id = ZT_DECIMAL;
+    } else {
+      const bool isSigned = strstr(type, "unsigned") == NULL;
+      if (startsWith(type, "tinyint")) id = isSigned ? ZT_TINY_SIGNED : ZT_TINY;
+      else if (startsWith(type, "smallint")) id = isSigned ? ZT_SHORT_SIGNED : ZT_SHORT;
+      else if (startsWith(type, "bigint")) id = isSigned ? ZT_LONGLONG_SIGNED : ZT_LONGLONG;
+      else id = isSigned ? ZT_LONG_SIGNED : ZT_LONG;
+    }
+    out.types.push_back(id);
+    out.charSizes.push_back(charSize);
+  }
+  return true;
+}
+
+// keys may not contain '=' or a newline, values no newline (ConvertToZDW.cpp:226-237)
+bool ConvertToZDW::metadataIsValid(const map<string, string>& metadata) {
+  for (map<string, string>::const_iterator it = metadata.begin(); it != metadata.end(); ++it) {
+    if (it->first.find_first_of("=\n") != string::npos) return false;
+    if (it->second.find('\n') != string::npos) return false;
+  }
+  return true;
+}
+
+int ConvertToZDW::loadMetadataFile(const char* filepath, map<string, string>& metadata) {
+  std::ifstream in(filepath);
+  if (!in) return -1;
+  string line;
+  int lineNo = 0;
+  while (std::getline(in, line)) {
+    ++lineNo;
+    if (line.empty()) continue;
+    const size_t eq = line.find('=');
+    if (eq == string::npos) return lineNo;
+    metadata[line.substr(0, eq)] = line.substr(eq + 1);
+  }
+  return 0;
+}
+
+// version u16 | metadata length u32 | key\0value\0... | name\0...\0 | type[nc] | charSize u16[nc]
+// (ConvertToZDW.cpp:673-737)
+void ConvertToZDW::writeFileHeader(FILE* out, const DescSchema& schema, const map<string, string>& metadata) {
+  string h;
+  const uint16_t version = (uint16_t)CONVERT_ZDW_CURRENT_VERSION;
+  h.append(reinterpret_cast<const char*>(&version), 2);
+  uint32_t metaLen = 0;
+  for (map<string, string>::const_iterator it = metadata.begin(); it != metadata.end(); ++it)
+    metaLen += (uint32_t)(it->first.size() + it->second.size() + 2);
+  h.append(reinterpret_cast<const char*>(&metaLen), 4);
+  for (map<string, string>::const_iterator it = metadata.begin(); it != metadata.end(); ++it) {
+    h.append(it->first).push_back('\0');
+    h.append(it->second).push_back('\0');
+  }
+  for (size_t c = 0; c < schema.names.size(); ++c) h.append(schema.names[c]).push_back('\0');
+  h.push_back('\0');
+  h.append(reinterpret_cast<const char*>(schema.types.data()), schema.types.size());
+  for (size_t c = 0; c < schema.charSizes.size(); ++c) {
+    const uint16_t cs = (uint16_t)schema.charSizes[c];
+    h.append(reinterpret_cast<const char*>(&cs), 2);
+  }
+  fwrite(h.data(), 1, h.size(), out);
+}
+
+// Round-trips the new file through unconvertDWfile (the one next to this executable) and compares with the source
+// bytes (ConvertToZDW.cpp:166-223).  The .desc.sql files are not compared.
+ConvertToZDW::ERR_CODE ConvertToZDW::validate(const char* zdwFile, const vector<string>& srcFiles, const char* exeName,
+                                              const char* outputDir) {
+  if (!bQuiet) statusOutput(INFO, "Unconverting %s back for validation...\n", zdwFile);
+  string dir = exeName;
+  const size_t slash = dir.rfind('/');
+  dir.resize(slash == string::npos ? 0 : slash + 1);
+  string decode = dir + "unconvertDWfile -q - ";
+  if (outputDir) decode += string("-d ") + outputDir + " ";
+  decode += zdwFile;
+  string cmd;
+  if (bStreamingInput) {
+    string zcat = "zcat ";
+    for (size_t i = 0; i < srcFiles.size(); ++i) zcat += srcFiles[i] + " ";
+    cmd = "/bin/bash -c \"cmp <(" + decode + ") <(" + zcat + ")\"";
+  } else if (bTrimTrailingSpaces) {
+    cmd = "/bin/bash -c \"cmp <(" + decode + ") <(" + dir + "trim_spaces " + srcFiles[0] + ")\"";
+  } else {
+    cmd = decode + " | cmp " + srcFiles[0];
+  }
+  if (!bQuiet) statusOutput(INFO, "VALIDATION COMMAND: %s\n", cmd.c_str());
+  return system(cmd.c_str()) == 0 ? OK : FILES_DIFFER;
+}
+
+ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub, const DescSchema& schema,
+                                                 const bool bValidate, const char* exeName, const char* outputDir,
+                                                 const char* zArgs, const map<string, string>& metadata) {
+  if (!metadataIsValid(metadata)) {
+    statusOutput(ERROR, "Invalid metadata parameter\n");
+    return BAD_METADATA_PARAM;
+  }
+  if (!gpu.open(gpuDevice)) {
+    statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n", exeName, gpu.lastError().c_str());
+    return UNKNOWN_ERROR;
+  }
+
+  // <outputDir or source dir>/<base>.zdw<ext>, written as <base>.creating.zdw<ext> and renamed on success (:629-657)
+  string basePath;
+  if (!outputDir) {
+    basePath = filestub;
+  } else {
+    const char* base = strrchr(filestub, '/');
+    basePath = string(outputDir) + "/" + (base ? base + 1 : filestub);
+  }
+  const string finalName = basePath + ".zdw" + compressorExtension();
+  const string tempName = basePath + ".creating.zdw" + compressorExtension();
+
+  string cmd = compressorCommand();
+  if (zArgs) cmd += string(" ") + zArgs;
+  cmd += " > " + tempName;
+  FILE* out = popen(cmd.c_str(), "w");
+  if (!out) {
+    statusOutput(ERROR, "Could not open the process '%s' for writing!\n", cmd.c_str());
+    return FILE_CREATION_ERR;
+  }
+  writeFileHeader(out, schema, metadata);
+
+  ERR_CODE res = OK;
+  vector<string> srcFiles;  // what validation compares against
+  FILE* tee = NULL;
+  string teeName;
+  if (bStreamingInput) {
+    // streamed input is kept (gzipped) for validation, like the reference's per-block temp files (:786-799)
+    if (bValidate) {
+      teeName = basePath + ".tmp.0.gz";
+      tee = popen(("gzip > " + teeName).c_str(), "w");
+      if (!tee) {
+        pclose(out);
+        unlink(tempName.c_str());
+        return CANT_OPEN_TEMP_FILE;
+      }
+      srcFiles.push_back(teeName);
+    }
+  } else {
+    srcFiles.push_back(string(filestub) + "." + getInputFileExtension());
+  }
+
+  zdwb_schema sch;
+  sch.ncols = (uint32_t)schema.types.size();
+  sch.types = schema.types.data();
+
+  uint64_t totalRows = 0;
+  uint32_t longestLine = 0;  // 0 = the 16 KiB start value (:965)
+  int blocks = 0;
+  bool wrongColumns = false;
+  vector<unsigned char> pending;  // the previous block, held back until we know whether another one follows
+  InputWindow win;
+  size_t windowBytes = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
+  if (!win.reserve(windowBytes)) {
+    res = OUT_OF_MEMORY;
+    goto Done;
+  }
+  for (;;) {
+    win.fill(in, tee);
+    if (win.len == 0 && win.eof) break;
+    ++blocks;
+    if (!bQuiet) {
+      if (blocks == 1) statusOutput(INFO, "\nProcessing %s\n", filestub);
+      else statusOutput(INFO, "\nProcessing block %d of %s (%llu rows so far)\n", blocks, filestub, (unsigned long long)totalRows);
+      statusOutput(INFO, "Compiling unique values\n");
+    }
+    zdwb_encode_opts eo;
+    memset(&eo, 0, sizeof(eo));
+    eo.trim_trailing_spaces = bTrimTrailingSpaces ? 1 : 0;
+    eo.more_input_follows = win.eof ? 0 : 1;
+    eo.prev_longest_line = longestLine;
+    eo.max_rows = rowsPerBlock;
+    zdwb_block_out blk;
+    const int rc = zdwb_encode_block(gpu.get(), &sch, win.buf, win.len, &eo, &blk);
+    if (rc == ZDWB_ERR_WRONG_COLUMNS) {
+      statusOutput(ERROR, "\nRow %u had the problem\n", blk.bad_row);  // one past the last good row (:810-812)
+      wrongColumns = true;
+      break;
+    }
+    if (rc == ZDWB_ERR_OOM) {
+      statusOutput(ERROR, "Not enough memory to run %s\n", exeName);
+      res = OUT_OF_MEMORY;
+      goto Done;
+    }
+    if (rc != ZDWB_OK) {
+      statusOutput(ERROR, "%s: GPU encode failed: %s\n", exeName, zdwb_last_error(gpu.get()));
+      res = UNKNOWN_ERROR;
+      goto Done;
+    }
+    if (blk.nrows == 0) {
+      if (!win.eof) {
+        // not one complete row in the window: widen it and try again
+        if (windowBytes >= MAX_WINDOW_BYTES) {
+          statusOutput(ERROR, "%s: a single row exceeds %zu bytes\n", exeName, (size_t)MAX_WINDOW_BYTES);
+          res = UNKNOWN_ERROR;
+          goto Done;
+        }
+        windowBytes = std::min(windowBytes * 2, MAX_WINDOW_BYTES);
+        if (!win.reserve(windowBytes)) {
+          res = OUT_OF_MEMORY;
+          goto Done;
+        }
+        --blocks;
+        continue;
+      }
+      --blocks;
+      break;  // only blank lines / an unterminated tail were left
+    }
+    if (!bQuiet) {
+      statusOutput(INFO, "\r%u rows\n", blk.nrows);
+      statusOutput(INFO, "\nWriting dictionary:\n%u bytes being stored for %u unique entries.  Generating %d-byte offsets...\n",
+                   (unsigned)blk.dict_bytes, (unsigned)blk.dict_entries, (int)blk.dict_index_size);
+      statusOutput(INFO, "\nWriting rows\n");
+    }
+    if (!pending.empty()) {
+      pending[8] = 0;  // another block follows (:841-842)
+      fwrite(pending.data(), 1, pending.size(), out);
+    }
+    pending.assign(blk.bytes, blk.bytes + blk.len);
+    longestLine = blk.longest_line;
+    totalRows += blk.nrows;
+    if (!bQuiet) statusOutput(INFO, "\r%u\nDone with block %d -- cleaning up...\n", blk.nrows, blocks);
+    win.consume((size_t)blk.tsv_consumed);
+  }
+  if (wrongColumns) {
+    // the reference returns straight out of processFile here: the pipe is left to the process exit and the
+    // .creating file stays on disk (:810-812).  We close the pipe but keep the file.
+    if (tee) pclose(tee);
+    pclose(out);
+    return WRONG_NUM_OF_COLUMNS_ON_A_ROW;
+  }
+  if (!pending.empty()) {
+    pending[8] = 1;
+    fwrite(pending.data(), 1, pending.size(), out);
+  } else {
+    statusOutput(ERROR, "Empty data file -- nothing to process\n");  // :824-835, result stays OK
+  }
+  if (tee) {
+    pclose(tee);
+    tee = NULL;
+  }
+  pclose(out);
+  out = NULL;
+
+  if (bValidate) {
+    const ERR_CODE v = validate(tempName.c_str(), srcFiles, exeName, outputDir);
+    if (v == OK) {
+      if (!bQuiet) statusOutput(INFO, "%s GOOD\n", finalName.c_str());
+    } else {
+      statusOutput(INFO, "%s BAD\n", finalName.c_str());
+      res = v;
+    }
+  }
+
+Done:
+  if (tee) pclose(tee);
+  if (out) pclose(out);
+  if (!teeName.empty()) unlink(teeName.c_str());
+  if (res == OK) {
+    if (!bQuiet) statusOutput(INFO, "Rows=%u\n", (unsigned)totalRows);  // grepped by callers (:928-930)
+    if (rename(tempName.c_str(), finalName.c_str()) == 0) {
+      if (!bQuiet) statusOutput(INFO, "Done\n");
+    } else {
+      res = FILE_CREATION_ERR;
+      statusOutput(INFO, "Final create file failed -- you can use %s instead.\n", tempName.c_str());
+    }
+  } else {
+    unlink(tempName.c_str());
+  }
+  return res;
+}
+
+ConvertToZDW::ERR_CODE ConvertToZDW::convertFile(const char* infile, const char* exeName, const bool bValidate, char* filestub,
+                                                 const char* outputDir, const char* zArgs,
+                                                 const map<string, string>& metadata) {
+  // the stub is the input path cut at its first ".sql" (:970-976)
+  strcpy(filestub, infile);
+  char* dot = strstr(filestub, ".sql");
+  if (!dot) return MISSING_SQL_FILE;
+  *dot = 0;
+
+  const string descName = string(filestub) + ".desc." + getInputFileExtension();
+  FILE* desc = fopen(descName.c_str(), "r");
+  if (!desc) return MISSING_DESC_FILE;
+  DescSchema schema;
+  const bool descOk = readDescFile(desc, schema);
+  fclose(desc);
+  if (!descOk) return DESC_FILE_MISSING_TYPE_INFO;
+
+  // <stub>.metadata is only consulted when no pairs were passed in (:991-999)
+  map<string, string> meta = metadata;
+  if (meta.empty()) {
+    const int r = loadMetadataFile((string(filestub) + ".metadata").c_str(), meta);
+    if (r > 0) return BAD_METADATA_FILE;
+  }
+
+  FILE* in = stdin;
+  if (!bStreamingInput) {
+    in = fopen((string(filestub) + "." + getInputFileExtension()).c_str(), "r");
+    if (!in) return MISSING_SQL_FILE;
+  }
+  ERR_CODE res = UNKNOWN_ERROR;
+  try {
+    res = processFile(in, filestub, schema, bValidate, exeName, outputDir, zArgs, meta);
+  } catch (const std::bad_alloc&) {
+    res = OUT_OF_MEMORY;
+  }
+  if (!bStreamingInput) fclose(in);
+  return res;
+}
+
+}  // namespace zdw
+}  // namespace adobe
