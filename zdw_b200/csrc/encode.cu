@@ -1,40 +1,46 @@
 // encode.cu -- TSV -> one ZDW block, entirely on the GPU.
 //
 // Kernel sequence for a block (reference functions replaced are cited per kernel):
-//   k_rows_count / k_rows_write   GetNextRow                     getnextrow.cpp:26-84
-//   k_row_longest                 m_LongestLine bookkeeping      getnextrow.cpp:57-65
-//   k_pass1                       parseInput + get_next_column   ConvertToZDW.cpp:329-414, :1048-1067
-//                                 + Dictionary::insert           dictionary.cpp:31-51
-//   k_ht_compact, sort_strings, k_sorted_lens, k_dict_emit
+//   k_tile_count, k_tile_scan     GetNextRow + get_next_column as a byte-tile census: row terminators, field separators,
+//                                 non-empty fields per 16 KiB tile and their prefix over the buffer
+//                                 (getnextrow.cpp:26-84, ConvertToZDW.cpp:1048-1067)
+//   k_find_cut                    block cut after max_rows rows (explicit block policy)
+//   k_pass1                       parseInput (ConvertToZDW.cpp:329-414) + Dictionary::insert (dictionary.cpp:31-51):
+//                                 one warp per tile, no CTA barrier; every non-empty field is classified (short text /
+//                                 long text / numeric) into warp-private queues and processed 32 at a time with
+//                                 convergent code; a compact RECORD (column, dictionary slot or number) per non-empty
+//                                 field is written in row order, so pass 2 never re-reads or re-parses the TSV
+//   k_ht_compact, sort_strings, k_sorted_lens, k_dict_slots, k_dict_emit
 //                                 Dictionary::write              dictionary.cpp:76-111
 //   k_col_stats, k_block_header   writeLookupColumnStats         ConvertToZDW.cpp:417-483, :839-842
-//   k_pass2                       writeBlockRows                 ConvertToZDW.cpp:486-606
-//                                 + Dictionary::getOffset        dictionary.cpp:53-59
+//   k_pass2, k_gather_tiles       writeBlockRows                 ConvertToZDW.cpp:486-606 + Dictionary::getOffset :53-59
 //
-// Data layout in HBM: the TSV block stays where it is (one read per pass); the only per-row index is
-// row_start/row_end (8 B/row).  Field boundaries are never materialised: both passes re-derive them from
-// the bytes with a 16-byte-per-thread classifier and a block-wide prefix count, so work is proportional
-// to bytes + non-empty fields, not to the (mostly empty) field count of wide analytics schemas.
+// Data layout in HBM: the TSV block is read twice (census, pass 1); records are 12 B per NON-EMPTY field (most
+// fields of analytics-shaped data are empty and cost nothing beyond their delimiter byte); the string hash set keeps
+// (start, len) of the first occurrence inside the TSV - strings are never copied until the dictionary is emitted.
 #include <algorithm>
 #include <vector>
 
 #include "common.cuh"
-#include "tsv.cuh"
 
 namespace zdwb {
 
 namespace {
 
 constexpr int ENC_THREADS = 256;
-constexpr int IDX_CH = 4;                             // 16-byte chunks per thread in the row indexer
-constexpr int IDX_TILE = ENC_THREADS * IDX_CH * 16;   // 16 KiB per CTA
+constexpr int ENC_WARPS = ENC_THREADS / 32;
+constexpr uint32_t TILE = 16384;          // bytes per warp tile
+constexpr uint32_t STEP = 512;            // bytes per warp step (32 lanes x 16 B)
 constexpr uint32_t HT_MAX_PROBE = 2048;
+constexpr uint32_t SHORT_MAX = 16;        // texts up to this length are hashed / compared by one lane, straight-line
+constexpr uint32_t QCAP = 64;             // entries per warp queue (at most 31 waiting + 32 pushed per round)
+constexpr uint32_t REC_EMPTY = 0xffffffffu;
 
 struct EncMeta {
   uint32_t bad_row;        // first row whose field count != schema (0xffffffff = none)
   uint32_t max_line;       // longest logical line incl. '\n' among the block's rows (+ tail rule)
   uint32_t ht_overflow;    // pass 1 gave up: hash table too small
-  uint32_t lookup_miss;    // pass 2 internal consistency counter (must stay 0)
+  uint32_t pad1;
   unsigned long long n_unique;
   unsigned long long dict_str_bytes;  // sum(len + 1)
   uint32_t max_str_len;
@@ -50,373 +56,632 @@ struct EncMeta {
   unsigned long long rows_bytes;
   uint32_t compact_count;
   uint32_t pad;
+  // census totals
+  uint32_t tot_rows, tot_tabs, tot_ne, last_break_p1;
+  // block cut (max_rows)
+  uint32_t cut_end_p1;     // position + 1 of the terminator of the block's last row
+  uint32_t next_start;     // first byte of the row after it
+};
+
+// per tile: counts, then (after k_tile_scan) exclusive prefixes
+struct TileAgg {
+  uint32_t rows, tabs, ne;
+  uint32_t bound_p1;   // position + 1 of the last boundary (separator, terminator, blank-line newline); 0 = none
+  uint32_t break_p1;   // position + 1 of the last row break (terminator or blank-line newline); 0 = none
 };
 
 // ---------------------------------------------------------------------------------------------
-// row index
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ENC_THREADS)
-    k_rows_count(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint64_t* __restrict__ tile_cnt) {
-  __shared__ uint64_t sh[ENC_THREADS / 32];
-  const int64_t p0 = lo + ((int64_t)blockIdx.x * ENC_THREADS + threadIdx.x) * (IDX_CH * 16);
-  uint64_t cnt = 0;
-#pragma unroll
-  for (int c = 0; c < IDX_CH; ++c) {
-    const int64_t p = p0 + c * 16;
-    if (p < (int64_t)n) {
-      ChunkMasks m = classify_chunk(buf, n, p, 0, (int64_t)n);
-      cnt += ((uint64_t)__popc(m.term) << 32) | (uint64_t)__popc(m.tab);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t t = 0;
-    for (int w = 0; w < ENC_THREADS / 32; ++w) t += sh[w];
-    tile_cnt[blockIdx.x] = t;
-  }
-}
-
-__global__ void __launch_bounds__(ENC_THREADS)
-    k_rows_write(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, const uint64_t* __restrict__ tile_base,
-                 uint32_t ncols, uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_end,
-                 EncMeta* __restrict__ meta) {
-  __shared__ uint64_t ws[34];
-  const int64_t p0 = lo + ((int64_t)blockIdx.x * ENC_THREADS + threadIdx.x) * (IDX_CH * 16);
-  ChunkMasks m[IDX_CH];
-  uint64_t cnt = 0;
-#pragma unroll
-  for (int c = 0; c < IDX_CH; ++c) {
-    const int64_t p = p0 + c * 16;
-    m[c] = ChunkMasks{0u, 0u, 0u};
-    if (p < (int64_t)n) {
-      m[c] = classify_chunk(buf, n, p, 0, (int64_t)n);
-      cnt += ((uint64_t)__popc(m[c].term) << 32) | (uint64_t)__popc(m[c].tab);
-    }
-  }
-  uint64_t excl = block_exclusive_scan64(cnt, ws, nullptr) + tile_base[blockIdx.x];
-  uint64_t rows_before = excl >> 32, tabs_before = excl & 0xffffffffull;
-  const uint64_t tabs_per_row = (uint64_t)ncols - 1;
-#pragma unroll
-  for (int c = 0; c < IDX_CH; ++c) {
-    uint32_t d = m[c].tab | m[c].term;
-    while (d) {
-      const int i = __ffs(d) - 1;
-      d &= d - 1;
-      if ((m[c].tab >> i) & 1u) {
-        ++tabs_before;
-      } else {
-        const uint64_t r = rows_before;
-        const uint64_t pos = (uint64_t)(p0 + c * 16 + i);
-        if (tabs_before != (r + 1) * tabs_per_row) atomicMin(&meta->bad_row, (uint32_t)r);
-        row_end[r] = (uint32_t)pos;
-        uint64_t s = pos + 1;
-        while (s < n && __ldg(buf + s) == (uint8_t)'\n') ++s;  // blank lines directly after a row are skipped
-        row_start[r + 1] = (uint32_t)s;
-        ++rows_before;
-      }
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    uint64_t s = 0;
-    while (s < n && __ldg(buf + s) == (uint8_t)'\n') ++s;
-    row_start[0] = (uint32_t)s;
-  }
-}
-
-// Longest logical line (incl. its '\n') among rows [0, nrows); with `tail_bytes` >= 2 the unterminated
-// tail participates as a line of tail_bytes + 1 (it fills the row buffer the same way before being dropped).
-__global__ void k_row_longest(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_end,
-                              uint32_t nrows, uint32_t tail_bytes, EncMeta* __restrict__ meta) {
-  uint32_t mx = 0;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
-    uint32_t L = row_end[r] - row_start[r] + 1;
-    mx = L > mx ? L : mx;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && tail_bytes >= 2) mx = mx > tail_bytes + 1 ? mx : tail_bytes + 1;
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&meta->max_line, mx);
-}
-
-// ---------------------------------------------------------------------------------------------
-// field walker: calls f(row, col, start, len) for every NON-EMPTY field of rows [row0, row0+k) whose
-// bytes are [b0, b1).
+// byte classification, one warp step = 512 bytes.
 //
-// Phase A (delimiter-parallel): one thread owns 32 bytes per iteration (two aligned 16-byte loads), builds the
-// tab / terminator / blank-line bit masks and - with bit arithmetic only - the mask of delimiters that close a
-// non-empty field (in analytics-shaped data most delimiters close empty fields and cost nothing further).  A
-// block-wide prefix count of delimiters gives every delimiter its (row, col).
-// Phase B (field-parallel): the non-empty fields of the iteration are queued in shared memory and handed out
-// one per thread, so the expensive per-field work (hashing, probing, number parsing) runs with full warps no
-// matter how the fields were distributed over the bytes.
+// Rules restated from the reference:
+//  * '\n' ends a logical row iff it is preceded by an EVEN number of consecutive backslashes
+//    (GetNextRow, getnextrow.cpp:44-53,72-77);
+//  * '\t' separates fields iff it is preceded by an EVEN number of consecutive backslashes
+//    (get_next_column, ConvertToZDW.cpp:1048-1067); a maximal-run count reproduces the reference's bounded backward
+//    scans because a delimiter byte itself is never a backslash;
+//  * an unescaped newline directly after another unescaped newline (or at offset 0) is a blank physical line and
+//    ends no row (getnextrow.cpp:39-43).
 // ---------------------------------------------------------------------------------------------
-constexpr int WALK_SPAN = 32;                          // bytes per thread per iteration
-constexpr int QCAP = 1024;                             // queued fields per round
+__device__ __forceinline__ bool odd_backslashes_before(const uint8_t* __restrict__ buf, int64_t p) {
+  uint32_t c = 0;
+  int64_t q = p - 1;
+  while (q >= 0 && __ldg(buf + q) == (uint8_t)'\\') {
+    ++c;
+    --q;
+  }
+  return (c & 1u) != 0;
+}
+__device__ __forceinline__ bool is_unescaped_newline(const uint8_t* __restrict__ buf, int64_t p) {
+  return __ldg(buf + p) == (uint8_t)'\n' && !odd_backslashes_before(buf, p);
+}
 
-struct WalkScratch {
-  uint32_t scan_ws[34];
-  int32_t last[ENC_THREADS];
-  int32_t wmax[ENC_THREADS / 32];
-  int32_t carry;
-  uint4 queue[QCAP];  // (row, col, start, len)
+struct WarpCarry {
+  uint32_t bs;      // the byte in front of the step is a backslash
+  uint32_t nl;      // ... is an unescaped newline (or the step starts at offset 0)
+  int64_t pb;       // position of the last boundary in front of the step (-1 = buffer start)
+  int64_t prb;      // position of the last row break in front of the step (-1 = buffer start)
+  uint32_t rows, tabs, ne;  // running counts in front of the step
 };
 
-constexpr int32_t NO_BOUNDARY = INT32_MIN;
+struct LaneStep {
+  uint32_t tab, term, skip;  // 16-bit masks for the lane's 16 bytes
+  uint32_t ne;               // delimiters that close a non-empty field
+  int64_t p0;                // position of the lane's first byte (may be negative / beyond n: masks are then empty)
+  int64_t pb, prb;           // last boundary / row break in front of the lane's chunk
+  uint32_t rows, tabs, nes;  // counts in front of the lane's chunk
+};
 
-template <class F>
-__device__ __forceinline__ void walk_tile_fields(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t b0,
-                                                 uint32_t b1, uint32_t row0, uint32_t ncols, bool trim, WalkScratch& ts,
-                                                 F&& f) {
-  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t pc0 = lo + ((((int64_t)b0 - lo) >> 4) << 4);
-  const uint32_t nsp = (uint32_t)(((int64_t)b1 - pc0 + WALK_SPAN - 1) / WALK_SPAN);
-  if (tid == 0) ts.carry = (int32_t)((int64_t)b0 - 1 - pc0);  // the byte before a row start is a boundary
-  uint32_t kbase = 0;
-  __syncthreads();
-  for (uint32_t it0 = 0; it0 < nsp; it0 += ENC_THREADS) {
-    const uint32_t j = it0 + tid;
-    const int64_t p0 = pc0 + (int64_t)j * WALK_SPAN;
-    uint32_t tab = 0, term = 0, skip = 0;
-    if (j < nsp) {
-      const ChunkMasks m0 = classify_chunk(buf, n, p0, (int64_t)b0, (int64_t)b1);
-      const ChunkMasks m1 = classify_chunk(buf, n, p0 + 16, (int64_t)b0, (int64_t)b1);
-      tab = m0.tab | (m1.tab << 16);
-      term = m0.term | (m1.term << 16);
-      skip = m0.skip | (m1.skip << 16);
+__device__ __forceinline__ void carry_init(const uint8_t* __restrict__ buf, int64_t p, const TileAgg& pre, WarpCarry& c) {
+  c.bs = (p > 0 && __ldg(buf + p - 1) == (uint8_t)'\\') ? 1u : 0u;
+  c.nl = p <= 0 ? 1u : (is_unescaped_newline(buf, p - 1) ? 1u : 0u);
+  c.pb = (int64_t)pre.bound_p1 - 1;
+  c.prb = (int64_t)pre.break_p1 - 1;
+  c.rows = pre.rows;
+  c.tabs = pre.tabs;
+  c.ne = pre.ne;
+}
+
+// Classifies the 512 bytes at step position s0 (s0 + 16 * lane is 16-byte aligned in memory).  Only positions in
+// [0, limit) are reported.  All 32 lanes must call.
+__device__ __forceinline__ LaneStep scan_step(const uint8_t* __restrict__ buf, int64_t limit, int64_t s0, WarpCarry& c) {
+  const unsigned lane = lane_id();
+  LaneStep L;
+  L.p0 = s0 + 16 * (int64_t)lane;
+  uint32_t tab = 0, nl = 0, bs = 0;
+  if (L.p0 < limit && L.p0 + 16 > 0) {
+    const uint4 v = ldg_stream_u4(buf + L.p0);
+    const int64_t ia = L.p0 < 0 ? -L.p0 : 0;
+    const int64_t ib = L.p0 + 16 > limit ? limit - L.p0 : 16;
+    const uint32_t in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
+    tab = chunk_mask(v, '\t') & in;
+    if (chunk_has(v, '\n')) nl = chunk_mask(v, '\n') & in;
+    if (chunk_has(v, '\\')) bs = chunk_mask(v, '\\') & in;
+  }
+  // escape parity: only delimiters that directly follow a backslash need the (rare) backward walk
+  uint32_t prev = __shfl_up_sync(0xffffffffu, bs >> 15, 1);
+  if (lane == 0) prev = c.bs;
+  uint32_t sus = (tab | nl) & ((bs << 1) | prev);
+  while (sus) {
+    const int i = __ffs(sus) - 1;
+    sus &= sus - 1;
+    if (odd_backslashes_before(buf, L.p0 + i)) {
+      tab &= ~(1u << i);
+      nl &= ~(1u << i);
     }
-    const uint32_t bound = tab | term | skip;
-    const uint32_t delims = tab | term;
-    const int32_t rel0 = (int32_t)(j * WALK_SPAN);
-    const int32_t mylast = bound ? rel0 + (31 - __clz(bound)) : NO_BOUNDARY;
-    ts.last[tid] = mylast;
-    const int32_t wm = __reduce_max_sync(0xffffffffu, mylast);
-    if (lane == 0) ts.wmax[warp] = wm;
-    __syncthreads();
-    // last boundary before this thread's span
-    int32_t pb = NO_BOUNDARY;
-    if (delims) {
-      int t = (int)tid - 1;
-      while (t >= 0 && (pb = ts.last[t]) == NO_BOUNDARY) --t;
-      if (t < 0) pb = ts.carry;
-    }
-    // delimiters whose preceding byte is not a boundary close a non-empty field
-    const uint32_t ne = delims & ~((bound << 1) | (pb == rel0 - 1 ? 1u : 0u));
-    uint32_t total;
-    const uint32_t excl = block_exclusive_scan(((uint32_t)__popc(ne) << 16) | (uint32_t)__popc(delims), ts.scan_ws, &total);
-    const uint32_t total_ne = total >> 16;
-    uint32_t row_f = 0, col_f = 0;
-    if (ne) {
-      const uint32_t k0 = kbase + (excl & 0xffffu);
-      const uint32_t q = k0 / ncols;
-      row_f = row0 + q;
-      col_f = k0 - q * ncols;
-    }
-    for (uint32_t base = 0; base < total_ne; base += QCAP) {
-      if (ne) {
-        uint32_t qi = excl >> 16;
-        uint32_t d = ne;
-        while (d) {
-          const int i = __ffs(d) - 1;
-          d &= d - 1;
-          if (qi >= base && qi < base + QCAP) {
-            const uint32_t below = (1u << i) - 1u;
-            uint32_t col = col_f + (uint32_t)__popc(delims & below);
-            uint32_t row = row_f;
-            while (col >= ncols) {
-              col -= ncols;
-              ++row;
-            }
-            const uint32_t lowb = bound & below;
-            const int32_t srel = (lowb ? rel0 + (31 - __clz(lowb)) : pb) + 1;
-            const uint32_t start = (uint32_t)(pc0 + srel);
-            const uint32_t end = (uint32_t)(p0 + i);
-            ts.queue[qi - base] = make_uint4(row, col, start, end - start);
-          }
-          ++qi;
-        }
-      }
-      __syncthreads();
-      const uint32_t cnt = min((uint32_t)QCAP, total_ne - base);
-      for (uint32_t t = tid; t < cnt; t += ENC_THREADS) {
-        const uint4 rec = ts.queue[t];
-        uint32_t len = rec.w;
-        if (trim) {  // -t: ConvertToZDW.cpp:295-313
-          while (len && __ldg(buf + rec.z + len - 1) == (uint8_t)' ') --len;
-        }
-        if (len) f(rec.x, rec.y, rec.z, len);
-      }
-      __syncthreads();
-    }
-    if (tid == 0) {
-      int32_t mx = NO_BOUNDARY;
+  }
+  // blank lines
+  uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
+  if (lane == 0) prevnl = c.nl;
+  uint32_t after_nl = ((nl << 1) | prevnl) & 0xffffu;
+  if (L.p0 <= 0 && L.p0 + 16 > 0) after_nl |= 1u << (-L.p0);  // offset 0 behaves like "just after a newline"
+  L.tab = tab;
+  L.skip = nl & after_nl;
+  L.term = nl & ~L.skip;
+  c.bs = __shfl_sync(0xffffffffu, bs >> 15, 31);
+  c.nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
+
+  // nearest boundary / row break in front of the lane's chunk: from the closest lower lane that has one
+  const uint32_t bound = L.tab | L.term | L.skip, brk = L.term | L.skip;
+  const int64_t mylast_b = bound ? L.p0 + (31 - __clz(bound)) : 0;
+  const int64_t mylast_r = brk ? L.p0 + (31 - __clz(brk)) : 0;
+  const unsigned has_b = __ballot_sync(0xffffffffu, bound != 0u), has_r = __ballot_sync(0xffffffffu, brk != 0u);
+  const unsigned lt = lanemask_lt();
+  {
+    const unsigned below = has_b & lt;
+    const int64_t v = __shfl_sync(0xffffffffu, mylast_b, below ? 31 - __clz(below) : 0);
+    L.pb = below ? v : c.pb;
+    const int64_t top = __shfl_sync(0xffffffffu, mylast_b, has_b ? 31 - __clz(has_b) : 0);
+    if (has_b) c.pb = top;
+  }
+  {
+    const unsigned below = has_r & lt;
+    const int64_t v = __shfl_sync(0xffffffffu, mylast_r, below ? 31 - __clz(below) : 0);
+    L.prb = below ? v : c.prb;
+    const int64_t top = __shfl_sync(0xffffffffu, mylast_r, has_r ? 31 - __clz(has_r) : 0);
+    if (has_r) c.prb = top;
+  }
+  // delimiters whose preceding byte is not a boundary close a non-empty field
+  const uint32_t delims = L.tab | L.term;
+  L.ne = delims & ~((bound << 1) | (L.pb == L.p0 - 1 ? 1u : 0u));
+  // counts in front of the lane: one packed inclusive scan (each count <= 16 per lane, <= 512 per step)
+  const uint32_t mine = (uint32_t)__popc(L.term) | ((uint32_t)__popc(L.tab) << 10) | ((uint32_t)__popc(L.ne) << 20);
+  uint32_t inc = mine;
 #pragma unroll
-      for (int w = 0; w < ENC_THREADS / 32; ++w) mx = ts.wmax[w] > mx ? ts.wmax[w] : mx;
-      if (mx != NO_BOUNDARY) ts.carry = mx;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (unsigned)o) inc += t;
+  }
+  const uint32_t ex = inc - mine;
+  L.rows = c.rows + (ex & 1023u);
+  L.tabs = c.tabs + ((ex >> 10) & 1023u);
+  L.nes = c.ne + (ex >> 20);
+  const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+  c.rows += tot & 1023u;
+  c.tabs += (tot >> 10) & 1023u;
+  c.ne += tot >> 20;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// census: counts per tile
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_tile_count(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, TileAgg* __restrict__ agg) {
+  const uint32_t tile = blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+  if (tile >= ntiles) return;
+  const int64_t t0 = lo + (int64_t)tile * TILE;
+  WarpCarry c;
+  TileAgg zero = {0u, 0u, 0u, 0u, 0u};
+  carry_init(buf, t0, zero, c);
+  // the boundary in front of the tile decides whether its first delimiter closes an empty field
+  c.pb = t0 - 2;
+  if (t0 <= 0) {
+    c.pb = -1;
+  } else {
+    const uint8_t b = __ldg(buf + t0 - 1);
+    if ((b == (uint8_t)'\t' || b == (uint8_t)'\n') && !odd_backslashes_before(buf, t0 - 1)) c.pb = t0 - 1;
+  }
+  int64_t last_b = -1, last_r = -1;
+  for (uint32_t s = 0; s < TILE; s += STEP) {
+    const LaneStep L = scan_step(buf, (int64_t)n, t0 + s, c);
+    (void)L;
+  }
+  last_b = c.pb >= t0 ? c.pb : -1;
+  last_r = c.prb >= t0 ? c.prb : -1;
+  if (lane_id() == 0) {
+    TileAgg a;
+    a.rows = c.rows;
+    a.tabs = c.tabs;
+    a.ne = c.ne;
+    a.bound_p1 = (uint32_t)(last_b + 1);
+    a.break_p1 = (uint32_t)(last_r + 1);
+    agg[tile] = a;
+  }
+}
+
+// single CTA: exclusive prefix of the tile aggregates (sums for the counts, running maximum for the positions)
+constexpr int TS_THREADS = 1024;
+__global__ void __launch_bounds__(TS_THREADS) k_tile_scan(TileAgg* __restrict__ agg, uint32_t ntiles, EncMeta* __restrict__ meta) {
+  __shared__ TileAgg sh[TS_THREADS];
+  const uint32_t per = (ntiles + TS_THREADS - 1) / TS_THREADS;
+  const uint32_t a = threadIdx.x * per, b = min(ntiles, a + per);
+  TileAgg acc = {0u, 0u, 0u, 0u, 0u};
+  for (uint32_t t = a; t < b; ++t) {
+    const TileAgg x = agg[t];
+    acc.rows += x.rows;
+    acc.tabs += x.tabs;
+    acc.ne += x.ne;
+    acc.bound_p1 = max(acc.bound_p1, x.bound_p1);
+    acc.break_p1 = max(acc.break_p1, x.break_p1);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  // Hillis-Steele over the 1024 partials
+  for (int o = 1; o < TS_THREADS; o <<= 1) {
+    TileAgg t = sh[threadIdx.x];
+    if ((int)threadIdx.x >= o) {
+      const TileAgg u = sh[threadIdx.x - o];
+      t.rows += u.rows;
+      t.tabs += u.tabs;
+      t.ne += u.ne;
+      t.bound_p1 = max(t.bound_p1, u.bound_p1);
+      t.break_p1 = max(t.break_p1, u.break_p1);
     }
-    kbase += total & 0xffffu;
     __syncthreads();
+    sh[threadIdx.x] = t;
+    __syncthreads();
+  }
+  TileAgg run = {0u, 0u, 0u, 0u, 0u};
+  if (threadIdx.x) run = sh[threadIdx.x - 1];
+  for (uint32_t t = a; t < b; ++t) {
+    const TileAgg x = agg[t];
+    agg[t] = run;
+    run.rows += x.rows;
+    run.tabs += x.tabs;
+    run.ne += x.ne;
+    run.bound_p1 = max(run.bound_p1, x.bound_p1);
+    run.break_p1 = max(run.break_p1, x.break_p1);
+  }
+  if (threadIdx.x == TS_THREADS - 1) {
+    const TileAgg tot = sh[TS_THREADS - 1];
+    meta->tot_rows = tot.rows;
+    meta->tot_tabs = tot.tabs;
+    meta->tot_ne = tot.ne;
+    meta->last_break_p1 = tot.break_p1;
+  }
+}
+
+// one warp: terminator of row `want` (0-based) -> meta->cut_end_p1, first byte of the next row -> meta->next_start
+__global__ void k_find_cut(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, const TileAgg* __restrict__ pre,
+                           uint32_t want, EncMeta* __restrict__ meta) {
+  // largest tile whose exclusive row prefix is <= want
+  uint32_t a = 0, b = ntiles;
+  while (b - a > 1) {
+    const uint32_t m = (a + b) >> 1;
+    if (pre[m].rows <= want) a = m;
+    else b = m;
+  }
+  const int64_t t0 = lo + (int64_t)a * TILE;
+  WarpCarry c;
+  carry_init(buf, t0, pre[a], c);
+  for (uint32_t s = 0; s < TILE; s += STEP) {
+    const LaneStep L = scan_step(buf, (int64_t)n, t0 + s, c);
+    uint32_t t = L.term;
+    while (t) {
+      const int i = __ffs(t) - 1;
+      t &= t - 1;
+      if (L.rows + (uint32_t)__popc(L.term & ((1u << i) - 1u)) == want) {
+        const uint64_t pos = (uint64_t)(L.p0 + i);
+        uint64_t nx = pos + 1;
+        while (nx < n && __ldg(buf + nx) == (uint8_t)'\n') ++nx;  // blank lines directly after a row are skipped
+        meta->cut_end_p1 = (uint32_t)(pos + 1);
+        meta->next_start = (uint32_t)nx;
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // string hash set (open addressing, 64-bit slots: (start+1) << 32 | len, 0 = empty)
 // ---------------------------------------------------------------------------------------------
-// Little-endian 32-bit words of the byte string that starts at an arbitrary address: aligned loads + funnel shift.
-// Reads at most one aligned word past the word holding the last requested byte.
-struct WordStream {
-  const uint32_t* w;
-  uint32_t sh, cur;
-  __device__ __forceinline__ explicit WordStream(const uint8_t* a) {
-    const uintptr_t u = reinterpret_cast<uintptr_t>(a);
-    w = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
-    sh = (uint32_t)(u & 3u) * 8u;
-    cur = __ldg(w);
-  }
-  __device__ __forceinline__ uint32_t next() {
-    const uint32_t nx = __ldg(++w);
-    const uint32_t r = __funnelshift_r(cur, nx, sh);
-    cur = nx;
-    return r;
-  }
-  // the next `rem` (1..3) bytes, zero-extended
-  __device__ __forceinline__ uint32_t tail(uint32_t rem) {
-    uint32_t r;
-    if (sh + rem * 8u <= 32u) r = cur >> sh;
-    else r = __funnelshift_r(cur, __ldg(w + 1), sh);
-    return r & ((1u << (rem * 8u)) - 1u);
-  }
-};
-
-__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
-
-// MurmurHash3 (x86_32) over the field bytes
-__device__ __forceinline__ uint32_t hash_bytes(const uint8_t* __restrict__ p, uint32_t len) {
-  WordStream ws(p);
-  uint32_t h = 0x9747b28cu;
-  uint32_t i = 0;
-  for (; i + 4 <= len; i += 4) {
-    uint32_t k = ws.next();
-    k *= 0xcc9e2d51u;
-    k = rotl32(k, 15);
-    k *= 0x1b873593u;
-    h ^= k;
-    h = rotl32(h, 13);
-    h = h * 5u + 0xe6546b64u;
-  }
-  if (len - i) {
-    uint32_t k = ws.tail(len - i);
-    k *= 0xcc9e2d51u;
-    k = rotl32(k, 15);
-    k *= 0x1b873593u;
-    h ^= k;
-  }
-  h ^= len;
-  h ^= h >> 16;
-  h *= 0x85ebca6bu;
-  h ^= h >> 13;
-  h *= 0xc2b2ae35u;
-  h ^= h >> 16;
-  return h;
-}
-
-__device__ __forceinline__ bool bytes_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len) {
-  WordStream sa(a), sb(b);
-  uint32_t i = 0;
-  for (; i + 4 <= len; i += 4)
-    if (sa.next() != sb.next()) return false;
-  if (len - i) return sa.tail(len - i) == sb.tail(len - i);
-  return true;
-}
-
 struct HashTable {
   unsigned long long* slots;
   uint32_t mask;
 };
 
-// returns true when a new entry was created
-__device__ __forceinline__ bool ht_insert(const HashTable ht, const uint8_t* __restrict__ buf, uint32_t start, uint32_t len,
-                                          EncMeta* __restrict__ meta) {
-  if (*reinterpret_cast<volatile uint32_t*>(&meta->ht_overflow)) return false;
-  uint32_t i = hash_bytes(buf + start, len) & ht.mask;
-  const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
-  for (uint32_t probe = 0; probe < HT_MAX_PROBE; ++probe) {
-    unsigned long long cur = ht.slots[i];
-    if (cur == 0ull) {
-      cur = atomicCAS(&ht.slots[i], 0ull, mine);
-      if (cur == 0ull) return true;
-    }
-    if ((uint32_t)cur == len) {
-      const uint32_t cs = (uint32_t)(cur >> 32) - 1u;
-      if (cs == start || bytes_equal(buf + cs, buf + start, len)) return false;
-    }
-    i = (i + 1) & ht.mask;
-  }
-  *reinterpret_cast<volatile uint32_t*>(&meta->ht_overflow) = 1u;
-  return false;
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+
+// The hash is a SUM of position-keyed word mixes, so one lane can evaluate it straight-line for short strings and a
+// group of lanes can evaluate it cooperatively for long ones, with the same result.
+__device__ __forceinline__ uint32_t mix_word(uint32_t w, uint32_t i) {
+  uint32_t x = w ^ (i * 0x9E3779B1u + 0x85EBCA77u);
+  x *= 0xCC9E2D51u;
+  x = rotl32(x, 15);
+  x *= 0x1B873593u;
+  return x;
+}
+__device__ __forceinline__ uint32_t finish_hash(uint32_t sum, uint32_t len) {
+  uint32_t h = sum ^ (len * 0x27D4EB2Fu);
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
 
-// returns the slot holding the string or 0xffffffff
-__device__ __forceinline__ uint32_t ht_find(const HashTable ht, const uint8_t* __restrict__ buf, uint32_t start,
-                                            uint32_t len) {
-  uint32_t i = hash_bytes(buf + start, len) & ht.mask;
-  for (uint32_t probe = 0; probe <= ht.mask; ++probe) {
-    const unsigned long long cur = ht.slots[i];
-    if (cur == 0ull) return 0xffffffffu;
-    if ((uint32_t)cur == len) {
-      const uint32_t cs = (uint32_t)(cur >> 32) - 1u;
-      if (cs == start || bytes_equal(buf + cs, buf + start, len)) return i;
-    }
-    i = (i + 1) & ht.mask;
+// Little-endian word k (bytes 4k .. 4k+3, zero beyond len) of the string at s; `wlast` = last readable aligned word.
+struct StrWords {
+  const uint32_t* w;
+  uint32_t sh;
+  const uint32_t* wlast;
+  __device__ __forceinline__ StrWords(const uint8_t* s, const uint32_t* last) : wlast(last) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+    w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    sh = (uint32_t)(a & 3u) * 8u;
   }
-  return 0xffffffffu;
+  __device__ __forceinline__ uint32_t word(uint32_t k, uint32_t len) const {
+    const uint32_t* p = w + k;
+    const uint32_t a = __ldg(p);
+    const uint32_t b = sh ? __ldg(p + 1 <= wlast ? p + 1 : wlast) : 0u;
+    const uint32_t x = __funnelshift_r(a, b, sh);
+    const uint32_t rem = len - 4u * k;
+    return rem >= 4u ? x : (x & ((1u << (8u * rem)) - 1u));
+  }
+};
+
+// short strings (len <= 16): the four masked words
+__device__ __forceinline__ void short_words(const uint8_t* s, uint32_t len, const uint32_t* wlast, uint32_t x[4]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t room = (uint32_t)min((ptrdiff_t)4, wlast - w);
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, room)), w2 = __ldg(w + min(2u, room)), w3 = __ldg(w + min(3u, room)),
+                 w4 = __ldg(w + min(4u, room));
+  x[0] = __funnelshift_r(w0, w1, sh);
+  x[1] = __funnelshift_r(w1, w2, sh);
+  x[2] = __funnelshift_r(w2, w3, sh);
+  x[3] = __funnelshift_r(w3, w4, sh);
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) {
+    const uint32_t got = len > 4u * k ? len - 4u * k : 0u;
+    x[k] = got >= 4u ? x[k] : (got ? (x[k] & ((1u << (8u * got)) - 1u)) : 0u);
+  }
+}
+__device__ __forceinline__ uint32_t short_hash(const uint32_t x[4], uint32_t len) {
+  uint32_t s = mix_word(x[0], 0);
+  if (len > 4) s += mix_word(x[1], 1);
+  if (len > 8) s += mix_word(x[2], 2);
+  if (len > 12) s += mix_word(x[3], 3);
+  return finish_hash(s, len);
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ENC_THREADS)
-    k_pass1(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, const uint32_t* __restrict__ row_start,
-            const uint32_t* __restrict__ row_end, uint32_t nrows, uint32_t rows_per_cta, uint32_t ncols,
-            const uint8_t* __restrict__ types, int trim, HashTable ht, uint32_t* __restrict__ colset,
-            unsigned long long* __restrict__ colmin, unsigned long long* __restrict__ colmax,
-            EncMeta* __restrict__ meta) {
-  __shared__ WalkScratch ts;
-  __shared__ unsigned long long s_new_bytes;
-  __shared__ uint32_t s_new_count, s_max_len;
-  if (threadIdx.x == 0) {
-    s_new_bytes = 0;
-    s_new_count = 0;
-    s_max_len = 0;
-  }
-  const uint32_t r0 = blockIdx.x * rows_per_cta;
-  const uint32_t r1 = min(nrows, r0 + rows_per_cta);
-  const uint32_t b0 = row_start[r0], b1 = row_end[r1 - 1] + 1;
-  walk_tile_fields(buf, n, lo, b0, b1, r0, ncols, trim != 0, ts, [&](uint32_t, uint32_t col, uint32_t start, uint32_t len) {
-    const uint8_t t = __ldg(types + col);
-    const uint8_t* p = buf + start;
-    if (is_text_like(t)) {
-      if (__ldcg(colset + col) == 0u) colset[col] = 1u;
-      if (ht_insert(ht, buf, start, len, meta)) {
-        atomicAdd(&s_new_count, 1u);
-        atomicAdd(&s_new_bytes, (unsigned long long)len + 1ull);
-        atomicMax(&s_max_len, len);
-      }
-    } else {
-      const uint64_t v = (t == ZDWB_CHAR) ? char_tuple(p, len, false) : parse_u64_field(p, len);
-      if (v != 0) {  // zero / empty numeric cells take no part in min/max: ConvertToZDW.cpp:362,386
-        if (__ldcg(colset + col) == 0u) colset[col] = 1u;
-        if (v < __ldcg(colmin + col)) atomicMin(colmin + col, (unsigned long long)v);
-        if (v > __ldcg(colmax + col)) atomicMax(colmax + col, (unsigned long long)v);
+struct P1Args {
+  const uint8_t* buf;
+  uint64_t n;          // readable bytes
+  int64_t lo;          // -(buf & 15)
+  int64_t limit;       // bytes of the block: delimiters at or beyond it are not part of it
+  uint32_t ntiles, ncols;
+  const TileAgg* pre;
+  const uint8_t* types;
+  int trim;
+  HashTable ht;
+  uint32_t* colset;
+  unsigned long long* colmin;
+  unsigned long long* colmax;
+  uint32_t* rec_col;             // [tot_ne]
+  unsigned long long* rec_val;   // [tot_ne] dictionary slot (text) or pass-2 number
+  uint32_t* row_rec;             // [rows + 1] records in front of row r
+  EncMeta* meta;
+};
+
+struct P1Warp {        // per-warp shared memory
+  uint4 q[3][QCAP];    // (start, len, col, ordinal) : 0 short text, 1 long text, 2 numeric / CHAR
+};
+
+struct P1Stats {
+  uint32_t new_count, max_len, max_line;
+  unsigned long long new_bytes;
+};
+
+// slot of the string (inserting it when absent); *is_new reports an insertion.  Per-lane version for len <= SHORT_MAX.
+__device__ __forceinline__ uint32_t ht_upsert_short(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, bool* is_new) {
+  uint32_t x[4];
+  short_words(A.buf + start, len, wlast, x);
+  uint32_t i = short_hash(x, len) & A.ht.mask;
+  const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
+  *is_new = false;
+  for (uint32_t probe = 0; probe < HT_MAX_PROBE; ++probe) {
+    unsigned long long cur = A.ht.slots[i];
+    if (cur == 0ull) {
+      cur = atomicCAS(&A.ht.slots[i], 0ull, mine);
+      if (cur == 0ull) {
+        *is_new = true;
+        return i;
       }
     }
-  });
-  __syncthreads();
-  if (threadIdx.x == 0 && s_new_count) {
-    atomicAdd(&meta->n_unique, (unsigned long long)s_new_count);
-    atomicAdd(&meta->dict_str_bytes, s_new_bytes);
-    atomicMax(&meta->max_str_len, s_max_len);
+    if ((uint32_t)cur == len) {
+      const uint32_t cs = (uint32_t)(cur >> 32) - 1u;
+      if (cs == start) return i;
+      uint32_t y[4];
+      short_words(A.buf + cs, len, wlast, y);
+      if (x[0] == y[0] && x[1] == y[1] && x[2] == y[2] && x[3] == y[3]) return i;
+    }
+    i = (i + 1) & A.ht.mask;
+  }
+  *reinterpret_cast<volatile uint32_t*>(&A.meta->ht_overflow) = 1u;
+  return 0;
+}
+
+// 8 lanes (one octet of the warp) work on one long string: gl = lane within the octet, `om` = the octet's lane mask.
+__device__ __forceinline__ uint32_t ht_upsert_long(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, unsigned gl,
+                                                   unsigned om, bool active, bool* is_new) {
+  *is_new = false;
+  const uint32_t nw = (len + 3u) >> 2;
+  uint32_t s = 0;
+  if (active) {
+    const StrWords me(A.buf + start, wlast);
+    for (uint32_t k = gl; k < nw; k += 8) s += mix_word(me.word(k, len), k);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  uint32_t i = finish_hash(s, len) & A.ht.mask;
+  const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
+  uint32_t result = 0;
+  bool done = !active;
+  for (uint32_t probe = 0; probe < HT_MAX_PROBE; ++probe) {
+    // every octet runs the same number of iterations (the shuffles below are warp-wide)
+    unsigned long long cur = 0;
+    if (!done) {
+      cur = A.ht.slots[i];
+      if (cur == 0ull) {
+        if (gl == 0) cur = atomicCAS(&A.ht.slots[i], 0ull, mine);
+      }
+    }
+    // lane 0 of the octet decides
+    const unsigned long long cur0 = __shfl_sync(0xffffffffu, cur, (lane_id() & ~7u));
+    bool match = false;
+    if (!done) {
+      if (cur0 == 0ull) {  // our CAS went through
+        *is_new = true;
+        result = i;
+        done = true;
+      } else if ((uint32_t)cur0 == len) {
+        const uint32_t cs = (uint32_t)(cur0 >> 32) - 1u;
+        match = true;
+        if (cs != start) {
+          const StrWords me(A.buf + start, wlast), other(A.buf + cs, wlast);
+          for (uint32_t k = gl; k < nw && match; k += 8) match = me.word(k, len) == other.word(k, len);
+        }
+      }
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, match || done);
+    if (!done) {
+      if ((votes & om) == om && (uint32_t)cur0 == len && cur0 != 0ull) {
+        result = i;
+        done = true;
+      } else {
+        i = (i + 1) & A.ht.mask;
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) return result;
+  }
+  if (!done) *reinterpret_cast<volatile uint32_t*>(&A.meta->ht_overflow) = 1u;
+  return result;
+}
+
+__device__ __forceinline__ uint32_t trimmed_len(const uint8_t* __restrict__ buf, uint32_t start, uint32_t len) {
+  while (len && __ldg(buf + start + len - 1) == (uint8_t)' ') --len;  // -t: ConvertToZDW.cpp:295-313
+  return len;
+}
+
+// processes up to 32 queued entries of class `cls`; lane l takes entry base + l (classes 0, 2) or octet o takes
+// entries base + o, base + 4 + o, ... (class 1)
+__device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, P1Warp& W, int cls, uint32_t count, P1Stats& st) {
+  const unsigned lane = lane_id();
+  if (cls == 1) {
+    const unsigned grp = lane >> 3, gl = lane & 7u, om = 0xffu << (grp * 8);
+    for (uint32_t e0 = 0; e0 < count; e0 += 4) {
+      const uint32_t e = e0 + grp;
+      const bool active = e < count;
+      const uint4 ent = W.q[1][active ? e : 0];
+      bool is_new;
+      const uint32_t slot = ht_upsert_long(A, wlast, ent.x, ent.y, gl, om, active, &is_new);
+      if (active && gl == 0) {
+        A.rec_col[ent.w] = ent.z;
+        A.rec_val[ent.w] = slot;
+        if (__ldcg(A.colset + ent.z) == 0u) A.colset[ent.z] = 1u;
+        if (is_new) {
+          ++st.new_count;
+          st.new_bytes += (unsigned long long)ent.y + 1ull;
+          st.max_len = max(st.max_len, ent.y);
+        }
+      }
+    }
+    return;
+  }
+  if (lane >= count) return;
+  const uint4 ent = W.q[cls][lane];
+  const uint32_t start = ent.x, len = ent.y, col = ent.z, ord = ent.w;
+  if (cls == 0) {
+    bool is_new;
+    const uint32_t slot = ht_upsert_short(A, wlast, start, len, &is_new);
+    A.rec_col[ord] = col;
+    A.rec_val[ord] = slot;
+    if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
+    if (is_new) {
+      ++st.new_count;
+      st.new_bytes += (unsigned long long)len + 1ull;
+      st.max_len = max(st.max_len, len);
+    }
+  } else {
+    const uint8_t t = __ldg(A.types + col);
+    const uint8_t* p = A.buf + start;
+    unsigned long long v1, v2;
+    if (t == ZDWB_CHAR) {
+      v1 = char_tuple(p, len, false);  // min/max rule, ConvertToZDW.cpp:358-361
+      v2 = char_tuple(p, len, true);   // pass-2 rule, :543-547
+    } else {
+      v1 = v2 = parse_u64_field(p, len);  // strtoull, :385,564
+    }
+    A.rec_col[ord] = col;
+    A.rec_val[ord] = v2;
+    if (v1 != 0) {  // zero / empty numeric cells take no part in min/max: :362,386
+      if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
+      if (v1 < __ldcg(A.colmin + col)) atomicMin(A.colmin + col, v1);
+      if (v1 > __ldcg(A.colmax + col)) atomicMax(A.colmax + col, v1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS) k_pass1(const P1Args A) {
+  __shared__ P1Warp sw[ENC_WARPS];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x * ENC_WARPS + warp;
+  if (tile >= A.ntiles) return;
+  P1Warp& W = sw[warp];
+  const int64_t t0 = A.lo + (int64_t)tile * TILE;
+  if (t0 >= A.limit) return;
+  const uint32_t* wlast = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.buf + A.n - 1) & ~(uintptr_t)3);
+  WarpCarry c;
+  carry_init(A.buf, t0, A.pre[tile], c);
+  P1Stats st = {0u, 0u, 0u, 0ull};
+  uint32_t qn[3] = {0u, 0u, 0u};
+  const uint32_t tabs_per_row = A.ncols - 1u;
+  if (tile == 0 && lane == 0) A.row_rec[0] = 0u;
+
+  for (uint32_t s = 0; s < TILE; s += STEP) {
+    if (t0 + s >= A.limit) break;
+    const LaneStep L = scan_step(A.buf, A.limit, t0 + s, c);
+    // ---- rows that end here: field-count check, longest line, record index of the next row
+    uint32_t tm = L.term;
+    while (tm) {
+      const int i = __ffs(tm) - 1;
+      tm &= tm - 1;
+      const uint32_t below = (1u << i) - 1u;
+      const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
+      const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
+      if (T != (R + 1u) * tabs_per_row) atomicMin(&A.meta->bad_row, R);  // cumulative: exact for the first bad row
+      const uint32_t brk = (L.term | L.skip) & below;
+      const int64_t row_start = (brk ? L.p0 + (31 - __clz(brk)) : L.prb) + 1;
+      st.max_line = max(st.max_line, (uint32_t)(L.p0 + i - row_start + 1));
+      A.row_rec[R + 1u] = L.nes + (uint32_t)__popc(L.ne & ((2u << i) - 1u));
+    }
+    // ---- non-empty fields: one per lane per round into the class queues
+    uint32_t rem = L.ne;
+    const uint32_t bound = L.tab | L.term | L.skip;
+    while (__any_sync(0xffffffffu, rem != 0u)) {
+      int cls = -1;
+      uint4 ent = make_uint4(0u, 0u, 0u, 0u);
+      if (rem) {
+        const int i = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const uint32_t below = (1u << i) - 1u;
+        const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
+        const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
+        const uint32_t col = T - R * tabs_per_row;
+        const uint32_t lowb = bound & below;
+        const uint32_t start = (uint32_t)((lowb ? L.p0 + (31 - __clz(lowb)) : L.pb) + 1);
+        uint32_t len = (uint32_t)(L.p0 + i) - start;
+        const uint32_t ord = L.nes + (uint32_t)__popc(L.ne & below);
+        if (col < A.ncols) {  // (a malformed row is reported through bad_row)
+          if (A.trim) len = trimmed_len(A.buf, start, len);
+          if (len == 0) {
+            A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one
+          } else {
+            cls = is_text_like(__ldg(A.types + col)) ? (len <= SHORT_MAX ? 0 : 1) : 2;
+            ent = make_uint4(start, len, col, ord);
+          }
+        } else {
+          A.rec_col[ord] = REC_EMPTY;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+        if (cls == k) W.q[k][qn[k] + __popc(m & lanemask_lt())] = ent;
+        qn[k] += __popc(m);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (qn[k] >= 32u) {
+          p1_process(A, wlast, W, k, 32u, st);
+          __syncwarp();
+          // move the leftovers to the front
+          const uint32_t left = qn[k] - 32u;
+          uint4 mv = make_uint4(0u, 0u, 0u, 0u);
+          if (lane < left) mv = W.q[k][32u + lane];
+          __syncwarp();
+          if (lane < left) W.q[k][lane] = mv;
+          qn[k] = left;
+          __syncwarp();
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (qn[k]) p1_process(A, wlast, W, k, qn[k], st);
+    __syncwarp();
+  }
+  // ---- warp totals
+  st.max_line = __reduce_max_sync(0xffffffffu, st.max_line);
+  st.max_len = __reduce_max_sync(0xffffffffu, st.max_len);
+  st.new_count = __reduce_add_sync(0xffffffffu, st.new_count);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) st.new_bytes += __shfl_xor_sync(0xffffffffu, st.new_bytes, o);
+  if (lane == 0) {
+    if (st.max_line) atomicMax(&A.meta->max_line, st.max_line);
+    if (st.new_count) {
+      atomicAdd(&A.meta->n_unique, (unsigned long long)st.new_count);
+      atomicAdd(&A.meta->dict_str_bytes, st.new_bytes);
+      atomicMax(&A.meta->max_str_len, st.max_len);
+    }
   }
 }
 
@@ -562,65 +827,61 @@ __global__ void k_block_header(uint8_t* __restrict__ out, const EncMeta* __restr
 // ---------------------------------------------------------------------------------------------
 // pass 2
 // ---------------------------------------------------------------------------------------------
-// One CTA encodes R consecutive rows.  The values of the rows (and of the row before the first one, which the
-// repeat flags of the first row compare against) are gathered into a shared-memory matrix by the field walker;
-// flags and value bytes are then produced row by row, one warp per row.  The tile's bytes go to its own slot of
-// a staging buffer (tile * tile_cap); k_gather_tiles packs the tiles once every tile length is known, which keeps
-// the row stream free of any cross-CTA dependency while it is being produced.
+// One CTA encodes R consecutive rows from their records.  The values of the rows (and of the row before the first
+// one, which the repeat flags of the first row compare against) are scattered into a shared-memory matrix; flags and
+// value bytes are then produced row by row, one warp per row.  The tile's bytes go to its own slot of a staging buffer
+// (tile * tile_cap); k_gather_tiles packs the tiles once every tile length is known, which keeps the row stream free
+// of any cross-CTA dependency while it is being produced.
 __global__ void __launch_bounds__(ENC_THREADS)
-    k_pass2(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, const uint32_t* __restrict__ row_start,
-            const uint32_t* __restrict__ row_end, uint32_t nrows, uint32_t rows_per_cta, uint32_t ncols,
-            const uint8_t* __restrict__ types, int trim, HashTable ht, const uint32_t* __restrict__ slot_off,
-            const int32_t* __restrict__ used_idx, const uint32_t* __restrict__ used_cols,
-            const uint8_t* __restrict__ csize, const unsigned long long* __restrict__ cbase, uint32_t U,
-            uint32_t nflag, uint64_t tile_cap, uint8_t* __restrict__ staging, uint64_t* __restrict__ tile_bytes,
-            EncMeta* __restrict__ meta) {
+    k_pass2(const uint32_t* __restrict__ rec_col, const unsigned long long* __restrict__ rec_val,
+            const uint32_t* __restrict__ row_rec, uint32_t nrows, uint32_t rows_per_cta, const uint8_t* __restrict__ types,
+            const uint32_t* __restrict__ slot_off, const int32_t* __restrict__ used_idx, const uint32_t* __restrict__ used_cols,
+            const uint8_t* __restrict__ csize, const unsigned long long* __restrict__ cbase, uint32_t U, uint32_t nflag,
+            uint64_t tile_cap, uint8_t* __restrict__ staging, uint64_t* __restrict__ tile_bytes) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  __shared__ WalkScratch ts;
-  // dynamic smem: nval[(R+1)*U] u64 | rowoff[R+1] u32 | usz[U] u8
+  // dynamic smem: nval[(R+1)*U] u64 | rowoff[R+1] u32 | rrec[R+2] u32 | usz[U] u8
   unsigned long long* nval = reinterpret_cast<unsigned long long*>(dsm);
   uint32_t* rowoff = reinterpret_cast<uint32_t*>(dsm + (size_t)(rows_per_cta + 1) * U * 8);
-  uint8_t* usz = reinterpret_cast<uint8_t*>(rowoff + rows_per_cta + 1);
+  uint32_t* rrec = rowoff + rows_per_cta + 1;
+  uint8_t* usz = reinterpret_cast<uint8_t*>(rrec + rows_per_cta + 2);
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   const uint32_t tile = blockIdx.x;
   const uint32_t r0 = tile * rows_per_cta;
   const uint32_t r1 = min(nrows, r0 + rows_per_cta);
   const uint32_t R = r1 - r0;
+  const uint32_t rw0 = r0 ? r0 - 1 : 0;     // first row whose records are needed
+  const uint32_t nrw = r1 - rw0;             // rows loaded
   for (uint32_t k = tid; k < (R + 1) * U; k += ENC_THREADS) nval[k] = 0ull;
   for (uint32_t u = tid; u < U; u += ENC_THREADS) usz[u] = csize[used_cols[u]];
-  // (walk_tile_fields starts with a __syncthreads)
+  for (uint32_t k = tid; k <= nrw; k += ENC_THREADS) rrec[k] = row_rec[rw0 + k];
+  __syncthreads();
 
-  // ---- values of the tile's rows and of the row before it
-  const uint32_t rw0 = r0 ? r0 - 1 : 0;
-  const uint32_t b0 = row_start[rw0], b1 = row_end[r1 - 1] + 1;
-  walk_tile_fields(buf, n, lo, b0, b1, rw0, ncols, trim != 0, ts, [&](uint32_t row, uint32_t col, uint32_t start, uint32_t len) {
-    const int32_t u = __ldg(used_idx + col);
-    if (u < 0) return;
-    const uint8_t t = __ldg(types + col);
-    const uint8_t* p = buf + start;
-    unsigned long long v;
-    if (is_text_like(t)) {
-      const uint32_t slot = ht_find(ht, buf, start, len);
-      if (slot == 0xffffffffu) {
-        atomicAdd(&meta->lookup_miss, 1u);
-        v = 0;
-      } else {
-        v = slot_off[slot];
+  // ---- values of the tile's rows and of the row before it, from the records
+  {
+    const uint32_t k0 = rrec[0], k1 = rrec[nrw];
+    for (uint32_t k = k0 + tid; k < k1; k += ENC_THREADS) {
+      const uint32_t col = rec_col[k];
+      if (col == REC_EMPTY) continue;
+      const int32_t u = __ldg(used_idx + col);
+      if (u < 0) continue;
+      // row of the record: last j with rrec[j] <= k
+      uint32_t a = 0, b = nrw;
+      while (b - a > 1) {
+        const uint32_t m = (a + b) >> 1;
+        if (rrec[m] <= k) a = m;
+        else b = m;
       }
-    } else if (t == ZDWB_CHAR) {
-      v = char_tuple(p, len, true);  // ConvertToZDW.cpp:543-547
-      if (v) v -= __ldg(cbase + col);
-    } else {
-      v = parse_u64_field(p, len);   // :564-566
-      if (v) v -= __ldg(cbase + col);
+      unsigned long long v = rec_val[k];
+      if (is_text_like(__ldg(types + col))) v = slot_off[(uint32_t)v];  // Dictionary::getOffset
+      else if (v) v -= __ldg(cbase + col);                               // ConvertToZDW.cpp:548,566
+      nval[(size_t)(rw0 + a + 1 - r0) * U + (uint32_t)u] = v;
     }
-    nval[(size_t)(row + 1 - r0) * U + (uint32_t)u] = v;
-  });
+  }
   __syncthreads();
 
   // ---- encoded length of every row: nflag + sum of the sizes of the changed columns
-  for (uint32_t j = warp; j < R; j += ENC_THREADS / 32) {
+  for (uint32_t j = warp; j < R; j += ENC_WARPS) {
     const unsigned long long* cur = nval + (size_t)(j + 1) * U;
     const unsigned long long* prv = nval + (size_t)j * U;
     uint32_t acc = 0;
@@ -654,7 +915,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
   uint8_t* tile_out = staging + (uint64_t)tile * tile_cap;
 
   // ---- emit: flag bytes, then the low columnSize bytes of every changed value (little-endian)
-  for (uint32_t j = warp; j < R; j += ENC_THREADS / 32) {
+  for (uint32_t j = warp; j < R; j += ENC_WARPS) {
     const unsigned long long* cur = nval + (size_t)(j + 1) * U;
     const unsigned long long* prv = nval + (size_t)j * U;
     uint8_t* orow = tile_out + rowoff[j];
@@ -685,6 +946,24 @@ __global__ void __launch_bounds__(ENC_THREADS)
     }
   }
 }
+
+// Little-endian 32-bit words of the byte string that starts at an arbitrary address: aligned loads + funnel shift.
+struct WordStream {
+  const uint32_t* w;
+  uint32_t sh, cur;
+  __device__ __forceinline__ explicit WordStream(const uint8_t* a) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(a);
+    w = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
+    sh = (uint32_t)(u & 3u) * 8u;
+    cur = __ldg(w);
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t nx = __ldg(++w);
+    const uint32_t r = __funnelshift_r(cur, nx, sh);
+    cur = nx;
+    return r;
+  }
+};
 
 // packs the staged tiles into the row stream: tile t's bytes go to out_rows + tile_off[t]
 __global__ void __launch_bounds__(ENC_THREADS)
@@ -777,98 +1056,83 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   }
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(types_d.p, schema->types, ncols, cudaMemcpyHostToDevice, st));
 
-  // ---- row index: count, scan, write
+  // ---- census: per-tile counts and their prefix
   const uint64_t span = (uint64_t)(-lo) + n;
-  const uint32_t idx_tiles = (uint32_t)((span + IDX_TILE - 1) / IDX_TILE);
-  DevBuf tile_cnt, total_d;
-  ZDWB_TRY(tile_cnt.alloc(ctx, (size_t)idx_tiles * 8));
-  ZDWB_TRY(total_d.alloc(ctx, 8));
+  const uint32_t ntiles = (uint32_t)((span + TILE - 1) / TILE);
+  const uint32_t tile_ctas = (ntiles + ENC_WARPS - 1) / ENC_WARPS;
+  DevBuf agg;
+  ZDWB_TRY(agg.alloc(ctx, (size_t)ntiles * sizeof(TileAgg)));
   {
-    KernelScope _ks(ctx, "k_rows_count");
-    k_rows_count<<<idx_tiles, ENC_THREADS, 0, st>>>(buf, n, lo, tile_cnt.as<uint64_t>());
+    KernelScope _ks(ctx, "k_tile_count");
+    k_tile_count<<<tile_ctas, ENC_THREADS, 0, st>>>(buf, n, lo, ntiles, agg.as<TileAgg>());
   }
   ZDWB_LAUNCH_CHECK(ctx);
-  ZDWB_TRY(exclusive_scan_u64(ctx, tile_cnt.as<uint64_t>(), tile_cnt.as<uint64_t>(), idx_tiles, total_d.as<uint64_t>()));
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->meta_host, total_d.p, 8, cudaMemcpyDeviceToHost, st));
+  {
+    KernelScope _ks(ctx, "k_tile_scan");
+    k_tile_scan<<<1, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, meta);
+  }
+  ZDWB_LAUNCH_CHECK(ctx);
+  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
   ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  const uint64_t packed = *static_cast<uint64_t*>(ctx->meta_host);
-  const uint64_t rows_total = packed >> 32;
+  const uint64_t rows_total = hmeta->tot_rows;
+  const uint64_t ne_total = hmeta->tot_ne;
+  const uint64_t tail_start = hmeta->last_break_p1;  // first byte after the last row break
   out->rows_in_buffer = rows_total;
   if (rows_total == 0) {
     out->tsv_consumed = opts->more_input_follows ? 0 : n;  // a window without a complete row: the caller widens it
     return ZDWB_OK;  // "Empty data file -- nothing to process", ConvertToZDW.cpp:824-835
   }
-  DevBuf row_start, row_end;
-  ZDWB_TRY(row_start.alloc(ctx, (size_t)(rows_total + 1) * 4));
-  ZDWB_TRY(row_end.alloc(ctx, (size_t)rows_total * 4));
-  {
-    KernelScope _ks(ctx, "k_rows_write");
-    k_rows_write<<<idx_tiles, ENC_THREADS, 0, st>>>(buf, n, lo, tile_cnt.as<uint64_t>(), ncols, row_start.as<uint32_t>(),
-                                                  row_end.as<uint32_t>(), meta);
-  }
-  ZDWB_LAUNCH_CHECK(ctx);
 
   const uint64_t nrows64 = (opts->max_rows && opts->max_rows < rows_total) ? opts->max_rows : rows_total;
   const uint32_t nrows = (uint32_t)nrows64;
   const bool took_all = nrows64 == rows_total;
   const bool is_last = took_all && !opts->more_input_follows;
 
-  // block extent + validation result
-  uint32_t h_last[2] = {0, 0};  // row_end[nrows-1], row_start[rows_total]
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, row_end.as<uint32_t>() + (nrows - 1), 4,
-                                     cudaMemcpyDeviceToHost, st));
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->meta_host) + 1028, row_start.as<uint32_t>() + rows_total, 4,
-                                     cudaMemcpyDeviceToHost, st));
-  ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  memcpy(h_last, reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, 8);
-  if (hmeta->bad_row < nrows) {
-    out->bad_row = hmeta->bad_row + 1;  // "Row %u had the problem": one past the last good row, ConvertToZDW.cpp:811
-    ctx->err = "Row " + std::to_string(out->bad_row) + " had the problem";
-    return ZDWB_ERR_WRONG_COLUMNS;
-  }
+  // ---- block extent
+  uint64_t limit;  // bytes that belong to the block
   uint32_t tail_bytes = 0;
-  if (is_last) {
-    out->tsv_consumed = n;
-    tail_bytes = (uint32_t)(n - h_last[1]);
-  } else if (took_all) {
-    out->tsv_consumed = h_last[1];  // the unterminated tail belongs to the next window
+  if (took_all) {
+    // the terminator of the last row is the last row break unless blank lines follow it; either way every
+    // delimiter in front of tail_start belongs to the block
+    limit = tail_start;
+    if (is_last) {
+      out->tsv_consumed = n;
+      tail_bytes = (uint32_t)(n - tail_start);
+    } else {
+      out->tsv_consumed = tail_start;  // the unterminated tail belongs to the next window
+    }
   } else {
-    // the next block starts at the first byte of row `nrows`
-    uint32_t nxt;
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->meta_host, row_start.as<uint32_t>() + nrows, 4, cudaMemcpyDeviceToHost, st));
+    {
+      KernelScope _ks(ctx, "k_find_cut");
+      k_find_cut<<<1, 32, 0, st>>>(buf, n, lo, ntiles, agg.as<TileAgg>(), nrows - 1, meta);
+    }
+    ZDWB_LAUNCH_CHECK(ctx);
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    nxt = *static_cast<uint32_t*>(ctx->meta_host);
-    out->tsv_consumed = nxt;
+    limit = hmeta->cut_end_p1;
+    out->tsv_consumed = hmeta->next_start;
   }
   out->nrows = nrows;
 
-  {
-    KernelScope _ks(ctx, "k_row_longest");
-    k_row_longest<<<std::min<uint32_t>((nrows + 255) / 256, 1024u), 256, 0, st>>>(row_start.as<uint32_t>(), row_end.as<uint32_t>(),
-                                                                              nrows, tail_bytes, meta);
-  }
-  ZDWB_LAUNCH_CHECK(ctx);
-
   // ---- pass 1 (retry with a larger hash set when it fills up)
-  const uint64_t block_bytes = (uint64_t)h_last[0] + 1;
-  const uint64_t avg_row = std::max<uint64_t>(1, block_bytes / nrows);
-  uint32_t rpc1 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 65536 / avg_row), 4096);
-  const uint32_t tiles1 = (nrows + rpc1 - 1) / rpc1;
-
-  DevBuf colset, colmin, colmax, slots;
+  const uint64_t block_bytes = limit;
+  DevBuf colset, colmin, colmax, slots, rec_col, rec_val, row_rec;
   ZDWB_TRY(colset.alloc(ctx, (size_t)ncols * 4));
   ZDWB_TRY(colmin.alloc(ctx, (size_t)ncols * 8));
   ZDWB_TRY(colmax.alloc(ctx, (size_t)ncols * 8));
+  ZDWB_TRY(rec_col.alloc(ctx, (size_t)(ne_total + 1) * 4));
+  ZDWB_TRY(rec_val.alloc(ctx, (size_t)(ne_total + 1) * 8));
+  ZDWB_TRY(row_rec.alloc(ctx, (size_t)(rows_total + 2) * 4));
   uint32_t cap_log2 = (uint32_t)std::max<long long>(10, std::min<long long>(ctx->ht_initial_log2, 31));
   while (cap_log2 < 31 && (1ull << cap_log2) < ctx->last_unique * 4) ++cap_log2;  // blocks of one file look alike
   {
-    // a block cannot hold more distinct non-empty strings than bytes / 2
+    // a block cannot hold more distinct non-empty strings than non-empty fields
     uint32_t need = 10;
-    while (need < 31 && (1ull << need) < block_bytes) ++need;
+    while (need < 31 && (1ull << need) < ne_total * 2) ++need;
     if (cap_log2 > need) cap_log2 = need;
   }
   HashTable ht{nullptr, 0};
+  const uint32_t p1_tiles = (uint32_t)(((uint64_t)(-lo) + limit + TILE - 1) / TILE);
   for (;;) {
     const uint64_t cap = 1ull << cap_log2;
     ZDWB_TRY(slots.alloc(ctx, cap * 8));
@@ -881,15 +1145,32 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
                                                        colset.as<uint32_t>(), ncols);
     }
     ZDWB_LAUNCH_CHECK(ctx);
+    P1Args A;
+    A.buf = buf;
+    A.n = n;
+    A.lo = lo;
+    A.limit = (int64_t)limit;
+    A.ntiles = p1_tiles;
+    A.ncols = ncols;
+    A.pre = agg.as<TileAgg>();
+    A.types = types_d.as<uint8_t>();
+    A.trim = opts->trim_trailing_spaces;
+    A.ht = ht;
+    A.colset = colset.as<uint32_t>();
+    A.colmin = colmin.as<unsigned long long>();
+    A.colmax = colmax.as<unsigned long long>();
+    A.rec_col = rec_col.as<uint32_t>();
+    A.rec_val = rec_val.as<unsigned long long>();
+    A.row_rec = row_rec.as<uint32_t>();
+    A.meta = meta;
     {
       KernelScope _ks(ctx, "k_pass1");
-      k_pass1<<<tiles1, ENC_THREADS, 0, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc1, ncols,
-                                            types_d.as<uint8_t>(), opts->trim_trailing_spaces, ht, colset.as<uint32_t>(),
-                                            colmin.as<unsigned long long>(), colmax.as<unsigned long long>(), meta);
+      k_pass1<<<(p1_tiles + ENC_WARPS - 1) / ENC_WARPS, ENC_THREADS, 0, st>>>(A);
     }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (hmeta->bad_row < nrows) break;
     if (!hmeta->ht_overflow && hmeta->n_unique * 2 <= cap) break;
     if (cap_log2 >= 31) {
       ctx->err = "encode: dictionary hash set exceeds 2^31 slots";
@@ -902,9 +1183,15 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     z.n_unique = 0;
     z.dict_str_bytes = 0;
     z.max_str_len = 0;
+    z.max_line = 0;
     *hmeta = z;
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(meta, hmeta, sizeof(EncMeta), cudaMemcpyHostToDevice, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
+  if (hmeta->bad_row < nrows) {
+    out->bad_row = hmeta->bad_row + 1;  // "Row %u had the problem": one past the last good row, ConvertToZDW.cpp:811
+    ctx->err = "Row " + std::to_string(out->bad_row) + " had the problem";
+    return ZDWB_ERR_WRONG_COLUMNS;
   }
   const uint64_t n_unique = hmeta->n_unique;
   ctx->last_unique = n_unique;
@@ -913,7 +1200,10 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ctx->err = "encode: block dictionary would reach 4 GiB (Dictionary::size is 32-bit, dictionary.h:62); use smaller blocks";
     return ZDWB_ERR_UNSUPPORTED;
   }
-  const uint32_t longest_field = longest_line_field(opts->prev_longest_line, hmeta->max_line);
+  // the unterminated tail fills the row buffer the same way before being dropped (getnextrow.cpp:57-69)
+  uint32_t max_line = hmeta->max_line;
+  if (tail_bytes >= 2) max_line = std::max(max_line, tail_bytes + 1);
+  const uint32_t longest_field = longest_line_field(opts->prev_longest_line, max_line);
 
   // ---- column statistics
   DevBuf csize, cbase, used_idx, used_cols;
@@ -971,20 +1261,17 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   uint32_t tiles2 = 0;
   uint64_t tile_cap = 0;
   if (U > 0) {
-    // rows per CTA: bounded by the shared-memory value matrix ((R+1) * U * 8 bytes) and a byte target
-    const size_t smem_budget = 64 * 1024;
-    const uint64_t by_smem = smem_budget / ((uint64_t)U * 8);
-    if (by_smem < 2) {
-      // even one row + its predecessor do not fit the default budget: allow the full 200 KiB
-      if ((uint64_t)U * 8 * 2 + 1024 > 180 * 1024) {
-        ctx->err = "encode: more than 11400 used columns in one block are not supported";
-        return ZDWB_ERR_UNSUPPORTED;
-      }
+    // rows per CTA: bounded by the shared-memory value matrix ((R+1) * U * 8 bytes) and a record-count target
+    if ((uint64_t)U * 8 * 2 + 1024 > 180 * 1024) {
+      ctx->err = "encode: more than 11400 used columns in one block are not supported";
+      return ZDWB_ERR_UNSUPPORTED;
     }
-    uint32_t rpc2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 65536 / avg_row), 1024);
-    if (by_smem >= 2) rpc2 = (uint32_t)std::min<uint64_t>(rpc2, by_smem - 1);
-    else rpc2 = 1;
-    const size_t smem = (size_t)(rpc2 + 1) * U * 8 + (size_t)(rpc2 + 1) * 4 + U + 16;
+    const uint64_t smem_budget = 64 * 1024;
+    const uint64_t by_smem = std::max<uint64_t>(2, smem_budget / ((uint64_t)U * 8));
+    const uint64_t rec_per_row = std::max<uint64_t>(1, ne_total / std::max<uint64_t>(rows_total, 1));
+    uint32_t rpc2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 4096 / rec_per_row), 1024);
+    rpc2 = (uint32_t)std::min<uint64_t>(rpc2, by_smem - 1);
+    const size_t smem = (size_t)(rpc2 + 1) * U * 8 + (size_t)(rpc2 + 1) * 4 + (size_t)(rpc2 + 2) * 4 + U + 16;
     ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     tiles2 = (nrows + rpc2 - 1) / rpc2;
     tile_cap = (((uint64_t)rpc2 * hmeta->max_row_bytes) + 15) & ~15ull;
@@ -994,21 +1281,15 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ZDWB_TRY(rows_total_d.alloc(ctx, 8));
     {
       KernelScope _ks(ctx, "k_pass2");
-      k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(buf, n, lo, row_start.as<uint32_t>(), row_end.as<uint32_t>(), nrows, rpc2, ncols,
-                                               types_d.as<uint8_t>(), opts->trim_trailing_spaces, ht, slot_off.as<uint32_t>(),
-                                               used_idx.as<int32_t>(), used_cols.as<uint32_t>(), csize.as<uint8_t>(),
-                                               cbase.as<unsigned long long>(), U, nflag, tile_cap, staging.as<uint8_t>(),
-                                               tile_bytes.as<uint64_t>(), meta);
+      k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(rec_col.as<uint32_t>(), rec_val.as<unsigned long long>(), row_rec.as<uint32_t>(),
+                                               nrows, rpc2, types_d.as<uint8_t>(), slot_off.as<uint32_t>(), used_idx.as<int32_t>(),
+                                               used_cols.as<uint32_t>(), csize.as<uint8_t>(), cbase.as<unsigned long long>(), U,
+                                               nflag, tile_cap, staging.as<uint8_t>(), tile_bytes.as<uint64_t>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u64(ctx, tile_bytes.as<uint64_t>(), tile_off.as<uint64_t>(), tiles2, rows_total_d.as<uint64_t>()));
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, rows_total_d.p, 8, cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    if (hmeta->lookup_miss) {
-      ctx->err = "encode: internal error, " + std::to_string(hmeta->lookup_miss) + " dictionary lookups missed in pass 2";
-      return ZDWB_ERR_CUDA;
-    }
     memcpy(&rows_bytes, reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, 8);
   }
 
@@ -1052,6 +1333,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   out->dict_entries = n_unique;
   out->dict_bytes = dict_total;
   out->dict_index_size = bytes_needed(dict_total);
+  (void)block_bytes;
   if (opts->output_on_device) {
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     out->bytes = outp;
