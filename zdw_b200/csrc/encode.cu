@@ -241,53 +241,63 @@ __global__ void __launch_bounds__(ENC_THREADS)
 
 // single CTA: exclusive prefix of the tile aggregates (sums for the counts, running maximum for the positions)
 constexpr int TS_THREADS = 1024;
+__device__ __forceinline__ TileAgg agg_join(const TileAgg& a, const TileAgg& b) {
+  TileAgg r;
+  r.rows = a.rows + b.rows;
+  r.tabs = a.tabs + b.tabs;
+  r.ne = a.ne + b.ne;
+  r.bound_p1 = max(a.bound_p1, b.bound_p1);
+  r.break_p1 = max(a.break_p1, b.break_p1);
+  return r;
+}
+__device__ __forceinline__ TileAgg agg_shfl_up(const TileAgg& a, int o) {
+  TileAgg r;
+  r.rows = __shfl_up_sync(0xffffffffu, a.rows, o);
+  r.tabs = __shfl_up_sync(0xffffffffu, a.tabs, o);
+  r.ne = __shfl_up_sync(0xffffffffu, a.ne, o);
+  r.bound_p1 = __shfl_up_sync(0xffffffffu, a.bound_p1, o);
+  r.break_p1 = __shfl_up_sync(0xffffffffu, a.break_p1, o);
+  return r;
+}
 __global__ void __launch_bounds__(TS_THREADS) k_tile_scan(TileAgg* __restrict__ agg, uint32_t ntiles, EncMeta* __restrict__ meta) {
-  __shared__ TileAgg sh[TS_THREADS];
-  const uint32_t per = (ntiles + TS_THREADS - 1) / TS_THREADS;
-  const uint32_t a = threadIdx.x * per, b = min(ntiles, a + per);
-  TileAgg acc = {0u, 0u, 0u, 0u, 0u};
-  for (uint32_t t = a; t < b; ++t) {
-    const TileAgg x = agg[t];
-    acc.rows += x.rows;
-    acc.tabs += x.tabs;
-    acc.ne += x.ne;
-    acc.bound_p1 = max(acc.bound_p1, x.bound_p1);
-    acc.break_p1 = max(acc.break_p1, x.break_p1);
-  }
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  // Hillis-Steele over the 1024 partials
-  for (int o = 1; o < TS_THREADS; o <<= 1) {
-    TileAgg t = sh[threadIdx.x];
-    if ((int)threadIdx.x >= o) {
-      const TileAgg u = sh[threadIdx.x - o];
-      t.rows += u.rows;
-      t.tabs += u.tabs;
-      t.ne += u.ne;
-      t.bound_p1 = max(t.bound_p1, u.bound_p1);
-      t.break_p1 = max(t.break_p1, u.break_p1);
+  __shared__ TileAgg wsum[32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const TileAgg zero = {0u, 0u, 0u, 0u, 0u};
+  TileAgg carry = zero;  // everything in front of the current round of 1024 tiles
+  for (uint32_t base = 0; base < ntiles; base += TS_THREADS) {
+    const uint32_t t = base + threadIdx.x;
+    const TileAgg mine = t < ntiles ? agg[t] : zero;
+    TileAgg inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const TileAgg u = agg_shfl_up(inc, o);
+      if (lane >= (unsigned)o) inc = agg_join(u, inc);
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      TileAgg w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const TileAgg u = agg_shfl_up(w, o);
+        if (lane >= (unsigned)o) w = agg_join(u, w);
+      }
+      wsum[lane] = w;  // inclusive over warps
     }
     __syncthreads();
-    sh[threadIdx.x] = t;
+    TileAgg ex = carry;
+    if (warp) ex = agg_join(ex, wsum[warp - 1]);
+    const TileAgg up = agg_shfl_up(inc, 1);
+    if (lane) ex = agg_join(ex, up);
+    if (t < ntiles) agg[t] = ex;
+    carry = agg_join(carry, wsum[31]);
     __syncthreads();
   }
-  TileAgg run = {0u, 0u, 0u, 0u, 0u};
-  if (threadIdx.x) run = sh[threadIdx.x - 1];
-  for (uint32_t t = a; t < b; ++t) {
-    const TileAgg x = agg[t];
-    agg[t] = run;
-    run.rows += x.rows;
-    run.tabs += x.tabs;
-    run.ne += x.ne;
-    run.bound_p1 = max(run.bound_p1, x.bound_p1);
-    run.break_p1 = max(run.break_p1, x.break_p1);
-  }
-  if (threadIdx.x == TS_THREADS - 1) {
-    const TileAgg tot = sh[TS_THREADS - 1];
-    meta->tot_rows = tot.rows;
-    meta->tot_tabs = tot.tabs;
-    meta->tot_ne = tot.ne;
-    meta->last_break_p1 = tot.break_p1;
+  if (threadIdx.x == 0) {
+    meta->tot_rows = carry.rows;
+    meta->tot_tabs = carry.tabs;
+    meta->tot_ne = carry.ne;
+    meta->last_break_p1 = carry.break_p1;
   }
 }
 
@@ -370,20 +380,22 @@ struct StrWords {
   }
 };
 
-// short strings (len <= 16): the four masked words
-__device__ __forceinline__ void short_words(const uint8_t* s, uint32_t len, const uint32_t* wlast, uint32_t x[4]) {
+// short strings: the first NW masked words (NW = 4 covers 16 bytes, NW = 5 the 19 digits of a 64-bit number)
+template <int NW>
+__device__ __forceinline__ void short_words(const uint8_t* s, uint32_t len, const uint32_t* wlast, uint32_t x[NW]) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(s);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
   const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  const uint32_t room = (uint32_t)min((ptrdiff_t)4, wlast - w);
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, room)), w2 = __ldg(w + min(2u, room)), w3 = __ldg(w + min(3u, room)),
-                 w4 = __ldg(w + min(4u, room));
-  x[0] = __funnelshift_r(w0, w1, sh);
-  x[1] = __funnelshift_r(w1, w2, sh);
-  x[2] = __funnelshift_r(w2, w3, sh);
-  x[3] = __funnelshift_r(w3, w4, sh);
+  const uint32_t room = (uint32_t)min((ptrdiff_t)NW, wlast - w);
+  uint32_t prev = __ldg(w);
 #pragma unroll
-  for (uint32_t k = 0; k < 4; ++k) {
+  for (uint32_t k = 0; k < NW; ++k) {
+    const uint32_t nx = __ldg(w + min(k + 1u, room));
+    x[k] = __funnelshift_r(prev, nx, sh);
+    prev = nx;
+  }
+#pragma unroll
+  for (uint32_t k = 0; k < NW; ++k) {
     const uint32_t got = len > 4u * k ? len - 4u * k : 0u;
     x[k] = got >= 4u ? x[k] : (got ? (x[k] & ((1u << (8u * got)) - 1u)) : 0u);
   }
@@ -418,8 +430,10 @@ struct P1Args {
   EncMeta* meta;
 };
 
-struct P1Warp {        // per-warp shared memory
-  uint4 q[3][QCAP];    // (start, len, col, ordinal) : 0 short text, 1 long text, 2 numeric / CHAR
+constexpr uint32_t QN = 320;  // fields a warp can hold: up to 31 left over + the 256 a step can produce, rounded up
+
+struct P1Warp {        // per-warp shared memory: non-empty fields in row order, not yet processed
+  uint32_t start[QN], len[QN], col[QN];
 };
 
 struct P1Stats {
@@ -427,10 +441,10 @@ struct P1Stats {
   unsigned long long new_bytes;
 };
 
-// slot of the string (inserting it when absent); *is_new reports an insertion.  Per-lane version for len <= SHORT_MAX.
-__device__ __forceinline__ uint32_t ht_upsert_short(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, bool* is_new) {
-  uint32_t x[4];
-  short_words(A.buf + start, len, wlast, x);
+// slot of the string (inserting it when absent); *is_new reports an insertion.  Per-lane version for len <= SHORT_MAX;
+// x = the string's four masked words.
+__device__ __forceinline__ uint32_t ht_upsert_short(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len,
+                                                    const uint32_t x[4], bool* is_new) {
   uint32_t i = short_hash(x, len) & A.ht.mask;
   const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
   *is_new = false;
@@ -447,7 +461,7 @@ __device__ __forceinline__ uint32_t ht_upsert_short(const P1Args& A, const uint3
       const uint32_t cs = (uint32_t)(cur >> 32) - 1u;
       if (cs == start) return i;
       uint32_t y[4];
-      short_words(A.buf + cs, len, wlast, y);
+      short_words<4>(A.buf + cs, len, wlast, y);
       if (x[0] == y[0] && x[1] == y[1] && x[2] == y[2] && x[3] == y[3]) return i;
     }
     i = (i + 1) & A.ht.mask;
@@ -519,62 +533,134 @@ __device__ __forceinline__ uint32_t trimmed_len(const uint8_t* __restrict__ buf,
   return len;
 }
 
-// processes up to 32 queued entries of class `cls`; lane l takes entry base + l (classes 0, 2) or octet o takes
-// entries base + o, base + 4 + o, ... (class 1)
-__device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, P1Warp& W, int cls, uint32_t count, P1Stats& st) {
+// strtoull of a field of 1..19 bytes that consists of decimal digits only (no overflow possible), from its masked
+// words - the common case; everything else (whitespace, signs, junk, 20+ characters) takes parse_u64_field.
+// Returns false when the field is not all digits.
+constexpr uint32_t NUM_FAST_MAX = 19;
+__device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, unsigned long long* out) {
+  unsigned long long v = 0;
+  bool ok = true;
+#pragma unroll
+  for (uint32_t k = 0; k < 5; ++k) {
+    if (4u * k < len) {
+      const uint32_t nd = min(4u, len - 4u * k);
+      const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
+      const uint32_t w = (x[k] & keep) | (0x30303030u & ~keep);       // pad with '0'
+      const uint32_t d = w - 0x30303030u;
+      ok = ok && (((w + 0x46464646u) | d) & 0x80808080u) == 0u;        // every byte in '0'..'9'
+      const uint32_t al = nd >= 4u ? d : (d << (8u * (4u - nd)));      // right-align: leading zero digits
+      const uint32_t pairs = (al & 0x00ff00ffu) * 10u + ((al >> 8) & 0x00ff00ffu);
+      const uint32_t v4 = (pairs & 0xffffu) * 100u + (pairs >> 16);
+      const uint32_t scale = nd == 4u ? 10000u : nd == 3u ? 1000u : nd == 2u ? 100u : 10u;
+      v = v * scale + v4;
+    }
+  }
+  *out = v;
+  return ok;
+}
+
+// Processes the 32 queued fields [off, off + 32) of the warp (fewer when `count` < 32): lane l takes field off + l.
+// Short fields are handled from registers with straight-line code; long texts are then worked off four at a time
+// by the octets of the warp.
+__device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, const P1Warp& W, uint32_t off, uint32_t count,
+                                           uint32_t ord0, P1Stats& st) {
   const unsigned lane = lane_id();
-  if (cls == 1) {
-    const unsigned grp = lane >> 3, gl = lane & 7u, om = 0xffu << (grp * 8);
-    for (uint32_t e0 = 0; e0 < count; e0 += 4) {
-      const uint32_t e = e0 + grp;
-      const bool active = e < count;
-      const uint4 ent = W.q[1][active ? e : 0];
-      bool is_new;
-      const uint32_t slot = ht_upsert_long(A, wlast, ent.x, ent.y, gl, om, active, &is_new);
-      if (active && gl == 0) {
-        A.rec_col[ent.w] = ent.z;
-        A.rec_val[ent.w] = slot;
-        if (__ldcg(A.colset + ent.z) == 0u) A.colset[ent.z] = 1u;
+  const bool valid = lane < count;
+  uint32_t start = 0, len = 0, col = 0;
+  uint8_t t = 0;
+  if (valid) {
+    start = W.start[off + lane];
+    len = W.len[off + lane];
+    col = W.col[off + lane];
+    t = __ldg(A.types + col);
+  }
+  const uint32_t ord = ord0 + lane;
+  const bool text = is_text_like(t);
+  bool is_long = false;
+  if (valid && len == 0) {
+    A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one (or the row is malformed)
+  } else if (valid) {
+    if (len <= (text ? SHORT_MAX : NUM_FAST_MAX)) {
+      uint32_t x[5];
+      short_words<5>(A.buf + start, len, wlast, x);
+      if (text) {
+        bool is_new;
+        const uint32_t slot = ht_upsert_short(A, wlast, start, len, x, &is_new);
+        A.rec_col[ord] = col;
+        A.rec_val[ord] = slot;
+        if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
         if (is_new) {
           ++st.new_count;
-          st.new_bytes += (unsigned long long)ent.y + 1ull;
-          st.max_len = max(st.max_len, ent.y);
+          st.new_bytes += (unsigned long long)len + 1ull;
+          st.max_len = max(st.max_len, len);
+        }
+      } else {
+        unsigned long long v1, v2;
+        if (t == ZDWB_CHAR) {
+          // sign-extended first byte (+ second byte * 256): min/max rule ConvertToZDW.cpp:358-361 (second byte only
+          // after a backslash), pass-2 rule :543-547 (always)
+          const long long b0 = (long long)(int8_t)(x[0] & 0xffu);
+          const long long b1 = len > 1 ? (long long)((int32_t)(int8_t)((x[0] >> 8) & 0xffu) * 256) : 0ll;
+          v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
+          v2 = (unsigned long long)(b0 + b1);
+        } else {
+          if (!digits_value(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);  // strtoull, :385,564
+          v2 = v1;
+        }
+        A.rec_col[ord] = col;
+        A.rec_val[ord] = v2;
+        if (v1 != 0) {  // zero / empty numeric cells take no part in min/max: :362,386
+          if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
+          if (v1 < __ldcg(A.colmin + col)) atomicMin(A.colmin + col, v1);
+          if (v1 > __ldcg(A.colmax + col)) atomicMax(A.colmax + col, v1);
         }
       }
-    }
-    return;
-  }
-  if (lane >= count) return;
-  const uint4 ent = W.q[cls][lane];
-  const uint32_t start = ent.x, len = ent.y, col = ent.z, ord = ent.w;
-  if (cls == 0) {
-    bool is_new;
-    const uint32_t slot = ht_upsert_short(A, wlast, start, len, &is_new);
-    A.rec_col[ord] = col;
-    A.rec_val[ord] = slot;
-    if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
-    if (is_new) {
-      ++st.new_count;
-      st.new_bytes += (unsigned long long)len + 1ull;
-      st.max_len = max(st.max_len, len);
-    }
-  } else {
-    const uint8_t t = __ldg(A.types + col);
-    const uint8_t* p = A.buf + start;
-    unsigned long long v1, v2;
-    if (t == ZDWB_CHAR) {
-      v1 = char_tuple(p, len, false);  // min/max rule, ConvertToZDW.cpp:358-361
-      v2 = char_tuple(p, len, true);   // pass-2 rule, :543-547
+    } else if (!text) {
+      unsigned long long v1, v2;
+      const uint8_t* p = A.buf + start;
+      if (t == ZDWB_CHAR) {
+        v1 = char_tuple(p, len, false);
+        v2 = char_tuple(p, len, true);
+      } else {
+        v1 = v2 = parse_u64_field(p, len);
+      }
+      A.rec_col[ord] = col;
+      A.rec_val[ord] = v2;
+      if (v1 != 0) {
+        if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
+        if (v1 < __ldcg(A.colmin + col)) atomicMin(A.colmin + col, v1);
+        if (v1 > __ldcg(A.colmax + col)) atomicMax(A.colmax + col, v1);
+      }
     } else {
-      v1 = v2 = parse_u64_field(p, len);  // strtoull, :385,564
+      is_long = true;
     }
-    A.rec_col[ord] = col;
-    A.rec_val[ord] = v2;
-    if (v1 != 0) {  // zero / empty numeric cells take no part in min/max: :362,386
-      if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
-      if (v1 < __ldcg(A.colmin + col)) atomicMin(A.colmin + col, v1);
-      if (v1 > __ldcg(A.colmax + col)) atomicMax(A.colmax + col, v1);
+  }
+  // ---- long texts: octet g takes the g-th, (g+4)-th, ... of them
+  unsigned todo = __ballot_sync(0xffffffffu, is_long);
+  const unsigned grp = lane >> 3, gl = lane & 7u, om = 0xffu << (grp * 8);
+  while (todo) {
+    // the source lane of this octet: the (grp+1)-th set bit of todo
+    unsigned m = todo;
+    for (unsigned k = 0; k < grp && m; ++k) m &= m - 1;
+    const bool active = m != 0u;
+    const int src = active ? __ffs(m) - 1 : 0;
+    const uint32_t s2 = __shfl_sync(0xffffffffu, start, src), l2 = __shfl_sync(0xffffffffu, len, src),
+                   c2 = __shfl_sync(0xffffffffu, col, src);
+    bool is_new;
+    const uint32_t slot = ht_upsert_long(A, wlast, s2, l2, gl, om, active, &is_new);
+    if (active && gl == 0) {
+      const uint32_t o2 = ord0 + (uint32_t)src;
+      A.rec_col[o2] = c2;
+      A.rec_val[o2] = slot;
+      if (__ldcg(A.colset + c2) == 0u) A.colset[c2] = 1u;
+      if (is_new) {
+        ++st.new_count;
+        st.new_bytes += (unsigned long long)l2 + 1ull;
+        st.max_len = max(st.max_len, l2);
+      }
     }
+    // drop the (up to) four texts just handled
+    for (int k = 0; k < 4 && todo; ++k) todo &= todo - 1;
   }
 }
 
@@ -590,7 +676,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_pass1(const P1Args A) {
   WarpCarry c;
   carry_init(A.buf, t0, A.pre[tile], c);
   P1Stats st = {0u, 0u, 0u, 0ull};
-  uint32_t qn[3] = {0u, 0u, 0u};
+  uint32_t qbase = c.ne;  // ordinal of the field held in queue slot 0
   const uint32_t tabs_per_row = A.ncols - 1u;
   if (tile == 0 && lane == 0) A.row_rec[0] = 0u;
 
@@ -611,63 +697,57 @@ __global__ void __launch_bounds__(ENC_THREADS) k_pass1(const P1Args A) {
       st.max_line = max(st.max_line, (uint32_t)(L.p0 + i - row_start + 1));
       A.row_rec[R + 1u] = L.nes + (uint32_t)__popc(L.ne & ((2u << i) - 1u));
     }
-    // ---- non-empty fields: one per lane per round into the class queues
+    // ---- non-empty fields go to the warp's queue; the slot is the field's ordinal, so no coordination is needed
     uint32_t rem = L.ne;
     const uint32_t bound = L.tab | L.term | L.skip;
-    while (__any_sync(0xffffffffu, rem != 0u)) {
-      int cls = -1;
-      uint4 ent = make_uint4(0u, 0u, 0u, 0u);
-      if (rem) {
-        const int i = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const uint32_t below = (1u << i) - 1u;
-        const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
-        const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
-        const uint32_t col = T - R * tabs_per_row;
-        const uint32_t lowb = bound & below;
-        const uint32_t start = (uint32_t)((lowb ? L.p0 + (31 - __clz(lowb)) : L.pb) + 1);
-        uint32_t len = (uint32_t)(L.p0 + i) - start;
-        const uint32_t ord = L.nes + (uint32_t)__popc(L.ne & below);
-        if (col < A.ncols) {  // (a malformed row is reported through bad_row)
-          if (A.trim) len = trimmed_len(A.buf, start, len);
-          if (len == 0) {
-            A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one
-          } else {
-            cls = is_text_like(__ldg(A.types + col)) ? (len <= SHORT_MAX ? 0 : 1) : 2;
-            ent = make_uint4(start, len, col, ord);
-          }
-        } else {
-          A.rec_col[ord] = REC_EMPTY;
-        }
+    while (rem) {
+      const int i = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const uint32_t below = (1u << i) - 1u;
+      const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
+      const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
+      uint32_t col = T - R * tabs_per_row;
+      const uint32_t lowb = bound & below;
+      const uint32_t start = (uint32_t)((lowb ? L.p0 + (31 - __clz(lowb)) : L.pb) + 1);
+      uint32_t len = (uint32_t)(L.p0 + i) - start;
+      const uint32_t q = L.nes + (uint32_t)__popc(L.ne & below) - qbase;
+      if (col >= A.ncols) {  // (a malformed row is reported through bad_row)
+        col = 0;
+        len = 0;
+      } else if (A.trim) {
+        len = trimmed_len(A.buf, start, len);
       }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == k);
-        if (cls == k) W.q[k][qn[k] + __popc(m & lanemask_lt())] = ent;
-        qn[k] += __popc(m);
+      W.start[q] = start;
+      W.len[q] = len;
+      W.col[q] = col;
+    }
+    __syncwarp();
+    // ---- work off full batches
+    const uint32_t have = c.ne - qbase;
+    uint32_t off = 0;
+    for (; off + 32u <= have; off += 32u) p1_process(A, wlast, W, off, 32u, qbase + off, st);
+    if (off) {
+      __syncwarp();
+      const uint32_t left = have - off;  // < 32
+      uint32_t a = 0, b = 0, d = 0;
+      if (lane < left) {
+        a = W.start[off + lane];
+        b = W.len[off + lane];
+        d = W.col[off + lane];
       }
       __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (qn[k] >= 32u) {
-          p1_process(A, wlast, W, k, 32u, st);
-          __syncwarp();
-          // move the leftovers to the front
-          const uint32_t left = qn[k] - 32u;
-          uint4 mv = make_uint4(0u, 0u, 0u, 0u);
-          if (lane < left) mv = W.q[k][32u + lane];
-          __syncwarp();
-          if (lane < left) W.q[k][lane] = mv;
-          qn[k] = left;
-          __syncwarp();
-        }
+      if (lane < left) {
+        W.start[lane] = a;
+        W.len[lane] = b;
+        W.col[lane] = d;
       }
+      qbase += off;
     }
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (qn[k]) p1_process(A, wlast, W, k, qn[k], st);
     __syncwarp();
+  }
+  {
+    const uint32_t have = c.ne - qbase;
+    if (have) p1_process(A, wlast, W, 0, have, qbase, st);
   }
   // ---- warp totals
   st.max_line = __reduce_max_sync(0xffffffffu, st.max_line);

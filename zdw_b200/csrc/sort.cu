@@ -4,9 +4,8 @@
 // dictionary.h:30-35) whose in-order walk defines the on-disk dictionary order (dictionary.cpp:99-108).
 //
 // Two paths, same result:
-//   * small dictionaries (n <= Ctx::small_sort_max, typical for analytics-shaped data): one CTA,
-//     bitonic network in shared memory over (8-byte big-endian prefix key, id), ties broken by a
-//     byte-wise compare of the remaining bytes;
+//   * small dictionaries (n <= Ctx::small_sort_max, typical for analytics-shaped data): rank by counting over
+//     16-byte big-endian prefix keys, all pairs in parallel, ties broken by a byte-wise compare of the remaining bytes;
 //   * large dictionaries: LSD radix sort on the 8-byte prefix, then iterative refinement - strings that
 //     still tie are re-sorted by (tie-group id, next 8 bytes) until every group is a singleton.  Because
 //     the strings are distinct and contain no NUL, zero padding makes "shorter prefix sorts first" fall
@@ -203,9 +202,13 @@ __global__ void k_scatter_order(const uint32_t* __restrict__ pos, const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// small path: one CTA, bitonic network in shared memory
+// small path: rank by counting.  rank(i) = #{ j : s_j < s_i }, all pairs compared on 16-byte big-endian prefix
+// keys held in shared memory; only pairs whose prefixes tie fall back to the bytes in memory.  O(n^2) key
+// compares spread over the whole GPU beat a one-CTA sorting network for the dictionary sizes of analytics-shaped
+// blocks (a few thousand strings).
 // ---------------------------------------------------------------------------------------------
-constexpr int SS_THREADS = 1024;
+constexpr int RK_THREADS = 256;
+constexpr int RK_JTILE = 1024;
 
 __device__ __forceinline__ bool str_less_from(const uint8_t* base, uint32_t sa, uint32_t la, uint32_t sb, uint32_t lb,
                                               uint32_t from) {
@@ -217,53 +220,40 @@ __device__ __forceinline__ bool str_less_from(const uint8_t* base, uint32_t sa, 
   return la < lb;
 }
 
-__global__ void __launch_bounds__(SS_THREADS)
-    k_small_sort(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
-                 uint32_t n, uint32_t npow2, uint32_t* __restrict__ order) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t* key = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* id = reinterpret_cast<uint32_t*>(smem_raw + (size_t)npow2 * 8);
-  for (uint32_t i = threadIdx.x; i < npow2; i += SS_THREADS) {
-    if (i < n) {
-      key[i] = prefix_key(base + starts[i], lens[i], 0);
-      id[i] = i;
-    } else {
-      key[i] = ~0ull;
-      id[i] = 0xffffffffu;  // sentinel: greater than every real string
-    }
-  }
+__global__ void k_rank_keys(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts,
+                            const uint32_t* __restrict__ lens, uint32_t n, ulonglong2* __restrict__ keys) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* s = base + starts[i];
+  const uint32_t len = lens[i];
+  keys[i] = make_ulonglong2(prefix_key(s, len, 0), prefix_key(s, len, 8));
+}
+
+__global__ void __launch_bounds__(RK_THREADS)
+    k_rank_count(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
+                 const ulonglong2* __restrict__ keys, uint32_t n, uint32_t* __restrict__ rank) {
+  __shared__ ulonglong2 sk[RK_JTILE];
+  const uint32_t j0 = blockIdx.y * RK_JTILE, jn = min((uint32_t)RK_JTILE, n - j0);
+  for (uint32_t t = threadIdx.x; t < jn; t += RK_THREADS) sk[t] = keys[j0 + t];
   __syncthreads();
-  for (uint32_t k = 2; k <= npow2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = threadIdx.x; t < (npow2 >> 1); t += SS_THREADS) {
-        // t-th compare-exchange pair of this stage: insert a zero bit at position log2(j)
-        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const uint32_t l = i | j;
-        const bool asc = (i & k) == 0;
-        const uint64_t ka = key[i], kb = key[l];
-        const uint32_t ia = id[i], ib = id[l];
-        bool a_less_b;  // strict
-        if (ia == 0xffffffffu) a_less_b = false;
-        else if (ib == 0xffffffffu) a_less_b = true;
-        else if (ka != kb) a_less_b = ka < kb;
-        else a_less_b = str_less_from(base, starts[ia], lens[ia], starts[ib], lens[ib], 8);
-        bool b_less_a;
-        if (ib == 0xffffffffu) b_less_a = false;
-        else if (ia == 0xffffffffu) b_less_a = true;
-        else if (ka != kb) b_less_a = kb < ka;
-        else b_less_a = !a_less_b && ia != ib;  // distinct strings: exactly one is smaller
-        const bool swap = asc ? b_less_a : a_less_b;
-        if (swap) {
-          key[i] = kb;
-          key[l] = ka;
-          id[i] = ib;
-          id[l] = ia;
-        }
-      }
-      __syncthreads();
+  const uint32_t i = blockIdx.x * RK_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2 me = keys[i];
+  uint32_t cnt = 0;
+  for (uint32_t t = 0; t < jn; ++t) {
+    const ulonglong2 o = sk[t];
+    if (o.x < me.x || (o.x == me.x && o.y < me.y)) {
+      ++cnt;
+    } else if (o.x == me.x && o.y == me.y && j0 + t != i) {
+      if (str_less_from(base, starts[j0 + t], lens[j0 + t], starts[i], lens[i], 16)) ++cnt;
     }
   }
-  for (uint32_t i = threadIdx.x; i < n; i += SS_THREADS) order[i] = id[i];
+  if (cnt) atomicAdd(rank + i, cnt);
+}
+
+__global__ void k_rank_scatter(const uint32_t* __restrict__ rank, uint32_t n, uint32_t* __restrict__ order) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[rank[i]] = i;
 }
 
 }  // namespace
@@ -275,15 +265,27 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
 
   // ---- small path
   long long small_max = ctx->small_sort_max;
-  if (small_max > 16384) small_max = 16384;
+  if (small_max > 32768) small_max = 32768;
   if ((long long)n <= small_max) {
-    uint32_t np2 = 2;
-    while (np2 < n) np2 <<= 1;
-    const size_t smem = (size_t)np2 * 12;
-    ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_small_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
+    DevBuf keys, rank;
+    ZDWB_TRY(keys.alloc(ctx, (size_t)n * sizeof(ulonglong2)));
+    ZDWB_TRY(rank.alloc(ctx, (size_t)n * 4));
+    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(rank.p, 0, (size_t)n * 4, st));
+    const unsigned gi = (n + RK_THREADS - 1) / RK_THREADS;
     {
-      KernelScope _ks(ctx, "k_small_sort");
-      k_small_sort<<<1, SS_THREADS, smem, st>>>(base, starts, lens, n, np2, order_out);
+      KernelScope _ks(ctx, "k_rank_keys");
+      k_rank_keys<<<gi, RK_THREADS, 0, st>>>(base, starts, lens, n, keys.as<ulonglong2>());
+    }
+    ZDWB_LAUNCH_CHECK(ctx);
+    {
+      KernelScope _ks(ctx, "k_rank_count");
+      k_rank_count<<<dim3(gi, (n + RK_JTILE - 1) / RK_JTILE), RK_THREADS, 0, st>>>(base, starts, lens, keys.as<ulonglong2>(), n,
+                                                                                 rank.as<uint32_t>());
+    }
+    ZDWB_LAUNCH_CHECK(ctx);
+    {
+      KernelScope _ks(ctx, "k_rank_scatter");
+      k_rank_scatter<<<gi, RK_THREADS, 0, st>>>(rank.as<uint32_t>(), n, order_out);
     }
     ZDWB_LAUNCH_CHECK(ctx);
     return ZDWB_OK;
