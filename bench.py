@@ -303,8 +303,8 @@ def run_cuda(args):
         nb = max(world, int(nb * avail / need))
         args.reduced_from = args.blocks
         args.blocks = nb
-    lo, hi = rank * nb // world, (rank + 1) * nb // world
-    my_blocks = list(range(lo, hi))
+    from zdw_b200.shard import block_range
+    my_blocks = list(block_range(rank, world, nb))
     rows = args.rows_per_block
 
     # ---- host (pinned) inputs
@@ -399,20 +399,28 @@ def run_cuda(args):
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop()
 
-    # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H inside the timed region)
-    def e2e_encode_pass():
-        tot = 0
-        for p, n in zip(host_ptrs, host_lens):
-            blk = L_encode_host(ctx, types, p, n)
-            tot += blk
-        return tot
+    # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region).  Blocks are
+    # independent, so E2E_LANES contexts (one host thread + stream each) work on different blocks at the same time: the
+    # PCIe copy of one block overlaps the kernels of another.  Every call is a plain zdwb_encode_block /
+    # zdwb_decode_block with host pointers; the ZDW blocks / TSV rows come back in pinned host memory.
+    lanes = [Context(local) for _ in range(max(1, args.e2e_lanes))]
+    pool = ThreadPoolExecutor(max_workers=len(lanes))
 
-    def e2e_decode_pass():
-        tot = 0
-        for zb in host_zdw:
-            r = ctx.decode_block(types, zb)
-            tot += r.length
-        return tot
+    def _run_lanes(fn, items):
+        def work(k):
+            tot = 0
+            for j in range(k, len(items), len(lanes)):
+                tot += fn(lanes[k], items[j])
+            return tot
+        return sum(pool.map(work, range(len(lanes))))
+
+    def e2e_encode_pass():
+        return _run_lanes(lambda c, it: L_encode_host(c, types, it[0], it[1]), list(zip(host_ptrs, host_lens)))
+
+    host_zdw_bufs = [(C.c_uint8 * len(zb)).from_buffer_copy(zb) for zb in host_zdw]
+
+    def e2e_decode_pass(items):
+        return _run_lanes(lambda c, it: L_decode_host(c, types, C.addressof(it), len(it)), items)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_encode_pass()
@@ -423,13 +431,17 @@ def run_cuda(args):
         d2h_enc = e2e_encode_pass()
     torch.cuda.synchronize(dev)
     t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
-    e2e_dec_blocks = host_zdw[:max(1, args.e2e_decode_blocks)]
+    e2e_dec_blocks = host_zdw_bufs[:max(1, args.e2e_decode_blocks)]
+    e2e_decode_pass(e2e_dec_blocks[:len(lanes)])  # warm the pinned output buffers of every lane
+    barrier()
     t0 = time.perf_counter()
-    d2h_dec = 0
-    for zb in e2e_dec_blocks:
-        d2h_dec += ctx.decode_block(types, zb).length
+    d2h_dec = e2e_decode_pass(e2e_dec_blocks)
     torch.cuda.synchronize(dev)
     t_e2e_dec = time.perf_counter() - t0
+    launches_e2e = sum(c.kernel_launches() for c in lanes)
+    pool.shutdown()
+    for c in lanes:
+        c.close()
 
     # ---- instrumented step: per-kernel CUDA-event times for the roofline
     ctx.set_tuning("kernel_timing", 1)
@@ -486,7 +498,7 @@ def run_cuda(args):
                        "roofline": roof(kt_dec, "decode")},
             "roofline": roof(kt_enc, "encode"),
             "e2e": {"value": tot_tsv / t_e2e_enc / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(tot_tsv),
-                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned,
+                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "lanes": args.e2e_lanes,
                     "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks),
                     "decode_d2h_bytes": int(d2h_dec_all)},
             "gpu_launches": int(launches_all),
@@ -552,6 +564,22 @@ def _cudart():
     return _CUDART
 
 
+def L_decode_host(ctx, types, ptr: int, n: int) -> int:
+    """Host ZDW block in, host TSV out (left in the context's pinned buffer), no copies through Python."""
+    from zdw_b200 import capi
+    tarr = (C.c_uint8 * len(types))(*types)
+    sch = capi._Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
+    o = capi._DecOpts()
+    o.at_end_of_file = 1
+    o.separator = 9
+    o.rownum_pos = -1
+    out = capi._RowsOut()
+    rc = ctx._L.zdwb_decode_block(ctx._h, C.byref(sch), C.c_void_p(ptr), n, C.byref(o), C.byref(out))
+    if rc:
+        raise RuntimeError(ctx.last_error())
+    return int(out.len)
+
+
 def L_encode_host(ctx, types, ptr: int, n: int) -> int:
     """Host pointer in, host bytes out, without copying the input through Python."""
     from zdw_b200 import capi
@@ -574,7 +602,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=TOTAL_BLOCKS)
     ap.add_argument("--rows-per-block", type=int, default=ROWS_PER_BLOCK)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-decode-blocks", type=int, default=8)
+    ap.add_argument("--e2e-decode-blocks", type=int, default=16)
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="contexts (host thread + stream) that overlap copies and kernels in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=131072, help="rows of the bounded cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")
     ap.add_argument("--ref-procs", type=int, default=32)
