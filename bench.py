@@ -439,6 +439,24 @@ def run_cuda(args):
     torch.cuda.synchronize(dev)
     t_e2e_dec = time.perf_counter() - t0
     launches_e2e = sum(c.kernel_launches() for c in lanes)
+    # plain pinned-host <-> device copies of one block: the PCIe ceiling the e2e numbers sit under
+    pcie = {}
+    try:
+        hp = torch.empty(host_lens[0], dtype=torch.uint8).pin_memory()
+        dp = torch.empty(host_lens[0], dtype=torch.uint8, device=dev)
+        for name, (dst, src) in (("h2d_gbs", (dp, hp)), ("d2h_gbs", (hp, dp))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            e1.record(stream)
+            e1.synchronize()
+            pcie[name] = 3 * host_lens[0] / (e0.elapsed_time(e1) / 1e3) / 1e9
+        del hp, dp
+    except Exception as ex:  # noqa: BLE001
+        pcie = {"error": str(ex)}
     pool.shutdown()
     for c in lanes:
         c.close()
@@ -498,7 +516,7 @@ def run_cuda(args):
                        "roofline": roof(kt_dec, "decode")},
             "roofline": roof(kt_enc, "encode"),
             "e2e": {"value": tot_tsv / t_e2e_enc / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(tot_tsv),
-                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "lanes": args.e2e_lanes,
+                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "lanes": args.e2e_lanes, "pcie_copy_gbs": pcie,
                     "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks),
                     "decode_d2h_bytes": int(d2h_dec_all)},
             "gpu_launches": int(launches_all),

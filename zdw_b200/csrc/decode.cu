@@ -49,6 +49,7 @@ struct DecParams {
   const unsigned long long* ubase;  // [U]
   const uint8_t* utype;        // [U]
   const uint32_t* planes;      // [4][W] bit k of the width of used column u, as flag-word masks
+  const uint32_t* nulmap;      // bit i = dictionary byte i is NUL (one all-ones word appended): entry lengths in O(1)
 };
 
 __device__ __forceinline__ uint32_t stream_byte(const DecParams& P, uint64_t s) {
@@ -322,43 +323,87 @@ struct FmtTables {
   uint32_t n_groups;
   uint32_t static_total;
   unsigned long long first_row;  // number of the block's first row, for the virtual row-number item
+  uint32_t rownum_item;          // index of that item, ITEM_ROWNUM (= none) otherwise
 };
 constexpr uint32_t ITEM_ROWNUM = 0xffffffffu;  // item_u marker: the item is the running row number, not a used column
 
-// strlen of the dictionary entry at s, at most `room` bytes: aligned 32-bit loads + zero-byte detect
-// (GetWord + strlen, UnconvertFromZDW.cpp:359-371,1380)
-__device__ __forceinline__ uint32_t dict_strlen(const uint8_t* __restrict__ s, uint64_t room) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  const uint32_t lead = (uint32_t)(a & 3u);
-  uint32_t x = __ldg(w) | ((1u << (lead * 8u)) - 1u);  // bytes in front of s never terminate
-  int64_t done = -(int64_t)lead;                       // bytes of the string covered so far
-  for (;;) {
-    const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;
-    if (z) {
-      const uint64_t l = (uint64_t)(done + ((__ffs(z) - 1) >> 3));
-      return (uint32_t)(l < room ? l : room);
+// bit i of nulmap = dictionary byte i is NUL; 16 bytes per thread
+__global__ void k_dict_nulmap(const uint8_t* __restrict__ dict, uint64_t dict_total, uint32_t* __restrict__ nulmap, uint64_t nwords) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  uint32_t m = 0;
+  const uint64_t b0 = w * 32;
+  if (b0 + 36 <= dict_total) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dict + b0);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    uint32_t prev = __ldg(p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t nx = __ldg(p + k + 1);
+      const uint32_t x = __funnelshift_r(prev, nx, sh);
+      prev = nx;
+      // exact zero-byte flags (bit 7 of every zero byte), gathered to 4 bits
+      const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+      m |= movemask4(z) << (4 * k);
     }
-    done += 4;
-    if ((uint64_t)done >= room) return (uint32_t)room;
-    x = __ldg(++w);
+  } else {
+    for (uint32_t i = 0; i < 32; ++i) {
+      const uint64_t b = b0 + i;
+      if (b >= dict_total || __ldg(dict + b) == 0) m |= 1u << i;  // everything past the dictionary terminates
+    }
+  }
+  nulmap[w] = m;
+}
+
+// strlen of the dictionary entry at byte `index` (GetWord + strlen, UnconvertFromZDW.cpp:359-371,1380), at most room
+__device__ __forceinline__ uint32_t dict_strlen(const DecParams& P, uint32_t index, uint64_t room) {
+  const uint32_t* bm = P.nulmap + (index >> 5);
+  const uint32_t sh = index & 31u;
+  uint32_t w = __ldg(bm) >> sh;
+  if (w) return (uint32_t)min((uint64_t)(__ffs(w) - 1), room);
+  uint64_t pos = 32u - sh;
+  for (;;) {
+    if (pos >= room) return (uint32_t)room;
+    w = __ldg(++bm);
+    if (w) return (uint32_t)min(pos + (uint64_t)(__ffs(w) - 1), room);
+    pos += 32;
   }
 }
 
+__device__ __forceinline__ uint32_t digits_u32(uint32_t x) {
+  return x < 10u ? 1u : x < 100u ? 2u : x < 1000u ? 3u : x < 10000u ? 4u : x < 100000u ? 5u : x < 1000000u ? 6u
+         : x < 10000000u ? 7u : x < 100000000u ? 8u : x < 1000000000u ? 9u : 10u;
+}
 __device__ __forceinline__ uint32_t digits_u64(unsigned long long v) {
-  if (v < 10ull) return 1;
-  if (v <= 0xffffffffull) {
-    const uint32_t x = (uint32_t)v;
-    return x < 100u ? 2u : x < 1000u ? 3u : x < 10000u ? 4u : x < 100000u ? 5u : x < 1000000u ? 6u : x < 10000000u ? 7u
-           : x < 100000000u ? 8u : x < 1000000000u ? 9u : 10u;
+  if (v <= 0xffffffffull) return digits_u32((uint32_t)v);
+  if (v < 100000000000000ull) {  // < 10^14
+    return v < 10000000000ull ? 10u : v < 100000000000ull ? 11u : v < 1000000000000ull ? 12u : v < 10000000000000ull ? 13u : 14u;
   }
-  uint32_t n = 10;
-  v /= 10000000000ull;
-  while (v) {
-    ++n;
-    v /= 10;
+  return v < 1000000000000000ull ? 15u : v < 10000000000000000ull ? 16u : v < 100000000000000000ull ? 17u
+         : v < 1000000000000000000ull ? 18u : v < 10000000000000000000ull ? 19u : 20u;
+}
+
+// decimal text of v, exactly len = digits_u64(v) characters, ending at d + len: 9-digit groups in 32-bit arithmetic
+__device__ __forceinline__ void write_u64(unsigned long long v, uint32_t len, uint8_t* __restrict__ d) {
+  uint32_t p = len;
+  while (v > 0xffffffffull) {
+    const unsigned long long q = v / 1000000000ull;
+    uint32_t r = (uint32_t)(v - q * 1000000000ull);
+    v = q;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const uint32_t t = r / 10u;
+      d[--p] = (uint8_t)('0' + (r - t * 10u));
+      r = t;
+    }
   }
-  return n;
+  uint32_t x = (uint32_t)v;
+  while (p) {
+    const uint32_t t = x / 10u;
+    d[--p] = (uint8_t)('0' + (x - t * 10u));
+    x = t;
+  }
 }
 
 // Length of the text of used column u holding stored value v.  Mirrors the switch in readNextRow
@@ -371,7 +416,7 @@ __device__ __forceinline__ uint32_t value_len(const DecParams& P, uint32_t u, ui
       meta->err = 1;
       return 0;
     }
-    return dict_strlen(P.blk + P.dict_base + index, P.dict_total - index);
+    return dict_strlen(P, index, P.dict_total - index);
   }
   if (t == ZDWB_CHAR) {  // :1396-1420
     if (v == 0) return 0;
@@ -428,8 +473,12 @@ __device__ __forceinline__ void value_write(const DecParams& P, uint32_t u, uint
   unsigned long long full = v ? v + P.ubase[u] : 0ull;
   if (is_signed_int_type(t) && (long long)full < 0) {
     // lltoa: value = -value (overflows for INT64_MIN), then signed % 10 and / 10; digit byte = rem + '0'
-    long long sv = (long long)(0ull - full);
     d[0] = (uint8_t)'-';
+    if (full != 0x8000000000000000ull) {
+      write_u64(0ull - full, len - 1, d + 1);
+      return;
+    }
+    long long sv = (long long)full;  // INT64_MIN: every remainder is negative
     uint32_t p = len;
     do {
       const long long rem = sv % 10;
@@ -438,21 +487,7 @@ __device__ __forceinline__ void value_write(const DecParams& P, uint32_t u, uint
     } while (sv != 0 && p > 1);
     return;
   }
-  uint32_t p = len;
-  if (full <= 0xffffffffull) {
-    uint32_t x = (uint32_t)full;
-    do {
-      const uint32_t q = x / 10u;
-      d[--p] = (uint8_t)('0' + (x - q * 10u));
-      x = q;
-    } while (p);
-    return;
-  }
-  do {
-    const unsigned long long q = full / 10ull;
-    d[--p] = (uint8_t)('0' + (uint32_t)(full - q * 10ull));
-    full = q;
-  } while (p);
+  write_u64(full, len, d);
 }
 
 constexpr uint32_t FMT_SHORT = 16;   // texts up to this length go through a thread's text cache
@@ -506,116 +541,180 @@ __device__ __forceinline__ void warp_write_template(const FmtTables& FT, const u
   }
 }
 
-// Shared-memory carve-up of k_dec_format (host and device must agree).
-struct FmtSmem {
-  size_t val, lenu, ioff, rowoff, sflag, planes, cinv, cinl, textc, obuf, total;
-  __host__ __device__ FmtSmem(uint32_t R, uint32_t U, uint32_t NI, uint32_t F, uint32_t W, uint32_t out_cap) {
-    size_t o = 0;
-    val = o;    o += (size_t)R * U * 8;
-    cinv = o;   o += (size_t)U * 8;
-    lenu = o;   o += (size_t)R * U * 4;
-    ioff = o;   o += (size_t)R * (NI + 1) * 4;
-    rowoff = o; o += (size_t)(R + 1) * 4;
-    planes = o; o += (size_t)4 * W * 4;
-    cinl = o;   o += (size_t)U * 4;
-    sflag = o;  o += (size_t)R * F;
-    o = (o + 15) & ~(size_t)15;
-    textc = o;  o += (size_t)DEC_THREADS * FMT_TEXTC;
-    obuf = o;   o += (size_t)out_cap + 16;
-    total = o;
-  }
+// ---------------------------------------------------------------------------------------------
+// streaming row writer: one warp owns a strip of consecutive rows and walks them in order, keeping for every used
+// column that is output its current value, text length and (for texts of up to 16 bytes) the rendered text in shared
+// memory.  A row only touches the columns its flag bits name; everything else is copied from the warp's state.  No
+// CTA-wide barrier, no cross-warp dependency: k_dec_row_lens measures every row first (same walk, lengths only), an
+// exclusive scan turns the lengths into row offsets, k_dec_write_rows then assembles each row in shared memory and
+// flushes it with coalesced stores.
+// ---------------------------------------------------------------------------------------------
+struct WarpLayout {        // byte offsets inside a warp's slice of dynamic shared memory
+  uint32_t o_len, o_val, o_textc, o_ioff, o_llist, o_rowbuf;
+  uint32_t stride;         // bytes per warp
+  uint32_t rowcap;         // bytes of row staging (0 = always assemble in global memory)
+  uint32_t warps;          // warps per CTA
 };
 
-// One strip of R rows: explicit values -> fill forward -> text lengths -> row offsets (decoupled look-back over
-// strips) -> rows assembled in shared memory -> coalesced stores.
-__global__ void __launch_bounds__(DEC_THREADS)
-    k_dec_format(const DecParams P, const FmtTables FT, const uint32_t* __restrict__ row_off, uint32_t R, uint32_t out_smem_cap,
-                 const unsigned long long* __restrict__ cin, uint64_t* __restrict__ strip_status, uint8_t* __restrict__ out,
-                 uint64_t out_cap, uint64_t* __restrict__ out_row_off, DecMeta* __restrict__ meta) {
-  extern __shared__ __align__(16) uint8_t dsm[];
-  __shared__ uint32_t s_strip, s_nexp, s_nlong;
-  __shared__ unsigned long long s_base;
-  const uint32_t U = P.U, F = P.F, NI = FT.n_items;
-  const FmtSmem L(R, U, NI, F, P.W, out_smem_cap);
-  unsigned long long* val = reinterpret_cast<unsigned long long*>(dsm + L.val);
-  unsigned long long* cinv = reinterpret_cast<unsigned long long*>(dsm + L.cinv);
-  uint32_t* lenu = reinterpret_cast<uint32_t*>(dsm + L.lenu);
-  uint32_t* ioff = reinterpret_cast<uint32_t*>(dsm + L.ioff);
-  uint32_t* rowoff = reinterpret_cast<uint32_t*>(dsm + L.rowoff);
-  uint32_t* planes = reinterpret_cast<uint32_t*>(dsm + L.planes);
-  uint32_t* cinl = reinterpret_cast<uint32_t*>(dsm + L.cinl);
-  uint8_t* sflag = dsm + L.sflag;
-  uint8_t* textc = dsm + L.textc + (size_t)threadIdx.x * FMT_TEXTC;
-  uint8_t* obuf = dsm + L.obuf;
-  unsigned long long* elist = reinterpret_cast<unsigned long long*>(obuf);  // explicit values; dead before obuf is used
-  uint32_t* llist = lenu;                                                   // long items; lenu is dead by then
-  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+struct WarpState {
+  uint32_t* len;              // [U]
+  unsigned long long* val;    // [U]
+  uint32_t* textc;            // [U][4]
+  uint32_t* ioff;             // [NI + 1]
+  uint32_t* llist;            // [1 + max(U, NI)]  ([0] = count)
+  uint8_t* rowbuf;
+};
 
-  if (tid == 0) {
-    s_strip = atomicAdd(&meta->tile_ticket, 1u);
-    s_nexp = 0;
-    s_nlong = 0;
-  }
-  for (uint32_t i = tid; i < 4 * P.W; i += DEC_THREADS) planes[i] = P.planes[i];
-  __syncthreads();
-  const uint32_t strip = s_strip;
-  const uint32_t r0 = strip * R, r1 = min(P.nrows, r0 + R), Rn = r1 - r0;
-  const uint8_t* rows = P.blk + P.rows_base;
+__device__ __forceinline__ uint32_t has_zero_byte(uint32_t x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
 
-  // ---- 1. where the explicit values of this strip are
-  for (uint32_t j = warp; j < Rn; j += DEC_WARPS) {
-    const uint32_t ro = row_off[r0 + j];
-    const uint8_t* rp = rows + ro;
-    for (uint32_t k = lane; k < F; k += 32) sflag[j * F + k] = __ldg(rp + k);
-    warp_parse_row(P, planes, rp, [&](uint32_t u, uint32_t voff) {
-      const uint32_t e = atomicAdd(&s_nexp, 1u);
-      elist[e] = ((unsigned long long)(ro + voff) << 32) | (unsigned long long)((j << 24) | u);
-    });
-  }
-  __syncthreads();
-  // ---- 2. load them and measure their text, all at once; same for the values carried into the strip
-  {
-    const uint32_t nexp = s_nexp;
-    for (uint32_t e = tid; e < nexp; e += DEC_THREADS) {
-      const unsigned long long ent = elist[e];
-      const uint32_t u = (uint32_t)ent & 0xffffffu, j = ((uint32_t)ent >> 24) & 0xffu;
-      const unsigned long long v = load_le(rows + (uint32_t)(ent >> 32), P.usz[u]);
-      val[(size_t)j * U + u] = v;
-      lenu[(size_t)j * U + u] = value_len(P, u, P.utype[u], v, meta);
-    }
-    for (uint32_t u = tid; u < U; u += DEC_THREADS) {
-      const unsigned long long v = cin[(size_t)strip * U + u];
-      cinv[u] = v;
-      cinl[u] = value_len(P, u, P.utype[u], v, meta);
-    }
-  }
-  __syncthreads();
-  // ---- 3. fill forward: a column keeps its value - and its text length - until a row flags it again (:1339-1345)
-  for (uint32_t u = tid; u < U; u += DEC_THREADS) {
-    unsigned long long v = cinv[u];
-    uint32_t len = cinl[u];
-    const uint32_t fb = u >> 3, bit = u & 7u;
-    for (uint32_t j = 0; j < Rn; ++j) {
-      if ((sflag[j * F + fb] >> bit) & 1u) {
-        v = val[(size_t)j * U + u];
-        len = lenu[(size_t)j * U + u];
+// New value v for used column u.  Returns true when the column now holds a dictionary text longer than 16 bytes,
+// whose length is still to be measured (octet_strlen); otherwise len[u] (and, when WRITE, textc[u]) are up to date.
+template <bool WRITE>
+__device__ __forceinline__ bool set_column(const DecParams& P, const WarpState& S, uint32_t u, unsigned long long v,
+                                           DecMeta* meta) {
+  const uint8_t t = P.utype[u];
+  if (WRITE) S.val[u] = v;
+  if (is_text_like(t)) {
+    if (v == 0) {
+      if (t == ZDWB_DECIMAL) {  // outputDefault(DECIMAL): "0.000000000000"
+        S.len[u] = 14;
+        if (WRITE) {
+          uint32_t* tc = S.textc + 4 * (size_t)u;
+          tc[0] = 0x30302e30u;
+          tc[1] = 0x30303030u;
+          tc[2] = 0x30303030u;
+          tc[3] = 0x00003030u;
+        }
       } else {
-        val[(size_t)j * U + u] = v;
-        lenu[(size_t)j * U + u] = len;
+        S.len[u] = 0;
       }
+      return false;
     }
+    const uint32_t index = (uint32_t)(v + P.ubase[u]);  // ULONG index: UnconvertFromZDW.cpp:1363
+    if ((uint64_t)index > P.dict_total) {                // :1364 (the reference allows index == dictionarySize)
+      meta->err = 1;
+      S.len[u] = 0;
+      if (WRITE) S.val[u] = 0;
+      return false;
+    }
+    const uint32_t l = dict_strlen(P, index, P.dict_total - index);
+    S.len[u] = l;
+    if (WRITE && l && l <= 16) {  // short texts are kept rendered; longer ones are copied from the dictionary per row
+      const uint8_t* s = P.blk + P.dict_base + index;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      const uint32_t* wend = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.blk + P.avail - 1) & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+      const uint32_t lim = (uint32_t)min((ptrdiff_t)4, wend - w);
+      const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, lim)), w2 = __ldg(w + min(2u, lim)), w3 = __ldg(w + min(3u, lim)),
+                     w4 = __ldg(w + min(4u, lim));
+      uint32_t* tc = S.textc + 4 * (size_t)u;
+      tc[0] = __funnelshift_r(w0, w1, sh);
+      tc[1] = __funnelshift_r(w1, w2, sh);
+      tc[2] = __funnelshift_r(w2, w3, sh);
+      tc[3] = __funnelshift_r(w3, w4, sh);
+    }
+    return false;
   }
-  __syncthreads();
-  // ---- 4. offset of every item's text among the dynamic bytes of its row; row lengths; strip total
-  for (uint32_t j = warp; j < Rn; j += DEC_WARPS) {
+  const uint32_t l = value_len(P, u, t, v, meta);
+  S.len[u] = l;
+  if (WRITE && l && l <= 16) value_write(P, u, t, v, l, reinterpret_cast<uint8_t*>(S.textc + 4 * (size_t)u));
+  return false;
+}
+
+// n bytes from the dictionary to a row by the 8 lanes of an octet, 4 bytes per lane per step
+__device__ __forceinline__ void octet_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, unsigned gl) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  for (uint32_t k = gl * 4; k < n; k += 32) {
+    const uint32_t nb = n - k;
+    const uint32_t lo = __ldg(w + (k >> 2));
+    const uint32_t hi = (sh + min(nb, 4u) * 8u > 32u) ? __ldg(w + (k >> 2) + 1) : 0u;
+    const uint32_t x = __funnelshift_r(lo, hi, sh);
+    d[k] = (uint8_t)x;
+    if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
+    if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
+    if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
+  }
+}
+
+__device__ __forceinline__ WarpState warp_state(uint8_t* dsm, const WarpLayout& L, unsigned warp) {
+  uint8_t* base = dsm + (size_t)warp * L.stride;
+  WarpState S;
+  S.len = reinterpret_cast<uint32_t*>(base + L.o_len);
+  S.val = reinterpret_cast<unsigned long long*>(base + L.o_val);
+  S.textc = reinterpret_cast<uint32_t*>(base + L.o_textc);
+  S.ioff = reinterpret_cast<uint32_t*>(base + L.o_ioff);
+  S.llist = reinterpret_cast<uint32_t*>(base + L.o_llist);
+  S.rowbuf = base + L.o_rowbuf;
+  return S;
+}
+
+// One warp per strip of RS rows.  WRITE = false: lengths only -> row_len[r].  WRITE = true: rows -> out.
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+    k_dec_rows(const DecParams P, const FmtTables FT, const int32_t* __restrict__ u_item, const uint32_t* __restrict__ row_off,
+               uint32_t RS, const WarpLayout L, const unsigned long long* __restrict__ cin, unsigned long long* __restrict__ row_len,
+               const unsigned long long* __restrict__ out_row_off, uint8_t* __restrict__ out, DecMeta* __restrict__ meta) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t strip = blockIdx.x * L.warps + warp;
+  const uint32_t r0 = strip * RS;
+  if (warp >= L.warps || r0 >= P.nrows) return;
+  const uint32_t r1 = min(P.nrows, r0 + RS);
+  const WarpState S = warp_state(dsm, L, warp);
+  const uint32_t U = P.U, NI = FT.n_items;
+  const uint8_t* rows = P.blk + P.rows_base;
+  const unsigned grp = lane >> 3, gl = lane & 7u;
+
+  // ---- state at the start of the strip: the values carried in
+  if (lane == 0 && WRITE) S.llist[0] = 0;
+  __syncwarp();
+  for (uint32_t u = lane; u < U; u += 32) {
+    S.len[u] = 0;
+    if (__ldg(u_item + u) < 0) continue;  // not output: never touched
+    const unsigned long long v = cin[(size_t)strip * U + u];
+    set_column<WRITE>(P, S, u, v, meta);
+  }
+  __syncwarp();
+  long long dyn = 0;  // dynamic bytes of the current row (lane-local share; summed when needed)
+  for (uint32_t u = lane; u < U; u += 32) dyn += S.len[u];
+
+  for (uint32_t r = r0; r < r1; ++r) {
+    const uint8_t* rp = rows + row_off[r];
+    // ---- the columns this row changes
+    int32_t delta = 0;
+    warp_parse_row(P, P.planes, rp, [&](uint32_t u, uint32_t voff) {
+      if (__ldg(u_item + u) < 0) return;
+      const unsigned long long v = load_le(rp + voff, P.usz[u]);
+      const int32_t old = (int32_t)S.len[u];
+      set_column<WRITE>(P, S, u, v, meta);
+      delta += (int32_t)S.len[u] - old;
+    });
+    __syncwarp();
+    dyn += delta;
+
+    if (!WRITE) {
+      long long tot = dyn;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0) {
+        unsigned long long rl = (unsigned long long)tot + FT.static_total;
+        if (FT.rownum_item != ITEM_ROWNUM) rl += digits_u64(FT.first_row + r);
+        row_len[r] = rl;
+      }
+      continue;
+    }
+
+    // ---- offset of every item's text among the dynamic bytes of the row
     uint32_t run = 0;
-    uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
     for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
       const uint32_t i = i0 + lane;
       uint32_t l = 0;
       if (i < NI) {
         const uint32_t iu = __ldg(FT.item_u + i);
-        l = iu == ITEM_ROWNUM ? digits_u64(FT.first_row + r0 + j) : lenu[(size_t)j * U + iu];
+        l = iu == ITEM_ROWNUM ? digits_u64(FT.first_row + r) : S.len[iu];
       }
       uint32_t inc = l;
 #pragma unroll
@@ -623,198 +722,77 @@ __global__ void __launch_bounds__(DEC_THREADS)
         uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= (unsigned)o) inc += t;
       }
-      if (i < NI) ioffj[i] = run + inc - l;
+      if (i < NI) S.ioff[i] = run + inc - l;
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) {
-      ioffj[NI] = run;
-      rowoff[j] = FT.static_total + run;
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t run = 0;
-    for (uint32_t j0 = 0; j0 < Rn; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      const uint32_t v = j < Rn ? rowoff[j] : 0u;
-      uint32_t inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (unsigned)o) inc += t;
-      }
-      if (j < Rn) rowoff[j] = run + inc - v;
-      run += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) {
-      rowoff[Rn] = run;
-      // publish this strip's byte count right away; the look-back itself happens after the rows are assembled
-      st_release_u64(&strip_status[strip], (strip == 0 ? LB_PFX : LB_AGG) | (uint64_t)run);
-    }
-  }
-  __syncthreads();
-  const uint32_t strip_bytes = rowoff[Rn];
+    if (lane == 0) S.ioff[NI] = run;
+    __syncwarp();
+    const unsigned long long g0 = out_row_off[r];
+    const uint32_t row_bytes = FT.static_total + run;
+    const bool staged = row_bytes <= L.rowcap;
+    uint8_t* dst = staged ? S.rowbuf : out + g0;
 
-  // warp 0: exclusive prefix of the strip totals (32 predecessors per step)
-  auto look_back = [&]() {
-    if (warp != 0) return;
-    uint64_t run = 0;
-    if (strip != 0) {
-      int64_t q = (int64_t)strip - 1;
-      for (;;) {
-        const int64_t idx = q - (int64_t)lane;
-        uint64_t sv = LB_PFX;  // in front of strip 0: an empty inclusive prefix
-        if (idx >= 0) {
-          do {
-            sv = ld_acquire_u64(&strip_status[idx]);
-          } while ((sv >> 62) == 0ull);
-        }
-        const unsigned pm = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
-        const unsigned take = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : 0xffffffffu;  // lanes up to the nearest prefix
-        uint64_t c = ((take >> lane) & 1u) ? (sv & LB_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        run += c;
-        if (pm) break;
-        q -= 32;
+    // ---- template, then the items
+    warp_write_template(FT, S.ioff, dst);
+    for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      if (i >= NI) continue;
+      const uint32_t o = S.ioff[i], l = S.ioff[i + 1] - o;
+      if (!l) continue;
+      const uint32_t u = __ldg(FT.item_u + i);
+      uint8_t* d = dst + __ldg(FT.item_pos + i) + o;
+      if (u == ITEM_ROWNUM) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261)
+        unsigned long long x = FT.first_row + r;
+        for (uint32_t p = l; p > 0; x /= 10ull) d[--p] = (uint8_t)('0' + (uint32_t)(x % 10ull));
+        continue;
       }
-      if (lane == 0) st_release_u64(&strip_status[strip], LB_PFX | (run + strip_bytes));
-    }
-    if (lane == 0) {
-      s_base = run;
-      if (r1 == P.nrows) {
-        meta->out_bytes = run + strip_bytes;
-        if (out_row_off) out_row_off[P.nrows] = run + strip_bytes;
-      }
-    }
-  };
-  const bool single_batch = strip_bytes <= out_smem_cap;
-  if (!single_batch) {
-    look_back();
-    __syncthreads();
-  }
-
-  // ---- 5. rows are assembled in shared memory, batch by batch.  A row that does not fit the shared buffer at all
-  // is assembled in global memory.
-  uint32_t jb = 0;
-  while (jb < Rn) {
-    uint32_t je = jb;
-    while (je < Rn && rowoff[je + 1] - rowoff[jb] <= out_smem_cap) ++je;
-    const bool direct = je == jb;
-    if (direct) je = jb + 1;
-    const uint32_t nbytes = rowoff[je] - rowoff[jb];
-    uint8_t* stage = direct ? out + s_base + rowoff[jb] : obuf;
-    const uint32_t nbr = je - jb;
-    if (direct && s_base + rowoff[je] > out_cap) break;  // host reruns with the exact size
-    // 5a. template
-    for (uint32_t j = jb + warp; j < je; j += DEC_WARPS)
-      warp_write_template(FT, ioff + (size_t)j * (NI + 1), stage + (rowoff[j] - rowoff[jb]));
-    // 5b. short texts: a thread owns an item for a run of consecutive rows and re-renders its text only when the
-    // value changes
-    {
-      const uint32_t nch = NI ? max(1u, min(DEC_THREADS / NI, nbr)) : 1u;
-      const uint32_t Lr = (nbr + nch - 1) / nch;
-      for (uint32_t w = tid; w < NI * nch; w += DEC_THREADS) {
-        const uint32_t i = w % NI, c = w / NI;
-        const uint32_t u = __ldg(FT.item_u + i), pos0 = __ldg(FT.item_pos + i);
-        const bool rownum = u == ITEM_ROWNUM;
-        const uint8_t t = rownum ? (uint8_t)ZDWB_LONGLONG : P.utype[u];
-        const bool textual = is_text_like(t);
-        bool have = false;
-        unsigned long long vprev = 0;
-        const uint32_t ja = jb + c * Lr, jz = min(je, ja + Lr);
-        for (uint32_t j = ja; j < jz; ++j) {
-          const uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
-          const uint32_t o = ioffj[i], l = ioffj[i + 1] - o;
-          if (!l) continue;
-          if (rownum) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261)
-            unsigned long long x = FT.first_row + r0 + j;
-            uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + pos0 + o;
-            for (uint32_t p = l; p > 0; x /= 10ull) d[--p] = (uint8_t)('0' + (uint32_t)(x % 10ull));
-            continue;
-          }
-          const unsigned long long v = val[(size_t)j * U + u];
-          if (textual && v != 0 && l > FMT_SHORT) {
-            llist[atomicAdd(&s_nlong, 1u)] = (j << 24) | i;  // NI < 2^24 checked by the host
-            continue;
-          }
-          if (!have || v != vprev) {
-            render_short(P, u, t, v, l, reinterpret_cast<uint32_t*>(textc));
-            have = true;
-            vprev = v;
-          }
-          uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + pos0 + o;
-          const uint32_t* tw = reinterpret_cast<const uint32_t*>(textc);
-          for (uint32_t k = 0; k < l; k += 4) {
-            const uint32_t x = tw[k >> 2], nb = l - k;
-            d[k] = (uint8_t)x;
-            if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
-            if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
-            if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // 5c. long texts straight from the dictionary: 8 lanes per text, 4 bytes per lane per step
-    {
-      const uint32_t nlong = s_nlong;
-      const uint32_t grp = lane >> 3, gl = lane & 7u;
-      for (uint32_t e = warp * 4 + grp; e < nlong; e += DEC_WARPS * 4) {
-        const uint32_t ent = llist[e];
-        const uint32_t i = ent & 0xffffffu, j = ent >> 24;
-        const uint32_t* ioffj = ioff + (size_t)j * (NI + 1);
-        const uint32_t o = ioffj[i], l = ioffj[i + 1] - o;
-        const uint32_t u = __ldg(FT.item_u + i);
-        const uint8_t* src = P.blk + P.dict_base + (uint32_t)(val[(size_t)j * U + u] + P.ubase[u]);
-        uint8_t* d = stage + (rowoff[j] - rowoff[jb]) + __ldg(FT.item_pos + i) + o;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-        for (uint32_t k = gl * 4; k < l; k += 32) {
-          const uint32_t nb = l - k;
-          const uint32_t lo = __ldg(w + (k >> 2));
-          const uint32_t hi = (sh + min(nb, 4u) * 8u > 32u) ? __ldg(w + (k >> 2) + 1) : 0u;
-          const uint32_t x = __funnelshift_r(lo, hi, sh);
+      if (l <= 16) {
+        const uint32_t* tw = S.textc + 4 * (size_t)u;
+        for (uint32_t k = 0; k < l; k += 4) {
+          const uint32_t x = tw[k >> 2], nb = l - k;
           d[k] = (uint8_t)x;
           if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
           if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
           if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
         }
+      } else if (is_text_like(P.utype[u])) {
+        S.llist[1 + atomicAdd(&S.llist[0], 1u)] = i;
+      } else {
+        value_write(P, u, P.utype[u], S.val[u], l, d);  // numbers of 17-20 characters
       }
     }
-    if (single_batch) look_back();
-    __syncthreads();
-    if (tid == 0) s_nlong = 0;
-    const uint64_t base = s_base;
-    if (!direct) {
-      if (base + rowoff[Rn] > out_cap) break;  // the host's size estimate was too small: it reruns with the exact size
-      // 5d. flush: 4-byte stores, the shared-memory side re-aligned by a funnel shift
-      uint8_t* gdst = out + base + rowoff[jb];
-      const uint32_t head = min(nbytes, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 3u)) & 3u));
-      if (tid < head) gdst[tid] = stage[tid];
-      const uint32_t nw = (nbytes - head) >> 2;
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
+    __syncwarp();
+    {
+      const uint32_t n = S.llist[0];
+      for (uint32_t e = grp; e < n; e += 4) {
+        const uint32_t i = S.llist[1 + e];
+        const uint32_t u = __ldg(FT.item_u + i);
+        const uint32_t o = S.ioff[i], l = S.ioff[i + 1] - o;
+        octet_copy(dst + __ldg(FT.item_pos + i) + o, P.blk + P.dict_base + (uint32_t)(S.val[u] + P.ubase[u]), l, gl);
+      }
+      __syncwarp();
+      if (lane == 0) S.llist[0] = 0;
+    }
+    __syncwarp();
+    // ---- flush: 4-byte stores, the shared-memory side re-aligned by a funnel shift
+    if (staged) {
+      uint8_t* gdst = out + g0;
+      const uint32_t head = min(row_bytes, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 3u)) & 3u));
+      if (lane < head) gdst[lane] = dst[lane];
+      const uint32_t nw = (row_bytes - head) >> 2;
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(dst);
       uint32_t* gw = reinterpret_cast<uint32_t*>(gdst + head);
       const uint32_t sh = head * 8u;
       if (sh == 0) {
-        for (uint32_t m = tid; m < nw; m += DEC_THREADS) gw[m] = sw[m];
+        for (uint32_t m = lane; m < nw; m += 32) gw[m] = sw[m];
       } else {
-        for (uint32_t m = tid; m < nw; m += DEC_THREADS) gw[m] = __funnelshift_r(sw[m], sw[m + 1], sh);
+        for (uint32_t m = lane; m < nw; m += 32) gw[m] = __funnelshift_r(sw[m], sw[m + 1], sh);
       }
       const uint32_t done = head + (nw << 2);
-      if (tid < nbytes - done) gdst[done + tid] = stage[done + tid];
+      if (lane < row_bytes - done) gdst[done + lane] = dst[done + lane];
+      __syncwarp();
     }
-    __syncthreads();
-    jb = je;
   }
-  const uint64_t base = s_base;
-  if (base + strip_bytes > out_cap) {
-    if (tid == 0) meta->overflow = 1;
-    return;
-  }
-  if (out_row_off)
-    for (uint32_t j = tid; j < Rn; j += DEC_THREADS) out_row_off[r0 + j] = base + rowoff[j];
 }
 
 struct HostBlockHeader {
@@ -979,6 +957,16 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   P.ubase = d_ubase.as<unsigned long long>();
   P.utype = d_utype.as<uint8_t>();
   P.planes = d_planes.as<uint32_t>();
+  // NUL bitmap of the dictionary: the length of any entry is then one or two word loads
+  DevBuf d_nulmap;
+  {
+    const uint64_t nwords = (H.dict_total + 31) / 32 + 1;
+    ZDWB_TRY(d_nulmap.alloc(ctx, nwords * 4));
+    KernelScope _ks(ctx, "k_dict_nulmap");
+    k_dict_nulmap<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(blk + H.dict_base, H.dict_total, d_nulmap.as<uint32_t>(), nwords);
+  }
+  ZDWB_LAUNCH_CHECK(ctx);
+  P.nulmap = d_nulmap.as<uint32_t>();
 
   // ---- output plan: static segments and dynamic items in output order
   const uint8_t sep = opts->separator;
@@ -1065,6 +1053,14 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   FT.n_groups = (uint32_t)sgrp.size();
   FT.static_total = static_total;
   FT.first_row = opts->first_row_number;
+  FT.rownum_item = ITEM_ROWNUM;
+  std::vector<int32_t> u_item(U ? U : 1, -1);  // used column -> item (-1: the column is not output)
+  for (uint32_t i = 0; i < NI; ++i) {
+    if (item_u[i] == ITEM_ROWNUM) FT.rownum_item = i;
+    else u_item[item_u[i]] = (int32_t)i;
+  }
+  DevBuf d_u_item;
+  ZDWB_TRY(upload(ctx, d_u_item, u_item));
 
   if (nrows == 0) {
     out->consumed = rows_base;
@@ -1177,27 +1173,12 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   }
   out->consumed = rows_base + consumed_stream;
 
-  // ---- strips
-  // rows per strip: about 32 KiB of TSV, bounded by the per-row tables of k_dec_format (val, lenu, ioff, flags)
-  if (U >= (1u << 24)) {
+  // ---- strips: one warp walks RS consecutive rows (k_dec_rows); about four waves of warps over the GPU
+  if (U >= (1u << 24) || NI >= (1u << 24)) {
     ctx->err = "decode: more than 2^24 used columns";
     return ZDWB_ERR_UNSUPPORTED;
   }
-  const size_t per_row = (size_t)12 * U + (size_t)4 * (NI + 1) + F + 4;
-  uint64_t est_row = (uint64_t)FT.static_total + (uint64_t)NI * 8;
-  if (ctx->last_out_per_row > est_row) est_row = ctx->last_out_per_row;
-  uint32_t R = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(32768 / std::max<uint64_t>(est_row, 1), 256));
-  R = (uint32_t)std::max<size_t>(1, std::min<size_t>(R, (40 * 1024) / per_row));
-  uint32_t out_smem_cap = (uint32_t)((std::max<size_t>({(size_t)32 * 1024, (size_t)2 * est_row, (size_t)R * U * 8}) + 15) & ~(size_t)15);
-  {
-    const size_t fixed = FmtSmem(R, U, NI, F, W, 0).total;
-    if (fixed + (size_t)R * U * 8 + 64 > 200 * 1024) {
-      ctx->err = "decode: too many used columns for the format kernel";
-      return ZDWB_ERR_UNSUPPORTED;
-    }
-    if (fixed + out_smem_cap > 200 * 1024) out_smem_cap = (uint32_t)((200 * 1024 - fixed) & ~(size_t)15);
-  }
-  const size_t smem_fmt = FmtSmem(R, U, NI, F, W, out_smem_cap).total;
+  uint32_t R = (uint32_t)std::max<uint64_t>(8, std::min<uint64_t>(64, nrows / ((uint64_t)ctx->sm_count * 48)));
   const uint32_t nstrips = (nrows + R - 1) / R;
 
   DevBuf cin, d_counts;
@@ -1261,72 +1242,115 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     ZDWB_LAUNCH_CHECK(ctx);
   }
 
-  // ---- output buffers.  The exact TSV size is only known once every field has been measured, which the
-  // format kernel does anyway; so size the buffer by an estimate, let strips that would not fit skip their
-  // writes (the look-back still yields the exact total) and rerun once with the exact size if needed.
-  uint64_t est_out_row = FT.static_total;
-  for (uint32_t i = 0; i < NI; ++i) est_out_row += (item_u[i] != ITEM_ROWNUM && is_text_like(utype[item_u[i]])) ? 16 : 8;
-  if (ctx->last_out_per_row > est_out_row) est_out_row = ctx->last_out_per_row;
-  uint64_t out_cap = (uint64_t)nrows * est_out_row + 4096;
+  // ---- shared-memory layout of a warp in k_dec_rows: lengths-only pass and writing pass
+  auto make_layout = [&](bool write, WarpLayout& L) -> bool {
+    const size_t Ue = std::max(U, 1u);
+    size_t o = 0;
+    L.o_len = (uint32_t)o;    o += Ue * 4;
+    o = (o + 7) & ~(size_t)7;
+    L.o_val = (uint32_t)o;    if (write) o += Ue * 8;
+    L.o_textc = (uint32_t)o;  if (write) o += Ue * 16;
+    L.o_ioff = (uint32_t)o;   if (write) o += ((size_t)NI + 1) * 4;
+    L.o_llist = (uint32_t)o;  if (write) o += (1 + (size_t)NI) * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.o_rowbuf = (uint32_t)o;
+    const size_t fixed = o;
+    if (fixed > 200 * 1024) return false;
+    uint32_t warps = 4;
+    size_t rowcap = 0;
+    if (write) {
+      // stage rows of up to ~2x the expected size; fewer warps per CTA before giving up staging
+      size_t expect = (size_t)FT.static_total + (size_t)NI * 8;
+      if (ctx->last_out_per_row > expect) expect = (size_t)ctx->last_out_per_row;
+      const size_t want = std::min<size_t>(std::max<size_t>(expect + expect / 2, 1024), 32 * 1024);
+      for (;; warps >>= 1) {
+        const size_t per_warp_budget = (size_t)(72 * 1024) / warps;  // ~3 CTAs of 4 warps per SM
+        if (fixed + 64 <= per_warp_budget) {
+          rowcap = std::min(want, per_warp_budget - fixed - 16) & ~(size_t)15;
+          break;
+        }
+        if (warps == 1) {
+          rowcap = fixed + 16 + 1024 <= 200 * 1024 ? 1024 : 0;
+          break;
+        }
+      }
+    }
+    L.rowcap = (uint32_t)rowcap;
+    L.warps = warps;
+    L.stride = (uint32_t)((fixed + (rowcap ? rowcap + 16 : 0) + 15) & ~(size_t)15);
+    return (size_t)L.stride * warps <= 200 * 1024;
+  };
+  WarpLayout L1, L2;
+  if (!make_layout(false, L1) || !make_layout(true, L2)) {
+    ctx->err = "decode: too many used columns for the row kernels";
+    return ZDWB_ERR_UNSUPPORTED;
+  }
+
+  // ---- pass A: length of every row, then the row offsets and the exact output size
   if (ctx->out_dev2) {
     cudaFreeAsync(ctx->out_dev2, st);
     ctx->out_dev2 = nullptr;
   }
-  if (opts->want_row_offsets) {
+  {
     DevBuf ro;
     ZDWB_TRY(ro.alloc(ctx, ((size_t)nrows + 1) * 8));
     ctx->out_dev2 = ro.detach();
   }
-  DevBuf status;
-  ZDWB_TRY(status.alloc(ctx, (size_t)nstrips * 8));
-  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_format, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-  DecMeta* hm = static_cast<DecMeta*>(ctx->meta_host);
-  for (int attempt = 0;; ++attempt) {
-    if (ctx->out_dev) {
-      cudaFreeAsync(ctx->out_dev, st);
-      ctx->out_dev = nullptr;
-    }
-    {
-      DevBuf ob;
-      ZDWB_TRY(ob.alloc(ctx, out_cap));
-      ctx->out_dev = ob.detach();
-    }
-    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, (size_t)nstrips * 8, st));
-    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(d_meta.p, 0, sizeof(DecMeta), st));
-    {
-      KernelScope _ks(ctx, "k_dec_format");
-      k_dec_format<<<nstrips, DEC_THREADS, smem_fmt, st>>>(P, FT, row_off.as<uint32_t>(), R, out_smem_cap,
-                                                        cin.as<unsigned long long>(), status.as<uint64_t>(),
-                                                        static_cast<uint8_t*>(ctx->out_dev), out_cap,
-                                                        static_cast<uint64_t*>(ctx->out_dev2), meta);
-    }
-    ZDWB_LAUNCH_CHECK(ctx);
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hm, meta, sizeof(DecMeta), cudaMemcpyDeviceToHost, st));
-    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    if (!hm->overflow) break;
-    if (attempt >= 1) {
-      ctx->err = "decode: output size estimate failed twice";
-      return ZDWB_ERR_CUDA;
-    }
-    out_cap = hm->out_bytes + 64;
+  unsigned long long* d_row_off = static_cast<unsigned long long*>(ctx->out_dev2);
+  DevBuf row_len;
+  ZDWB_TRY(row_len.alloc(ctx, (size_t)nrows * 8));
+  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+  {
+    KernelScope _ks(ctx, "k_dec_row_lens");
+    k_dec_rows<false><<<(nstrips + L1.warps - 1) / L1.warps, 32 * L1.warps, (size_t)L1.stride * L1.warps, st>>>(
+      P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L1, cin.as<unsigned long long>(), row_len.as<unsigned long long>(),
+      nullptr, nullptr, meta);
   }
-  ctx->last_out_per_row = (hm->out_bytes / nrows) + (hm->out_bytes / nrows) / 8 + 16;
+  ZDWB_LAUNCH_CHECK(ctx);
+  ZDWB_TRY(exclusive_scan_u64(ctx, reinterpret_cast<const uint64_t*>(row_len.p), reinterpret_cast<uint64_t*>(d_row_off), nrows,
+                              reinterpret_cast<uint64_t*>(d_row_off + nrows)));
+  DecMeta* hm = static_cast<DecMeta*>(ctx->meta_host);
+  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hm, meta, sizeof(DecMeta), cudaMemcpyDeviceToHost, st));
+  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, d_row_off + nrows, 8, cudaMemcpyDeviceToHost, st));
+  ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   if (hm->err) {
     ctx->err = "decode: dictionary offset out of range";
     return ZDWB_ERR_CORRUPT;  // CORRUPTED_DATA_ERROR, UnconvertFromZDW.cpp:1364-1365
   }
+  memcpy(&hm->out_bytes, reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, 8);
+  ctx->last_out_per_row = hm->out_bytes / nrows;
+
+  // ---- pass B: the rows
+  if (ctx->out_dev) {
+    cudaFreeAsync(ctx->out_dev, st);
+    ctx->out_dev = nullptr;
+  }
+  {
+    DevBuf ob;
+    ZDWB_TRY(ob.alloc(ctx, hm->out_bytes + 64));
+    ctx->out_dev = ob.detach();
+  }
+  {
+    KernelScope _ks(ctx, "k_dec_write_rows");
+    k_dec_rows<true><<<(nstrips + L2.warps - 1) / L2.warps, 32 * L2.warps, (size_t)L2.stride * L2.warps, st>>>(
+      P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L2, cin.as<unsigned long long>(), nullptr, d_row_off,
+      static_cast<uint8_t*>(ctx->out_dev), meta);
+  }
+  ZDWB_LAUNCH_CHECK(ctx);
   const uint64_t out_len = hm->out_bytes;
   out->len = out_len;
   if (opts->output_on_device) {
+    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     out->tsv = static_cast<const uint8_t*>(ctx->out_dev);
-    out->row_off = static_cast<const uint64_t*>(ctx->out_dev2);
+    out->row_off = opts->want_row_offsets ? static_cast<const uint64_t*>(ctx->out_dev2) : nullptr;
     return ZDWB_OK;
   }
   if (ctx->out_host_cap < out_len) {
     if (ctx->out_host) cudaFreeHost(ctx->out_host);
     ctx->out_host = nullptr;
     ctx->out_host_cap = 0;
-    const size_t cap = std::max<size_t>(out_len, 1 << 20);
+    const size_t cap = std::max<size_t>(out_len + out_len / 4, 1 << 20);  // headroom: blocks of a file vary a little
     ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host, cap, cudaHostAllocDefault));
     ctx->out_host_cap = cap;
   }
@@ -1337,8 +1361,8 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
       if (ctx->out_host2) cudaFreeHost(ctx->out_host2);
       ctx->out_host2 = nullptr;
       ctx->out_host2_cap = 0;
-      ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host2, std::max<size_t>(rb, 1 << 16), cudaHostAllocDefault));
-      ctx->out_host2_cap = std::max<size_t>(rb, 1 << 16);
+      ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host2, std::max<size_t>(rb + rb / 4, 1 << 16), cudaHostAllocDefault));
+      ctx->out_host2_cap = std::max<size_t>(rb + rb / 4, 1 << 16);
     }
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host2, ctx->out_dev2, rb, cudaMemcpyDeviceToHost, st));
     out->row_off = static_cast<const uint64_t*>(ctx->out_host2);

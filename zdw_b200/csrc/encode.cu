@@ -1422,7 +1422,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
       if (ctx->out_host) cudaFreeHost(ctx->out_host);
       ctx->out_host = nullptr;
       ctx->out_host_cap = 0;
-      size_t cap = std::max<size_t>(total_len, 1 << 20);
+      size_t cap = std::max<size_t>(total_len + total_len / 4, 1 << 20);  // headroom: blocks of a file vary a little
       ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host, cap, cudaHostAllocDefault));
       ctx->out_host_cap = cap;
     }
