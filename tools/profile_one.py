@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--mode", default="both", choices=["both", "encode", "decode"])
     ap.add_argument("--timing", type=int, default=0)
+    ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (repeatable)")
     args = ap.parse_args()
 
     import torch
@@ -43,6 +44,9 @@ def main():
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
     if args.timing:
         ctx.set_tuning("kernel_timing", 1)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        ctx.set_tuning(k, int(v))
     blk = ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
     z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)
     bench._d2d(torch, z, blk.dev_ptr, blk.length)

@@ -558,8 +558,8 @@ struct WarpLayout {        // byte offsets inside a warp's slice of dynamic shar
 
 struct WarpState {
   uint32_t* len;              // [U]
-  unsigned long long* val;    // [U]
-  uint32_t* textc;            // [U][4]
+  uint32_t* aux;              // [U] dictionary index of the column's text (text-like columns)
+  uint32_t* textc;            // [U][4] rendered text of up to 16 bytes; numbers of 17-20 characters park their value here
   uint32_t* ioff;             // [NI + 1]
   uint32_t* llist;            // [1 + max(U, NI)]  ([0] = count)
   uint8_t* rowbuf;
@@ -567,13 +567,11 @@ struct WarpState {
 
 __device__ __forceinline__ uint32_t has_zero_byte(uint32_t x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
 
-// New value v for used column u.  Returns true when the column now holds a dictionary text longer than 16 bytes,
-// whose length is still to be measured (octet_strlen); otherwise len[u] (and, when WRITE, textc[u]) are up to date.
+// New value v for used column u: updates len[u] and, when WRITE, what the row writer needs to emit the text.
 template <bool WRITE>
-__device__ __forceinline__ bool set_column(const DecParams& P, const WarpState& S, uint32_t u, unsigned long long v,
+__device__ __forceinline__ void set_column(const DecParams& P, const WarpState& S, uint32_t u, unsigned long long v,
                                            DecMeta* meta) {
   const uint8_t t = P.utype[u];
-  if (WRITE) S.val[u] = v;
   if (is_text_like(t)) {
     if (v == 0) {
       if (t == ZDWB_DECIMAL) {  // outputDefault(DECIMAL): "0.000000000000"
@@ -588,38 +586,47 @@ __device__ __forceinline__ bool set_column(const DecParams& P, const WarpState& 
       } else {
         S.len[u] = 0;
       }
-      return false;
+      return;
     }
     const uint32_t index = (uint32_t)(v + P.ubase[u]);  // ULONG index: UnconvertFromZDW.cpp:1363
     if ((uint64_t)index > P.dict_total) {                // :1364 (the reference allows index == dictionarySize)
       meta->err = 1;
       S.len[u] = 0;
-      if (WRITE) S.val[u] = 0;
-      return false;
+      return;
     }
     const uint32_t l = dict_strlen(P, index, P.dict_total - index);
     S.len[u] = l;
-    if (WRITE && l && l <= 16) {  // short texts are kept rendered; longer ones are copied from the dictionary per row
-      const uint8_t* s = P.blk + P.dict_base + index;
-      const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-      const uint32_t* wend = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.blk + P.avail - 1) & ~(uintptr_t)3);
-      const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-      const uint32_t lim = (uint32_t)min((ptrdiff_t)4, wend - w);
-      const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, lim)), w2 = __ldg(w + min(2u, lim)), w3 = __ldg(w + min(3u, lim)),
-                     w4 = __ldg(w + min(4u, lim));
-      uint32_t* tc = S.textc + 4 * (size_t)u;
-      tc[0] = __funnelshift_r(w0, w1, sh);
-      tc[1] = __funnelshift_r(w1, w2, sh);
-      tc[2] = __funnelshift_r(w2, w3, sh);
-      tc[3] = __funnelshift_r(w3, w4, sh);
+    if (WRITE) {
+      S.aux[u] = index;
+      if (l && l <= 16) {  // short texts are kept rendered; longer ones are copied from the dictionary per row
+        const uint8_t* s = P.blk + P.dict_base + index;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t* wend = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.blk + P.avail - 1) & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+        const uint32_t lim = (uint32_t)min((ptrdiff_t)4, wend - w);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, lim)), w2 = __ldg(w + min(2u, lim)), w3 = __ldg(w + min(3u, lim)),
+                       w4 = __ldg(w + min(4u, lim));
+        uint32_t* tc = S.textc + 4 * (size_t)u;
+        tc[0] = __funnelshift_r(w0, w1, sh);
+        tc[1] = __funnelshift_r(w1, w2, sh);
+        tc[2] = __funnelshift_r(w2, w3, sh);
+        tc[3] = __funnelshift_r(w3, w4, sh);
+      }
     }
-    return false;
+    return;
   }
   const uint32_t l = value_len(P, u, t, v, meta);
   S.len[u] = l;
-  if (WRITE && l && l <= 16) value_write(P, u, t, v, l, reinterpret_cast<uint8_t*>(S.textc + 4 * (size_t)u));
-  return false;
+  if (WRITE && l) {
+    uint32_t* tc = S.textc + 4 * (size_t)u;
+    if (l <= 16) {
+      value_write(P, u, t, v, l, reinterpret_cast<uint8_t*>(tc));
+    } else {  // 17-20 characters: rendered per row from the parked value
+      tc[0] = (uint32_t)v;
+      tc[1] = (uint32_t)(v >> 32);
+    }
+  }
 }
 
 // n bytes from the dictionary to a row by the 8 lanes of an octet, 4 bytes per lane per step
@@ -643,7 +650,7 @@ __device__ __forceinline__ WarpState warp_state(uint8_t* dsm, const WarpLayout& 
   uint8_t* base = dsm + (size_t)warp * L.stride;
   WarpState S;
   S.len = reinterpret_cast<uint32_t*>(base + L.o_len);
-  S.val = reinterpret_cast<unsigned long long*>(base + L.o_val);
+  S.aux = reinterpret_cast<uint32_t*>(base + L.o_val);
   S.textc = reinterpret_cast<uint32_t*>(base + L.o_textc);
   S.ioff = reinterpret_cast<uint32_t*>(base + L.o_ioff);
   S.llist = reinterpret_cast<uint32_t*>(base + L.o_llist);
@@ -669,7 +676,7 @@ __global__ void __launch_bounds__(128)
   const unsigned grp = lane >> 3, gl = lane & 7u;
 
   // ---- state at the start of the strip: the values carried in
-  if (lane == 0 && WRITE) S.llist[0] = 0;
+  if (lane == 0) S.llist[0] = 0;
   __syncwarp();
   for (uint32_t u = lane; u < U; u += 32) {
     S.len[u] = 0;
@@ -683,17 +690,29 @@ __global__ void __launch_bounds__(128)
 
   for (uint32_t r = r0; r < r1; ++r) {
     const uint8_t* rp = rows + row_off[r];
-    // ---- the columns this row changes
-    int32_t delta = 0;
+    // ---- the columns this row changes: the flag walk only lists them, the values are then applied 32 at a time
     warp_parse_row(P, P.planes, rp, [&](uint32_t u, uint32_t voff) {
       if (__ldg(u_item + u) < 0) return;
-      const unsigned long long v = load_le(rp + voff, P.usz[u]);
-      const int32_t old = (int32_t)S.len[u];
-      set_column<WRITE>(P, S, u, v, meta);
-      delta += (int32_t)S.len[u] - old;
+      const uint32_t e = atomicAdd(&S.llist[0], 1u);
+      S.llist[1 + e] = u;
+      S.ioff[e] = voff;
     });
     __syncwarp();
-    dyn += delta;
+    {
+      const uint32_t n = S.llist[0];
+      int32_t delta = 0;
+      for (uint32_t e = lane; e < n; e += 32) {
+        const uint32_t u = S.llist[1 + e];
+        const unsigned long long v = load_le(rp + S.ioff[e], P.usz[u]);
+        const int32_t old = (int32_t)S.len[u];
+        set_column<WRITE>(P, S, u, v, meta);
+        delta += (int32_t)S.len[u] - old;
+      }
+      dyn += delta;
+      __syncwarp();
+      if (lane == 0) S.llist[0] = 0;
+      __syncwarp();
+    }
 
     if (!WRITE) {
       long long tot = dyn;
@@ -757,8 +776,9 @@ __global__ void __launch_bounds__(128)
         }
       } else if (is_text_like(P.utype[u])) {
         S.llist[1 + atomicAdd(&S.llist[0], 1u)] = i;
-      } else {
-        value_write(P, u, P.utype[u], S.val[u], l, d);  // numbers of 17-20 characters
+      } else {  // numbers of 17-20 characters
+        const uint32_t* tc = S.textc + 4 * (size_t)u;
+        value_write(P, u, P.utype[u], (unsigned long long)tc[0] | ((unsigned long long)tc[1] << 32), l, d);
       }
     }
     __syncwarp();
@@ -768,7 +788,7 @@ __global__ void __launch_bounds__(128)
         const uint32_t i = S.llist[1 + e];
         const uint32_t u = __ldg(FT.item_u + i);
         const uint32_t o = S.ioff[i], l = S.ioff[i + 1] - o;
-        octet_copy(dst + __ldg(FT.item_pos + i) + o, P.blk + P.dict_base + (uint32_t)(S.val[u] + P.ubase[u]), l, gl);
+        octet_copy(dst + __ldg(FT.item_pos + i) + o, P.blk + P.dict_base + S.aux[u], l, gl);
       }
       __syncwarp();
       if (lane == 0) S.llist[0] = 0;
@@ -1248,17 +1268,19 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     size_t o = 0;
     L.o_len = (uint32_t)o;    o += Ue * 4;
     o = (o + 7) & ~(size_t)7;
-    L.o_val = (uint32_t)o;    if (write) o += Ue * 8;
+    L.o_val = (uint32_t)o;    if (write) o += Ue * 4;
+    o = (o + 15) & ~(size_t)15;
     L.o_textc = (uint32_t)o;  if (write) o += Ue * 16;
-    L.o_ioff = (uint32_t)o;   if (write) o += ((size_t)NI + 1) * 4;
-    L.o_llist = (uint32_t)o;  if (write) o += (1 + (size_t)NI) * 4;
+    L.o_ioff = (uint32_t)o;   o += ((size_t)NI + 1) * 4;
+    L.o_llist = (uint32_t)o;  o += (1 + (size_t)NI) * 4;
     o = (o + 15) & ~(size_t)15;
     L.o_rowbuf = (uint32_t)o;
     const size_t fixed = o;
     if (fixed > 200 * 1024) return false;
     uint32_t warps = 4;
+    while (warps > 1 && fixed * warps > 200 * 1024) warps >>= 1;
     size_t rowcap = 0;
-    if (write) {
+    if (write && ctx->dec_stage_rows) {
       // stage rows of up to ~2x the expected size; fewer warps per CTA before giving up staging
       size_t expect = (size_t)FT.static_total + (size_t)NI * 8;
       if (ctx->last_out_per_row > expect) expect = (size_t)ctx->last_out_per_row;
