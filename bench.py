@@ -92,7 +92,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polled in the background.  It is started BEFORE the warm-up steps: its start-up (NVML init, first
+    query) stalls kernel launches for some hundred milliseconds, which must not land in the timed region; only the
+    samples whose timestamps fall inside [t_begin, t_end] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -102,11 +105,11 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin: float | None = None, t_end: float | None = None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -115,20 +118,28 @@ class ClockSampler:
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, sm_all = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
+            sm_all.append(clk)
+            if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                continue
+            sm.append(clk)
+            mx.append(cmax)
             for k, nme in enumerate(names):
-                if f[2 + k].lower().startswith("active"):
+                if f[3 + k].lower().startswith("active"):
                     reasons.add(nme)
+        if not sm and sm_all:  # region shorter than the polling period: fall back to every sample of the run
+            sm, mx = sm_all, [max(sm_all)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -373,18 +384,24 @@ def run_cuda(args):
     if rt.length != host_lens[0] or not torch.equal(back, dev_tsv[0][:host_lens[0]]):
         raise SystemExit("parity gate failed: decode(encode(block 0)) != block 0")
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_sampler = time.time()
     for _ in range(args.warmup):
         encode_pass()
         decode_pass()
     barrier()
+    while time.time() - t_sampler < 2.0:  # let the poller get past its start-up before timing starts (extra warm-up)
+        encode_pass()
+        decode_pass()
+    barrier()
 
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = ctx.kernel_launches()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     enc_ms, dec_ms = [], []
     barrier()
     t_wall0 = time.perf_counter()
+    t_epoch0 = time.time()
     for _ in range(args.steps):
         ev[0].record(stream)
         encode_pass()
@@ -397,7 +414,7 @@ def run_cuda(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.kernel_launches() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_epoch0, time.time())
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region).  Blocks are
     # independent, so E2E_LANES contexts (one host thread + stream each) work on different blocks at the same time: the
@@ -473,6 +490,9 @@ def run_cuda(args):
     # ---- reduce over ranks: time = max, bytes = sum
     enc_t = sum(enc_ms) / 1e3
     dec_t = sum(dec_ms) / 1e3
+    if os.environ.get("ZDW_BENCH_DEBUG"):
+        print(f"[rank {rank}] enc_ms={enc_ms} dec_ms={dec_ms} kt_dec={sorted(kt_dec.items(), key=lambda kv: -kv[1][1])[:4]}",
+              file=sys.stderr, flush=True)
     vals = torch.tensor([enc_t, dec_t, t_e2e_enc, t_e2e_dec, t_wall], dtype=torch.float64, device=dev)
     sums = torch.tensor([tsv_bytes, zdw_bytes, float(d2h_enc), float(d2h_dec), float(launches),
                          float(sum(host_lens[:len(e2e_dec_blocks)]))], dtype=torch.float64, device=dev)
