@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--mode", default="both", choices=["both", "encode", "decode"])
     ap.add_argument("--timing", type=int, default=0)
     ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (repeatable)")
+    ap.add_argument("--sweep", default="", help="name=v1,v2,...: time encode + decode kernels for every value of one knob")
     args = ap.parse_args()
 
     import torch
@@ -47,6 +48,30 @@ def main():
     for kv in args.tune:
         k, v = kv.split("=")
         ctx.set_tuning(k, int(v))
+    if args.sweep:
+        name, vals = args.sweep.split("=")
+        ctx.set_tuning("kernel_timing", 1)
+        ref = None
+        for v in [int(x) for x in vals.split(",")]:
+            ctx.set_tuning(name, v)
+            best = {}
+            for _ in range(3):
+                blk = ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
+                for k, (cnt, ms) in ctx.kernel_times().items():
+                    best[k] = min(best.get(k, 1e9), ms)
+                z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)
+                bench._d2d(torch, z, blk.dev_ptr, blk.length)
+                if ref is None:
+                    ref = z[:blk.length].clone()
+                else:
+                    assert ref.numel() == blk.length and bool((ref == z[:blk.length]).all()), "encoded block differs between knob values"
+                ctx.decode_block(types, z.data_ptr(), blk.length, input_on_device=True, output_on_device=True)
+                for k, (cnt, ms) in ctx.kernel_times().items():
+                    best[k] = min(best.get(k, 1e9), ms)
+            enc = sum(ms for k, ms in best.items() if not k.startswith(("k_dec", "k_carry", "k_dict_nulmap")))
+            top = sorted(best.items(), key=lambda kv: -kv[1])[:6]
+            print(f"{name}={v}: sum_ms={sum(best.values()):.3f} " + " ".join(f"{k}={ms:.3f}" for k, ms in top), flush=True)
+        return
     blk = ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
     z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)
     bench._d2d(torch, z, blk.dev_ptr, blk.length)

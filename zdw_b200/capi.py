@@ -6,6 +6,7 @@ there is deliberately no CPU path in the product.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from pathlib import Path
 
@@ -29,7 +30,9 @@ class ZdwError(RuntimeError):
 
 
 def lib_path() -> Path:
-    return _HERE / "libzdw_b200.so"
+    # ZDWB_LIB: developer override used by tools/ to A/B two builds of the same library (never a fallback)
+    override = os.environ.get("ZDWB_LIB")
+    return Path(override) if override else _HERE / "libzdw_b200.so"
 
 
 class _Schema(C.Structure):

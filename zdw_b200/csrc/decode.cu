@@ -384,26 +384,78 @@ __device__ __forceinline__ uint32_t digits_u64(unsigned long long v) {
          : v < 1000000000000000000ull ? 18u : v < 10000000000000000000ull ? 19u : 20u;
 }
 
-// decimal text of v, exactly len = digits_u64(v) characters, ending at d + len: 9-digit groups in 32-bit arithmetic
-__device__ __forceinline__ void write_u64(unsigned long long v, uint32_t len, uint8_t* __restrict__ d) {
-  uint32_t p = len;
-  while (v > 0xffffffffull) {
-    const unsigned long long q = v / 1000000000ull;
-    uint32_t r = (uint32_t)(v - q * 1000000000ull);
-    v = q;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const uint32_t t = r / 10u;
-      d[--p] = (uint8_t)('0' + (r - t * 10u));
-      r = t;
-    }
+// four decimal digits of x (< 10000) as ASCII, most significant digit in the lowest byte: two 2-digit fields are split
+// into tens and ones side by side (x / 100 = x * 5243 >> 19 for x < 43699, y / 10 = y * 103 >> 10 for y < 179)
+__host__ __device__ __forceinline__ uint32_t ascii4(uint32_t x) {
+  const uint32_t hi = (x * 5243u) >> 19;
+  const uint32_t p = hi | ((x - hi * 100u) << 16);
+  const uint32_t tens = ((p * 103u) >> 10) & 0x000f000fu;
+  const uint32_t ones = p - tens * 10u;
+  return (tens | (ones << 8)) + 0x30303030u;
+}
+
+#ifdef __CUDA_ARCH__
+#define ZDWB_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
+#else
+#define ZDWB_FUNNEL_R(lo, hi, sh) ((uint32_t)((((uint64_t)(hi) << 32) | (uint64_t)(lo)) >> ((sh) & 31u)))
+#endif
+
+// Decimal text of `full` as llutoa / lltoa print it (UnconvertFromZDW.cpp:318-356), exactly len characters, left-aligned
+// in w[0..4] (the first character is the lowest byte of w[0]); bytes past len are unspecified.  Straight-line: the 20
+// zero-padded digits are produced four at a time and the leading zeros shifted out.  `neg` = the value prints with a
+// minus sign (len counts it); INT64_MIN keeps the reference's digits 0x30 - d.
+__host__ __device__ __forceinline__ void render_int(unsigned long long full, bool neg, uint32_t len, uint32_t w[5]) {
+  const unsigned long long mag = neg ? 0ull - full : full;
+  uint32_t a, b, c;
+  if (mag <= 0xffffffffull) {
+    const uint32_t x = (uint32_t)mag;
+    a = 0;
+    b = x / 100000000u;
+    c = x - b * 100000000u;
+  } else {
+    const unsigned long long q = mag / 100000000ull;
+    c = (uint32_t)(mag - q * 100000000ull);
+    const unsigned long long q2 = q / 100000000ull;
+    b = (uint32_t)(q - q2 * 100000000ull);
+    a = (uint32_t)q2;
   }
-  uint32_t x = (uint32_t)v;
-  while (p) {
-    const uint32_t t = x / 10u;
-    d[--p] = (uint8_t)('0' + (x - t * 10u));
-    x = t;
+  const uint32_t bh = b / 10000u, ch = c / 10000u;
+  uint32_t e0 = ascii4(a), e1 = ascii4(bh), e2 = ascii4(b - bh * 10000u), e3 = ascii4(ch), e4 = ascii4(c - ch * 10000u);
+  if (neg && full == 0x8000000000000000ull) {  // every remainder is negative: digit byte = 0x30 - d
+    e0 = 0x60606060u - e0;
+    e1 = 0x60606060u - e1;
+    e2 = 0x60606060u - e2;
+    e3 = 0x60606060u - e3;
+    e4 = 0x60606060u - e4;
   }
+  const uint32_t nd = len - (neg ? 1u : 0u);  // digits
+  const uint32_t s = 20u - nd, ws = s >> 2, bs = (s & 3u) * 8u;
+  if (ws & 4u) e0 = e4;
+  if (ws & 2u) {
+    e0 = e2;
+    e1 = e3;
+    e2 = e4;
+  }
+  if (ws & 1u) {
+    e0 = e1;
+    e1 = e2;
+    e2 = e3;
+    e3 = e4;
+  }
+  uint32_t x0 = ZDWB_FUNNEL_R(e0, e1, bs), x1 = ZDWB_FUNNEL_R(e1, e2, bs), x2 = ZDWB_FUNNEL_R(e2, e3, bs),
+           x3 = ZDWB_FUNNEL_R(e3, e4, bs), x4 = e4 >> bs;
+  if (neg) {  // make room for the sign
+    x4 = (x4 << 8) | (x3 >> 24);
+    x3 = (x3 << 8) | (x2 >> 24);
+    x2 = (x2 << 8) | (x1 >> 24);
+    x1 = (x1 << 8) | (x0 >> 24);
+    x0 = (x0 << 8) | (uint32_t)'-';
+  }
+  w[0] = x0;
+  w[1] = x1;
+  w[2] = x2;
+  w[3] = x3;
+  w[4] = x4;
 }
 
 // Length of the text of used column u holding stored value v.  Mirrors the switch in readNextRow
@@ -432,101 +484,6 @@ __device__ __forceinline__ uint32_t value_len(const DecParams& P, uint32_t u, ui
   }
   return digits_u64(full);
 }
-
-// Writes the text of used column u (len bytes, len > 0) to d (shared or global memory).
-__device__ __forceinline__ void value_write(const DecParams& P, uint32_t u, uint8_t t, unsigned long long v, uint32_t len,
-                                            uint8_t* __restrict__ d) {
-  if (is_text_like(t)) {
-    if (v == 0) {
-      const char* z = "0.000000000000";
-      for (uint32_t k = 0; k < len; ++k) d[k] = (uint8_t)z[k];
-      return;
-    }
-    const uint8_t* s = P.blk + P.dict_base + (uint32_t)(v + P.ubase[u]);
-    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-    uint32_t cur = __ldg(w);
-    uint32_t k = 0;
-    for (; k + 4 <= len; k += 4) {
-      const uint32_t nx = __ldg(++w);
-      const uint32_t x = __funnelshift_r(cur, nx, sh);
-      cur = nx;
-      d[k] = (uint8_t)x;
-      d[k + 1] = (uint8_t)(x >> 8);
-      d[k + 2] = (uint8_t)(x >> 16);
-      d[k + 3] = (uint8_t)(x >> 24);
-    }
-    if (k < len) {
-      uint32_t x = cur >> sh;
-      if (sh + (len - k) * 8u > 32u) x = __funnelshift_r(cur, __ldg(w + 1), sh);
-      for (; k < len; ++k, x >>= 8) d[k] = (uint8_t)x;
-    }
-    return;
-  }
-  if (t == ZDWB_CHAR) {
-    const unsigned long long tu = v + P.ubase[u];
-    d[0] = (uint8_t)tu;
-    if (len > 1) d[1] = (uint8_t)(tu >> 8);
-    return;
-  }
-  unsigned long long full = v ? v + P.ubase[u] : 0ull;
-  if (is_signed_int_type(t) && (long long)full < 0) {
-    // lltoa: value = -value (overflows for INT64_MIN), then signed % 10 and / 10; digit byte = rem + '0'
-    d[0] = (uint8_t)'-';
-    if (full != 0x8000000000000000ull) {
-      write_u64(0ull - full, len - 1, d + 1);
-      return;
-    }
-    long long sv = (long long)full;  // INT64_MIN: every remainder is negative
-    uint32_t p = len;
-    do {
-      const long long rem = sv % 10;
-      sv /= 10;
-      d[--p] = (uint8_t)(rem + 0x30);
-    } while (sv != 0 && p > 1);
-    return;
-  }
-  write_u64(full, len, d);
-}
-
-constexpr uint32_t FMT_SHORT = 16;   // texts up to this length go through a thread's text cache
-constexpr uint32_t FMT_TEXTC = 24;   // bytes of text cache per thread (20 digits fit)
-
-// Renders the text (len <= FMT_TEXTC; dictionary strings: len <= FMT_SHORT) of used column u into the thread's
-// word-aligned text cache.  The dictionary path is straight-line so that lanes with different lengths stay converged.
-__device__ __forceinline__ void render_short(const DecParams& P, uint32_t u, uint8_t t, unsigned long long v, uint32_t len,
-                                             uint32_t* __restrict__ tc) {
-  if (is_text_like(t)) {
-    if (v == 0) {  // outputDefault(DECIMAL): "0.000000000000"
-      tc[0] = 0x30302e30u;
-      tc[1] = 0x30303030u;
-      tc[2] = 0x30303030u;
-      tc[3] = 0x00003030u;
-      return;
-    }
-    const uint8_t* s = P.blk + P.dict_base + (uint32_t)(v + P.ubase[u]);
-    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t* wend = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.blk + P.avail - 1) & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-    const uint32_t room = (uint32_t)min((ptrdiff_t)4, wend - w);  // whole words readable after *w (block end)
-    const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, room)), w2 = __ldg(w + min(2u, room)), w3 = __ldg(w + min(3u, room)),
-                   w4 = __ldg(w + min(4u, room));
-    tc[0] = __funnelshift_r(w0, w1, sh);
-    tc[1] = __funnelshift_r(w1, w2, sh);
-    tc[2] = __funnelshift_r(w2, w3, sh);
-    tc[3] = __funnelshift_r(w3, w4, sh);
-    return;
-  }
-  value_write(P, u, t, v, len, reinterpret_cast<uint8_t*>(tc));
-}
-
-// all 32 lanes copy n bytes (dictionary -> row)
-__device__ __forceinline__ void warp_copy_bytes(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n) {
-  for (uint32_t k = lane_id(); k < n; k += 32) d[k] = __ldg(s + k);
-}
-
 
 // One warp writes the template bytes of a row, one group (up to 4 bytes of one segment) per lane per step.
 __device__ __forceinline__ void warp_write_template(const FmtTables& FT, const uint32_t* __restrict__ ioffj,
@@ -620,11 +577,17 @@ __device__ __forceinline__ void set_column(const DecParams& P, const WarpState& 
   S.len[u] = l;
   if (WRITE && l) {
     uint32_t* tc = S.textc + 4 * (size_t)u;
-    if (l <= 16) {
-      value_write(P, u, t, v, l, reinterpret_cast<uint8_t*>(tc));
-    } else {  // 17-20 characters: rendered per row from the parked value
-      tc[0] = (uint32_t)v;
-      tc[1] = (uint32_t)(v >> 32);
+    if (t == ZDWB_CHAR) {  // one byte, or a backslash and the byte after it (UnconvertFromZDW.cpp:1396-1420)
+      tc[0] = (uint32_t)(v + P.ubase[u]) & 0xffffu;
+    } else {  // integers: up to 20 characters, the last four live in the column's aux word
+      const unsigned long long full = v ? v + P.ubase[u] : 0ull;
+      uint32_t w[5];
+      render_int(full, is_signed_int_type(t) && (long long)full < 0, l, w);
+      tc[0] = w[0];
+      tc[1] = w[1];
+      tc[2] = w[2];
+      tc[3] = w[3];
+      S.aux[u] = w[4];
     }
   }
 }
@@ -660,7 +623,7 @@ __device__ __forceinline__ WarpState warp_state(uint8_t* dsm, const WarpLayout& 
 
 // One warp per strip of RS rows.  WRITE = false: lengths only -> row_len[r].  WRITE = true: rows -> out.
 template <bool WRITE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 10)
     k_dec_rows(const DecParams P, const FmtTables FT, const int32_t* __restrict__ u_item, const uint32_t* __restrict__ row_off,
                uint32_t RS, const WarpLayout L, const unsigned long long* __restrict__ cin, unsigned long long* __restrict__ row_len,
                const unsigned long long* __restrict__ out_row_off, uint8_t* __restrict__ out, DecMeta* __restrict__ meta) {
@@ -765,20 +728,17 @@ __global__ void __launch_bounds__(128)
         for (uint32_t p = l; p > 0; x /= 10ull) d[--p] = (uint8_t)('0' + (uint32_t)(x % 10ull));
         continue;
       }
-      if (l <= 16) {
+      if (l <= 16 || !is_text_like(P.utype[u])) {  // rendered text: 16 bytes in the cache, numbers up to 4 more in aux
         const uint32_t* tw = S.textc + 4 * (size_t)u;
         for (uint32_t k = 0; k < l; k += 4) {
-          const uint32_t x = tw[k >> 2], nb = l - k;
+          const uint32_t x = k < 16u ? tw[k >> 2] : S.aux[u], nb = l - k;
           d[k] = (uint8_t)x;
           if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
           if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
           if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
         }
-      } else if (is_text_like(P.utype[u])) {
+      } else {
         S.llist[1 + atomicAdd(&S.llist[0], 1u)] = i;
-      } else {  // numbers of 17-20 characters
-        const uint32_t* tc = S.textc + 4 * (size_t)u;
-        value_write(P, u, P.utype[u], (unsigned long long)tc[0] | ((unsigned long long)tc[1] << 32), l, d);
       }
     }
     __syncwarp();

@@ -533,13 +533,13 @@ __device__ __forceinline__ uint32_t trimmed_len(const uint8_t* __restrict__ buf,
   return len;
 }
 
-// strtoull of a field of 1..19 bytes that consists of decimal digits only (no overflow possible), from its masked
-// words - the common case; everything else (whitespace, signs, junk, 20+ characters) takes parse_u64_field.
-// Returns false when the field is not all digits.
-constexpr uint32_t NUM_FAST_MAX = 19;
+// strtoull of a field of 1..20 bytes that consists of decimal digits only, from its masked words - the common case;
+// everything else (whitespace, signs, junk, 21+ characters) takes parse_u64_field.  Twenty digits can exceed 2^64 - 1:
+// strtoull then saturates.  Returns false when the field is not all digits.
+constexpr uint32_t NUM_FAST_MAX = 20;
 __device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, unsigned long long* out) {
   unsigned long long v = 0;
-  bool ok = true;
+  bool ok = true, ovf = false;
 #pragma unroll
   for (uint32_t k = 0; k < 5; ++k) {
     if (4u * k < len) {
@@ -552,18 +552,182 @@ __device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, 
       const uint32_t pairs = (al & 0x00ff00ffu) * 10u + ((al >> 8) & 0x00ff00ffu);
       const uint32_t v4 = (pairs & 0xffffu) * 100u + (pairs >> 16);
       const uint32_t scale = nd == 4u ? 10000u : nd == 3u ? 1000u : nd == 2u ? 100u : 10u;
+      if (k == 4u && nd == 4u)  // the 17th..20th digit: v * 10^4 + v4 > 2^64 - 1 ?
+        ovf = v > 1844674407370955ull || (v == 1844674407370955ull && v4 > 1615u);
       v = v * scale + v4;
     }
   }
-  *out = v;
+  *out = ovf ? ~0ull : v;
   return ok;
 }
 
-// Processes the 32 queued fields [off, off + 32) of the warp (fewer when `count` < 32): lane l takes field off + l.
-// Short fields are handled from registers with straight-line code; long texts are then worked off four at a time
-// by the octets of the warp.
+// ---------------------------------------------------------------------------------------------
+// Field processing.  The warp's main queue holds every non-empty field in row order (slot = ordinal).  In a batch of
+// 32, everything that fits 20 bytes - numbers, CHAR cells and texts of up to SHORT_MAX bytes, the bulk of
+// analytics-shaped data - is served from five register words loaded once; texts of SHORT_MAX+1 .. MID_MAX bytes are
+// parked in a small per-warp ring and worked off 32 at a time, one lane each; the rare longer texts are handled in
+// place by the octets of the warp.
+// ---------------------------------------------------------------------------------------------
+#ifndef P1_SQ
+#define P1_SQ 64
+#endif
+#ifndef P1_MINB
+#define P1_MINB 4
+#endif
+#ifndef P1_LDCG
+#define P1_LDCG 0
+#endif
+constexpr uint32_t SQ = P1_SQ;     // entries of the side queue (at most 31 waiting + 32 pushed)
+constexpr uint32_t MID_MAX = 64;   // longest text handled by a single lane
+
+struct P1Side {
+  uint32_t start[SQ], len[SQ], col[SQ], ord[SQ];
+};
+struct SideQ {  // warp-uniform, in registers
+  uint32_t head, n;
+};
+
+__device__ __forceinline__ void side_push(P1Side& Q, SideQ& q, bool want, uint32_t start, uint32_t len, uint32_t col, uint32_t ord) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (want) {
+    const uint32_t i = (q.head + q.n + (uint32_t)__popc(m & lanemask_lt())) & (SQ - 1u);
+    Q.start[i] = start;
+    Q.len[i] = len;
+    Q.col[i] = col;
+    Q.ord[i] = ord;
+  }
+  q.n += (uint32_t)__popc(m);
+}
+
+__device__ __forceinline__ void note_new_string(P1Stats& st, uint32_t len) {
+  ++st.new_count;
+  st.new_bytes += (unsigned long long)len + 1ull;
+  st.max_len = max(st.max_len, len);
+}
+
+// Column statistics.  The loads that filter the atomics may come from a stale L1 line: the three arrays only move one
+// way (set 0 -> 1, min down, max up), so a stale value can cost a redundant atomic but never skips a needed one.
+#if P1_LDCG
+#define P1_LD(p) __ldcg(p)
+#else
+#define P1_LD(p) (*(p))
+#endif
+__device__ __forceinline__ void note_column_set(const P1Args& A, uint32_t col) {
+  if (P1_LD(A.colset + col) == 0u) A.colset[col] = 1u;
+}
+__device__ __forceinline__ void note_column_value(const P1Args& A, uint32_t col, unsigned long long v1) {
+  if (v1 != 0) {  // zero / empty numeric cells take no part in min/max: ConvertToZDW.cpp:362,386
+    note_column_set(A, col);
+    if (v1 < P1_LD(A.colmin + col)) atomicMin(A.colmin + col, v1);
+    if (v1 > P1_LD(A.colmax + col)) atomicMax(A.colmax + col, v1);
+  }
+}
+
+// one text of SHORT_MAX+1 .. MID_MAX bytes by a single lane: words streamed four at a time through a funnel shift
+__device__ __forceinline__ void midtext_one(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, uint32_t col,
+                                            uint32_t ord, P1Stats& st) {
+  const uint32_t nw = (len + 3u) >> 2;
+  const uint32_t tail = len & 3u, tail_mask = tail ? ((1u << (8u * tail)) - 1u) : 0xffffffffu;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(A.buf + start);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t room = (uint32_t)min((ptrdiff_t)(MID_MAX / 4 + 1), wlast - w);  // whole words readable after *w
+  uint32_t sum = 0;
+  {
+    uint32_t prev = __ldg(w);
+    for (uint32_t k0 = 0; k0 < nw; k0 += 4u) {
+      const uint32_t n0 = __ldg(w + min(k0 + 1u, room)), n1 = __ldg(w + min(k0 + 2u, room)), n2 = __ldg(w + min(k0 + 3u, room)),
+                     n3 = __ldg(w + min(k0 + 4u, room));
+      uint32_t x0 = __funnelshift_r(prev, n0, sh), x1 = __funnelshift_r(n0, n1, sh), x2 = __funnelshift_r(n1, n2, sh),
+               x3 = __funnelshift_r(n2, n3, sh);
+      prev = n3;
+      const uint32_t left = nw - k0;  // words of the text in this group (>= 1)
+      if (left == 1u) x0 &= tail_mask;
+      if (left == 2u) x1 &= tail_mask;
+      if (left == 3u) x2 &= tail_mask;
+      if (left == 4u) x3 &= tail_mask;
+      sum += mix_word(x0, k0);
+      if (left > 1u) sum += mix_word(x1, k0 + 1u);
+      if (left > 2u) sum += mix_word(x2, k0 + 2u);
+      if (left > 3u) sum += mix_word(x3, k0 + 3u);
+    }
+  }
+  uint32_t i = finish_hash(sum, len) & A.ht.mask;
+  const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
+  bool is_new = false, found = false;
+  for (uint32_t probe = 0; probe < HT_MAX_PROBE; ++probe) {
+    unsigned long long cur = A.ht.slots[i];
+    if (cur == 0ull) {
+      cur = atomicCAS(&A.ht.slots[i], 0ull, mine);
+      if (cur == 0ull) {
+        is_new = true;
+        found = true;
+        break;
+      }
+    }
+    if ((uint32_t)cur == len) {
+      const uint32_t cs = (uint32_t)(cur >> 32) - 1u;
+      uint32_t diff = 0;
+      if (cs != start) {
+        const uintptr_t b = reinterpret_cast<uintptr_t>(A.buf + cs);
+        const uint32_t* v = reinterpret_cast<const uint32_t*>(b & ~(uintptr_t)3);
+        const uint32_t sh2 = (uint32_t)(b & 3u) * 8u;
+        const uint32_t room2 = (uint32_t)min((ptrdiff_t)(MID_MAX / 4 + 1), wlast - v);
+        uint32_t p1 = __ldg(w), p2 = __ldg(v);
+        for (uint32_t k0 = 0; k0 < nw && diff == 0u; k0 += 4u) {
+          const uint32_t a0 = __ldg(w + min(k0 + 1u, room)), a1 = __ldg(w + min(k0 + 2u, room)), a2 = __ldg(w + min(k0 + 3u, room)),
+                         a3 = __ldg(w + min(k0 + 4u, room));
+          const uint32_t b0 = __ldg(v + min(k0 + 1u, room2)), b1 = __ldg(v + min(k0 + 2u, room2)),
+                         b2 = __ldg(v + min(k0 + 3u, room2)), b3 = __ldg(v + min(k0 + 4u, room2));
+          uint32_t d0 = __funnelshift_r(p1, a0, sh) ^ __funnelshift_r(p2, b0, sh2);
+          uint32_t d1 = __funnelshift_r(a0, a1, sh) ^ __funnelshift_r(b0, b1, sh2);
+          uint32_t d2 = __funnelshift_r(a1, a2, sh) ^ __funnelshift_r(b1, b2, sh2);
+          uint32_t d3 = __funnelshift_r(a2, a3, sh) ^ __funnelshift_r(b2, b3, sh2);
+          p1 = a3;
+          p2 = b3;
+          const uint32_t left = nw - k0;
+          if (left == 1u) d0 &= tail_mask;
+          if (left == 2u) d1 &= tail_mask;
+          if (left == 3u) d2 &= tail_mask;
+          if (left == 4u) d3 &= tail_mask;
+          diff = d0 | (left > 1u ? d1 : 0u) | (left > 2u ? d2 : 0u) | (left > 3u ? d3 : 0u);
+        }
+      }
+      if (diff == 0u) {
+        found = true;
+        break;
+      }
+    }
+    i = (i + 1) & A.ht.mask;
+  }
+  if (!found) {
+    *reinterpret_cast<volatile uint32_t*>(&A.meta->ht_overflow) = 1u;
+    i = 0;
+  }
+  A.rec_col[ord] = col;
+  A.rec_val[ord] = i;
+  note_column_set(A, col);
+  if (is_new) note_new_string(st, len);
+}
+
+__device__ __forceinline__ void p1_midtext(const P1Args& A, const uint32_t* wlast, const P1Side& Q, uint32_t head, uint32_t count,
+                                           P1Stats& st) {
+  const unsigned lane = lane_id();
+  if (lane < count) {
+    const uint32_t qi = (head + lane) & (SQ - 1u);
+    midtext_one(A, wlast, Q.start[qi], Q.len[qi], Q.col[qi], Q.ord[qi], st);
+  }
+  __syncwarp();
+}
+
+struct P1Queues {
+  P1Side* mid;
+  SideQ qm;
+};
+
+// Processes the queued fields [off, off + count) of the warp's main queue (count <= 32): lane l takes field off + l.
 __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, const P1Warp& W, uint32_t off, uint32_t count,
-                                           uint32_t ord0, P1Stats& st) {
+                                           uint32_t ord0, P1Stats& st, P1Queues& SQs, bool flush) {
   const unsigned lane = lane_id();
   const bool valid = lane < count;
   uint32_t start = 0, len = 0, col = 0;
@@ -575,12 +739,12 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
     t = __ldg(A.types + col);
   }
   const uint32_t ord = ord0 + lane;
+  const bool live = valid && len != 0u;
   const bool text = is_text_like(t);
-  bool is_long = false;
-  if (valid && len == 0) {
-    A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one (or the row is malformed)
-  } else if (valid) {
-    if (len <= (text ? SHORT_MAX : NUM_FAST_MAX)) {
+  if (valid && len == 0u) A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one (or the row is malformed)
+  bool is_mid = false, is_long = false;
+  if (live) {
+    if (len <= (text ? SHORT_MAX : NUM_FAST_MAX) || t == ZDWB_CHAR) {
       uint32_t x[5];
       short_words<5>(A.buf + start, len, wlast, x);
       if (text) {
@@ -588,17 +752,13 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
         const uint32_t slot = ht_upsert_short(A, wlast, start, len, x, &is_new);
         A.rec_col[ord] = col;
         A.rec_val[ord] = slot;
-        if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
-        if (is_new) {
-          ++st.new_count;
-          st.new_bytes += (unsigned long long)len + 1ull;
-          st.max_len = max(st.max_len, len);
-        }
+        note_column_set(A, col);
+        if (is_new) note_new_string(st, len);
       } else {
         unsigned long long v1, v2;
         if (t == ZDWB_CHAR) {
           // sign-extended first byte (+ second byte * 256): min/max rule ConvertToZDW.cpp:358-361 (second byte only
-          // after a backslash), pass-2 rule :543-547 (always)
+          // after a backslash), pass-2 rule :543-547 (always); bytes past the field read as NUL (x is masked)
           const long long b0 = (long long)(int8_t)(x[0] & 0xffu);
           const long long b1 = len > 1 ? (long long)((int32_t)(int8_t)((x[0] >> 8) & 0xffu) * 256) : 0ll;
           v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
@@ -609,63 +769,56 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
         }
         A.rec_col[ord] = col;
         A.rec_val[ord] = v2;
-        if (v1 != 0) {  // zero / empty numeric cells take no part in min/max: :362,386
-          if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
-          if (v1 < __ldcg(A.colmin + col)) atomicMin(A.colmin + col, v1);
-          if (v1 > __ldcg(A.colmax + col)) atomicMax(A.colmax + col, v1);
-        }
+        note_column_value(A, col, v1);
       }
-    } else if (!text) {
-      unsigned long long v1, v2;
-      const uint8_t* p = A.buf + start;
-      if (t == ZDWB_CHAR) {
-        v1 = char_tuple(p, len, false);
-        v2 = char_tuple(p, len, true);
-      } else {
-        v1 = v2 = parse_u64_field(p, len);
-      }
+    } else if (!text) {  // a number of more than 20 characters
+      const unsigned long long v = parse_u64_field(A.buf + start, len);
       A.rec_col[ord] = col;
-      A.rec_val[ord] = v2;
-      if (v1 != 0) {
-        if (__ldcg(A.colset + col) == 0u) A.colset[col] = 1u;
-        if (v1 < __ldcg(A.colmin + col)) atomicMin(A.colmin + col, v1);
-        if (v1 > __ldcg(A.colmax + col)) atomicMax(A.colmax + col, v1);
-      }
+      A.rec_val[ord] = v;
+      note_column_value(A, col, v);
     } else {
-      is_long = true;
+      is_mid = len <= MID_MAX;
+      is_long = !is_mid;
     }
   }
+  side_push(*SQs.mid, SQs.qm, is_mid, start, len, col, ord);
   // ---- long texts: octet g takes the g-th, (g+4)-th, ... of them
   unsigned todo = __ballot_sync(0xffffffffu, is_long);
-  const unsigned grp = lane >> 3, gl = lane & 7u, om = 0xffu << (grp * 8);
-  while (todo) {
-    // the source lane of this octet: the (grp+1)-th set bit of todo
-    unsigned m = todo;
-    for (unsigned k = 0; k < grp && m; ++k) m &= m - 1;
-    const bool active = m != 0u;
-    const int src = active ? __ffs(m) - 1 : 0;
-    const uint32_t s2 = __shfl_sync(0xffffffffu, start, src), l2 = __shfl_sync(0xffffffffu, len, src),
-                   c2 = __shfl_sync(0xffffffffu, col, src);
-    bool is_new;
-    const uint32_t slot = ht_upsert_long(A, wlast, s2, l2, gl, om, active, &is_new);
-    if (active && gl == 0) {
-      const uint32_t o2 = ord0 + (uint32_t)src;
-      A.rec_col[o2] = c2;
-      A.rec_val[o2] = slot;
-      if (__ldcg(A.colset + c2) == 0u) A.colset[c2] = 1u;
-      if (is_new) {
-        ++st.new_count;
-        st.new_bytes += (unsigned long long)l2 + 1ull;
-        st.max_len = max(st.max_len, l2);
+  if (todo) {
+    const unsigned grp = lane >> 3, gl = lane & 7u, om = 0xffu << (grp * 8);
+    while (todo) {
+      // the source lane of this octet: the (grp+1)-th set bit of todo
+      unsigned m = todo;
+      for (unsigned k = 0; k < grp && m; ++k) m &= m - 1;
+      const bool active = m != 0u;
+      const int src = active ? __ffs(m) - 1 : 0;
+      const uint32_t s2 = __shfl_sync(0xffffffffu, start, src), l2 = __shfl_sync(0xffffffffu, len, src),
+                     c2 = __shfl_sync(0xffffffffu, col, src);
+      bool is_new;
+      const uint32_t slot = ht_upsert_long(A, wlast, s2, l2, gl, om, active, &is_new);
+      if (active && gl == 0) {
+        const uint32_t o2 = ord0 + (uint32_t)src;
+        A.rec_col[o2] = c2;
+        A.rec_val[o2] = slot;
+        note_column_set(A, c2);
+        if (is_new) note_new_string(st, l2);
       }
+      // drop the (up to) four texts just handled
+      for (int k = 0; k < 4 && todo; ++k) todo &= todo - 1;
     }
-    // drop the (up to) four texts just handled
-    for (int k = 0; k < 4 && todo; ++k) todo &= todo - 1;
+  }
+  if (SQs.qm.n >= 32u || (flush && SQs.qm.n)) {
+    __syncwarp();
+    const uint32_t take = min(SQs.qm.n, 32u);
+    p1_midtext(A, wlast, *SQs.mid, SQs.qm.head, take, st);
+    SQs.qm.head = (SQs.qm.head + take) & (SQ - 1u);
+    SQs.qm.n -= take;
   }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS) k_pass1(const P1Args A) {
+__global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) {
   __shared__ P1Warp sw[ENC_WARPS];
+  __shared__ P1Side s_mid[ENC_WARPS];
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t tile = blockIdx.x * ENC_WARPS + warp;
   if (tile >= A.ntiles) return;
@@ -676,56 +829,68 @@ __global__ void __launch_bounds__(ENC_THREADS) k_pass1(const P1Args A) {
   WarpCarry c;
   carry_init(A.buf, t0, A.pre[tile], c);
   P1Stats st = {0u, 0u, 0u, 0ull};
+  P1Queues SQs;
+  SQs.mid = &s_mid[warp];
+  SQs.qm.head = SQs.qm.n = 0u;
   uint32_t qbase = c.ne;  // ordinal of the field held in queue slot 0
   const uint32_t tabs_per_row = A.ncols - 1u;
   if (tile == 0 && lane == 0) A.row_rec[0] = 0u;
 
-  for (uint32_t s = 0; s < TILE; s += STEP) {
-    if (t0 + s >= A.limit) break;
-    const LaneStep L = scan_step(A.buf, A.limit, t0 + s, c);
-    // ---- rows that end here: field-count check, longest line, record index of the next row
-    uint32_t tm = L.term;
-    while (tm) {
-      const int i = __ffs(tm) - 1;
-      tm &= tm - 1;
-      const uint32_t below = (1u << i) - 1u;
-      const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
-      const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
-      if (T != (R + 1u) * tabs_per_row) atomicMin(&A.meta->bad_row, R);  // cumulative: exact for the first bad row
-      const uint32_t brk = (L.term | L.skip) & below;
-      const int64_t row_start = (brk ? L.p0 + (31 - __clz(brk)) : L.prb) + 1;
-      st.max_line = max(st.max_line, (uint32_t)(L.p0 + i - row_start + 1));
-      A.row_rec[R + 1u] = L.nes + (uint32_t)__popc(L.ne & ((2u << i) - 1u));
-    }
-    // ---- non-empty fields go to the warp's queue; the slot is the field's ordinal, so no coordination is needed
-    uint32_t rem = L.ne;
-    const uint32_t bound = L.tab | L.term | L.skip;
-    while (rem) {
-      const int i = __ffs(rem) - 1;
-      rem &= rem - 1;
-      const uint32_t below = (1u << i) - 1u;
-      const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
-      const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
-      uint32_t col = T - R * tabs_per_row;
-      const uint32_t lowb = bound & below;
-      const uint32_t start = (uint32_t)((lowb ? L.p0 + (31 - __clz(lowb)) : L.pb) + 1);
-      uint32_t len = (uint32_t)(L.p0 + i) - start;
-      const uint32_t q = L.nes + (uint32_t)__popc(L.ne & below) - qbase;
-      if (col >= A.ncols) {  // (a malformed row is reported through bad_row)
-        col = 0;
-        len = 0;
-      } else if (A.trim) {
-        len = trimmed_len(A.buf, start, len);
+  // One call site for the field processing keeps the kernel small (it is instruction-cache sensitive): the loop runs
+  // one extra round after the last step, in which the leftover fields and the side queue are flushed.
+  for (uint32_t s = 0;; s += STEP) {
+    const bool last = s >= TILE || t0 + (int64_t)s >= A.limit;
+    if (!last) {
+      const LaneStep L = scan_step(A.buf, A.limit, t0 + s, c);
+      // ---- rows that end here: field-count check, longest line, record index of the next row
+      uint32_t tm = L.term;
+      while (tm) {
+        const int i = __ffs(tm) - 1;
+        tm &= tm - 1;
+        const uint32_t below = (1u << i) - 1u;
+        const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
+        const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
+        if (T != (R + 1u) * tabs_per_row) atomicMin(&A.meta->bad_row, R);  // cumulative: exact for the first bad row
+        const uint32_t brk = (L.term | L.skip) & below;
+        const int64_t row_start = (brk ? L.p0 + (31 - __clz(brk)) : L.prb) + 1;
+        st.max_line = max(st.max_line, (uint32_t)(L.p0 + i - row_start + 1));
+        A.row_rec[R + 1u] = L.nes + (uint32_t)__popc(L.ne & ((2u << i) - 1u));
       }
-      W.start[q] = start;
-      W.len[q] = len;
-      W.col[q] = col;
+      // ---- non-empty fields go to the warp's queue; the slot is the field's ordinal, so no coordination is needed
+      uint32_t rem = L.ne;
+      const uint32_t bound = L.tab | L.term | L.skip;
+      while (rem) {
+        const int i = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const uint32_t below = (1u << i) - 1u;
+        const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
+        const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
+        uint32_t col = T - R * tabs_per_row;
+        const uint32_t lowb = bound & below;
+        const uint32_t start = (uint32_t)((lowb ? L.p0 + (31 - __clz(lowb)) : L.pb) + 1);
+        uint32_t len = (uint32_t)(L.p0 + i) - start;
+        const uint32_t q = L.nes + (uint32_t)__popc(L.ne & below) - qbase;
+        if (col >= A.ncols) {  // (a malformed row is reported through bad_row)
+          col = 0;
+          len = 0;
+        } else if (A.trim) {
+          len = trimmed_len(A.buf, start, len);
+        }
+        W.start[q] = start;
+        W.len[q] = len;
+        W.col[q] = col;
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    // ---- work off full batches
+    // ---- work off full batches (in the extra round: whatever is left, and the side queue)
     const uint32_t have = c.ne - qbase;
     uint32_t off = 0;
-    for (; off + 32u <= have; off += 32u) p1_process(A, wlast, W, off, 32u, qbase + off, st);
+    while (off + 32u <= have || (last && (off < have || SQs.qm.n))) {
+      const uint32_t cnt = min(32u, have - off);
+      p1_process(A, wlast, W, off, cnt, qbase + off, st, SQs, last);
+      off += cnt;
+    }
+    if (last) break;
     if (off) {
       __syncwarp();
       const uint32_t left = have - off;  // < 32
@@ -744,10 +909,6 @@ __global__ void __launch_bounds__(ENC_THREADS) k_pass1(const P1Args A) {
       qbase += off;
     }
     __syncwarp();
-  }
-  {
-    const uint32_t have = c.ne - qbase;
-    if (have) p1_process(A, wlast, W, 0, have, qbase, st);
   }
   // ---- warp totals
   st.max_line = __reduce_max_sync(0xffffffffu, st.max_line);
