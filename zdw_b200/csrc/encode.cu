@@ -580,23 +580,26 @@ __device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, 
 constexpr uint32_t SQ = P1_SQ;     // entries of the side queue (at most 31 waiting + 32 pushed)
 constexpr uint32_t MID_MAX = 64;   // longest text handled by a single lane
 
-struct P1Side {
+struct P1Side {  // a ring; `end` = entries ever pushed, `done` = entries ever taken (warp-uniform, kept here)
   uint32_t start[SQ], len[SQ], col[SQ], ord[SQ];
-};
-struct SideQ {  // warp-uniform, in registers
-  uint32_t head, n;
+  uint32_t end, done;
 };
 
-__device__ __forceinline__ void side_push(P1Side& Q, SideQ& q, bool want, uint32_t start, uint32_t len, uint32_t col, uint32_t ord) {
+// all lanes call; returns the number of entries waiting afterwards
+__device__ __forceinline__ uint32_t side_push(P1Side& Q, bool want, uint32_t start, uint32_t len, uint32_t col, uint32_t ord) {
   const unsigned m = __ballot_sync(0xffffffffu, want);
+  const uint32_t end = Q.end;
   if (want) {
-    const uint32_t i = (q.head + q.n + (uint32_t)__popc(m & lanemask_lt())) & (SQ - 1u);
+    const uint32_t i = (end + (uint32_t)__popc(m & lanemask_lt())) & (SQ - 1u);
     Q.start[i] = start;
     Q.len[i] = len;
     Q.col[i] = col;
     Q.ord[i] = ord;
   }
-  q.n += (uint32_t)__popc(m);
+  __syncwarp();
+  const uint32_t e2 = end + (uint32_t)__popc(m);
+  if (m && lane_id() == 0) Q.end = e2;
+  return e2 - Q.done;
 }
 
 __device__ __forceinline__ void note_new_string(P1Stats& st, uint32_t len) {
@@ -623,15 +626,15 @@ __device__ __forceinline__ void note_column_value(const P1Args& A, uint32_t col,
   }
 }
 
-// one text of SHORT_MAX+1 .. MID_MAX bytes by a single lane: words streamed four at a time through a funnel shift
-__device__ __forceinline__ void midtext_one(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, uint32_t col,
+// one text, any length, by a single lane: words streamed four at a time through a funnel shift
+__device__ __forceinline__ void text_one(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, uint32_t col,
                                             uint32_t ord, P1Stats& st) {
   const uint32_t nw = (len + 3u) >> 2;
   const uint32_t tail = len & 3u, tail_mask = tail ? ((1u << (8u * tail)) - 1u) : 0xffffffffu;
   const uintptr_t a = reinterpret_cast<uintptr_t>(A.buf + start);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
   const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  const uint32_t room = (uint32_t)min((ptrdiff_t)(MID_MAX / 4 + 1), wlast - w);  // whole words readable after *w
+  const uint32_t room = (uint32_t)min((ptrdiff_t)0x7fffffff, wlast - w);  // whole words readable after *w
   uint32_t sum = 0;
   {
     uint32_t prev = __ldg(w);
@@ -672,7 +675,7 @@ __device__ __forceinline__ void midtext_one(const P1Args& A, const uint32_t* wla
         const uintptr_t b = reinterpret_cast<uintptr_t>(A.buf + cs);
         const uint32_t* v = reinterpret_cast<const uint32_t*>(b & ~(uintptr_t)3);
         const uint32_t sh2 = (uint32_t)(b & 3u) * 8u;
-        const uint32_t room2 = (uint32_t)min((ptrdiff_t)(MID_MAX / 4 + 1), wlast - v);
+        const uint32_t room2 = (uint32_t)min((ptrdiff_t)0x7fffffff, wlast - v);
         uint32_t p1 = __ldg(w), p2 = __ldg(v);
         for (uint32_t k0 = 0; k0 < nw && diff == 0u; k0 += 4u) {
           const uint32_t a0 = __ldg(w + min(k0 + 1u, room)), a1 = __ldg(w + min(k0 + 2u, room)), a2 = __ldg(w + min(k0 + 3u, room)),
@@ -710,24 +713,10 @@ __device__ __forceinline__ void midtext_one(const P1Args& A, const uint32_t* wla
   if (is_new) note_new_string(st, len);
 }
 
-__device__ __forceinline__ void p1_midtext(const P1Args& A, const uint32_t* wlast, const P1Side& Q, uint32_t head, uint32_t count,
-                                           P1Stats& st) {
-  const unsigned lane = lane_id();
-  if (lane < count) {
-    const uint32_t qi = (head + lane) & (SQ - 1u);
-    midtext_one(A, wlast, Q.start[qi], Q.len[qi], Q.col[qi], Q.ord[qi], st);
-  }
-  __syncwarp();
-}
-
-struct P1Queues {
-  P1Side* mid;
-  SideQ qm;
-};
-
 // Processes the queued fields [off, off + count) of the warp's main queue (count <= 32): lane l takes field off + l.
+// Q[0] parks texts of up to SHORT_MAX bytes, Q[1] texts of up to MID_MAX bytes.
 __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, const P1Warp& W, uint32_t off, uint32_t count,
-                                           uint32_t ord0, P1Stats& st, P1Queues& SQs, bool flush) {
+                                           uint32_t ord0, P1Stats& st, P1Side* Q, bool flush) {
   const unsigned lane = lane_id();
   const bool valid = lane < count;
   uint32_t start = 0, len = 0, col = 0;
@@ -742,48 +731,35 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
   const bool live = valid && len != 0u;
   const bool text = is_text_like(t);
   if (valid && len == 0u) A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one (or the row is malformed)
-  bool is_mid = false, is_long = false;
-  if (live) {
-    if (len <= (text ? SHORT_MAX : NUM_FAST_MAX) || t == ZDWB_CHAR) {
+  if (live && !text) {
+    unsigned long long v1, v2;
+    if (len <= NUM_FAST_MAX || t == ZDWB_CHAR) {
       uint32_t x[5];
       short_words<5>(A.buf + start, len, wlast, x);
-      if (text) {
-        bool is_new;
-        const uint32_t slot = ht_upsert_short(A, wlast, start, len, x, &is_new);
-        A.rec_col[ord] = col;
-        A.rec_val[ord] = slot;
-        note_column_set(A, col);
-        if (is_new) note_new_string(st, len);
+      if (t == ZDWB_CHAR) {
+        // sign-extended first byte (+ second byte * 256): min/max rule ConvertToZDW.cpp:358-361 (second byte only
+        // after a backslash), pass-2 rule :543-547 (always); bytes past the field read as NUL (x is masked)
+        const long long b0 = (long long)(int8_t)(x[0] & 0xffu);
+        const long long b1 = len > 1 ? (long long)((int32_t)(int8_t)((x[0] >> 8) & 0xffu) * 256) : 0ll;
+        v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
+        v2 = (unsigned long long)(b0 + b1);
       } else {
-        unsigned long long v1, v2;
-        if (t == ZDWB_CHAR) {
-          // sign-extended first byte (+ second byte * 256): min/max rule ConvertToZDW.cpp:358-361 (second byte only
-          // after a backslash), pass-2 rule :543-547 (always); bytes past the field read as NUL (x is masked)
-          const long long b0 = (long long)(int8_t)(x[0] & 0xffu);
-          const long long b1 = len > 1 ? (long long)((int32_t)(int8_t)((x[0] >> 8) & 0xffu) * 256) : 0ll;
-          v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
-          v2 = (unsigned long long)(b0 + b1);
-        } else {
-          if (!digits_value(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);  // strtoull, :385,564
-          v2 = v1;
-        }
-        A.rec_col[ord] = col;
-        A.rec_val[ord] = v2;
-        note_column_value(A, col, v1);
+        if (!digits_value(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);  // strtoull, :385,564
+        v2 = v1;
       }
-    } else if (!text) {  // a number of more than 20 characters
-      const unsigned long long v = parse_u64_field(A.buf + start, len);
-      A.rec_col[ord] = col;
-      A.rec_val[ord] = v;
-      note_column_value(A, col, v);
-    } else {
-      is_mid = len <= MID_MAX;
-      is_long = !is_mid;
+    } else {  // a number of more than 20 characters
+      v1 = v2 = parse_u64_field(A.buf + start, len);
     }
+    A.rec_col[ord] = col;
+    A.rec_val[ord] = v2;
+    note_column_value(A, col, v1);
   }
-  side_push(*SQs.mid, SQs.qm, is_mid, start, len, col, ord);
+  const bool is_text = live && text;
+  uint32_t waiting[2];
+  waiting[0] = side_push(Q[0], is_text && len <= SHORT_MAX, start, len, col, ord);
+  waiting[1] = side_push(Q[1], is_text && len > SHORT_MAX && len <= MID_MAX, start, len, col, ord);
   // ---- long texts: octet g takes the g-th, (g+4)-th, ... of them
-  unsigned todo = __ballot_sync(0xffffffffu, is_long);
+  unsigned todo = __ballot_sync(0xffffffffu, is_text && len > MID_MAX);
   if (todo) {
     const unsigned grp = lane >> 3, gl = lane & 7u, om = 0xffu << (grp * 8);
     while (todo) {
@@ -807,18 +783,28 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
       for (int k = 0; k < 4 && todo; ++k) todo &= todo - 1;
     }
   }
-  if (SQs.qm.n >= 32u || (flush && SQs.qm.n)) {
-    __syncwarp();
-    const uint32_t take = min(SQs.qm.n, 32u);
-    p1_midtext(A, wlast, *SQs.mid, SQs.qm.head, take, st);
-    SQs.qm.head = (SQs.qm.head + take) & (SQ - 1u);
-    SQs.qm.n -= take;
+  // ---- parked texts, 32 of a kind at a time (one call site: the loop is not unrolled)
+#pragma unroll 1
+  for (uint32_t qi = 0; qi < 2u; ++qi) {
+    uint32_t n = qi ? waiting[1] : waiting[0];
+    while (n >= 32u || (flush && n)) {
+      P1Side& S = Q[qi];
+      const uint32_t take = min(n, 32u), head = S.done;
+      if (lane < take) {
+        const uint32_t e = (head + lane) & (SQ - 1u);
+        text_one(A, wlast, S.start[e], S.len[e], S.col[e], S.ord[e], st);
+      }
+      __syncwarp();
+      if (lane == 0) S.done = head + take;
+      __syncwarp();
+      n -= take;
+    }
   }
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) {
   __shared__ P1Warp sw[ENC_WARPS];
-  __shared__ P1Side s_mid[ENC_WARPS];
+  __shared__ P1Side s_side[ENC_WARPS][2];
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t tile = blockIdx.x * ENC_WARPS + warp;
   if (tile >= A.ntiles) return;
@@ -829,9 +815,9 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
   WarpCarry c;
   carry_init(A.buf, t0, A.pre[tile], c);
   P1Stats st = {0u, 0u, 0u, 0ull};
-  P1Queues SQs;
-  SQs.mid = &s_mid[warp];
-  SQs.qm.head = SQs.qm.n = 0u;
+  P1Side* Q = s_side[warp];
+  if (lane < 2) Q[lane].end = Q[lane].done = 0u;
+  __syncwarp();
   uint32_t qbase = c.ne;  // ordinal of the field held in queue slot 0
   const uint32_t tabs_per_row = A.ncols - 1u;
   if (tile == 0 && lane == 0) A.row_rec[0] = 0u;
@@ -885,9 +871,11 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
     // ---- work off full batches (in the extra round: whatever is left, and the side queue)
     const uint32_t have = c.ne - qbase;
     uint32_t off = 0;
-    while (off + 32u <= have || (last && (off < have || SQs.qm.n))) {
+    bool flushed = false;
+    while (off + 32u <= have || (last && !flushed)) {
       const uint32_t cnt = min(32u, have - off);
-      p1_process(A, wlast, W, off, cnt, qbase + off, st, SQs, last);
+      flushed = last && off + cnt == have;
+      p1_process(A, wlast, W, off, cnt, qbase + off, st, Q, flushed);
       off += cnt;
     }
     if (last) break;
