@@ -301,6 +301,44 @@ __global__ void __launch_bounds__(TS_THREADS) k_tile_scan(TileAgg* __restrict__ 
   }
 }
 
+// The same prefix over many CTAs: every CTA scans 1024 tiles in place and reports its total; k_tile_scan then runs over
+// the CTA totals (and fills in the census totals), k_tile_scan_add folds them back in.
+__global__ void __launch_bounds__(TS_THREADS) k_tile_scan_local(TileAgg* __restrict__ agg, uint32_t ntiles, TileAgg* __restrict__ part) {
+  __shared__ TileAgg wsum[32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const TileAgg zero = {0u, 0u, 0u, 0u, 0u};
+  const uint32_t t = blockIdx.x * TS_THREADS + threadIdx.x;
+  const TileAgg mine = t < ntiles ? agg[t] : zero;
+  TileAgg inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const TileAgg u = agg_shfl_up(inc, o);
+    if (lane >= (unsigned)o) inc = agg_join(u, inc);
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    TileAgg w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const TileAgg u = agg_shfl_up(w, o);
+      if (lane >= (unsigned)o) w = agg_join(u, w);
+    }
+    wsum[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  TileAgg ex = zero;
+  if (warp) ex = wsum[warp - 1];
+  const TileAgg up = agg_shfl_up(inc, 1);
+  if (lane) ex = agg_join(ex, up);
+  if (t < ntiles) agg[t] = ex;
+  if (threadIdx.x == 0) part[blockIdx.x] = wsum[31];
+}
+__global__ void __launch_bounds__(TS_THREADS) k_tile_scan_add(TileAgg* __restrict__ agg, uint32_t ntiles, const TileAgg* __restrict__ part) {
+  const uint32_t t = blockIdx.x * TS_THREADS + threadIdx.x;
+  if (t < ntiles && blockIdx.x) agg[t] = agg_join(part[blockIdx.x], agg[t]);
+}
+
 // one warp: terminator of row `want` (0-based) -> meta->cut_end_p1, first byte of the next row -> meta->next_start
 __global__ void k_find_cut(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, const TileAgg* __restrict__ pre,
                            uint32_t want, EncMeta* __restrict__ meta) {
@@ -400,14 +438,6 @@ __device__ __forceinline__ void short_words(const uint8_t* s, uint32_t len, cons
     x[k] = got >= 4u ? x[k] : (got ? (x[k] & ((1u << (8u * got)) - 1u)) : 0u);
   }
 }
-__device__ __forceinline__ uint32_t short_hash(const uint32_t x[4], uint32_t len) {
-  uint32_t s = mix_word(x[0], 0);
-  if (len > 4) s += mix_word(x[1], 1);
-  if (len > 8) s += mix_word(x[2], 2);
-  if (len > 12) s += mix_word(x[3], 3);
-  return finish_hash(s, len);
-}
-
 // ---------------------------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------------------------
@@ -440,35 +470,6 @@ struct P1Stats {
   uint32_t new_count, max_len, max_line;
   unsigned long long new_bytes;
 };
-
-// slot of the string (inserting it when absent); *is_new reports an insertion.  Per-lane version for len <= SHORT_MAX;
-// x = the string's four masked words.
-__device__ __forceinline__ uint32_t ht_upsert_short(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len,
-                                                    const uint32_t x[4], bool* is_new) {
-  uint32_t i = short_hash(x, len) & A.ht.mask;
-  const unsigned long long mine = ((unsigned long long)(start + 1u) << 32) | len;
-  *is_new = false;
-  for (uint32_t probe = 0; probe < HT_MAX_PROBE; ++probe) {
-    unsigned long long cur = A.ht.slots[i];
-    if (cur == 0ull) {
-      cur = atomicCAS(&A.ht.slots[i], 0ull, mine);
-      if (cur == 0ull) {
-        *is_new = true;
-        return i;
-      }
-    }
-    if ((uint32_t)cur == len) {
-      const uint32_t cs = (uint32_t)(cur >> 32) - 1u;
-      if (cs == start) return i;
-      uint32_t y[4];
-      short_words<4>(A.buf + cs, len, wlast, y);
-      if (x[0] == y[0] && x[1] == y[1] && x[2] == y[2] && x[3] == y[3]) return i;
-    }
-    i = (i + 1) & A.ht.mask;
-  }
-  *reinterpret_cast<volatile uint32_t*>(&A.meta->ht_overflow) = 1u;
-  return 0;
-}
 
 // 8 lanes (one octet of the warp) work on one long string: gl = lane within the octet, `om` = the octet's lane mask.
 __device__ __forceinline__ uint32_t ht_upsert_long(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, unsigned gl,
@@ -574,11 +575,14 @@ __device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, 
 #ifndef P1_MINB
 #define P1_MINB 4
 #endif
+#ifndef P1_BAL
+#define P1_BAL 1
+#endif
 #ifndef P1_LDCG
 #define P1_LDCG 0
 #endif
+constexpr uint32_t MID_MAX = 128;  // longest text handled by a single lane
 constexpr uint32_t SQ = P1_SQ;     // entries of the side queue (at most 31 waiting + 32 pushed)
-constexpr uint32_t MID_MAX = 64;   // longest text handled by a single lane
 
 struct P1Side {  // a ring; `end` = entries ever pushed, `done` = entries ever taken (warp-uniform, kept here)
   uint32_t start[SQ], len[SQ], col[SQ], ord[SQ];
@@ -714,7 +718,7 @@ __device__ __forceinline__ void text_one(const P1Args& A, const uint32_t* wlast,
 }
 
 // Processes the queued fields [off, off + count) of the warp's main queue (count <= 32): lane l takes field off + l.
-// Q[0] parks texts of up to SHORT_MAX bytes, Q[1] texts of up to MID_MAX bytes.
+// Q[0] parks texts of up to SHORT_MAX bytes, Q[1] texts of up to MID_MAX bytes; longer ones go to the octets at once.
 __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, const P1Warp& W, uint32_t off, uint32_t count,
                                            uint32_t ord0, P1Stats& st, P1Side* Q, bool flush) {
   const unsigned lane = lane_id();
@@ -827,6 +831,7 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
   for (uint32_t s = 0;; s += STEP) {
     const bool last = s >= TILE || t0 + (int64_t)s >= A.limit;
     if (!last) {
+      const uint32_t ne_before = c.ne;
       const LaneStep L = scan_step(A.buf, A.limit, t0 + s, c);
       // ---- rows that end here: field-count check, longest line, record index of the next row
       uint32_t tm = L.term;
@@ -842,6 +847,52 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
         st.max_line = max(st.max_line, (uint32_t)(L.p0 + i - row_start + 1));
         A.row_rec[R + 1u] = L.nes + (uint32_t)__popc(L.ne & ((2u << i) - 1u));
       }
+#if P1_BAL
+      // ---- non-empty fields go to the warp's queue, slot = ordinal.  Two phases, so that a lane that scanned a run of
+      // short fields does not hold up the warp: every lane first drops the bit position (lane * 16 + bit) of each of
+      // its closing delimiters into the field's slot; then the step's fields are dealt out evenly, field k to lane
+      // k & 31, which fetches the scanning lane's masks by shuffle and works out column, start and length.
+      {
+        uint32_t rem = L.ne, q = L.nes - qbase;
+        while (rem) {
+          W.start[q++] = lane * 16u + (uint32_t)(__ffs(rem) - 1);
+          rem &= rem - 1;
+        }
+      }
+      __syncwarp();
+      {
+        const uint32_t nf = c.ne - ne_before, qb = ne_before - qbase;
+        const uint32_t pk_tt = L.tab | (L.term << 16), pk_bd = L.tab | L.term | L.skip;
+        const uint32_t colbase = L.tabs - L.rows * tabs_per_row;
+        for (uint32_t k0 = 0; k0 < nf; k0 += 32u) {
+          const uint32_t k = k0 + lane;
+          const bool mine = k < nf;
+          const uint32_t pos = mine ? W.start[qb + k] : 0u;
+          const int j = (int)(pos >> 4);
+          const uint32_t i = pos & 15u;
+          const uint32_t tt = __shfl_sync(0xffffffffu, pk_tt, j), bd = __shfl_sync(0xffffffffu, pk_bd, j);
+          const uint32_t cb = __shfl_sync(0xffffffffu, colbase, j);
+          const int64_t pb_j = __shfl_sync(0xffffffffu, L.pb, j);
+          if (mine) {
+            const uint32_t below = (1u << i) - 1u;
+            const int64_t p0 = t0 + (int64_t)s + 16 * (int64_t)j;
+            uint32_t col = cb + (uint32_t)__popc(tt & below) - (uint32_t)__popc((tt >> 16) & below) * tabs_per_row;
+            const uint32_t lowb = bd & below;
+            const uint32_t start = (uint32_t)((lowb ? p0 + (31 - __clz(lowb)) : pb_j) + 1);
+            uint32_t len = (uint32_t)(p0 + i) - start;
+            if (col >= A.ncols) {  // (a malformed row is reported through bad_row)
+              col = 0;
+              len = 0;
+            } else if (A.trim) {
+              len = trimmed_len(A.buf, start, len);
+            }
+            W.start[qb + k] = start;
+            W.len[qb + k] = len;
+            W.col[qb + k] = col;
+          }
+        }
+      }
+#else
       // ---- non-empty fields go to the warp's queue; the slot is the field's ordinal, so no coordination is needed
       uint32_t rem = L.ne;
       const uint32_t bound = L.tab | L.term | L.skip;
@@ -866,6 +917,7 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
         W.len[q] = len;
         W.col[q] = col;
       }
+#endif
       __syncwarp();
     }
     // ---- work off full batches (in the extra round: whatever is left, and the side queue)
@@ -1061,11 +1113,28 @@ __global__ void k_block_header(uint8_t* __restrict__ out, const EncMeta* __restr
 // value bytes are then produced row by row, one warp per row.  The tile's bytes go to its own slot of a staging buffer
 // (tile * tile_cap); k_gather_tiles packs the tiles once every tile length is known, which keeps the row stream free
 // of any cross-CTA dependency while it is being produced.
+// what pass 2 needs to know about a column, in one 16-byte load
+struct ColInfo {
+  unsigned long long base;  // ConvertToZDW.cpp:455 (0 for text-like columns)
+  int32_t u;                // index among the used columns, -1 = unused in this block
+  uint32_t text;            // the value is a dictionary slot
+};
+__global__ void k_col_info(const uint8_t* __restrict__ types, const int32_t* __restrict__ used_idx,
+                           const unsigned long long* __restrict__ cbase, uint32_t ncols, ColInfo* __restrict__ info) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  ColInfo ci;
+  ci.base = cbase[c];
+  ci.u = used_idx[c];
+  ci.text = is_text_like(types[c]) ? 1u : 0u;
+  info[c] = ci;
+}
+
 __global__ void __launch_bounds__(ENC_THREADS)
     k_pass2(const uint32_t* __restrict__ rec_col, const unsigned long long* __restrict__ rec_val,
-            const uint32_t* __restrict__ row_rec, uint32_t nrows, uint32_t rows_per_cta, const uint8_t* __restrict__ types,
-            const uint32_t* __restrict__ slot_off, const int32_t* __restrict__ used_idx, const uint32_t* __restrict__ used_cols,
-            const uint8_t* __restrict__ csize, const unsigned long long* __restrict__ cbase, uint32_t U, uint32_t nflag,
+            const uint32_t* __restrict__ row_rec, uint32_t nrows, uint32_t rows_per_cta, const ColInfo* __restrict__ cinfo,
+            const uint32_t* __restrict__ slot_off, const uint32_t* __restrict__ used_cols,
+            const uint8_t* __restrict__ csize, uint32_t U, uint32_t nflag,
             uint64_t tile_cap, uint8_t* __restrict__ staging, uint64_t* __restrict__ tile_bytes) {
   extern __shared__ __align__(16) uint8_t dsm[];
   // dynamic smem: nval[(R+1)*U] u64 | rowoff[R+1] u32 | rrec[R+2] u32 | usz[U] u8
@@ -1086,25 +1155,52 @@ __global__ void __launch_bounds__(ENC_THREADS)
   for (uint32_t k = tid; k <= nrw; k += ENC_THREADS) rrec[k] = row_rec[rw0 + k];
   __syncthreads();
 
-  // ---- values of the tile's rows and of the row before it, from the records
+  // ---- values of the tile's rows and of the row before it, from the records; four records per thread and round, so
+  // that the dependent loads (record -> column info -> dictionary offset) of different records overlap
   {
     const uint32_t k0 = rrec[0], k1 = rrec[nrw];
-    for (uint32_t k = k0 + tid; k < k1; k += ENC_THREADS) {
-      const uint32_t col = rec_col[k];
-      if (col == REC_EMPTY) continue;
-      const int32_t u = __ldg(used_idx + col);
-      if (u < 0) continue;
-      // row of the record: last j with rrec[j] <= k
-      uint32_t a = 0, b = nrw;
-      while (b - a > 1) {
-        const uint32_t m = (a + b) >> 1;
-        if (rrec[m] <= k) a = m;
-        else b = m;
+    constexpr int NR = 4;
+    for (uint32_t kb = k0 + tid; kb < k1; kb += NR * ENC_THREADS) {
+      uint32_t col[NR];
+      unsigned long long v[NR];
+      ColInfo ci[NR];
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        const uint32_t k = kb + (uint32_t)j * ENC_THREADS;
+        col[j] = k < k1 ? rec_col[k] : REC_EMPTY;
+        v[j] = k < k1 ? rec_val[k] : 0ull;
       }
-      unsigned long long v = rec_val[k];
-      if (is_text_like(__ldg(types + col))) v = slot_off[(uint32_t)v];  // Dictionary::getOffset
-      else if (v) v -= __ldg(cbase + col);                               // ConvertToZDW.cpp:548,566
-      nval[(size_t)(rw0 + a + 1 - r0) * U + (uint32_t)u] = v;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        ci[j].u = -1;
+        ci[j].text = 0;
+        ci[j].base = 0;
+        if (col[j] != REC_EMPTY) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(cinfo + col[j]));
+          ci[j].base = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+          ci[j].u = (int32_t)q.z;
+          ci[j].text = q.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        if (ci[j].u < 0) continue;
+        if (ci[j].text) v[j] = __ldg(slot_off + (uint32_t)v[j]);  // Dictionary::getOffset
+        else if (v[j]) v[j] -= ci[j].base;                        // ConvertToZDW.cpp:548,566
+      }
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        if (ci[j].u < 0) continue;
+        const uint32_t k = kb + (uint32_t)j * ENC_THREADS;
+        // row of the record: last a with rrec[a] <= k
+        uint32_t a = 0, b = nrw;
+        while (b - a > 1) {
+          const uint32_t m = (a + b) >> 1;
+          if (rrec[m] <= k) a = m;
+          else b = m;
+        }
+        nval[(size_t)(rw0 + a + 1 - r0) * U + (uint32_t)ci[j].u] = v[j];
+      }
     }
   }
   __syncthreads();
@@ -1297,10 +1393,17 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   }
   ZDWB_LAUNCH_CHECK(ctx);
   {
+    const uint32_t nparts = (ntiles + TS_THREADS - 1) / TS_THREADS;
+    DevBuf part;
+    ZDWB_TRY(part.alloc(ctx, (size_t)nparts * sizeof(TileAgg)));
     KernelScope _ks(ctx, "k_tile_scan");
-    k_tile_scan<<<1, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, meta);
+    k_tile_scan_local<<<nparts, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, part.as<TileAgg>());
+    ZDWB_LAUNCH_CHECK(ctx);
+    k_tile_scan<<<1, TS_THREADS, 0, st>>>(part.as<TileAgg>(), nparts, meta);
+    ZDWB_LAUNCH_CHECK(ctx);
+    k_tile_scan_add<<<nparts, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, part.as<TileAgg>());
+    ZDWB_LAUNCH_CHECK(ctx);
   }
-  ZDWB_LAUNCH_CHECK(ctx);
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
   ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
   const uint64_t rows_total = hmeta->tot_rows;
@@ -1486,7 +1589,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
 
   // ---- pass 2 into the staging buffer
   uint64_t rows_bytes = 0;
-  DevBuf staging, tile_bytes, tile_off, rows_total_d;
+  DevBuf staging, tile_bytes, tile_off, rows_total_d, colinfo;
   uint32_t tiles2 = 0;
   uint64_t tile_cap = 0;
   if (U > 0) {
@@ -1508,11 +1611,18 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ZDWB_TRY(tile_bytes.alloc(ctx, (size_t)tiles2 * 8));
     ZDWB_TRY(tile_off.alloc(ctx, (size_t)tiles2 * 8));
     ZDWB_TRY(rows_total_d.alloc(ctx, 8));
+    ZDWB_TRY(colinfo.alloc(ctx, (size_t)ncols * sizeof(ColInfo)));
+    {
+      KernelScope _ks(ctx, "k_col_info");
+      k_col_info<<<(ncols + 255) / 256, 256, 0, st>>>(types_d.as<uint8_t>(), used_idx.as<int32_t>(), cbase.as<unsigned long long>(), ncols,
+                                                    colinfo.as<ColInfo>());
+    }
+    ZDWB_LAUNCH_CHECK(ctx);
     {
       KernelScope _ks(ctx, "k_pass2");
       k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(rec_col.as<uint32_t>(), rec_val.as<unsigned long long>(), row_rec.as<uint32_t>(),
-                                               nrows, rpc2, types_d.as<uint8_t>(), slot_off.as<uint32_t>(), used_idx.as<int32_t>(),
-                                               used_cols.as<uint32_t>(), csize.as<uint8_t>(), cbase.as<unsigned long long>(), U,
+                                               nrows, rpc2, colinfo.as<ColInfo>(), slot_off.as<uint32_t>(),
+                                               used_cols.as<uint32_t>(), csize.as<uint8_t>(), U,
                                                nflag, tile_cap, staging.as<uint8_t>(), tile_bytes.as<uint64_t>());
     }
     ZDWB_LAUNCH_CHECK(ctx);

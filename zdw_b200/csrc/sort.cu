@@ -239,13 +239,22 @@ __global__ void __launch_bounds__(RK_THREADS)
   const uint32_t i = blockIdx.x * RK_THREADS + threadIdx.x;
   if (i >= n) return;
   const ulonglong2 me = keys[i];
-  uint32_t cnt = 0;
+  // branch-free main loop: strictly smaller prefix keys are counted, equal ones only noted
+  uint32_t cnt = 0, ties = 0;
+#pragma unroll 8
   for (uint32_t t = 0; t < jn; ++t) {
     const ulonglong2 o = sk[t];
-    if (o.x < me.x || (o.x == me.x && o.y < me.y)) {
-      ++cnt;
-    } else if (o.x == me.x && o.y == me.y && j0 + t != i) {
-      if (str_less_from(base, starts[j0 + t], lens[j0 + t], starts[i], lens[i], 16)) ++cnt;
+    const bool eqx = o.x == me.x;
+    cnt += (o.x < me.x || (eqx && o.y < me.y)) ? 1u : 0u;
+    ties += (eqx && o.y == me.y) ? 1u : 0u;
+  }
+  const bool self_here = i >= j0 && i < j0 + jn;
+  if (ties > (self_here ? 1u : 0u)) {  // strings that agree on their first 16 bytes: compare the rest in memory
+    for (uint32_t t = 0; t < jn; ++t) {
+      const ulonglong2 o = sk[t];
+      if (o.x == me.x && o.y == me.y && j0 + t != i &&
+          str_less_from(base, starts[j0 + t], lens[j0 + t], starts[i], lens[i], 16))
+        ++cnt;
     }
   }
   if (cnt) atomicAdd(rank + i, cnt);
