@@ -69,7 +69,7 @@ def test_golden_radix_sort_path(ctx, name):
     try:
         got = G.encode_file_with_product(ctx, sch, tsv)
     finally:
-        ctx.set_tuning("small_sort_max", 16384)
+        ctx.set_tuning("small_sort_max", 65536)
         ctx.set_tuning("ht_initial_log2", 20)
     assert got == want, G.first_diff(got, want)
 
@@ -82,7 +82,7 @@ def test_corpus_radix_sort_path(ctx):
             if case[0].startswith(("d7", "d9", "mixed", "d1_", "d8_used25")):
                 _check_case(ctx, case)
     finally:
-        ctx.set_tuning("small_sort_max", 16384)
+        ctx.set_tuning("small_sort_max", 65536)
         ctx.set_tuning("ht_initial_log2", 20)
 
 
@@ -108,6 +108,21 @@ def test_device_resident_unaligned_input(ctx):
     _, want_blk = G.split_header(want)
     tsv = case[2]
     for shift in (0, 1, 3, 8, 15, 16, 17):
+        t = torch.zeros(len(tsv) + 64, dtype=torch.uint8, device="cuda")
+        t[shift:shift + len(tsv)] = torch.frombuffer(bytearray(tsv), dtype=torch.uint8).cuda()
+        torch.cuda.synchronize()
+        blk = ctx.encode_block(sch.types, t.data_ptr() + shift, len(tsv), input_on_device=True, output_on_device=True)
+        got = G.dev_bytes(blk.dev_ptr, blk.length)
+        assert got == want_blk, f"shift {shift}: {G.first_diff(got, want_blk)}"
+
+
+def test_device_resident_unaligned_leading_empty_field(ctx):
+    """An empty first field at offset 0 of a buffer that is not 16-byte aligned (offset 0 acts as a boundary)."""
+    import torch
+    sch = O.parse_desc(corpus.desc([("a", "varchar(8)"), ("b", "varchar(8)"), ("c", "int(11)")]))
+    tsv = b"\tfoo\t1\n\tbar\t2\nx\t\t3\n"
+    _, want_blk = G.split_header(O.encode(sch, tsv).data)
+    for shift in (0, 1, 5, 15):
         t = torch.zeros(len(tsv) + 64, dtype=torch.uint8, device="cuda")
         t[shift:shift + len(tsv)] = torch.frombuffer(bytearray(tsv), dtype=torch.uint8).cuda()
         torch.cuda.synchronize()

@@ -25,7 +25,7 @@ struct Ctx {
   unsigned long long launches = 0;
   int sm_count = 148;
   // tuning knobs
-  long long small_sort_max = 16384;  // dictionaries up to this many entries take the single-CTA sort
+  long long small_sort_max = 65536;  // dictionaries up to this many entries are ranked by tile sort + binary search
   long long ht_initial_log2 = 20;    // first-try size of the string hash set (grown x8 on overflow)
   long long dec_stage_rows = 0;      // assemble rows in shared memory (1) or straight in global memory (0)
   long long dec_tile_bytes = 8192;   // row-stream bytes per CTA in the decoder's row-boundary discovery

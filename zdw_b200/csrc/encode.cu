@@ -182,7 +182,9 @@ __device__ __forceinline__ LaneStep scan_step(const uint8_t* __restrict__ buf, i
   }
   // delimiters whose preceding byte is not a boundary close a non-empty field
   const uint32_t delims = L.tab | L.term;
-  L.ne = delims & ~((bound << 1) | (L.pb == L.p0 - 1 ? 1u : 0u));
+  uint32_t after_bound = (bound << 1) | (L.pb == L.p0 - 1 ? 1u : 0u);
+  if (L.p0 < 0 && L.p0 + 16 > 0) after_bound |= 1u << (-L.p0);  // offset 0 behaves like "just after a boundary"
+  L.ne = delims & ~after_bound;
   // counts in front of the lane: one packed inclusive scan (each count <= 16 per lane, <= 512 per step)
   const uint32_t mine = (uint32_t)__popc(L.term) | ((uint32_t)__popc(L.tab) << 10) | ((uint32_t)__popc(L.ne) << 20);
   uint32_t inc = mine;
@@ -205,36 +207,77 @@ __device__ __forceinline__ LaneStep scan_step(const uint8_t* __restrict__ buf, i
 // ---------------------------------------------------------------------------------------------
 // census: counts per tile
 // ---------------------------------------------------------------------------------------------
+// The census needs totals only, so it runs a lighter version of scan_step: the same masks, but counts are summed per
+// lane and reduced once per tile, and "the byte in front is a boundary" travels as one bit instead of a position.
 __global__ void __launch_bounds__(ENC_THREADS)
     k_tile_count(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, TileAgg* __restrict__ agg) {
   const uint32_t tile = blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
   if (tile >= ntiles) return;
-  const int64_t t0 = lo + (int64_t)tile * TILE;
-  WarpCarry c;
-  TileAgg zero = {0u, 0u, 0u, 0u, 0u};
-  carry_init(buf, t0, zero, c);
-  // the boundary in front of the tile decides whether its first delimiter closes an empty field
-  c.pb = t0 - 2;
-  if (t0 <= 0) {
-    c.pb = -1;
-  } else {
+  const unsigned lane = lane_id();
+  const int64_t t0 = lo + (int64_t)tile * TILE, limit = (int64_t)n;
+  uint32_t c_bs = (t0 > 0 && __ldg(buf + t0 - 1) == (uint8_t)'\\') ? 1u : 0u;
+  uint32_t c_nl = t0 <= 0 ? 1u : (is_unescaped_newline(buf, t0 - 1) ? 1u : 0u);
+  uint32_t c_bd = t0 == 0 ? 1u : 0u;  // the byte in front of the tile is a boundary (buffer start counts as one)
+  if (t0 > 0) {
     const uint8_t b = __ldg(buf + t0 - 1);
-    if ((b == (uint8_t)'\t' || b == (uint8_t)'\n') && !odd_backslashes_before(buf, t0 - 1)) c.pb = t0 - 1;
+    if ((b == (uint8_t)'\t' || b == (uint8_t)'\n') && !odd_backslashes_before(buf, t0 - 1)) c_bd = 1u;
   }
-  int64_t last_b = -1, last_r = -1;
+  uint32_t rows = 0, tabs = 0, ne = 0;
+  int32_t last_b = -1, last_r = -1;  // offsets inside the tile
   for (uint32_t s = 0; s < TILE; s += STEP) {
-    const LaneStep L = scan_step(buf, (int64_t)n, t0 + s, c);
-    (void)L;
+    const int64_t p0 = t0 + s + 16 * (int64_t)lane;
+    uint32_t tab = 0, nl = 0, bs = 0;
+    if (p0 < limit && p0 + 16 > 0) {
+      const uint4 v = ldg_stream_u4(buf + p0);
+      const int64_t ia = p0 < 0 ? -p0 : 0;
+      const int64_t ib = p0 + 16 > limit ? limit - p0 : 16;
+      const uint32_t in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
+      tab = chunk_mask(v, '\t') & in;
+      if (chunk_has(v, '\n')) nl = chunk_mask(v, '\n') & in;
+      if (chunk_has(v, '\\')) bs = chunk_mask(v, '\\') & in;
+    }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, bs >> 15, 1);
+    if (lane == 0) prev = c_bs;
+    uint32_t sus = (tab | nl) & ((bs << 1) | prev);
+    while (sus) {  // escape parity: only delimiters that directly follow a backslash need the (rare) backward walk
+      const int i = __ffs(sus) - 1;
+      sus &= sus - 1;
+      if (odd_backslashes_before(buf, p0 + i)) {
+        tab &= ~(1u << i);
+        nl &= ~(1u << i);
+      }
+    }
+    uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
+    if (lane == 0) prevnl = c_nl;
+    uint32_t after_nl = ((nl << 1) | prevnl) & 0xffffu;
+    const bool has_zero = p0 <= 0 && p0 + 16 > 0;
+    if (has_zero) after_nl |= 1u << (-p0);
+    const uint32_t skip = nl & after_nl, term = nl & ~skip, bound = tab | nl;
+    uint32_t prevbd = __shfl_up_sync(0xffffffffu, bound >> 15, 1);
+    if (lane == 0) prevbd = c_bd;
+    uint32_t after_bound = (bound << 1) | prevbd;
+    if (has_zero) after_bound |= 1u << (-p0);
+    rows += (uint32_t)__popc(term);
+    tabs += (uint32_t)__popc(tab);
+    ne += (uint32_t)__popc((tab | term) & ~after_bound);
+    if (bound) last_b = (int32_t)(s + 16u * lane) + (31 - __clz(bound));
+    if (nl) last_r = (int32_t)(s + 16u * lane) + (31 - __clz(nl));
+    c_bs = __shfl_sync(0xffffffffu, bs >> 15, 31);
+    c_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
+    c_bd = __shfl_sync(0xffffffffu, bound >> 15, 31);
   }
-  last_b = c.pb >= t0 ? c.pb : -1;
-  last_r = c.prb >= t0 ? c.prb : -1;
-  if (lane_id() == 0) {
+  rows = __reduce_add_sync(0xffffffffu, rows);
+  tabs = __reduce_add_sync(0xffffffffu, tabs);
+  ne = __reduce_add_sync(0xffffffffu, ne);
+  last_b = __reduce_max_sync(0xffffffffu, last_b);
+  last_r = __reduce_max_sync(0xffffffffu, last_r);
+  if (lane == 0) {
     TileAgg a;
-    a.rows = c.rows;
-    a.tabs = c.tabs;
-    a.ne = c.ne;
-    a.bound_p1 = (uint32_t)(last_b + 1);
-    a.break_p1 = (uint32_t)(last_r + 1);
+    a.rows = rows;
+    a.tabs = tabs;
+    a.ne = ne;
+    a.bound_p1 = last_b >= 0 ? (uint32_t)(t0 + last_b + 1) : 0u;
+    a.break_p1 = last_r >= 0 ? (uint32_t)(t0 + last_r + 1) : 0u;
     agg[tile] = a;
   }
 }

@@ -202,19 +202,35 @@ __global__ void k_scatter_order(const uint32_t* __restrict__ pos, const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// small path: rank by counting.  rank(i) = #{ j : s_j < s_i }, all pairs compared on 16-byte big-endian prefix
-// keys held in shared memory; only pairs whose prefixes tie fall back to the bytes in memory.  O(n^2) key
-// compares spread over the whole GPU beat a one-CTA sorting network for the dictionary sizes of analytics-shaped
-// blocks (a few thousand strings).
+// small path: rank by counting.  rank(i) = #{ j : s_j < s_i } = sum over tiles of 1024 strings of the lower bound of
+// s_i's 16-byte big-endian prefix key among the tile's sorted keys (bitonic sort in shared memory, then one binary
+// search per string and tile); only strings whose prefixes tie fall back to the bytes in memory.  n^2 / 100 key
+// compares spread over the whole GPU, three launches, no multi-pass radix machinery.
 // ---------------------------------------------------------------------------------------------
 constexpr int RK_THREADS = 256;
 constexpr int RK_JTILE = 1024;
 
+// four bytes at an arbitrary address, all of them inside the buffer (only aligned words that hold one of them are read)
+__device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t lo = __ldg(w), hi = sh ? __ldg(w + 1) : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+// strcmp order of two strings that agree on their first `from` bytes: four bytes at a time, compared as big-endian
+// numbers (= unsigned byte order), then the tail; a proper prefix sorts first
 __device__ __forceinline__ bool str_less_from(const uint8_t* base, uint32_t sa, uint32_t la, uint32_t sb, uint32_t lb,
                                               uint32_t from) {
   const uint32_t m = la < lb ? la : lb;
-  for (uint32_t i = from; i < m; ++i) {
-    uint8_t a = __ldg(base + sa + i), b = __ldg(base + sb + i);
+  uint32_t i = from;
+  for (; i + 4 <= m; i += 4) {
+    const uint32_t a = load4_unaligned(base + sa + i), b = load4_unaligned(base + sb + i);
+    if (a != b) return __byte_perm(a, 0, 0x0123) < __byte_perm(b, 0, 0x0123);
+  }
+  for (; i < m; ++i) {
+    const uint8_t a = __ldg(base + sa + i), b = __ldg(base + sb + i);
     if (a != b) return a < b;
   }
   return la < lb;
@@ -229,35 +245,80 @@ __global__ void k_rank_keys(const uint8_t* __restrict__ base, const uint32_t* __
   keys[i] = make_ulonglong2(prefix_key(s, len, 0), prefix_key(s, len, 8));
 }
 
-__global__ void __launch_bounds__(RK_THREADS)
-    k_rank_count(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
-                 const ulonglong2* __restrict__ keys, uint32_t n, uint32_t* __restrict__ rank) {
-  __shared__ ulonglong2 sk[RK_JTILE];
-  const uint32_t j0 = blockIdx.y * RK_JTILE, jn = min((uint32_t)RK_JTILE, n - j0);
-  for (uint32_t t = threadIdx.x; t < jn; t += RK_THREADS) sk[t] = keys[j0 + t];
-  __syncthreads();
-  const uint32_t i = blockIdx.x * RK_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const ulonglong2 me = keys[i];
-  // branch-free main loop: strictly smaller prefix keys are counted, equal ones only noted
-  uint32_t cnt = 0, ties = 0;
-#pragma unroll 8
-  for (uint32_t t = 0; t < jn; ++t) {
-    const ulonglong2 o = sk[t];
-    const bool eqx = o.x == me.x;
-    cnt += (o.x < me.x || (eqx && o.y < me.y)) ? 1u : 0u;
-    ties += (eqx && o.y == me.y) ? 1u : 0u;
+// (x, y) as one 128-bit big number
+__device__ __forceinline__ bool key_less(const ulonglong2& a, const ulonglong2& b) { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+
+// Sorts every tile of RK_JTILE prefix keys (with the string ids as payload) in shared memory: bitonic network, one
+// compare-exchange per thread and stage.  Short tiles are padded with (max key, max id), which sort behind everything.
+constexpr int RK_SORT_THREADS = RK_JTILE / 2;
+__global__ void __launch_bounds__(RK_SORT_THREADS)
+    k_rank_tile_sort(const ulonglong2* __restrict__ keys, uint32_t n, ulonglong2* __restrict__ skeys, uint32_t* __restrict__ sidx) {
+  __shared__ ulonglong2 k[RK_JTILE];
+  __shared__ uint32_t id[RK_JTILE];
+  const uint32_t j0 = blockIdx.x * RK_JTILE;
+  for (uint32_t t = threadIdx.x; t < RK_JTILE; t += RK_SORT_THREADS) {
+    const uint32_t g = j0 + t;
+    k[t] = g < n ? keys[g] : make_ulonglong2(~0ull, ~0ull);
+    id[t] = g < n ? g : 0xffffffffu;
   }
-  const bool self_here = i >= j0 && i < j0 + jn;
-  if (ties > (self_here ? 1u : 0u)) {  // strings that agree on their first 16 bytes: compare the rest in memory
-    for (uint32_t t = 0; t < jn; ++t) {
-      const ulonglong2 o = sk[t];
-      if (o.x == me.x && o.y == me.y && j0 + t != i &&
-          str_less_from(base, starts[j0 + t], lens[j0 + t], starts[i], lens[i], 16))
-        ++cnt;
+  __syncthreads();
+  for (uint32_t size = 2; size <= RK_JTILE; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      const uint32_t t = threadIdx.x;
+      const uint32_t lo = 2u * t - (t & (stride - 1u)), hi = lo + stride;
+      const bool asc = (lo & size) == 0u;
+      const ulonglong2 a = k[lo], b = k[hi];
+      const uint32_t ia = id[lo], ib = id[hi];
+      const bool a_gt_b = key_less(b, a) || (!key_less(a, b) && ia > ib);
+      if (a_gt_b == asc) {
+        k[lo] = b;
+        k[hi] = a;
+        id[lo] = ib;
+        id[hi] = ia;
+      }
+      __syncthreads();
     }
   }
-  if (cnt) atomicAdd(rank + i, cnt);
+  for (uint32_t t = threadIdx.x; t < RK_JTILE; t += RK_SORT_THREADS) {
+    const uint32_t g = j0 + t;
+    if (g < n) {
+      skeys[g] = k[t];
+      sidx[g] = id[t];
+    }
+  }
+}
+
+// rank(i) += #{ j in tile : s_j < s_i }: lower bound of key_i among the tile's sorted keys; the strings that agree
+// with s_i on all 16 prefix bytes (a run right at the lower bound) are compared in memory.
+constexpr int RK_IPT = 4;  // strings per thread
+__global__ void __launch_bounds__(RK_THREADS)
+    k_rank_count(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
+                 const ulonglong2* __restrict__ keys, const ulonglong2* __restrict__ skeys, const uint32_t* __restrict__ sidx,
+                 uint32_t n, uint32_t* __restrict__ rank) {
+  __shared__ ulonglong2 sk[RK_JTILE];
+  const uint32_t j0 = blockIdx.y * RK_JTILE, jn = min((uint32_t)RK_JTILE, n - j0);
+  for (uint32_t t = threadIdx.x; t < jn; t += RK_THREADS) sk[t] = skeys[j0 + t];
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < RK_IPT; ++r) {
+    const uint32_t i = (blockIdx.x * RK_IPT + (uint32_t)r) * RK_THREADS + threadIdx.x;
+    if (i >= n) break;
+    const ulonglong2 me = keys[i];
+    uint32_t lo = 0, hi = jn;
+    while (lo < hi) {
+      const uint32_t m = (lo + hi) >> 1;
+      if (key_less(sk[m], me)) lo = m + 1;
+      else hi = m;
+    }
+    uint32_t cnt = lo;
+    for (uint32_t t = lo; t < jn; ++t) {
+      const ulonglong2 o = sk[t];
+      if (o.x != me.x || o.y != me.y) break;
+      const uint32_t j = sidx[j0 + t];
+      if (j != i && str_less_from(base, starts[j], lens[j], starts[i], lens[i], 16)) ++cnt;
+    }
+    if (cnt) atomicAdd(rank + i, cnt);
+  }
 }
 
 __global__ void k_rank_scatter(const uint32_t* __restrict__ rank, uint32_t n, uint32_t* __restrict__ order) {
@@ -274,22 +335,29 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
 
   // ---- small path
   long long small_max = ctx->small_sort_max;
-  if (small_max > 32768) small_max = 32768;
+  if (small_max > (1 << 20)) small_max = 1 << 20;
   if ((long long)n <= small_max) {
-    DevBuf keys, rank;
+    DevBuf keys, rank, skeys, sidx;
     ZDWB_TRY(keys.alloc(ctx, (size_t)n * sizeof(ulonglong2)));
+    ZDWB_TRY(skeys.alloc(ctx, (size_t)n * sizeof(ulonglong2)));
+    ZDWB_TRY(sidx.alloc(ctx, (size_t)n * 4));
     ZDWB_TRY(rank.alloc(ctx, (size_t)n * 4));
     ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(rank.p, 0, (size_t)n * 4, st));
-    const unsigned gi = (n + RK_THREADS - 1) / RK_THREADS;
+    const unsigned gi = (n + RK_THREADS - 1) / RK_THREADS, ntile = (n + RK_JTILE - 1) / RK_JTILE;
     {
       KernelScope _ks(ctx, "k_rank_keys");
       k_rank_keys<<<gi, RK_THREADS, 0, st>>>(base, starts, lens, n, keys.as<ulonglong2>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
     {
+      KernelScope _ks(ctx, "k_rank_tile_sort");
+      k_rank_tile_sort<<<ntile, RK_SORT_THREADS, 0, st>>>(keys.as<ulonglong2>(), n, skeys.as<ulonglong2>(), sidx.as<uint32_t>());
+    }
+    ZDWB_LAUNCH_CHECK(ctx);
+    {
       KernelScope _ks(ctx, "k_rank_count");
-      k_rank_count<<<dim3(gi, (n + RK_JTILE - 1) / RK_JTILE), RK_THREADS, 0, st>>>(base, starts, lens, keys.as<ulonglong2>(), n,
-                                                                                 rank.as<uint32_t>());
+      k_rank_count<<<dim3((gi + RK_IPT - 1) / RK_IPT, ntile), RK_THREADS, 0, st>>>(
+        base, starts, lens, keys.as<ulonglong2>(), skeys.as<ulonglong2>(), sidx.as<uint32_t>(), n, rank.as<uint32_t>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
     {
