@@ -179,16 +179,17 @@ __global__ void __launch_bounds__(DEC_THREADS)
 // column widths (shared or global memory): the value bytes selected by flag byte j are
 // sum_k 2^k * popc(flags & plane_k byte j).
 // ---------------------------------------------------------------------------------------------
+// `fb0` = the flag byte of lane j for the first round (j < F), loaded ahead of time by the caller.
 template <class CB>
 __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint32_t* __restrict__ planes,
-                                               const uint8_t* __restrict__ rp, CB&& cb) {
+                                               const uint8_t* __restrict__ rp, uint32_t fb0, CB&& cb) {
   const unsigned lane = lane_id();
   uint32_t run = P.F;
   for (uint32_t j0 = 0; j0 < P.F; j0 += 32) {
     const uint32_t j = j0 + lane;
     uint32_t fb = 0, bl = 0;
     if (j < P.F) {
-      fb = __ldg(rp + j);
+      fb = j0 ? (uint32_t)__ldg(rp + j) : fb0;
       if (fb) {
         const uint32_t sh = (j & 3u) * 8u, w = j >> 2;
         bl = __popc(fb & (planes[w] >> sh)) + 2u * __popc(fb & (planes[P.W + w] >> sh)) +
@@ -214,6 +215,9 @@ __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint32_
     }
     run += tot;
   }
+}
+__device__ __forceinline__ uint32_t first_flag_byte(const DecParams& P, const uint8_t* __restrict__ rp) {
+  return lane_id() < P.F ? (uint32_t)__ldg(rp + lane_id()) : 0u;
 }
 
 // little-endian value of sz (1..8) bytes at an arbitrary address: two aligned 64-bit loads
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
   for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row(P, planes, rp, [&](uint32_t u, uint32_t voff) {
+    warp_parse_row(P, planes, rp, first_flag_byte(P, rp), [&](uint32_t u, uint32_t voff) {
       atomicMax(&last_row[u], rl);
       if (flag_counts) atomicAdd(&flag_counts[u], 1ull);
       if (validate && is_text_like(P.utype[u])) {
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
   for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row(P, planes, rp, [&](uint32_t u, uint32_t voff) {
+    warp_parse_row(P, planes, rp, first_flag_byte(P, rp), [&](uint32_t u, uint32_t voff) {
       if (last_row[u] == rl) sval[(size_t)blockIdx.x * P.U + u] = load_le(rp + voff, P.usz[u]);
     });
   }
@@ -485,77 +489,88 @@ __device__ __forceinline__ uint32_t value_len(const DecParams& P, uint32_t u, ui
   return digits_u64(full);
 }
 
-// One warp writes the template bytes of a row, one group (up to 4 bytes of one segment) per lane per step.
+// One warp writes the template bytes of a row, one group (up to 4 bytes of one segment) per lane per step; the group
+// descriptors of four steps are fetched before any of them is used.
 __device__ __forceinline__ void warp_write_template(const FmtTables& FT, const uint32_t* __restrict__ ioffj,
                                                     uint8_t* __restrict__ row) {
-  for (uint32_t g = lane_id(); g < FT.n_groups; g += 32) {
-    const uint4 sg = __ldg(FT.sgrp + g);
-    uint8_t* d = row + sg.z + ioffj[sg.y];
-    d[0] = (uint8_t)sg.x;
-    if (sg.w > 1) d[1] = (uint8_t)(sg.x >> 8);
-    if (sg.w > 2) d[2] = (uint8_t)(sg.x >> 16);
-    if (sg.w > 3) d[3] = (uint8_t)(sg.x >> 24);
+  for (uint32_t g0 = lane_id(); g0 < FT.n_groups; g0 += 128) {
+    uint4 sg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t g = g0 + 32u * (uint32_t)k;
+      sg[k] = g < FT.n_groups ? __ldg(FT.sgrp + g) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (sg[k].w == 0u) continue;
+      uint8_t* d = row + sg[k].z + ioffj[sg[k].y];
+      d[0] = (uint8_t)sg[k].x;
+      if (sg[k].w > 1) d[1] = (uint8_t)(sg[k].x >> 8);
+      if (sg[k].w > 2) d[2] = (uint8_t)(sg[k].x >> 16);
+      if (sg[k].w > 3) d[3] = (uint8_t)(sg[k].x >> 24);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// streaming row writer: one warp owns a strip of consecutive rows and walks them in order, keeping for every used
-// column that is output its current value, text length and (for texts of up to 16 bytes) the rendered text in shared
-// memory.  A row only touches the columns its flag bits name; everything else is copied from the warp's state.  No
-// CTA-wide barrier, no cross-warp dependency: k_dec_row_lens measures every row first (same walk, lengths only), an
-// exclusive scan turns the lengths into row offsets, k_dec_write_rows then assembles each row in shared memory and
-// flushes it with coalesced stores.
+// streaming row writer: one warp owns a strip of consecutive rows and walks them in order, keeping for every output
+// item (a used column that is output, or the running row number) its text length and, for rendered texts - dictionary
+// strings of up to 16 bytes and all numbers - the text itself in shared memory.  A row only touches the items its flag
+// bits name; everything else is copied from the warp's state.  No CTA-wide barrier, no cross-warp dependency:
+// k_dec_row_lens measures every row first (same walk, lengths only), an exclusive scan turns the lengths into row
+// offsets, k_dec_write_rows then assembles each row straight in global memory.
 // ---------------------------------------------------------------------------------------------
 struct WarpLayout {        // byte offsets inside a warp's slice of dynamic shared memory
-  uint32_t o_len, o_val, o_textc, o_ioff, o_llist, o_rowbuf;
+  uint32_t o_len, o_val, o_textc, o_ioff, o_llist;
   uint32_t stride;         // bytes per warp
-  uint32_t rowcap;         // bytes of row staging (0 = always assemble in global memory)
   uint32_t warps;          // warps per CTA
 };
 
-struct WarpState {
-  uint32_t* len;              // [U]
-  uint32_t* aux;              // [U] dictionary index of the column's text (text-like columns)
-  uint32_t* textc;            // [U][4] rendered text of up to 16 bytes; numbers of 17-20 characters park their value here
+constexpr uint32_t LEN_LONG_TEXT = 0x80000000u;  // flag in len[]: the text lives in the dictionary (more than 16 bytes)
+constexpr uint32_t LEN_MASK = 0x7fffffffu;
+
+struct WarpState {            // all indexed by output item
+  uint32_t* len;              // [NI] text length (| LEN_LONG_TEXT)
+  uint32_t* aux;              // [NI] dictionary index of a long text; characters 17..20 of a number
+  uint32_t* textc;            // [NI][4] rendered text, first 16 bytes
   uint32_t* ioff;             // [NI + 1]
-  uint32_t* llist;            // [1 + max(U, NI)]  ([0] = count)
-  uint8_t* rowbuf;
+  uint32_t* llist;            // [1 + NI]  ([0] = count)
 };
 
-__device__ __forceinline__ uint32_t has_zero_byte(uint32_t x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
-
-// New value v for used column u: updates len[u] and, when WRITE, what the row writer needs to emit the text.
+// New value v for used column u = output item i: updates len[i] and, when WRITE, what the row writer needs to emit it.
 template <bool WRITE>
-__device__ __forceinline__ void set_column(const DecParams& P, const WarpState& S, uint32_t u, unsigned long long v,
+__device__ __forceinline__ void set_column(const DecParams& P, const WarpState& S, uint32_t u, uint32_t i, unsigned long long v,
                                            DecMeta* meta) {
   const uint8_t t = P.utype[u];
   if (is_text_like(t)) {
     if (v == 0) {
       if (t == ZDWB_DECIMAL) {  // outputDefault(DECIMAL): "0.000000000000"
-        S.len[u] = 14;
+        S.len[i] = 14;
         if (WRITE) {
-          uint32_t* tc = S.textc + 4 * (size_t)u;
+          uint32_t* tc = S.textc + 4 * (size_t)i;
           tc[0] = 0x30302e30u;
           tc[1] = 0x30303030u;
           tc[2] = 0x30303030u;
           tc[3] = 0x00003030u;
         }
       } else {
-        S.len[u] = 0;
+        S.len[i] = 0;
       }
       return;
     }
     const uint32_t index = (uint32_t)(v + P.ubase[u]);  // ULONG index: UnconvertFromZDW.cpp:1363
     if ((uint64_t)index > P.dict_total) {                // :1364 (the reference allows index == dictionarySize)
       meta->err = 1;
-      S.len[u] = 0;
+      S.len[i] = 0;
       return;
     }
     const uint32_t l = dict_strlen(P, index, P.dict_total - index);
-    S.len[u] = l;
+    if (l >= LEN_LONG_TEXT) meta->err = 1;  // (cannot happen: a dictionary is smaller than 4 GiB and entries end at a NUL)
+    S.len[i] = l > 16 ? (l | LEN_LONG_TEXT) : l;
     if (WRITE) {
-      S.aux[u] = index;
-      if (l && l <= 16) {  // short texts are kept rendered; longer ones are copied from the dictionary per row
+      if (l > 16) {
+        S.aux[i] = index;  // copied from the dictionary row by row
+      } else if (l) {      // short texts are kept rendered
         const uint8_t* s = P.blk + P.dict_base + index;
         const uintptr_t a = reinterpret_cast<uintptr_t>(s);
         const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
@@ -564,7 +579,7 @@ __device__ __forceinline__ void set_column(const DecParams& P, const WarpState& 
         const uint32_t lim = (uint32_t)min((ptrdiff_t)4, wend - w);
         const uint32_t w0 = __ldg(w), w1 = __ldg(w + min(1u, lim)), w2 = __ldg(w + min(2u, lim)), w3 = __ldg(w + min(3u, lim)),
                        w4 = __ldg(w + min(4u, lim));
-        uint32_t* tc = S.textc + 4 * (size_t)u;
+        uint32_t* tc = S.textc + 4 * (size_t)i;
         tc[0] = __funnelshift_r(w0, w1, sh);
         tc[1] = __funnelshift_r(w1, w2, sh);
         tc[2] = __funnelshift_r(w2, w3, sh);
@@ -574,12 +589,12 @@ __device__ __forceinline__ void set_column(const DecParams& P, const WarpState& 
     return;
   }
   const uint32_t l = value_len(P, u, t, v, meta);
-  S.len[u] = l;
+  S.len[i] = l;
   if (WRITE && l) {
-    uint32_t* tc = S.textc + 4 * (size_t)u;
+    uint32_t* tc = S.textc + 4 * (size_t)i;
     if (t == ZDWB_CHAR) {  // one byte, or a backslash and the byte after it (UnconvertFromZDW.cpp:1396-1420)
       tc[0] = (uint32_t)(v + P.ubase[u]) & 0xffffu;
-    } else {  // integers: up to 20 characters, the last four live in the column's aux word
+    } else {  // integers: up to 20 characters, the last four live in the item's aux word
       const unsigned long long full = v ? v + P.ubase[u] : 0ull;
       uint32_t w[5];
       render_int(full, is_signed_int_type(t) && (long long)full < 0, l, w);
@@ -587,7 +602,7 @@ __device__ __forceinline__ void set_column(const DecParams& P, const WarpState& 
       tc[1] = w[1];
       tc[2] = w[2];
       tc[3] = w[3];
-      S.aux[u] = w[4];
+      S.aux[i] = w[4];
     }
   }
 }
@@ -617,7 +632,6 @@ __device__ __forceinline__ WarpState warp_state(uint8_t* dsm, const WarpLayout& 
   S.textc = reinterpret_cast<uint32_t*>(base + L.o_textc);
   S.ioff = reinterpret_cast<uint32_t*>(base + L.o_ioff);
   S.llist = reinterpret_cast<uint32_t*>(base + L.o_llist);
-  S.rowbuf = base + L.o_rowbuf;
   return S;
 }
 
@@ -637,24 +651,33 @@ __global__ void __launch_bounds__(128, 10)
   const uint32_t U = P.U, NI = FT.n_items;
   const uint8_t* rows = P.blk + P.rows_base;
   const unsigned grp = lane >> 3, gl = lane & 7u;
+  const bool has_rownum = FT.rownum_item != ITEM_ROWNUM;
 
   // ---- state at the start of the strip: the values carried in
+  for (uint32_t i = lane; i < NI; i += 32) S.len[i] = 0;
   if (lane == 0) S.llist[0] = 0;
   __syncwarp();
   for (uint32_t u = lane; u < U; u += 32) {
-    S.len[u] = 0;
-    if (__ldg(u_item + u) < 0) continue;  // not output: never touched
-    const unsigned long long v = cin[(size_t)strip * U + u];
-    set_column<WRITE>(P, S, u, v, meta);
+    const int32_t i = __ldg(u_item + u);
+    if (i < 0) continue;  // not output: never touched
+    set_column<WRITE>(P, S, u, (uint32_t)i, cin[(size_t)strip * U + u], meta);
   }
   __syncwarp();
-  long long dyn = 0;  // dynamic bytes of the current row (lane-local share; summed when needed)
-  for (uint32_t u = lane; u < U; u += 32) dyn += S.len[u];
+  long long dyn = 0;  // dynamic bytes of the current row without the row number (lane-local share; summed when needed)
+  for (uint32_t i = lane; i < NI; i += 32) dyn += S.len[i] & LEN_MASK;
 
+  // the row's offset and its first flag bytes are fetched one row ahead
+  uint32_t ro = row_off[r0];
+  uint32_t fb = first_flag_byte(P, rows + ro);
   for (uint32_t r = r0; r < r1; ++r) {
-    const uint8_t* rp = rows + row_off[r];
+    const uint8_t* rp = rows + ro;
+    const uint32_t fb_now = fb;
+    if (r + 1 < r1) {
+      ro = row_off[r + 1];
+      fb = first_flag_byte(P, rows + ro);
+    }
     // ---- the columns this row changes: the flag walk only lists them, the values are then applied 32 at a time
-    warp_parse_row(P, P.planes, rp, [&](uint32_t u, uint32_t voff) {
+    warp_parse_row(P, P.planes, rp, fb_now, [&](uint32_t u, uint32_t voff) {
       if (__ldg(u_item + u) < 0) return;
       const uint32_t e = atomicAdd(&S.llist[0], 1u);
       S.llist[1 + e] = u;
@@ -666,12 +689,26 @@ __global__ void __launch_bounds__(128, 10)
       int32_t delta = 0;
       for (uint32_t e = lane; e < n; e += 32) {
         const uint32_t u = S.llist[1 + e];
+        const uint32_t i = (uint32_t)__ldg(u_item + u);
         const unsigned long long v = load_le(rp + S.ioff[e], P.usz[u]);
-        const int32_t old = (int32_t)S.len[u];
-        set_column<WRITE>(P, S, u, v, meta);
-        delta += (int32_t)S.len[u] - old;
+        const int32_t old = (int32_t)(S.len[i] & LEN_MASK);
+        set_column<WRITE>(P, S, u, i, v, meta);
+        delta += (int32_t)(S.len[i] & LEN_MASK) - old;
       }
       dyn += delta;
+      if (WRITE && has_rownum && lane == 0) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261): a number like any other
+        const unsigned long long x = FT.first_row + r;
+        const uint32_t l = digits_u64(x);
+        uint32_t w[5];
+        render_int(x, false, l, w);
+        uint32_t* tc = S.textc + 4 * (size_t)FT.rownum_item;
+        tc[0] = w[0];
+        tc[1] = w[1];
+        tc[2] = w[2];
+        tc[3] = w[3];
+        S.aux[FT.rownum_item] = w[4];
+        S.len[FT.rownum_item] = l;
+      }
       __syncwarp();
       if (lane == 0) S.llist[0] = 0;
       __syncwarp();
@@ -683,7 +720,7 @@ __global__ void __launch_bounds__(128, 10)
       for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
       if (lane == 0) {
         unsigned long long rl = (unsigned long long)tot + FT.static_total;
-        if (FT.rownum_item != ITEM_ROWNUM) rl += digits_u64(FT.first_row + r);
+        if (has_rownum) rl += digits_u64(FT.first_row + r);
         row_len[r] = rl;
       }
       continue;
@@ -693,11 +730,7 @@ __global__ void __launch_bounds__(128, 10)
     uint32_t run = 0;
     for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
       const uint32_t i = i0 + lane;
-      uint32_t l = 0;
-      if (i < NI) {
-        const uint32_t iu = __ldg(FT.item_u + i);
-        l = iu == ITEM_ROWNUM ? digits_u64(FT.first_row + r) : S.len[iu];
-      }
+      const uint32_t l = i < NI ? (S.len[i] & LEN_MASK) : 0u;
       uint32_t inc = l;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -709,36 +742,28 @@ __global__ void __launch_bounds__(128, 10)
     }
     if (lane == 0) S.ioff[NI] = run;
     __syncwarp();
-    const unsigned long long g0 = out_row_off[r];
-    const uint32_t row_bytes = FT.static_total + run;
-    const bool staged = row_bytes <= L.rowcap;
-    uint8_t* dst = staged ? S.rowbuf : out + g0;
+    uint8_t* dst = out + out_row_off[r];
 
     // ---- template, then the items
     warp_write_template(FT, S.ioff, dst);
     for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
       const uint32_t i = i0 + lane;
       if (i >= NI) continue;
-      const uint32_t o = S.ioff[i], l = S.ioff[i + 1] - o;
+      const uint32_t lf = S.len[i], l = lf & LEN_MASK;
       if (!l) continue;
-      const uint32_t u = __ldg(FT.item_u + i);
-      uint8_t* d = dst + __ldg(FT.item_pos + i) + o;
-      if (u == ITEM_ROWNUM) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261)
-        unsigned long long x = FT.first_row + r;
-        for (uint32_t p = l; p > 0; x /= 10ull) d[--p] = (uint8_t)('0' + (uint32_t)(x % 10ull));
+      if (lf & LEN_LONG_TEXT) {
+        S.llist[1 + atomicAdd(&S.llist[0], 1u)] = i;
         continue;
       }
-      if (l <= 16 || !is_text_like(P.utype[u])) {  // rendered text: 16 bytes in the cache, numbers up to 4 more in aux
-        const uint32_t* tw = S.textc + 4 * (size_t)u;
-        for (uint32_t k = 0; k < l; k += 4) {
-          const uint32_t x = k < 16u ? tw[k >> 2] : S.aux[u], nb = l - k;
-          d[k] = (uint8_t)x;
-          if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
-          if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
-          if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
-        }
-      } else {
-        S.llist[1 + atomicAdd(&S.llist[0], 1u)] = i;
+      // rendered text: 16 bytes in the cache, numbers up to 4 more in aux
+      uint8_t* d = dst + __ldg(FT.item_pos + i) + S.ioff[i];
+      const uint32_t* tw = S.textc + 4 * (size_t)i;
+      for (uint32_t k = 0; k < l; k += 4) {
+        const uint32_t x = k < 16u ? tw[k >> 2] : S.aux[i], nb = l - k;
+        d[k] = (uint8_t)x;
+        if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
+        if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
+        if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
       }
     }
     __syncwarp();
@@ -746,32 +771,12 @@ __global__ void __launch_bounds__(128, 10)
       const uint32_t n = S.llist[0];
       for (uint32_t e = grp; e < n; e += 4) {
         const uint32_t i = S.llist[1 + e];
-        const uint32_t u = __ldg(FT.item_u + i);
-        const uint32_t o = S.ioff[i], l = S.ioff[i + 1] - o;
-        octet_copy(dst + __ldg(FT.item_pos + i) + o, P.blk + P.dict_base + S.aux[u], l, gl);
+        octet_copy(dst + __ldg(FT.item_pos + i) + S.ioff[i], P.blk + P.dict_base + S.aux[i], S.len[i] & LEN_MASK, gl);
       }
       __syncwarp();
       if (lane == 0) S.llist[0] = 0;
     }
     __syncwarp();
-    // ---- flush: 4-byte stores, the shared-memory side re-aligned by a funnel shift
-    if (staged) {
-      uint8_t* gdst = out + g0;
-      const uint32_t head = min(row_bytes, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 3u)) & 3u));
-      if (lane < head) gdst[lane] = dst[lane];
-      const uint32_t nw = (row_bytes - head) >> 2;
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(dst);
-      uint32_t* gw = reinterpret_cast<uint32_t*>(gdst + head);
-      const uint32_t sh = head * 8u;
-      if (sh == 0) {
-        for (uint32_t m = lane; m < nw; m += 32) gw[m] = sw[m];
-      } else {
-        for (uint32_t m = lane; m < nw; m += 32) gw[m] = __funnelshift_r(sw[m], sw[m + 1], sh);
-      }
-      const uint32_t done = head + (nw << 2);
-      if (lane < row_bytes - done) gdst[done + lane] = dst[done + lane];
-      __syncwarp();
-    }
   }
 }
 
@@ -1224,42 +1229,21 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
 
   // ---- shared-memory layout of a warp in k_dec_rows: lengths-only pass and writing pass
   auto make_layout = [&](bool write, WarpLayout& L) -> bool {
-    const size_t Ue = std::max(U, 1u);
+    const size_t NIe = std::max(NI, 1u);
     size_t o = 0;
-    L.o_len = (uint32_t)o;    o += Ue * 4;
+    L.o_len = (uint32_t)o;    o += NIe * 4;
     o = (o + 7) & ~(size_t)7;
-    L.o_val = (uint32_t)o;    if (write) o += Ue * 4;
+    L.o_val = (uint32_t)o;    if (write) o += NIe * 4;
     o = (o + 15) & ~(size_t)15;
-    L.o_textc = (uint32_t)o;  if (write) o += Ue * 16;
+    L.o_textc = (uint32_t)o;  if (write) o += NIe * 16;
     L.o_ioff = (uint32_t)o;   o += ((size_t)NI + 1) * 4;
     L.o_llist = (uint32_t)o;  o += (1 + (size_t)NI) * 4;
     o = (o + 15) & ~(size_t)15;
-    L.o_rowbuf = (uint32_t)o;
-    const size_t fixed = o;
-    if (fixed > 200 * 1024) return false;
+    if (o > 200 * 1024) return false;
     uint32_t warps = 4;
-    while (warps > 1 && fixed * warps > 200 * 1024) warps >>= 1;
-    size_t rowcap = 0;
-    if (write && ctx->dec_stage_rows) {
-      // stage rows of up to ~2x the expected size; fewer warps per CTA before giving up staging
-      size_t expect = (size_t)FT.static_total + (size_t)NI * 8;
-      if (ctx->last_out_per_row > expect) expect = (size_t)ctx->last_out_per_row;
-      const size_t want = std::min<size_t>(std::max<size_t>(expect + expect / 2, 1024), 32 * 1024);
-      for (;; warps >>= 1) {
-        const size_t per_warp_budget = (size_t)(72 * 1024) / warps;  // ~3 CTAs of 4 warps per SM
-        if (fixed + 64 <= per_warp_budget) {
-          rowcap = std::min(want, per_warp_budget - fixed - 16) & ~(size_t)15;
-          break;
-        }
-        if (warps == 1) {
-          rowcap = fixed + 16 + 1024 <= 200 * 1024 ? 1024 : 0;
-          break;
-        }
-      }
-    }
-    L.rowcap = (uint32_t)rowcap;
+    while (warps > 1 && o * warps > 200 * 1024) warps >>= 1;
     L.warps = warps;
-    L.stride = (uint32_t)((fixed + (rowcap ? rowcap + 16 : 0) + 15) & ~(size_t)15);
+    L.stride = (uint32_t)o;
     return (size_t)L.stride * warps <= 200 * 1024;
   };
   WarpLayout L1, L2;
