@@ -63,8 +63,8 @@ class Synth:
         self.L.synth_max_row_bytes.restype = C.c_uint32
         fixture = lzma.decompress((ROOT / "tests" / "golden" / "analytics-hits.sql.xz").read_bytes())
         self.desc = (ROOT / "tests" / "golden" / "analytics-hits.desc.sql").read_bytes()
-        import oracle as O  # desc parsing only (the reference's ReadDescFile rules)
-        self.schema = O.parse_desc(self.desc)
+        from zdw_b200.desc import parse_desc  # the product's own .desc.sql rules (host side)
+        self.schema = parse_desc(self.desc)
         self.h = self.L.synth_profile_create(fixture, len(fixture), self.schema.ncols)
         if not self.h:
             raise RuntimeError("fixture does not parse")

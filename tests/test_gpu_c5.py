@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 @pytest.mark.gpu
 def test_c5_high_cardinality_block():
-    p = subprocess.run([sys.executable, str(ROOT / "tools" / "c5_check.py"), "--rows", "400000", "--oracle-rows", "60000"],
+    p = subprocess.run([sys.executable, str(ROOT / "tests" / "c5_check.py"), "--rows", "400000", "--oracle-rows", "60000"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     res = json.loads(p.stdout.strip().splitlines()[-1])
@@ -24,7 +24,7 @@ def test_c5_high_cardinality_block():
 
 @pytest.mark.gpu
 def test_c5_decode_through_unconvert_api(tmp_path):
-    sys.path.insert(0, str(ROOT / "tools"))
+    sys.path.insert(0, str(ROOT / "tests"))
     import c5_check
     import oracle as O
     tsv = c5_check.make_rows(50000)
