@@ -103,6 +103,8 @@ class ClockSampler:
         self.p = None
 
     def start(self):
+        if os.environ.get("ZDW_BENCH_NOCLOCK"):  # diagnostics only: a run without the poller reports no clocks
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -264,7 +266,7 @@ def run_reference(args):
 def workload_config(args, note=None):
     cfg = {"workload": (f"C4 synthetic analytics-hits-shaped TSV: 2086 columns (256 populated), {args.blocks} blocks x "
                         f"{args.rows_per_block} rows, seed {SEED}, block-sharded over {args.gpus} GPU(s)"),
-           "blocks": args.blocks, "rows_per_block": args.rows_per_block, "parallelism": f"block-shard x{args.gpus}",
+           "blocks": args.blocks, "rows_per_block": args.rows_per_block, "parallelism": f"block-shard x{args.gpus}", "lanes_per_gpu": getattr(args, "lanes", 1),
            "l2": "inputs larger than L2 (every block is ~0.5 GB and is read once per pass)"}
     if note:
         cfg["note"] = note
@@ -363,13 +365,47 @@ def run_cuda(args):
     for z, n in zip(dev_zdw, zdw_lens):
         host_zdw.append(z[:n].cpu().numpy().tobytes())
 
+    # Blocks are independent, so RES_LANES contexts (one host thread + stream each) take the rank's blocks round-robin:
+    # the host-side bookkeeping of one block (metadata read-backs, launch preparation) overlaps the kernels of another.
+    # Every lane's stream is forked from / joined back into `stream`, so CUDA events on `stream` bracket all of it.
+    res_lanes = [ctx]
+    res_streams = [stream]
+    for _ in range(max(1, args.lanes) - 1):
+        ls = torch.cuda.Stream(device=dev)
+        c2 = Context(local)
+        c2.set_stream(ls.cuda_stream)
+        res_lanes.append(c2)
+        res_streams.append(ls)
+    res_pool = ThreadPoolExecutor(max_workers=len(res_lanes))
+
+    def _res_pass(fn, items):
+        if len(res_lanes) == 1:
+            for it in items:
+                fn(ctx, it)
+            return
+        fork = torch.cuda.Event()
+        fork.record(stream)
+        for ls in res_streams[1:]:
+            ls.wait_event(fork)
+
+        def work(k):
+            torch.cuda.set_device(dev)
+            for j in range(k, len(items), len(res_lanes)):
+                fn(res_lanes[k], items[j])
+        list(res_pool.map(work, range(len(res_lanes))))
+        for ls in res_streams[1:]:
+            join = torch.cuda.Event()
+            join.record(ls)
+            stream.wait_event(join)
+
+    enc_items = list(zip(dev_tsv, host_lens))
+    dec_items = list(zip(dev_zdw, zdw_lens))
+
     def encode_pass():
-        for t, n in zip(dev_tsv, host_lens):
-            ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
+        _res_pass(lambda c, it: c.encode_block(types, it[0].data_ptr(), it[1], input_on_device=True, output_on_device=True), enc_items)
 
     def decode_pass():
-        for z, n in zip(dev_zdw, zdw_lens):
-            ctx.decode_block(types, z.data_ptr(), n, input_on_device=True, output_on_device=True)
+        _res_pass(lambda c, it: c.decode_block(types, it[0].data_ptr(), it[1], input_on_device=True, output_on_device=True), dec_items)
 
     def barrier():
         if world > 1:
@@ -396,7 +432,7 @@ def run_cuda(args):
         decode_pass()
     barrier()
 
-    launches0 = ctx.kernel_launches()
+    launches0 = sum(c.kernel_launches() for c in res_lanes)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     enc_ms, dec_ms = [], []
     barrier()
@@ -413,7 +449,7 @@ def run_cuda(args):
         dec_ms.append(ev[1].elapsed_time(ev[2]))
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = ctx.kernel_launches() - launches0
+    launches = sum(c.kernel_launches() for c in res_lanes) - launches0
     clocks = sampler.stop(t_epoch0, time.time())
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region).  Blocks are
@@ -641,6 +677,7 @@ def main():
     ap.add_argument("--rows-per-block", type=int, default=ROWS_PER_BLOCK)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-decode-blocks", type=int, default=16)
+    ap.add_argument("--lanes", type=int, default=2, help="contexts (host thread + stream) that share the rank's blocks in the device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="contexts (host thread + stream) that overlap copies and kernels in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=131072, help="rows of the bounded cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")

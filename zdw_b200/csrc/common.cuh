@@ -39,6 +39,10 @@ struct Ctx {
   size_t out_host2_cap = 0;
   std::vector<unsigned long long> flag_counts;  // -s statistics of the last decoded block
   void* in_stage = nullptr;    // pinned staging for pageable host inputs (unused when caller memory is pinned)
+  // pinned arena for the small tables of a call (schema, widths, output template): copies from pageable memory go
+  // through the driver's own staging and serialise with other driver work; from here they are plain async copies
+  void* stage_host = nullptr;
+  size_t stage_cap = 0, stage_used = 0;
   // small pinned scratch for device->host readbacks of metadata
   void* meta_host = nullptr;
   // optional per-kernel timing (CUDA events on the launching stream), for the roofline report
@@ -113,11 +117,11 @@ struct DevBuf {
     release();
     ctx = c;
     bytes = n ? n : 16;
-    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, c->pool, c->stream);
     if (e != cudaSuccess) {
       p = nullptr;
       char b[256];
-      snprintf(b, sizeof(b), "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      snprintf(b, sizeof(b), "cudaMallocFromPoolAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
       c->err = b;
       (void)cudaGetLastError();
       return e == cudaErrorMemoryAllocation ? ZDWB_ERR_OOM : ZDWB_ERR_CUDA;
@@ -140,6 +144,44 @@ struct DevBuf {
     return reinterpret_cast<T*>(p);
   }
 };
+
+// Pinned arena of the context: stage_reset() at the start of a call (the stream is idle then), stage_take() hands out
+// 16-byte aligned pieces that stay valid until the next reset.
+inline int stage_reset(Ctx* c) {
+  if (c->stage_used) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);  // copies of an earlier call that ended early
+    if (e != cudaSuccess) {
+      c->err = std::string("cudaStreamSynchronize failed: ") + cudaGetErrorString(e);
+      (void)cudaGetLastError();
+      return ZDWB_ERR_CUDA;
+    }
+  }
+  c->stage_used = 0;
+  return ZDWB_OK;
+}
+inline void* stage_take(Ctx* c, size_t n) {
+  const size_t need = (n + 15) & ~(size_t)15;
+  if (c->stage_used + need > c->stage_cap) {
+    // grow: pieces already handed out must stay valid, so the old arena is only released once the stream is idle
+    size_t cap = c->stage_cap ? c->stage_cap * 2 : (size_t)1 << 20;
+    while (cap < need) cap *= 2;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    if (c->stage_host) {
+      cudaStreamSynchronize(c->stream);
+      cudaFreeHost(c->stage_host);
+    }
+    c->stage_host = p;
+    c->stage_cap = cap;
+    c->stage_used = 0;
+  }
+  void* r = static_cast<uint8_t*>(c->stage_host) + c->stage_used;
+  c->stage_used += need;
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // column types

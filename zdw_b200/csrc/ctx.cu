@@ -39,18 +39,33 @@ int zdwb_ctx_create(int device, size_t workspace_hint, zdwb_ctx** out) {
     return ZDWB_ERR_CUDA;
   }
   c->stream = c->own_stream;
-  if (cudaDeviceGetDefaultMemPool(&c->pool, device) == cudaSuccess) {
-    unsigned long long thr = ~0ull;  // keep freed blocks cached in the pool between calls
+  {
+    // A pool per context: contexts on different streams (block-parallel lanes) then never wait for, or fragment, each
+    // other's cached blocks.  Freed blocks stay cached in the pool between calls.
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
+      (void)cudaGetLastError();
+      cudaStreamDestroy(c->own_stream);
+      delete c;
+      return ZDWB_ERR_CUDA;
+    }
+    unsigned long long thr = ~0ull;
     cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   if (cudaHostAlloc(&c->meta_host, 4096, cudaHostAllocDefault) != cudaSuccess) {
+    cudaMemPoolDestroy(c->pool);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return ZDWB_ERR_OOM;
   }
   if (workspace_hint) {
     void* p = nullptr;
-    if (cudaMallocAsync(&p, workspace_hint, c->stream) == cudaSuccess) cudaFreeAsync(p, c->stream);
+    if (cudaMallocFromPoolAsync(&p, workspace_hint, c->pool, c->stream) == cudaSuccess) cudaFreeAsync(p, c->stream);
     cudaStreamSynchronize(c->stream);
     (void)cudaGetLastError();
   }
@@ -68,6 +83,8 @@ void zdwb_ctx_destroy(zdwb_ctx* c) {
   if (c->out_host) cudaFreeHost(c->out_host);
   if (c->out_host2) cudaFreeHost(c->out_host2);
   if (c->meta_host) cudaFreeHost(c->meta_host);
+  if (c->stage_host) cudaFreeHost(c->stage_host);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }

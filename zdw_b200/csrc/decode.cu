@@ -797,8 +797,14 @@ int fetch(Ctx* ctx, const uint8_t* blk, bool on_device, uint64_t avail, uint64_t
     memcpy(dst, blk + off, len);
     return ZDWB_OK;
   }
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(dst, blk + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+  void* bounce = stage_take(ctx, len);
+  if (!bounce) {
+    ctx->err = "decode: pinned staging allocation failed";
+    return ZDWB_ERR_OOM;
+  }
+  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(bounce, blk + off, len, cudaMemcpyDeviceToHost, ctx->stream));
   ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(dst, bounce, len);
   return ZDWB_OK;
 }
 
@@ -810,8 +816,16 @@ void append_default(std::string& blob, uint8_t type) {  // outputDefault, Unconv
 template <typename T>
 int upload(Ctx* ctx, DevBuf& d, const std::vector<T>& v) {
   ZDWB_TRY(d.alloc(ctx, v.size() * sizeof(T) + 16));
-  if (!v.empty())
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  if (!v.empty()) {
+    const size_t n = v.size() * sizeof(T);
+    void* pinned = stage_take(ctx, n);
+    if (!pinned) {
+      ctx->err = "decode: pinned staging allocation failed";
+      return ZDWB_ERR_OOM;
+    }
+    memcpy(pinned, v.data(), n);
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(d.p, pinned, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   return ZDWB_OK;
 }
 
@@ -820,6 +834,7 @@ int upload(Ctx* ctx, DevBuf& d, const std::vector<T>& v) {
 int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size_t avail, const zdwb_decode_opts* opts,
                       zdwb_rows_out* out) {
   memset(out, 0, sizeof(*out));
+  ZDWB_TRY(stage_reset(ctx));
   cudaStream_t st = ctx->stream;
   const uint32_t nc = schema->ncols;
   if (nc == 0 || !schema->types) {

@@ -1382,6 +1382,7 @@ uint32_t longest_line_field(uint32_t prev, uint32_t max_line) {
 int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
                       zdwb_block_out* out) {
   memset(out, 0, sizeof(*out));
+  ZDWB_TRY(stage_reset(ctx));
   cudaStream_t st = ctx->stream;
   const uint32_t ncols = schema->ncols;
   if (ncols == 0 || !schema->types) {
@@ -1418,11 +1419,16 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   EncMeta* meta = meta_d.as<EncMeta>();
   EncMeta* hmeta = static_cast<EncMeta*>(ctx->meta_host);
   ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(meta, 0, sizeof(EncMeta), st));
+  ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(&meta->bad_row, 0xff, 4, st));  // 0xffffffff = no malformed row
   {
-    const uint32_t ff = 0xffffffffu;
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(&meta->bad_row, &ff, 4, cudaMemcpyHostToDevice, st));
+    void* pinned = stage_take(ctx, ncols);
+    if (!pinned) {
+      ctx->err = "encode: pinned staging allocation failed";
+      return ZDWB_ERR_OOM;
+    }
+    memcpy(pinned, schema->types, ncols);
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(types_d.p, pinned, ncols, cudaMemcpyHostToDevice, st));
   }
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(types_d.p, schema->types, ncols, cudaMemcpyHostToDevice, st));
 
   // ---- census: per-tile counts and their prefix
   const uint64_t span = (uint64_t)(-lo) + n;
