@@ -291,6 +291,33 @@ def cpu_baseline_sample(synth: Synth, rows: int):
         shutil.rmtree(scratch, ignore_errors=True)
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_node(torch, index: int):
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist), so that the pinned host
+    buffers of the e2e leg are allocated and first touched next to the GPU's PCIe root.  Best effort; returns a note."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        cpus = _parse_cpulist(Path(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read_text())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local cpulist)"
+        os.sched_setaffinity(0, cpus)
+        node = Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text().strip()
+        return f"numa node {node} of GPU {bdf}: {len(cpus)} cpus"
+    except Exception as ex:  # noqa: BLE001
+        return f"unchanged ({type(ex).__name__})"
+
+
 def run_cuda(args):
     import torch
 
@@ -304,6 +331,7 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_node(torch, local)  # before any pinned allocation: first touch decides the NUMA node
     L = load_library()
     synth = Synth()
     types = synth.schema.types
@@ -572,7 +600,7 @@ def run_cuda(args):
                        "roofline": roof(kt_dec, "decode")},
             "roofline": roof(kt_enc, "encode"),
             "e2e": {"value": tot_tsv / t_e2e_enc / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(tot_tsv),
-                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "lanes": args.e2e_lanes, "pcie_copy_gbs": pcie,
+                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "cpu_affinity": affinity, "lanes": args.e2e_lanes, "pcie_copy_gbs": pcie,
                     "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks),
                     "decode_d2h_bytes": int(d2h_dec_all)},
             "gpu_launches": int(launches_all),

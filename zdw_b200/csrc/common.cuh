@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -20,7 +21,13 @@ struct Ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaMemPool_t pool = nullptr;
+  // device arena (arena_alloc / arena_release / arena_reset below): the scratch and the outputs of a call
+  struct Chunk {
+    uint8_t* p;
+    size_t cap, used;
+  };
+  std::vector<Chunk> chunks;
+  size_t arena_live = 0, arena_high = 0;  // bytes in use now / most bytes in use during this call
   std::string err;
   unsigned long long launches = 0;
   int sm_count = 148;
@@ -104,7 +111,71 @@ struct Status {
     ZDWB_CUDA_TRY(ctx, cudaGetLastError());                                                        \
   } while (0)
 
-// Scoped device allocation from the context's stream-ordered pool.
+// Device memory of a call comes from a per-context stack arena: one big cudaMalloc'd chunk that every call re-uses from
+// the bottom, so a call in steady state makes no driver-level memory-management call at all (those serialise with
+// other driver work such as NVML queries, and cost host time per block).  Allocation bumps the top of the last chunk;
+// scoped buffers die in reverse order of construction, so releasing the top one pops it and the space is re-used
+// within the call (everything runs on the context's one stream, so re-use is ordered).  A chunk that is too small is
+// followed by another one; arena_reset() at the start of the next call merges them into one of the size that was needed.
+inline void* arena_alloc(Ctx* c, size_t n) {
+  n = (n + 255) & ~(size_t)255;
+  if (c->chunks.empty() || c->chunks.back().used + n > c->chunks.back().cap) {
+    size_t total = 0;
+    for (const Ctx::Chunk& k : c->chunks) total += k.cap;
+    size_t cap = std::max<size_t>(n, std::max<size_t>((size_t)64 << 20, total / 2));
+    void* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (cap == n || cudaMalloc(&p, n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+      }
+      cap = n;
+    }
+    c->chunks.push_back(Ctx::Chunk{static_cast<uint8_t*>(p), cap, 0});
+  }
+  Ctx::Chunk& k = c->chunks.back();
+  void* r = k.p + k.used;
+  k.used += n;
+  c->arena_live += n;
+  if (c->arena_live > c->arena_high) c->arena_high = c->arena_live;
+  return r;
+}
+inline void arena_release(Ctx* c, void* p, size_t n) {
+  n = (n + 255) & ~(size_t)255;
+  if (c->chunks.empty()) return;
+  Ctx::Chunk& k = c->chunks.back();
+  if (static_cast<uint8_t*>(p) + n == k.p + k.used) {  // the top allocation: pop it
+    k.used -= n;
+    c->arena_live -= n;
+  }  // anything else stays until the next reset
+}
+// Start of a call: everything handed out before (including the previous call's outputs) is gone.
+inline int arena_reset(Ctx* c) {
+  if (c->chunks.size() > 1) {
+    cudaStreamSynchronize(c->stream);
+    size_t total = 0;
+    for (const Ctx::Chunk& k : c->chunks) {
+      total += k.cap;
+      cudaFree(k.p);
+    }
+    c->chunks.clear();
+    const size_t want = std::max(total, c->arena_high + c->arena_high / 4);
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) == cudaSuccess) c->chunks.push_back(Ctx::Chunk{static_cast<uint8_t*>(p), want, 0});
+    else (void)cudaGetLastError();  // arena_alloc will try smaller pieces
+  }
+  for (Ctx::Chunk& k : c->chunks) k.used = 0;
+  c->arena_live = 0;
+  c->arena_high = 0;
+  return ZDWB_OK;
+}
+inline void arena_destroy(Ctx* c) {
+  for (const Ctx::Chunk& k : c->chunks) cudaFree(k.p);
+  c->chunks.clear();
+}
+
+// Scoped device allocation from the context's arena.
 struct DevBuf {
   Ctx* ctx = nullptr;
   void* p = nullptr;
@@ -117,24 +188,22 @@ struct DevBuf {
     release();
     ctx = c;
     bytes = n ? n : 16;
-    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, c->pool, c->stream);
-    if (e != cudaSuccess) {
-      p = nullptr;
+    p = arena_alloc(c, bytes);
+    if (!p) {
       char b[256];
-      snprintf(b, sizeof(b), "cudaMallocFromPoolAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      snprintf(b, sizeof(b), "device allocation of %zu bytes failed", bytes);
       c->err = b;
-      (void)cudaGetLastError();
-      return e == cudaErrorMemoryAllocation ? ZDWB_ERR_OOM : ZDWB_ERR_CUDA;
+      return ZDWB_ERR_OOM;
     }
     return ZDWB_OK;
   }
   void release() {
     if (p) {
-      cudaFreeAsync(p, ctx->stream);
+      arena_release(ctx, p, bytes);
       p = nullptr;
     }
   }
-  void* detach() {
+  void* detach() {  // the buffer outlives this object: it stays valid until the next call on the context
     void* q = p;
     p = nullptr;
     return q;
@@ -158,6 +227,12 @@ inline int stage_reset(Ctx* c) {
   }
   c->stage_used = 0;
   return ZDWB_OK;
+}
+// start of an encode / decode call
+inline int call_begin(Ctx* c) {
+  int rc = stage_reset(c);
+  if (rc != ZDWB_OK) return rc;
+  return arena_reset(c);
 }
 inline void* stage_take(Ctx* c, size_t n) {
   const size_t need = (n + 15) & ~(size_t)15;

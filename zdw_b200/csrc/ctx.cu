@@ -39,35 +39,14 @@ int zdwb_ctx_create(int device, size_t workspace_hint, zdwb_ctx** out) {
     return ZDWB_ERR_CUDA;
   }
   c->stream = c->own_stream;
-  {
-    // A pool per context: contexts on different streams (block-parallel lanes) then never wait for, or fragment, each
-    // other's cached blocks.  Freed blocks stay cached in the pool between calls.
-    cudaMemPoolProps props;
-    memset(&props, 0, sizeof(props));
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = device;
-    if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
-      (void)cudaGetLastError();
-      cudaStreamDestroy(c->own_stream);
-      delete c;
-      return ZDWB_ERR_CUDA;
-    }
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   if (cudaHostAlloc(&c->meta_host, 4096, cudaHostAllocDefault) != cudaSuccess) {
-    cudaMemPoolDestroy(c->pool);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return ZDWB_ERR_OOM;
   }
-  if (workspace_hint) {
-    void* p = nullptr;
-    if (cudaMallocFromPoolAsync(&p, workspace_hint, c->pool, c->stream) == cudaSuccess) cudaFreeAsync(p, c->stream);
-    cudaStreamSynchronize(c->stream);
-    (void)cudaGetLastError();
+  if (workspace_hint) {  // size the arena up front
+    void* p = arena_alloc(c, workspace_hint);
+    if (p) arena_release(c, p, workspace_hint);
   }
   *out = c;
   return ZDWB_OK;
@@ -77,14 +56,11 @@ void zdwb_ctx_destroy(zdwb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  if (c->out_dev) cudaFreeAsync(c->out_dev, c->stream);
-  if (c->out_dev2) cudaFreeAsync(c->out_dev2, c->stream);
-  cudaStreamSynchronize(c->stream);
+  arena_destroy(c);
   if (c->out_host) cudaFreeHost(c->out_host);
   if (c->out_host2) cudaFreeHost(c->out_host2);
   if (c->meta_host) cudaFreeHost(c->meta_host);
   if (c->stage_host) cudaFreeHost(c->stage_host);
-  if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }

@@ -834,7 +834,7 @@ int upload(Ctx* ctx, DevBuf& d, const std::vector<T>& v) {
 int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size_t avail, const zdwb_decode_opts* opts,
                       zdwb_rows_out* out) {
   memset(out, 0, sizeof(*out));
-  ZDWB_TRY(stage_reset(ctx));
+  ZDWB_TRY(call_begin(ctx));
   cudaStream_t st = ctx->stream;
   const uint32_t nc = schema->ncols;
   if (nc == 0 || !schema->types) {
@@ -1268,10 +1268,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   }
 
   // ---- pass A: length of every row, then the row offsets and the exact output size
-  if (ctx->out_dev2) {
-    cudaFreeAsync(ctx->out_dev2, st);
-    ctx->out_dev2 = nullptr;
-  }
+  ctx->out_dev2 = nullptr;
   {
     DevBuf ro;
     ZDWB_TRY(ro.alloc(ctx, ((size_t)nrows + 1) * 8));
@@ -1303,10 +1300,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   ctx->last_out_per_row = hm->out_bytes / nrows;
 
   // ---- pass B: the rows
-  if (ctx->out_dev) {
-    cudaFreeAsync(ctx->out_dev, st);
-    ctx->out_dev = nullptr;
-  }
+  ctx->out_dev = nullptr;
   {
     DevBuf ob;
     ZDWB_TRY(ob.alloc(ctx, hm->out_bytes + 64));

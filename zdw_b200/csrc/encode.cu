@@ -1382,7 +1382,7 @@ uint32_t longest_line_field(uint32_t prev, uint32_t max_line) {
 int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
                       zdwb_block_out* out) {
   memset(out, 0, sizeof(*out));
-  ZDWB_TRY(stage_reset(ctx));
+  ZDWB_TRY(call_begin(ctx));
   cudaStream_t st = ctx->stream;
   const uint32_t ncols = schema->ncols;
   if (ncols == 0 || !schema->types) {
@@ -1682,10 +1682,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   }
 
   // ---- output buffer of the exact size: header + dictionary + column stats, then the packed rows
-  if (ctx->out_dev) {
-    cudaFreeAsync(ctx->out_dev, st);
-    ctx->out_dev = nullptr;
-  }
+  ctx->out_dev = nullptr;
   {
     DevBuf ob;
     ZDWB_TRY(ob.alloc(ctx, rows_base + rows_bytes + 64));
