@@ -791,7 +791,24 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
         v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
         v2 = (unsigned long long)(b0 + b1);
       } else {
-        if (!digits_value(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);  // strtoull, :385,564
+        // strtoull (:385,564): an optional sign in front of the digits ('-' negates modulo 2^64; with a sign at most
+        // 19 digits are left, which cannot overflow); anything else - white space, junk - takes the exact byte walk
+        const uint32_t c0 = x[0] & 0xffu;
+        const bool sign = c0 == (uint32_t)'-' || c0 == (uint32_t)'+';
+        uint32_t dl = len;
+        if (sign) {
+          x[0] = __funnelshift_r(x[0], x[1], 8);
+          x[1] = __funnelshift_r(x[1], x[2], 8);
+          x[2] = __funnelshift_r(x[2], x[3], 8);
+          x[3] = __funnelshift_r(x[3], x[4], 8);
+          x[4] >>= 8;
+          dl = len - 1u;
+        }
+        if (dl != 0u && digits_value(x, dl, &v1)) {
+          if (c0 == (uint32_t)'-') v1 = 0ull - v1;
+        } else {
+          v1 = parse_u64_field(A.buf + start, len);
+        }
         v2 = v1;
       }
     } else {  // a number of more than 20 characters
