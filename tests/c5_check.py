@@ -35,6 +35,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--oracle-rows", type=int, default=100_000)
+    ap.add_argument("--api", action="store_true", help="also time the getRow loop of the C++ API (ours and the reference's)")
+    ap.add_argument("--api-rows", type=int, default=1_000_000)
+    ap.add_argument("--api-rows-per-block", type=int, default=0)
     args = ap.parse_args()
     import torch
 
@@ -93,6 +96,43 @@ def main():
     back = torch.empty(dec.length, dtype=torch.uint8, device=dev)
     bench._d2d(torch, back, dec.dev_ptr, dec.length)
     res["roundtrip_bit_exact"] = dec.length == len(tsv) and bool(torch.equal(back, t[:len(tsv)]))
+
+    # decode through the row-at-a-time C++ API: the getRow loop of test_unconvert_api without printf,
+    # the same source built against this repository's host classes and against the unmodified reference
+    if args.api:
+        import gpuutil as G
+        import shutil
+        import subprocess
+        import tempfile
+        tmp = tempfile.mkdtemp(dir="/dev/shm" if Path("/dev/shm").is_dir() else None)
+        try:
+            n_api = min(args.api_rows, args.rows)
+            part = b"\n".join(tsv.split(b"\n", n_api)[:n_api]) + b"\n"
+            image = G.encode_file_with_product(ctx, sch, part, rows_per_block=args.api_rows_per_block)
+            (Path(tmp) / "c5.zdw").write_bytes(image)
+            api = {"rows": n_api, "zdw_bytes": len(image)}
+            for name, tool in (("zdw_b200", ROOT / "zdw_b200" / "bin" / "api_rowloop"), ("reference", ROOT / "oracle" / "_ref" / "api_rowloop")):
+                if not tool.exists():
+                    api[name] = None
+                    continue
+                best = None
+                for k in range(3):  # run 0 checks the rows (checksum), runs 1-2 time the API alone; best of the two
+                    pr = subprocess.run([str(tool)] + (["--checksum"] if k == 0 else []) + ["c5.zdw"], cwd=tmp, capture_output=True,
+                                        text=True, timeout=1200)
+                    if pr.returncode != 0:
+                        raise SystemExit(f"{tool} failed: {pr.stderr[-500:]}")
+                    r = json.loads(pr.stdout.strip().splitlines()[-1])
+                    if k == 0:
+                        fnv = r["fnv1a"]
+                    elif best is None or r["mb_per_s"] > best["mb_per_s"]:
+                        best = r
+                best["fnv1a"] = fnv
+                api[name] = best
+            if api.get("zdw_b200") and api.get("reference"):
+                api["same_rows"] = (api["zdw_b200"]["rows"], api["zdw_b200"]["fnv1a"]) == (api["reference"]["rows"], api["reference"]["fnv1a"])
+            res["unconvert_api"] = api
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     print(json.dumps(res))
 
 

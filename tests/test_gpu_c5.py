@@ -36,3 +36,19 @@ def test_c5_decode_through_unconvert_api(tmp_path):
         assert p.returncode == 0, p.stderr[-500:]
         outs.append(p.stdout)
     assert outs[0] == outs[1] == tsv
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test", "movie_tickets", "analytics-hits"])
+def test_api_rowloop_twins_agree_on_goldens(tmp_path, name):
+    """The getRow loop (tests/api_rowloop.cpp) built against our host classes and against the unmodified reference
+    walks the reference's own golden files to the same rows: same count, same checksum over every field byte."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle as O
+    (tmp_path / "g.zdw").write_bytes(O.golden(f"{name}.zdw"))
+    res = []
+    for tool in (ROOT / "zdw_b200" / "bin" / "api_rowloop", ROOT / "oracle" / "_ref" / "api_rowloop"):
+        p = subprocess.run([str(tool), "--checksum", "g.zdw"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-500:]
+        res.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    assert (res[0]["rows"], res[0]["tsv_bytes"], res[0]["fnv1a"]) == (res[1]["rows"], res[1]["tsv_bytes"], res[1]["fnv1a"])

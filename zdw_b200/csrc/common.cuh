@@ -40,8 +40,10 @@ struct Ctx {
   // outputs owned by the context (valid until the next call)
   void* out_dev = nullptr;     // device output buffer
   void* out_dev2 = nullptr;    // second device output (row offsets)
-  void* out_host = nullptr;    // pinned host output
+  void* out_host = nullptr;    // host output: pinned, or plain malloc'd memory for a one-off result (out_host_pinned)
   size_t out_host_cap = 0;
+  bool out_host_pinned = true;
+  unsigned long long decode_calls = 0;  // host-output decode calls served so far
   void* out_host2 = nullptr;
   size_t out_host2_cap = 0;
   std::vector<unsigned long long> flag_counts;  // -s statistics of the last decoded block
@@ -213,6 +215,16 @@ struct DevBuf {
     return reinterpret_cast<T*>(p);
   }
 };
+
+// host output buffer of the context (see Ctx::out_host)
+inline void out_host_release(Ctx* c) {
+  if (c->out_host) {
+    if (c->out_host_pinned) cudaFreeHost(c->out_host);
+    else free(c->out_host);
+  }
+  c->out_host = nullptr;
+  c->out_host_cap = 0;
+}
 
 // Pinned arena of the context: stage_reset() at the start of a call (the stream is idle then), stage_take() hands out
 // 16-byte aligned pieces that stay valid until the next reset.

@@ -57,7 +57,7 @@ void zdwb_ctx_destroy(zdwb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   arena_destroy(c);
-  if (c->out_host) cudaFreeHost(c->out_host);
+  out_host_release(c);
   if (c->out_host2) cudaFreeHost(c->out_host2);
   if (c->meta_host) cudaFreeHost(c->meta_host);
   if (c->stage_host) cudaFreeHost(c->stage_host);

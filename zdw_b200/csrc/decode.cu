@@ -1321,13 +1321,26 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     out->row_off = opts->want_row_offsets ? static_cast<const uint64_t*>(ctx->out_dev2) : nullptr;
     return ZDWB_OK;
   }
-  if (ctx->out_host_cap < out_len) {
-    if (ctx->out_host) cudaFreeHost(ctx->out_host);
-    ctx->out_host = nullptr;
-    ctx->out_host_cap = 0;
-    const size_t cap = std::max<size_t>(out_len + out_len / 4, 1 << 20);  // headroom: blocks of a file vary a little
-    ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host, cap, cudaHostAllocDefault));
-    ctx->out_host_cap = cap;
+  // Pinning memory costs about as much as copying into it a few times over: worth it when more blocks follow and re-use
+  // the buffer, not for a context whose first block is also the file's last - that one result goes to plain memory.
+  const bool one_off = ctx->decode_calls == 0 && H.last;
+  ++ctx->decode_calls;
+  if (ctx->out_host_cap < out_len || (!ctx->out_host_pinned && !one_off)) {
+    out_host_release(ctx);
+    if (one_off) {
+      ctx->out_host = malloc(out_len + 64);
+      if (!ctx->out_host) {
+        ctx->err = "decode: host allocation failed";
+        return ZDWB_ERR_OOM;
+      }
+      ctx->out_host_pinned = false;
+      ctx->out_host_cap = out_len;
+    } else {
+      const size_t cap = std::max<size_t>(out_len + out_len / 4, 1 << 20);  // headroom: blocks of a file vary a little
+      ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host, cap, cudaHostAllocDefault));
+      ctx->out_host_pinned = true;
+      ctx->out_host_cap = cap;
+    }
   }
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, out_len, cudaMemcpyDeviceToHost, st));
   if (opts->want_row_offsets) {

@@ -1741,11 +1741,10 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     out->bytes = outp;
   } else {
     if (ctx->out_host_cap < total_len) {
-      if (ctx->out_host) cudaFreeHost(ctx->out_host);
-      ctx->out_host = nullptr;
-      ctx->out_host_cap = 0;
+      out_host_release(ctx);
       size_t cap = std::max<size_t>(total_len + total_len / 4, 1 << 20);  // headroom: blocks of a file vary a little
       ZDWB_CUDA_TRY(ctx, cudaHostAlloc(&ctx->out_host, cap, cudaHostAllocDefault));
+      ctx->out_host_pinned = true;
       ctx->out_host_cap = cap;
     }
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host, outp, total_len, cudaMemcpyDeviceToHost, st));

@@ -4,6 +4,7 @@
 #include <assert.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <strings.h>
 #include <sys/stat.h>
 
@@ -45,6 +46,19 @@ bool endsWith(const string& s, const char* suffix) {
 
 }  // namespace
 
+namespace {
+// ZDW_HOST_TIMING=1: wall-clock of the host-side stages on stderr (diagnostics)
+bool hostTiming() {
+  static const bool on = getenv("ZDW_HOST_TIMING") != NULL;
+  return on;
+}
+double nowSeconds() {
+  timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+}  // namespace
+
 ZDWException::ZDWException(const ERR_CODE errcode)
     : std::runtime_error(UnconvertFromZDW_Base::ERR_CODE_TEXTS[errcode]), code(errcode) {}
 
@@ -58,12 +72,20 @@ ZdwInput::ZdwInput()
 
 ZdwInput::~ZdwInput() {
   if (fp && isPipe) pclose(fp);
+  else if (fp && fp != stdin) fclose(fp);
   free(buf);
 }
 
 bool ZdwInput::openCommand(const string& cmd) {
   fp = popen(cmd.c_str(), "r");
   isPipe = true;
+  return fp != NULL;
+}
+
+bool ZdwInput::openFile(const string& path) {
+  fp = fopen(path.c_str(), "rb");
+  isPipe = false;
+  if (fp) setvbuf(fp, NULL, _IONBF, 0);  // reads go straight into the block buffer, in large pieces
   return fp != NULL;
 }
 
@@ -143,9 +165,9 @@ UnconvertFromZDW_Base::UnconvertFromZDW_Base(const string& fileName, const bool 
   else if (endsWith(inFileName, ".bz2")) cmd = "bzip2 -d --stdout " + inFileName + " 2>/dev/null";
   else if (endsWith(inFileName, ".xz")) cmd = "xzcat " + inFileName;
   else if (endsWith(inFileName, ".zst")) cmd = "zstd -d --stdout " + inFileName + " 2>/dev/null";
-  else cmd = "cat " + inFileName;
   input = new internal::ZdwInput();
-  input->openCommand(cmd);
+  if (cmd.empty()) input->openFile(inFileName);  // reference: popen("cat <file>") - same bytes, one copy and one process less
+  else input->openCommand(cmd);
 }
 
 UnconvertFromZDW_Base::~UnconvertFromZDW_Base() { delete input; }
@@ -263,6 +285,7 @@ ERR_CODE UnconvertFromZDW_Base::readHeader() {
   if (!isReadOpen()) return FILE_OPEN_ERR;
   if (eState != ZDW_BEGIN) return HEADER_ALREADY_READ_ERR;
   if (!statusOutput) statusOutput = defaultStatusOutputCallback;
+  if (!bOutputDescFileOnly) gpu.prefetch(gpuDevice);  // CUDA start-up overlaps the reading of the header and first block
 
   readBytes(&version, 2);
   if (version > UNCONVERT_ZDW_VERSION) return UNSUPPORTED_ZDW_VERSION_ERR;
@@ -542,13 +565,18 @@ ERR_CODE UnconvertFromZDW_Base::peekBlock(BlockInfo& info) {
   info.maxRowBytes = info.numSetColumns + valueBytes;
   info.rowsOffset = statsAt + nc + 8 * used;
   // buffer the whole block: its rows cannot take more than numLines * maxRowBytes
+  const double tRead0 = nowSeconds();
   input->ensure(info.rowsOffset + (size_t)info.numLines * info.maxRowBytes + 1);
+  if (hostTiming()) fprintf(stderr, "[zdw host] input buffered %.3f s (%zu bytes)\n", nowSeconds() - tRead0, input->available());
   return OK;
 }
 
 ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
                                             bool wantFlagCounts, zdwb_rows_out* out) {
-  if (!gpu.open(gpuDevice)) {
+  const double tOpen0 = nowSeconds();
+  const bool opened = gpu.open(gpuDevice);
+  if (hostTiming()) fprintf(stderr, "[zdw host] gpu.open %.3f s\n", nowSeconds() - tOpen0);
+  if (!opened) {
     statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n",
                  exeName.empty() ? "UnconvertFromZDW" : exeName.c_str(), gpu.lastError().c_str());
     return PROCESSING_ERROR;
@@ -583,7 +611,11 @@ ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char
     if (UseVirtualExportRowColumn() && outputColumns[indexForVirtualRowColumn] != IGNORE_COLUMN)
       o.rownum_pos = outputColumns[indexForVirtualRowColumn];
   }
+  const double tDec0 = nowSeconds();
   const int rc = zdwb_decode_block(gpu.get(), &sch, input->data(), input->available(), &o, out);
+  if (hostTiming())
+    fprintf(stderr, "[zdw host] zdwb_decode_block %.3f s (%zu bytes available, %llu bytes out)\n", nowSeconds() - tDec0,
+            input->available(), (unsigned long long)out->len);
   switch (rc) {
     case ZDWB_OK: return OK;
     case ZDWB_ERR_CORRUPT: return CORRUPTED_DATA_ERROR;  // reference :1364-1365

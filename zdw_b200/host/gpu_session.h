@@ -4,6 +4,7 @@
 
 #include <cstdlib>
 #include <string>
+#include <thread>
 
 #include "zdw_b200.h"
 
@@ -12,19 +13,38 @@ namespace zdw {
 
 class GpuSession {
  public:
-  GpuSession() : ctx_(NULL), rc_(ZDWB_OK) {}
+  GpuSession() : ctx_(NULL), rc_(ZDWB_OK), device_(-1), pending_(false) {}
   ~GpuSession() { close(); }
-  // device < 0: take $ZDW_GPU or device 0
+  static int resolve(int device) {  // device < 0: take $ZDW_GPU or device 0
+    if (device >= 0) return device;
+    const char* e = getenv("ZDW_GPU");
+    return e ? atoi(e) : 0;
+  }
+  // Starts creating the context on a helper thread (CUDA start-up takes a few hundred milliseconds): the caller goes
+  // on reading its input and meets the context again in open().
+  void prefetch(int device = -1) {
+    if (ctx_ || pending_) return;
+    device_ = resolve(device);
+    pending_ = true;
+    worker_ = std::thread([this]() { rc_ = zdwb_ctx_create(device_, 0, &ctx_); });
+  }
   bool open(int device = -1) {
-    if (ctx_) return true;
-    if (device < 0) {
-      const char* e = getenv("ZDW_GPU");
-      device = e ? atoi(e) : 0;
+    device = resolve(device);
+    if (pending_) {
+      worker_.join();
+      pending_ = false;
+      if (device_ != device) close();  // the device was changed after the prefetch
     }
+    if (ctx_) return true;
+    device_ = device;
     rc_ = zdwb_ctx_create(device, 0, &ctx_);
     return rc_ == ZDWB_OK;
   }
   void close() {
+    if (pending_) {
+      worker_.join();
+      pending_ = false;
+    }
     if (ctx_) zdwb_ctx_destroy(ctx_);
     ctx_ = NULL;
   }
@@ -37,6 +57,9 @@ class GpuSession {
   GpuSession& operator=(const GpuSession&);
   zdwb_ctx* ctx_;
   int rc_;
+  int device_;
+  bool pending_;
+  std::thread worker_;
 };
 
 }  // namespace zdw

@@ -67,6 +67,7 @@ class ZdwInput {
   ZdwInput();
   ~ZdwInput();
   bool openCommand(const std::string& cmd);
+  bool openFile(const std::string& path);  // an uncompressed file is read directly (the reference pipes it through cat)
   void openStdin();
   bool is_open() const { return fp != NULL; }
   // makes at least n bytes available at data() unless the stream ends first; returns what is available
