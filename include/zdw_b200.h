@@ -107,7 +107,13 @@ typedef struct {
                                    window; it is left unconsumed (tsv_consumed points at it) and isLast is written as 0 */
   uint32_t prev_longest_line;   /* m_LongestLine carried in from earlier blocks of the file (0 = 16384 start value,
                                    ConvertToZDW.cpp:965; the field is cumulative, getnextrow.cpp:57-65) */
-  uint32_t reserved1;
+  uint32_t spill_cols;          /* with max_rows: the first spill_cols columns of the row AFTER the block's last row also go
+                                   through pass 1 - their strings enter this block's dictionary, their numbers its column
+                                   ranges - and that row's length counts for longestLine; the row itself is not part of
+                                   the block.  This is the reference's interrupted row when it runs low on memory
+                                   (ConvertToZDW.cpp:334-355,404-413; stringheap.cpp:75-86): with
+                                   (max_rows, spill_cols) per block any file the reference cut on its own can be
+                                   reproduced byte for byte.  0 = none. */
   uint64_t max_rows;            /* 0 = every row in the buffer; else close the block after this many rows */
 } zdwb_encode_opts;
 

@@ -374,11 +374,43 @@ int zo_write_file_header(const zo_schema* s, const zo_encode_opts* o, uint8_t** 
 /* (signed char) promoted to ULONGLONG as x86 g++ does: ConvertToZDW.cpp:359,543 */
 static uint64_t sx(char ch) { return (uint64_t)(int64_t)(signed char)ch; }
 
+/* one row (its first ncols_todo columns) through the per-column part of parseInput, ConvertToZDW.cpp:338-401 */
+static void pass1_fields(const zo_schema* s, const fieldvec* cols, uint32_t ncols_todo, uint8_t* minmaxset, uint64_t* cmin,
+                         uint64_t* cmax, dict* uniq) {
+  for (uint32_t c = 0; c < ncols_todo; ++c) {
+    const char* f = cols->v[c];
+    if (!f[0]) continue;
+    const uint8_t t = s->types[c];
+    if (is_text_like(t)) {
+      minmaxset[c] = 1;
+      dict_insert(uniq, f);
+    } else {
+      uint64_t val;
+      if (t == ZO_CHAR) {
+        val = sx(f[0]);
+        if (f[0] == '\\') val += (uint64_t)(int64_t)((int)(signed char)f[1] * 256); /* :360-361 */
+      } else {
+        val = strtoull(f, NULL, 10); /* :385 */
+      }
+      if (val > 0) {
+        if (minmaxset[c]) {
+          if (val > cmax[c]) cmax[c] = val;
+          else if (val < cmin[c]) cmin[c] = val;
+        } else {
+          cmax[c] = cmin[c] = val;
+          minmaxset[c] = 1;
+        }
+      }
+    }
+  }
+}
+
 int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_encode_opts* o,
                    uint8_t** out_p, size_t* out_len, zo_encode_info* info) {
   const uint32_t nc = s->ncols;
   const int trim = o ? o->trim_trailing_spaces : 0;
-  const uint32_t rpb = o ? o->rows_per_block : 0;
+  const uint32_t nplan = o ? o->nplan : 0;
+  const uint32_t rpb = (o && !nplan) ? o->rows_per_block : 0;
   obuf out = {0};
   zo_encode_info inf;
   memset(&inf, 0, sizeof(inf));
@@ -399,7 +431,7 @@ int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_en
 
   /* explicit block policy: total row count decides which block is the last one */
   uint64_t total_rows = 0;
-  if (rpb) {
+  if (rpb || nplan) {
     memf f = {tsv, n, 0};
     uint32_t rs = 16 * 1024;
     char* r2 = (char*)malloc(rs);
@@ -420,6 +452,12 @@ int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_en
       limit = rpb;
       last = 0;
     }
+    uint32_t spill = 0;
+    if (nplan && inf.nblocks < nplan && rows_done + o->plan_rows[inf.nblocks] < total_rows) {
+      limit = o->plan_rows[inf.nblocks];
+      spill = o->plan_spill ? o->plan_spill[inf.nblocks] : 0;
+      last = 0;
+    }
     size_t k;
     while ((!limit || numRows < limit) && (k = get_data_row(&in, &row, &rowSize, &cols, trim))) {
       if (k != nc) {
@@ -427,33 +465,21 @@ int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_en
         rc = ZO_ENC_WRONG_NUM_OF_COLUMNS_ON_A_ROW;
         goto done;
       }
-      for (uint32_t c = 0; c < nc; ++c) {
-        const char* f = cols.v[c];
-        if (!f[0]) continue;
-        const uint8_t t = s->types[c];
-        if (is_text_like(t)) {
-          minmaxset[c] = 1;
-          dict_insert(&uniq, f);
-        } else {
-          uint64_t val;
-          if (t == ZO_CHAR) {
-            val = sx(f[0]);
-            if (f[0] == '\\') val += (uint64_t)(int64_t)((int)(signed char)f[1] * 256); /* :360-361 */
-          } else {
-            val = strtoull(f, NULL, 10); /* :385 */
-          }
-          if (val > 0) {
-            if (minmaxset[c]) {
-              if (val > cmax[c]) cmax[c] = val;
-              else if (val < cmin[c]) cmin[c] = val;
-            } else {
-              cmax[c] = cmin[c] = val;
-              minmaxset[c] = 1;
-            }
-          }
-        }
-      }
+      pass1_fields(s, &cols, nc, minmaxset, cmin, cmax, &uniq);
       ++numRows;
+    }
+    if (limit && numRows == limit && !last) {
+      /* the interrupted row: read in full (the row buffer grows with it, getnextrow.cpp:57-65), its leading columns
+         feed the dictionary and the column ranges, then it is left for the next block (fsetpos, :867) */
+      const size_t keep = in.pos;
+      k = get_data_row(&in, &row, &rowSize, &cols, trim);
+      if (k && k != nc) {
+        inf.bad_row = numRows + 1;
+        rc = ZO_ENC_WRONG_NUM_OF_COLUMNS_ON_A_ROW;
+        goto done;
+      }
+      if (k) pass1_fields(s, &cols, spill < nc ? spill : nc, minmaxset, cmin, cmax, &uniq);
+      in.pos = keep;
     }
     if (!numRows) break; /* :824-835 "Empty data file -- nothing to process" (only possible on block 1) */
 
@@ -696,6 +722,7 @@ int zo_decode_file(const uint8_t* zdw, size_t n, const zo_decode_opts* o, uint8_
   do {
     /* ---- parseBlockHeader, :758-1000 */
     uint32_t numLines = 0, lineLen = 0;
+    const size_t block_at = r.pos;
     if (!rd_bytes(&r, &numLines, 4) || !rd_bytes(&r, &lineLen, 4) || !rd_bytes(&r, &last, 1)) {
       rc = ZO_DEC_GZREAD_FAILED;
       goto done;
@@ -726,6 +753,10 @@ int zo_decode_file(const uint8_t* zdw, size_t n, const zo_decode_opts* o, uint8_
     memset(cval, 0, (size_t)nc * 8);
 
     /* ---- rows: readNextRow, :1270-1464 */
+    if (inf.nblocks < 16) {
+      inf.block_rows[inf.nblocks] = numLines;
+      inf.block_offset[inf.nblocks] = block_at;
+    }
     for (uint32_t rr = 0; rr < numLines; ++rr) {
       /* `while (rowsRead < numLines && !isFinished())`, :1577: input->eof() is true once every byte has been
        * consumed, so rows of zero bytes (no used column) at the very end of the file are never read */

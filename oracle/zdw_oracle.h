@@ -62,6 +62,14 @@ typedef struct {
   uint32_t nmeta;
   const char* const* meta_keys;
   const char* const* meta_vals;
+  /* explicit block plan (overrides rows_per_block when nplan > 0): block k closes after plan_rows[k] rows; the first
+     plan_spill[k] columns of the row that follows have already gone through pass 1 by then - the reference's
+     interrupted row (ConvertToZDW.cpp:334-355,404-413; stringheap.cpp:75-86): its strings stay in the
+     closed block's dictionary, its numbers in the column ranges, the row itself opens the next block.  Rows left after
+     the plan form one last block. */
+  uint32_t nplan;
+  const uint32_t* plan_rows;
+  const uint32_t* plan_spill;
 } zo_encode_opts;
 
 typedef struct {
@@ -94,6 +102,8 @@ typedef struct {
   uint32_t nblocks;
   uint32_t line_length;      /* exportFileLineLength of the last block */
   size_t consumed;           /* bytes of the image consumed */
+  uint32_t block_rows[16];   /* numRows of the first 16 blocks (block-plan recovery in the tests) */
+  uint64_t block_offset[16]; /* byte offset of their block headers inside the image */
 } zo_decode_info;
 
 /* UnconvertFromZDWToFile<BufferedOutput>::unconvert data path (UnconvertFromZDW.cpp:1030-1219,

@@ -22,8 +22,9 @@ def split_header(image: bytes):
     return image[:hl], image[hl:]
 
 
-def encode_file_with_product(ctx, sch, tsv: bytes, trim=False, rows_per_block=0) -> bytes:
-    """File image = oracle-independent header bytes + product blocks (the host stitcher in miniature)."""
+def encode_file_with_product(ctx, sch, tsv: bytes, trim=False, rows_per_block=0, plan=None) -> bytes:
+    """File image = oracle-independent header bytes + product blocks (the host stitcher in miniature).
+    plan: [(rows, spill_columns), ...] explicit block boundaries; rows left after the plan form one last block."""
     # header: version 11, empty metadata, names, types, char sizes (ConvertToZDW.cpp:673-737)
     hdr = (11).to_bytes(2, "little") + (0).to_bytes(4, "little")
     for nme in sch.names:
@@ -32,8 +33,12 @@ def encode_file_with_product(ctx, sch, tsv: bytes, trim=False, rows_per_block=0)
     out = bytearray(hdr)
     pos = 0
     longest = 0
+    plan = list(plan or [])
+    k = 0
     while True:
-        blk = ctx.encode_block(sch.types, tsv[pos:], trim=trim, prev_longest_line=longest, max_rows=rows_per_block)
+        rows, spill = plan[k] if k < len(plan) else (rows_per_block, 0)
+        k += 1
+        blk = ctx.encode_block(sch.types, tsv[pos:], trim=trim, prev_longest_line=longest, max_rows=rows, spill_cols=spill)
         if blk.nrows == 0:
             break
         out += blk.data

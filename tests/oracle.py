@@ -37,7 +37,8 @@ class _Schema(C.Structure):
 
 class _EncOpts(C.Structure):
     _fields_ = [("trim", C.c_int), ("rows_per_block", C.c_uint32), ("nmeta", C.c_uint32),
-                ("keys", C.POINTER(C.c_char_p)), ("vals", C.POINTER(C.c_char_p))]
+                ("keys", C.POINTER(C.c_char_p)), ("vals", C.POINTER(C.c_char_p)),
+                ("nplan", C.c_uint32), ("plan_rows", C.POINTER(C.c_uint32)), ("plan_spill", C.POINTER(C.c_uint32))]
 
 
 class _EncInfo(C.Structure):
@@ -51,7 +52,8 @@ class _DecOpts(C.Structure):
 
 class _DecInfo(C.Structure):
     _fields_ = [("version", C.c_uint16), ("ncols", C.c_uint32), ("total_rows", C.c_uint64), ("nblocks", C.c_uint32),
-                ("line_length", C.c_uint32), ("consumed", C.c_size_t)]
+                ("line_length", C.c_uint32), ("consumed", C.c_size_t), ("block_rows", C.c_uint32 * 16),
+                ("block_offset", C.c_uint64 * 16)]
 
 
 _lib = None
@@ -118,12 +120,18 @@ class EncodeResult:
     dict_entries: int
 
 
-def encode(sch: Schema, tsv: bytes, trim: bool = False, rows_per_block: int = 0, metadata: dict | None = None) -> EncodeResult:
+def encode(sch: Schema, tsv: bytes, trim: bool = False, rows_per_block: int = 0, metadata: dict | None = None,
+           plan=None) -> EncodeResult:
+    """plan: [(rows, spill_columns), ...] - explicit block boundaries with the reference's interrupted-row spill."""
     s = _c_schema(sch)
     md = sorted((metadata or {}).items())
     keys = (C.c_char_p * max(len(md), 1))(*[k.encode() for k, _ in md])
     vals = (C.c_char_p * max(len(md), 1))(*[v.encode() for _, v in md])
-    o = _EncOpts(int(trim), rows_per_block, len(md), C.cast(keys, C.POINTER(C.c_char_p)), C.cast(vals, C.POINTER(C.c_char_p)))
+    plan = list(plan or [])
+    prow = (C.c_uint32 * max(len(plan), 1))(*[int(r) for r, _ in plan])
+    pspill = (C.c_uint32 * max(len(plan), 1))(*[int(c) for _, c in plan])
+    o = _EncOpts(int(trim), rows_per_block, len(md), C.cast(keys, C.POINTER(C.c_char_p)), C.cast(vals, C.POINTER(C.c_char_p)),
+                 len(plan), C.cast(prow, C.POINTER(C.c_uint32)), C.cast(pspill, C.POINTER(C.c_uint32)))
     out = C.c_void_p()
     n = C.c_size_t()
     info = _EncInfo()
@@ -144,6 +152,8 @@ class DecodeResult:
     nblocks: int
     line_length: int
     consumed: int
+    block_rows: list = None     # numRows of the first 16 blocks
+    block_offset: list = None   # offsets of their block headers in the image
 
 
 def decode(zdw: bytes, out_col: list | None = None, n_out: int = 0, sep: bytes = b"\t") -> DecodeResult:
@@ -158,7 +168,9 @@ def decode(zdw: bytes, out_col: list | None = None, n_out: int = 0, sep: bytes =
     data = C.string_at(out, n.value) if out.value else b""
     if out.value:
         lib().zo_free(out)
-    return DecodeResult(rc, data, info.version, info.ncols, info.total_rows, info.nblocks, info.line_length, info.consumed)
+    nb = min(info.nblocks, 16)
+    return DecodeResult(rc, data, info.version, info.ncols, info.total_rows, info.nblocks, info.line_length, info.consumed,
+                        list(info.block_rows[:nb]), list(info.block_offset[:nb]))
 
 
 def read_header(zdw: bytes):

@@ -136,3 +136,28 @@ def test_empty_inputs(ctx):
     for tsv in (b"", b"\n\n\n", b"x"):
         blk = ctx.encode_block(sch.types, tsv)
         assert blk.nrows == 0 and blk.length == 0
+
+
+@pytest.mark.parametrize("plan", [[(1000, 0)], [(1000, 3), (500, 1)], [(7, 8)], [(2999, 2)], [(1, 1), (1, 9), (1, 4)]])
+def test_explicit_block_plan_with_spill(ctx, plan):
+    """(rows, spilled columns) per block - the reference's interrupted row - against the oracle."""
+    case = next(c for c in CASES if c[0] == "mixed_3000")
+    sch = O.parse_desc(case[1])
+    want = O.encode(sch, case[2], plan=plan).data
+    got = G.encode_file_with_product(ctx, sch, case[2], plan=plan)
+    assert got == want, G.first_diff(got, want)
+
+
+def test_reproduces_a_file_the_reference_cut_on_its_own(ctx):
+    """The compiled reference splits a dictionary-heavy input when it runs low on memory (--mem-limit); with the block
+    plan recovered from its output the CUDA encoder writes the same bytes, spilled strings included."""
+    import c5_check
+    import test_block_plan as BP
+    if not O.have_ref():
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    sch = O.parse_desc(c5_check.DESC)
+    tsv, image = BP.reference_mem_limit_file(600_000, 140)
+    plan = BP.recover_plan(sch, tsv, image)
+    assert plan and any(spill for _, spill in plan)
+    got = G.encode_file_with_product(ctx, sch, tsv, plan=plan)
+    assert got == image, G.first_diff(got, image)

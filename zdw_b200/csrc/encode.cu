@@ -61,6 +61,8 @@ struct EncMeta {
   // block cut (max_rows)
   uint32_t cut_end_p1;     // position + 1 of the terminator of the block's last row
   uint32_t next_start;     // first byte of the row after it
+  uint32_t spill_end;      // position + 1 of the delimiter that closes the last spilled column of that row
+  uint32_t spill_row_len;  // length of that row incl. its terminator (0 = there is no complete row)
 };
 
 // per tile: counts, then (after k_tile_scan) exclusive prefixes
@@ -410,6 +412,36 @@ __global__ void k_find_cut(const uint8_t* __restrict__ buf, uint64_t n, int64_t 
       }
     }
   }
+}
+
+// The row after the block's last one (the reference's interrupted row): one thread walks it from
+// `start` with the delimiter rules of scan_step and reports where its first `spill_cols` columns end and how long it is.
+__global__ void k_find_spill(const uint8_t* __restrict__ buf, uint64_t n, uint32_t start, uint32_t spill_cols,
+                             EncMeta* __restrict__ meta) {
+  uint32_t closed = 0, spill_end = start, odd = 0;
+  uint32_t row_len = 0;
+  for (uint64_t p = start; p < n; ++p) {
+    const uint8_t b = buf[p];
+    if (b == (uint8_t)'\\') {
+      odd ^= 1u;
+      continue;
+    }
+    const bool escaped = odd != 0u;
+    odd = 0;
+    if (escaped) continue;
+    if (b == (uint8_t)'\t' || b == (uint8_t)'\n') {
+      if (closed < spill_cols) {
+        ++closed;
+        spill_end = (uint32_t)p + 1u;
+      }
+      if (b == (uint8_t)'\n') {
+        row_len = (uint32_t)(p - start) + 1u;
+        break;
+      }
+    }
+  }
+  meta->spill_end = row_len ? spill_end : start;  // an unterminated tail is not a row: nothing spills
+  meta->spill_row_len = row_len;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1488,6 +1520,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
 
   // ---- block extent
   uint64_t limit;  // bytes that belong to the block
+  uint32_t spill_row_len = 0;  // the interrupted row was read in full before it was dropped: it counts for longestLine
   uint32_t tail_bytes = 0;
   if (took_all) {
     // the terminator of the last row is the last row break unless blank lines follow it; either way every
@@ -1509,6 +1542,19 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     limit = hmeta->cut_end_p1;
     out->tsv_consumed = hmeta->next_start;
+    if (opts->spill_cols) {
+      {
+        KernelScope _ks(ctx, "k_find_spill");
+        k_find_spill<<<1, 1, 0, st>>>(buf, n, hmeta->next_start, opts->spill_cols, meta);
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
+      ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (hmeta->spill_row_len) {
+        limit = hmeta->spill_end;  // pass 1 takes every field whose closing delimiter lies in front of this
+        spill_row_len = hmeta->spill_row_len;
+      }
+    }
   }
   out->nrows = nrows;
 
@@ -1601,6 +1647,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   // the unterminated tail fills the row buffer the same way before being dropped (getnextrow.cpp:57-69)
   uint32_t max_line = hmeta->max_line;
   if (tail_bytes >= 2) max_line = std::max(max_line, tail_bytes + 1);
+  max_line = std::max(max_line, spill_row_len);
   const uint32_t longest_field = longest_line_field(opts->prev_longest_line, max_line);
 
   // ---- column statistics
