@@ -288,3 +288,20 @@ def test_unconvert_api_matches_reference(name):
             (d / "x.zdw").write_bytes(z)
             outs.append(run(tool_dir, "test_unconvert_api", ["-ci", sel, "x.zdw"], d)[:2])
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_block_plan_flag_reproduces_the_references_memory_cut():
+    """convertDWfile --block-plan=rows:spill with the plan recovered from a file the reference cut under --mem-limit."""
+    import c5_check
+    import test_block_plan as BP
+    sch = O.parse_desc(c5_check.DESC)
+    tsv, image = BP.reference_mem_limit_file(600_000, 140)
+    plan = BP.recover_plan(sch, tsv, image)
+    with Work() as d:
+        (d / "x.sql").write_bytes(tsv)
+        (d / "x.desc.sql").write_bytes(c5_check.DESC)
+        flag = "--block-plan=" + ",".join(f"{r}:{s}" for r, s in plan)
+        rc, out, err = run(BIN, "convertDWfile", ["-q", flag, "--block-bytes=16777216", "x.sql"], d, timeout=600)
+        assert rc == 0, (out + err)[-500:]
+        assert (d / "x.zdw.gz").read_bytes() == image

@@ -303,8 +303,28 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     eo.more_input_follows = win.eof ? 0 : 1;
     eo.prev_longest_line = longestLine;
     eo.max_rows = rowsPerBlock;
+    const bool planned = (size_t)(blocks - 1) < blockPlan.size();
+    if (planned) {
+      eo.max_rows = blockPlan[blocks - 1].first;
+      eo.spill_cols = blockPlan[blocks - 1].second;
+    }
     zdwb_block_out blk;
     const int rc = zdwb_encode_block(gpu.get(), &sch, win.buf, win.len, &eo, &blk);
+    if (rc == ZDWB_OK && planned && !win.eof && blk.rows_in_buffer <= eo.max_rows) {
+      // the window must hold the planned rows and the complete row after them: widen it and try again
+      if (windowBytes >= MAX_WINDOW_BYTES) {
+        statusOutput(ERROR, "%s: block %d of the plan does not fit %zu bytes\n", exeName, blocks, (size_t)MAX_WINDOW_BYTES);
+        res = UNKNOWN_ERROR;
+        goto Done;
+      }
+      windowBytes = std::min(windowBytes * 2, MAX_WINDOW_BYTES);
+      if (!win.reserve(windowBytes)) {
+        res = OUT_OF_MEMORY;
+        goto Done;
+      }
+      --blocks;
+      continue;
+    }
     if (rc == ZDWB_ERR_WRONG_COLUMNS) {
       statusOutput(ERROR, "\nRow %u had the problem\n", blk.bad_row);  // one past the last good row (:810-812)
       wrongColumns = true;

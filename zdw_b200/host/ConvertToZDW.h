@@ -62,6 +62,9 @@ class ConvertToZDW {
   // longer fit a window of `bytes` TSV bytes, whichever comes first.
   void setRowsPerBlock(uint64_t rows) { rowsPerBlock = rows; }
   void setBlockBytes(size_t bytes) { blockBytes = bytes; }
+  // explicit block plan: block k closes after rows[k] rows and the first spill[k] columns of the row that follows count
+  // for its dictionary and column ranges (the reference's interrupted row); rows left form a last block
+  void setBlockPlan(const std::vector<std::pair<uint64_t, uint32_t> >& plan) { blockPlan = plan; }
   void setGpuDevice(int device) { gpuDevice = device; }
 
  private:
@@ -86,6 +89,7 @@ class ConvertToZDW {
   bool bTrimTrailingSpaces;
   const bool bStreamingInput;
   uint64_t rowsPerBlock;
+  std::vector<std::pair<uint64_t, uint32_t> > blockPlan;
   size_t blockBytes;
   int gpuDevice;
   GpuSession gpu;

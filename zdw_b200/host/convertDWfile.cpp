@@ -1,6 +1,6 @@
 // convertDWfile -- command line front end of the TSV -> ZDW encoder (B200 build).
 // Flags, messages and exit codes follow the reference CLI (cplusplus/convertDWfile.cpp:44-66, :98-260); the
-// --rows-per-block / --block-bytes / --gpu options are additions of this build.
+// --rows-per-block / --block-plan / --block-bytes / --gpu options are additions of this build.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,6 +45,8 @@ void printUsage(const char* exe) {
         "\t--metadata-file=<filename> supply a filepath to specify key-value pairs (formatted as '<key>=<value>' pairs, each on a separate line) to store as file metadata for every file being converted\n"
         "\n"
         "\t--rows-per-block=<N>  (B200 build) close a ZDW block every N rows [default=no row limit]\n"
+        "\t--block-plan=<rows:spill,...>  (B200 build) explicit blocks: rows per block and the columns of the next row that\n"
+        "\t                      (B200 build) were already parsed when the reference closed the block (reproduces its memory-driven cuts)\n"
         "\t--block-bytes=<N>     (B200 build) TSV bytes per block window [default=1 GiB]\n"
         "\t--gpu=<N>             (B200 build) CUDA device to use [default=$ZDW_GPU or 0]\n"
         "\n"
@@ -74,6 +76,7 @@ struct Options {
   const char* zArgs;
   std::map<std::string, std::string> metadata;
   unsigned long long rowsPerBlock;
+  std::vector<std::pair<uint64_t, uint32_t> > blockPlan;
   unsigned long long blockBytes;
   int gpu;
   std::vector<const char*> files;
@@ -157,6 +160,20 @@ int main(int argc, char* argv[]) {
           opt.rowsPerBlock = strtoull(flag + 15, NULL, 10);
           break;
         }
+        if (!strncmp(flag, "block-plan=", 11)) {  // rows:spill,rows:spill,...
+          const char* at = flag + 11;
+          while (*at) {
+            char* end = NULL;
+            const unsigned long long rows = strtoull(at, &end, 10);
+            unsigned long spill = 0;
+            if (end && *end == ':') spill = strtoul(end + 1, &end, 10);
+            if (!end || end == at || rows == 0) return reportFailure(ConvertToZDW::BAD_PARAMETER);
+            opt.blockPlan.push_back(std::make_pair((uint64_t)rows, (uint32_t)spill));
+            at = *end == ',' ? end + 1 : end;
+            if (*end && *end != ',') return reportFailure(ConvertToZDW::BAD_PARAMETER);
+          }
+          break;
+        }
         if (!strncmp(flag, "block-bytes=", 12)) {
           opt.blockBytes = strtoull(flag + 12, NULL, 10);
           break;
@@ -182,6 +199,7 @@ int main(int argc, char* argv[]) {
     conv.compressor = opt.compressor;
     if (opt.trim) conv.trimTrailingSpaces();
     if (opt.rowsPerBlock) conv.setRowsPerBlock(opt.rowsPerBlock);
+    if (!opt.blockPlan.empty()) conv.setBlockPlan(opt.blockPlan);
     if (opt.blockBytes) conv.setBlockBytes((size_t)opt.blockBytes);
     conv.setGpuDevice(opt.gpu);
     const ConvertToZDW::ERR_CODE res =
