@@ -27,7 +27,7 @@ struct Ctx {
     size_t cap, used;
   };
   std::vector<Chunk> chunks;
-  size_t arena_live = 0, arena_high = 0;  // bytes in use now / most bytes in use during this call
+  size_t arena_cur = 0;  // chunk allocations currently come from
   std::string err;
   unsigned long long launches = 0;
   int sm_count = 148;
@@ -114,15 +114,32 @@ struct Status {
     ZDWB_CUDA_TRY(ctx, cudaGetLastError());                                                        \
   } while (0)
 
-// Device memory of a call comes from a per-context stack arena: one big cudaMalloc'd chunk that every call re-uses from
-// the bottom, so a call in steady state makes no driver-level memory-management call at all (those serialise with
-// other driver work such as NVML queries, and cost host time per block).  Allocation bumps the top of the last chunk;
-// scoped buffers die in reverse order of construction, so releasing the top one pops it and the space is re-used
-// within the call (everything runs on the context's one stream, so re-use is ordered).  A chunk that is too small is
-// followed by another one; arena_reset() at the start of the next call merges them into one of the size that was needed.
+// Device memory of a call comes from a per-context stack arena: a few big cudaMalloc'd chunks that every call re-uses
+// from the bottom, so a call in steady state makes no driver-level memory-management call at all (those serialise with
+// other driver work such as NVML queries, and cost host time per block).  Allocation bumps the top of the current
+// chunk; scoped buffers die in reverse order of construction, so releasing the top one pops it and the space is
+// re-used within the call (everything runs on the context's one stream, so re-use is ordered).  When the current chunk
+// is full the arena moves on to the next one that is empty and large enough, or adds one; chunks are kept for the
+// life of the context, so the second call of a kind already finds what the first one needed.
 inline void* arena_alloc(Ctx* c, size_t n) {
   n = (n + 255) & ~(size_t)255;
-  if (c->chunks.empty() || c->chunks.back().used + n > c->chunks.back().cap) {
+  for (;;) {
+    if (c->arena_cur < c->chunks.size()) {
+      Ctx::Chunk& k = c->chunks[c->arena_cur];
+      if (k.used + n <= k.cap) {
+        void* r = k.p + k.used;
+        k.used += n;
+        return r;
+      }
+      // later chunks are empty (stack discipline): take the first one that is large enough
+      size_t j = c->arena_cur + 1;
+      while (j < c->chunks.size() && c->chunks[j].cap < n) ++j;
+      if (j < c->chunks.size()) {
+        if (j != c->arena_cur + 1) std::swap(c->chunks[j], c->chunks[c->arena_cur + 1]);
+        ++c->arena_cur;
+        continue;
+      }
+    }
     size_t total = 0;
     for (const Ctx::Chunk& k : c->chunks) total += k.cap;
     size_t cap = std::max<size_t>(n, std::max<size_t>((size_t)64 << 20, total / 2));
@@ -136,41 +153,24 @@ inline void* arena_alloc(Ctx* c, size_t n) {
       cap = n;
     }
     c->chunks.push_back(Ctx::Chunk{static_cast<uint8_t*>(p), cap, 0});
+    if (c->chunks.size() > 1 && c->arena_cur + 1 != c->chunks.size() - 1)
+      std::swap(c->chunks.back(), c->chunks[c->arena_cur + 1]);
+    c->arena_cur = c->chunks.size() == 1 ? 0 : c->arena_cur + 1;
   }
-  Ctx::Chunk& k = c->chunks.back();
-  void* r = k.p + k.used;
-  k.used += n;
-  c->arena_live += n;
-  if (c->arena_live > c->arena_high) c->arena_high = c->arena_live;
-  return r;
 }
 inline void arena_release(Ctx* c, void* p, size_t n) {
   n = (n + 255) & ~(size_t)255;
-  if (c->chunks.empty()) return;
-  Ctx::Chunk& k = c->chunks.back();
+  if (c->arena_cur >= c->chunks.size()) return;
+  Ctx::Chunk& k = c->chunks[c->arena_cur];
   if (static_cast<uint8_t*>(p) + n == k.p + k.used) {  // the top allocation: pop it
     k.used -= n;
-    c->arena_live -= n;
+    if (k.used == 0 && c->arena_cur > 0) --c->arena_cur;
   }  // anything else stays until the next reset
 }
 // Start of a call: everything handed out before (including the previous call's outputs) is gone.
 inline int arena_reset(Ctx* c) {
-  if (c->chunks.size() > 1) {
-    cudaStreamSynchronize(c->stream);
-    size_t total = 0;
-    for (const Ctx::Chunk& k : c->chunks) {
-      total += k.cap;
-      cudaFree(k.p);
-    }
-    c->chunks.clear();
-    const size_t want = std::max(total, c->arena_high + c->arena_high / 4);
-    void* p = nullptr;
-    if (cudaMalloc(&p, want) == cudaSuccess) c->chunks.push_back(Ctx::Chunk{static_cast<uint8_t*>(p), want, 0});
-    else (void)cudaGetLastError();  // arena_alloc will try smaller pieces
-  }
   for (Ctx::Chunk& k : c->chunks) k.used = 0;
-  c->arena_live = 0;
-  c->arena_high = 0;
+  c->arena_cur = 0;
   return ZDWB_OK;
 }
 inline void arena_destroy(Ctx* c) {
