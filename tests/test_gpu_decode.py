@@ -190,3 +190,22 @@ def test_roundtrip_property_large_random(ctx):
     got, _, _ = G.decode_file_with_product(ctx, img)
     assert got == tsv  # canonical numerics: lossless
     assert img == O.encode(sch, tsv).data
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_row_group_width_forced(ctx, lanes):
+    """The row kernels give a strip to 8, 16 or 32 lanes (narrow schemas: several rows per warp).  Every width must
+    decode every schema: forced here on the whole corpus, the wide golden, projections and the in-memory layout."""
+    ctx.set_tuning("dec_group_lanes", lanes)
+    try:
+        for case in FAST:
+            _check_case(ctx, case)
+        for name in ("analytics-hits", "movie_tickets"):
+            img = O.golden(f"{name}.zdw")
+            want = O.decode(img)
+            got, _, _ = G.decode_file_with_product(ctx, img)
+            assert got == want.tsv, f"{name}: {G.first_diff(got, want.tsv)}"
+        test_column_projection(ctx)
+        test_in_memory_layout_and_row_offsets(ctx)
+    finally:
+        ctx.set_tuning("dec_group_lanes", 0)

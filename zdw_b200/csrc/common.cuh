@@ -34,6 +34,7 @@ struct Ctx {
   // tuning knobs
   long long small_sort_max = 65536;  // dictionaries up to this many entries are ranked by tile sort + binary search
   long long ht_initial_log2 = 20;    // first-try size of the string hash set (grown x8 on overflow)
+  long long dec_group_lanes = 0;     // lanes per strip in the row kernels: 8, 16, 32 (0 = by schema width)
   long long dec_strip_rows = 0;      // rows per strip of the row kernels (0 = automatic)
   long long dec_tile_bytes = 8192;   // row-stream bytes per CTA in the decoder's row-boundary discovery
   unsigned long long last_out_per_row = 0;  // decoded bytes per row of the previous block (sizes the next output)

@@ -179,14 +179,21 @@ __global__ void __launch_bounds__(DEC_THREADS)
 // column widths (shared or global memory): the value bytes selected by flag byte j are
 // sum_k 2^k * popc(flags & plane_k byte j).
 // ---------------------------------------------------------------------------------------------
-// `fb0` = the flag byte of lane j for the first round (j < F), loaded ahead of time by the caller.
-template <class CB>
+// A group of G consecutive lanes (G = 32: the whole warp; 8 or 16: narrow schemas, several rows per warp) works on one
+// row.  group_mask = the lanes of the caller's group, for the *_sync primitives.
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane_id() & ~(unsigned)(G - 1)));
+}
+
+// `fb0` = the flag byte of group lane j for the first round (j < F), loaded ahead of time by the caller.
+template <int G, class CB>
 __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint32_t* __restrict__ planes,
                                                const uint8_t* __restrict__ rp, uint32_t fb0, CB&& cb) {
-  const unsigned lane = lane_id();
+  const unsigned gl = lane_id() & (unsigned)(G - 1), gm = group_mask<G>();
   uint32_t run = P.F;
-  for (uint32_t j0 = 0; j0 < P.F; j0 += 32) {
-    const uint32_t j = j0 + lane;
+  for (uint32_t j0 = 0; j0 < P.F; j0 += G) {
+    const uint32_t j = j0 + gl;
     uint32_t fb = 0, bl = 0;
     if (j < P.F) {
       fb = j0 ? (uint32_t)__ldg(rp + j) : fb0;
@@ -198,11 +205,11 @@ __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint32_
     }
     uint32_t inc = bl;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= (unsigned)o) inc += t;
+    for (int o = 1; o < G; o <<= 1) {
+      uint32_t t = __shfl_up_sync(gm, inc, o, G);
+      if (gl >= (unsigned)o) inc += t;
     }
-    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t tot = __shfl_sync(gm, inc, G - 1, G);
     uint32_t voff = run + inc - bl;
     while (fb) {
       const int b = __ffs(fb) - 1;
@@ -216,8 +223,10 @@ __device__ __forceinline__ void warp_parse_row(const DecParams& P, const uint32_
     run += tot;
   }
 }
+template <int G>
 __device__ __forceinline__ uint32_t first_flag_byte(const DecParams& P, const uint8_t* __restrict__ rp) {
-  return lane_id() < P.F ? (uint32_t)__ldg(rp + lane_id()) : 0u;
+  const unsigned gl = lane_id() & (unsigned)(G - 1);
+  return gl < P.F ? (uint32_t)__ldg(rp + gl) : 0u;
 }
 
 // little-endian value of sz (1..8) bytes at an arbitrary address: two aligned 64-bit loads
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
   for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row(P, planes, rp, first_flag_byte(P, rp), [&](uint32_t u, uint32_t voff) {
+    warp_parse_row<32>(P, planes, rp, first_flag_byte<32>(P, rp), [&](uint32_t u, uint32_t voff) {
       atomicMax(&last_row[u], rl);
       if (flag_counts) atomicAdd(&flag_counts[u], 1ull);
       if (validate && is_text_like(P.utype[u])) {
@@ -260,7 +269,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
   for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row(P, planes, rp, first_flag_byte(P, rp), [&](uint32_t u, uint32_t voff) {
+    warp_parse_row<32>(P, planes, rp, first_flag_byte<32>(P, rp), [&](uint32_t u, uint32_t voff) {
       if (last_row[u] == rl) sval[(size_t)blockIdx.x * P.U + u] = load_le(rp + voff, P.usz[u]);
     });
   }
@@ -489,15 +498,16 @@ __device__ __forceinline__ uint32_t value_len(const DecParams& P, uint32_t u, ui
   return digits_u64(full);
 }
 
-// One warp writes the template bytes of a row, one group (up to 4 bytes of one segment) per lane per step; the group
-// descriptors of four steps are fetched before any of them is used.
+// The lanes of a row group write the template bytes of a row, one piece of up to 4 bytes of one segment per lane and
+// step; the descriptors of four steps are fetched before any of them is used.
+template <int G>
 __device__ __forceinline__ void warp_write_template(const FmtTables& FT, const uint32_t* __restrict__ ioffj,
                                                     uint8_t* __restrict__ row) {
-  for (uint32_t g0 = lane_id(); g0 < FT.n_groups; g0 += 128) {
+  for (uint32_t g0 = lane_id() & (unsigned)(G - 1); g0 < FT.n_groups; g0 += 4 * G) {
     uint4 sg[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t g = g0 + 32u * (uint32_t)k;
+      const uint32_t g = g0 + (uint32_t)(G * k);
       sg[k] = g < FT.n_groups ? __ldg(FT.sgrp + g) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
@@ -635,59 +645,63 @@ __device__ __forceinline__ WarpState warp_state(uint8_t* dsm, const WarpLayout& 
   return S;
 }
 
-// One warp per strip of RS rows.  WRITE = false: lengths only -> row_len[r].  WRITE = true: rows -> out.
-template <bool WRITE>
+// One group of G lanes per strip of RS rows.  WRITE = false: lengths only -> row_len[r].  WRITE = true: rows -> out.
+// G = 32 for wide schemas; with at most 8 (16) output items and flag bytes a warp walks 4 (2) strips side by side, so
+// that narrow tables do not leave three quarters of every warp idle.
+template <bool WRITE, int G>
 __global__ void __launch_bounds__(128, 10)
     k_dec_rows(const DecParams P, const FmtTables FT, const int32_t* __restrict__ u_item, const uint32_t* __restrict__ row_off,
                uint32_t RS, const WarpLayout L, const unsigned long long* __restrict__ cin, unsigned long long* __restrict__ row_len,
                const unsigned long long* __restrict__ out_row_off, uint8_t* __restrict__ out, DecMeta* __restrict__ meta) {
   extern __shared__ __align__(16) uint8_t dsm[];
+  constexpr uint32_t GPW = 32 / G;  // groups per warp
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint32_t strip = blockIdx.x * L.warps + warp;
+  const unsigned gl = lane & (unsigned)(G - 1), gm = group_mask<G>();
+  const uint32_t group = warp * GPW + lane / G;               // group within the CTA
+  const uint32_t strip = blockIdx.x * L.warps * GPW + group;
   const uint32_t r0 = strip * RS;
   if (warp >= L.warps || r0 >= P.nrows) return;
   const uint32_t r1 = min(P.nrows, r0 + RS);
-  const WarpState S = warp_state(dsm, L, warp);
+  const WarpState S = warp_state(dsm, L, group);
   const uint32_t U = P.U, NI = FT.n_items;
   const uint8_t* rows = P.blk + P.rows_base;
-  const unsigned grp = lane >> 3, gl = lane & 7u;
   const bool has_rownum = FT.rownum_item != ITEM_ROWNUM;
 
   // ---- state at the start of the strip: the values carried in
-  for (uint32_t i = lane; i < NI; i += 32) S.len[i] = 0;
-  if (lane == 0) S.llist[0] = 0;
-  __syncwarp();
-  for (uint32_t u = lane; u < U; u += 32) {
+  for (uint32_t i = gl; i < NI; i += G) S.len[i] = 0;
+  if (gl == 0) S.llist[0] = 0;
+  __syncwarp(gm);
+  for (uint32_t u = gl; u < U; u += G) {
     const int32_t i = __ldg(u_item + u);
     if (i < 0) continue;  // not output: never touched
     set_column<WRITE>(P, S, u, (uint32_t)i, cin[(size_t)strip * U + u], meta);
   }
-  __syncwarp();
+  __syncwarp(gm);
   long long dyn = 0;  // dynamic bytes of the current row without the row number (lane-local share; summed when needed)
-  for (uint32_t i = lane; i < NI; i += 32) dyn += S.len[i] & LEN_MASK;
+  for (uint32_t i = gl; i < NI; i += G) dyn += S.len[i] & LEN_MASK;
 
   // the row's offset and its first flag bytes are fetched one row ahead
   uint32_t ro = row_off[r0];
-  uint32_t fb = first_flag_byte(P, rows + ro);
+  uint32_t fb = first_flag_byte<G>(P, rows + ro);
   for (uint32_t r = r0; r < r1; ++r) {
     const uint8_t* rp = rows + ro;
     const uint32_t fb_now = fb;
     if (r + 1 < r1) {
       ro = row_off[r + 1];
-      fb = first_flag_byte(P, rows + ro);
+      fb = first_flag_byte<G>(P, rows + ro);
     }
-    // ---- the columns this row changes: the flag walk only lists them, the values are then applied 32 at a time
-    warp_parse_row(P, P.planes, rp, fb_now, [&](uint32_t u, uint32_t voff) {
+    // ---- the columns this row changes: the flag walk only lists them, the values are then applied G at a time
+    warp_parse_row<G>(P, P.planes, rp, fb_now, [&](uint32_t u, uint32_t voff) {
       if (__ldg(u_item + u) < 0) return;
       const uint32_t e = atomicAdd(&S.llist[0], 1u);
       S.llist[1 + e] = u;
       S.ioff[e] = voff;
     });
-    __syncwarp();
+    __syncwarp(gm);
     {
       const uint32_t n = S.llist[0];
       int32_t delta = 0;
-      for (uint32_t e = lane; e < n; e += 32) {
+      for (uint32_t e = gl; e < n; e += G) {
         const uint32_t u = S.llist[1 + e];
         const uint32_t i = (uint32_t)__ldg(u_item + u);
         const unsigned long long v = load_le(rp + S.ioff[e], P.usz[u]);
@@ -696,7 +710,7 @@ __global__ void __launch_bounds__(128, 10)
         delta += (int32_t)(S.len[i] & LEN_MASK) - old;
       }
       dyn += delta;
-      if (WRITE && has_rownum && lane == 0) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261): a number like any other
+      if (WRITE && has_rownum && gl == 0) {  // virtual_export_row (UnconvertFromZDW.cpp:1256-1261): a number like any other
         const unsigned long long x = FT.first_row + r;
         const uint32_t l = digits_u64(x);
         uint32_t w[5];
@@ -709,16 +723,16 @@ __global__ void __launch_bounds__(128, 10)
         S.aux[FT.rownum_item] = w[4];
         S.len[FT.rownum_item] = l;
       }
-      __syncwarp();
-      if (lane == 0) S.llist[0] = 0;
-      __syncwarp();
+      __syncwarp(gm);
+      if (gl == 0) S.llist[0] = 0;
+      __syncwarp(gm);
     }
 
     if (!WRITE) {
       long long tot = dyn;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (lane == 0) {
+      for (int o = G / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(gm, tot, o, G);
+      if (gl == 0) {
         unsigned long long rl = (unsigned long long)tot + FT.static_total;
         if (has_rownum) rl += digits_u64(FT.first_row + r);
         row_len[r] = rl;
@@ -728,26 +742,26 @@ __global__ void __launch_bounds__(128, 10)
 
     // ---- offset of every item's text among the dynamic bytes of the row
     uint32_t run = 0;
-    for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
-      const uint32_t i = i0 + lane;
+    for (uint32_t i0 = 0; i0 < NI; i0 += G) {
+      const uint32_t i = i0 + gl;
       const uint32_t l = i < NI ? (S.len[i] & LEN_MASK) : 0u;
       uint32_t inc = l;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (unsigned)o) inc += t;
+      for (int o = 1; o < G; o <<= 1) {
+        uint32_t t = __shfl_up_sync(gm, inc, o, G);
+        if (gl >= (unsigned)o) inc += t;
       }
       if (i < NI) S.ioff[i] = run + inc - l;
-      run += __shfl_sync(0xffffffffu, inc, 31);
+      run += __shfl_sync(gm, inc, G - 1, G);
     }
-    if (lane == 0) S.ioff[NI] = run;
-    __syncwarp();
+    if (gl == 0) S.ioff[NI] = run;
+    __syncwarp(gm);
     uint8_t* dst = out + out_row_off[r];
 
     // ---- template, then the items
-    warp_write_template(FT, S.ioff, dst);
-    for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
-      const uint32_t i = i0 + lane;
+    warp_write_template<G>(FT, S.ioff, dst);
+    for (uint32_t i0 = 0; i0 < NI; i0 += G) {
+      const uint32_t i = i0 + gl;
       if (i >= NI) continue;
       const uint32_t lf = S.len[i], l = lf & LEN_MASK;
       if (!l) continue;
@@ -766,17 +780,17 @@ __global__ void __launch_bounds__(128, 10)
         if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
       }
     }
-    __syncwarp();
+    __syncwarp(gm);
     {
       const uint32_t n = S.llist[0];
-      for (uint32_t e = grp; e < n; e += 4) {
+      for (uint32_t e = gl >> 3; e < n; e += G / 8) {  // the octets of the group
         const uint32_t i = S.llist[1 + e];
-        octet_copy(dst + __ldg(FT.item_pos + i) + S.ioff[i], P.blk + P.dict_base + S.aux[i], S.len[i] & LEN_MASK, gl);
+        octet_copy(dst + __ldg(FT.item_pos + i) + S.ioff[i], P.blk + P.dict_base + S.aux[i], S.len[i] & LEN_MASK, gl & 7u);
       }
-      __syncwarp();
-      if (lane == 0) S.llist[0] = 0;
+      __syncwarp(gm);
+      if (gl == 0) S.llist[0] = 0;
     }
-    __syncwarp();
+    __syncwarp(gm);
   }
 }
 
@@ -1180,8 +1194,14 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   }
   // about 48 strips per SM (two waves of the 24 resident warps), rounded down to a power of two: measured on C4,
   // 16- and 32-row strips run 7-25 % faster than 18, 24 or 40 (profiles/README.md)
+  // lanes per strip in the row kernels: a whole warp, or 8 / 16 lanes when the schema is narrow enough for every
+  // per-row step (flag bytes, output items) to fit one round of that many lanes
+  const uint32_t G = (ctx->dec_group_lanes == 8 || ctx->dec_group_lanes == 16 || ctx->dec_group_lanes == 32)
+                         ? (uint32_t)ctx->dec_group_lanes
+                         : (NI <= 8 && F <= 8) ? 8u : (NI <= 16 && F <= 16) ? 16u : 32u;
+  const uint32_t GPW = 32 / G;
   uint32_t R = 8;
-  while (R < 64 && (uint64_t)R * 2 <= nrows / ((uint64_t)ctx->sm_count * 48)) R *= 2;
+  while (R < 64 && (uint64_t)R * 2 <= nrows / ((uint64_t)ctx->sm_count * 48 * GPW)) R *= 2;
   if (ctx->dec_strip_rows > 0) R = (uint32_t)ctx->dec_strip_rows;
   const uint32_t nstrips = (nrows + R - 1) / R;
 
@@ -1259,11 +1279,12 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     L.o_llist = (uint32_t)o;  o += (1 + (size_t)NI) * 4;
     o = (o + 15) & ~(size_t)15;
     if (o > 200 * 1024) return false;
+    // L.stride = bytes of one strip group's state; a CTA holds L.warps * GPW of them
     uint32_t warps = 4;
-    while (warps > 1 && o * warps > 200 * 1024) warps >>= 1;
+    while (warps > 1 && o * warps * GPW > 200 * 1024) warps >>= 1;
     L.warps = warps;
     L.stride = (uint32_t)o;
-    return (size_t)L.stride * warps <= 200 * 1024;
+    return (size_t)L.stride * warps * GPW <= 200 * 1024;
   };
   WarpLayout L1, L2;
   if (!make_layout(false, L1) || !make_layout(true, L2)) {
@@ -1281,13 +1302,31 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   unsigned long long* d_row_off = static_cast<unsigned long long*>(ctx->out_dev2);
   DevBuf row_len;
   ZDWB_TRY(row_len.alloc(ctx, (size_t)nrows * 8));
-  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-  ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+  auto launch_rows = [&](bool write, const WarpLayout& L, unsigned long long* lens, const unsigned long long* offs, uint8_t* dst) -> int {
+    const uint32_t per_cta = L.warps * GPW;
+    const unsigned grid = (nstrips + per_cta - 1) / per_cta, block = 32 * L.warps;
+    const size_t smem = (size_t)L.stride * per_cta;
+#define ZDWB_ROWS(W_, G_)                                                                                                  \
+  do {                                                                                                                     \
+    ZDWB_CUDA_TRY(ctx, (cudaFuncSetAttribute(k_dec_rows<W_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024))); \
+    k_dec_rows<W_, G_><<<grid, block, smem, st>>>(P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L,              \
+                                                  cin.as<unsigned long long>(), lens, offs, dst, meta);                    \
+  } while (0)
+    if (write) {
+      if (G == 8) ZDWB_ROWS(true, 8);
+      else if (G == 16) ZDWB_ROWS(true, 16);
+      else ZDWB_ROWS(true, 32);
+    } else {
+      if (G == 8) ZDWB_ROWS(false, 8);
+      else if (G == 16) ZDWB_ROWS(false, 16);
+      else ZDWB_ROWS(false, 32);
+    }
+#undef ZDWB_ROWS
+    return ZDWB_OK;
+  };
   {
     KernelScope _ks(ctx, "k_dec_row_lens");
-    k_dec_rows<false><<<(nstrips + L1.warps - 1) / L1.warps, 32 * L1.warps, (size_t)L1.stride * L1.warps, st>>>(
-      P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L1, cin.as<unsigned long long>(), row_len.as<unsigned long long>(),
-      nullptr, nullptr, meta);
+    ZDWB_TRY(launch_rows(false, L1, row_len.as<unsigned long long>(), nullptr, nullptr));
   }
   ZDWB_LAUNCH_CHECK(ctx);
   ZDWB_TRY(exclusive_scan_u64(ctx, reinterpret_cast<const uint64_t*>(row_len.p), reinterpret_cast<uint64_t*>(d_row_off), nrows,
@@ -1312,9 +1351,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   }
   {
     KernelScope _ks(ctx, "k_dec_write_rows");
-    k_dec_rows<true><<<(nstrips + L2.warps - 1) / L2.warps, 32 * L2.warps, (size_t)L2.stride * L2.warps, st>>>(
-      P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L2, cin.as<unsigned long long>(), nullptr, d_row_off,
-      static_cast<uint8_t*>(ctx->out_dev), meta);
+    ZDWB_TRY(launch_rows(true, L2, nullptr, d_row_off, static_cast<uint8_t*>(ctx->out_dev)));
   }
   ZDWB_LAUNCH_CHECK(ctx);
   const uint64_t out_len = hm->out_bytes;
