@@ -138,12 +138,14 @@ __global__ void k_dec_descend(const uint64_t* __restrict__ in, uint32_t n_in, ui
   }
 }
 
-// warp-cooperative row length at stream offset p
-__device__ __forceinline__ uint32_t warp_row_len(const DecParams& P, uint64_t p) {
-  const unsigned lane = lane_id();
+// row length at stream offset p, worked out by the GL lanes of a group (GL = 32: the whole warp)
+template <int GL>
+__device__ __forceinline__ uint32_t group_row_len(const DecParams& P, uint64_t p) {
+  const unsigned gl = lane_id() & (unsigned)(GL - 1);
+  const unsigned gm = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << (lane_id() & ~(unsigned)(GL - 1)));
   uint32_t acc = 0;
-  for (uint32_t w0 = 0; w0 < P.W; w0 += 32) {
-    const uint32_t w = w0 + lane;
+  for (uint32_t w0 = 0; w0 < P.W; w0 += GL) {
+    const uint32_t w = w0 + gl;
     if (w < P.W) {
       uint32_t word = 0;
 #pragma unroll
@@ -152,23 +154,26 @@ __device__ __forceinline__ uint32_t warp_row_len(const DecParams& P, uint64_t p)
              4u * __popc(word & P.planes[2 * P.W + w]) + 8u * __popc(word & P.planes[3 * P.W + w]);
     }
   }
-  acc = __reduce_add_sync(0xffffffffu, acc);
+#pragma unroll
+  for (int o = GL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gm, acc, o, GL);
   return P.F + acc;
 }
 
+// one group of GL lanes per tile walks the true chain of rows and records row_off[r]
+template <int GL>
 __global__ void __launch_bounds__(DEC_THREADS)
     k_dec_row_starts(const DecParams P, uint32_t T, uint32_t ntiles, const uint64_t* __restrict__ ent,
                      uint32_t* __restrict__ row_off) {
-  const uint32_t tile = blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+  const uint32_t tile = (blockIdx.x * DEC_WARPS + (threadIdx.x >> 5)) * (32 / GL) + lane_id() / GL;
   if (tile >= ntiles) return;
   const uint64_t st = ent[tile];
   uint64_t r = st >> 32;
   uint64_t p = (uint64_t)tile * T + (uint32_t)st;
   const uint64_t pend = (uint64_t)(tile + 1) * T;
   while (p < pend && r <= P.nrows) {
-    if (lane_id() == 0) row_off[r] = (uint32_t)p;
+    if ((lane_id() & (unsigned)(GL - 1)) == 0) row_off[r] = (uint32_t)p;
     if (r == P.nrows) break;
-    p += warp_row_len(P, p);
+    p += group_row_len<GL>(P, p);
     ++r;
   }
 }
@@ -241,6 +246,7 @@ __device__ __forceinline__ unsigned long long load_le(const uint8_t* __restrict_
 
 // last explicit value of every used column inside a strip of R rows; optionally (-t / -s) bounds-checks the
 // dictionary offset of every explicit value (UnconvertFromZDW.cpp:1527-1560) and counts the set flag bits per column
+template <int GL>
 __global__ void __launch_bounds__(DEC_THREADS)
     k_dec_strip_summary(const DecParams P, const uint32_t* __restrict__ row_off, uint32_t R, int validate,
                         unsigned long long* __restrict__ flag_counts, unsigned long long* __restrict__ sval,
@@ -251,12 +257,14 @@ __global__ void __launch_bounds__(DEC_THREADS)
   for (uint32_t u = threadIdx.x; u < P.U; u += DEC_THREADS) last_row[u] = -1;
   __syncthreads();
   const uint32_t r0 = blockIdx.x * R, r1 = min(P.nrows, r0 + R);
-  const unsigned warp = threadIdx.x >> 5;
+  // a row per group of GL lanes: DEC_WARPS * 32 / GL rows are walked at a time
+  constexpr uint32_t GPW = 32 / GL;
+  const uint32_t first = r0 + (threadIdx.x >> 5) * GPW + lane_id() / GL;
   const uint8_t* rows = P.blk + P.rows_base;
-  for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
+  for (uint32_t r = first; r < r1; r += DEC_WARPS * GPW) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row<32>(P, planes, rp, first_flag_byte<32>(P, rp), [&](uint32_t u, uint32_t voff) {
+    warp_parse_row<GL>(P, planes, rp, first_flag_byte<GL>(P, rp), [&](uint32_t u, uint32_t voff) {
       atomicMax(&last_row[u], rl);
       if (flag_counts) atomicAdd(&flag_counts[u], 1ull);
       if (validate && is_text_like(P.utype[u])) {
@@ -266,10 +274,10 @@ __global__ void __launch_bounds__(DEC_THREADS)
     });
   }
   __syncthreads();
-  for (uint32_t r = r0 + warp; r < r1; r += DEC_WARPS) {
+  for (uint32_t r = first; r < r1; r += DEC_WARPS * GPW) {
     const int32_t rl = (int32_t)(r - r0);
     const uint8_t* rp = rows + row_off[r];
-    warp_parse_row<32>(P, planes, rp, first_flag_byte<32>(P, rp), [&](uint32_t u, uint32_t voff) {
+    warp_parse_row<GL>(P, planes, rp, first_flag_byte<GL>(P, rp), [&](uint32_t u, uint32_t voff) {
       if (last_row[u] == rl) sval[(size_t)blockIdx.x * P.U + u] = load_le(rp + voff, P.usz[u]);
     });
   }
@@ -1041,6 +1049,11 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     seg_of.push_back(seg);
   }
   const uint32_t NI = (uint32_t)item_u.size();
+  // lanes per row in the row-walking kernels: a whole warp, or 8 / 16 lanes when the schema is narrow enough for every
+  // per-row step (flag bytes, output items) to fit one round of that many lanes - a warp then walks 4 / 2 rows at once
+  const uint32_t GL = (ctx->dec_group_lanes == 8 || ctx->dec_group_lanes == 16 || ctx->dec_group_lanes == 32)
+                          ? (uint32_t)ctx->dec_group_lanes
+                          : (NI <= 8 && F <= 8) ? 8u : (NI <= 16 && F <= 16) ? 16u : 32u;
   const uint32_t static_total = (uint32_t)blob.size();
   std::vector<uint4> sgrp;
   for (uint32_t k = 0; k < static_total;) {
@@ -1165,8 +1178,11 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     // with a single tile the root entry is the tile entry
     {
       KernelScope _ks(ctx, "k_dec_row_starts");
-      k_dec_row_starts<<<(ntiles + DEC_WARPS - 1) / DEC_WARPS, DEC_THREADS, 0, st>>>(P, T, ntiles, ent_parent->as<uint64_t>(),
-                                                                                  row_off.as<uint32_t>());
+      const uint32_t per_cta = DEC_WARPS * (32 / GL);
+      const unsigned grid = (ntiles + per_cta - 1) / per_cta;
+      if (GL == 8) k_dec_row_starts<8><<<grid, DEC_THREADS, 0, st>>>(P, T, ntiles, ent_parent->as<uint64_t>(), row_off.as<uint32_t>());
+      else if (GL == 16) k_dec_row_starts<16><<<grid, DEC_THREADS, 0, st>>>(P, T, ntiles, ent_parent->as<uint64_t>(), row_off.as<uint32_t>());
+      else k_dec_row_starts<32><<<grid, DEC_THREADS, 0, st>>>(P, T, ntiles, ent_parent->as<uint64_t>(), row_off.as<uint32_t>());
     }
     ctx->launches++;
     cudaError_t le = cudaGetLastError();
@@ -1196,9 +1212,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   // 16- and 32-row strips run 7-25 % faster than 18, 24 or 40 (profiles/README.md)
   // lanes per strip in the row kernels: a whole warp, or 8 / 16 lanes when the schema is narrow enough for every
   // per-row step (flag bytes, output items) to fit one round of that many lanes
-  const uint32_t G = (ctx->dec_group_lanes == 8 || ctx->dec_group_lanes == 16 || ctx->dec_group_lanes == 32)
-                         ? (uint32_t)ctx->dec_group_lanes
-                         : (NI <= 8 && F <= 8) ? 8u : (NI <= 16 && F <= 16) ? 16u : 32u;
+  const uint32_t G = GL;
   const uint32_t GPW = 32 / G;
   uint32_t R = 8;
   while (R < 64 && (uint64_t)R * 2 <= nrows / ((uint64_t)ctx->sm_count * 48 * GPW)) R *= 2;
@@ -1217,12 +1231,19 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     ZDWB_TRY(sval.alloc(ctx, (size_t)nstrips * U * 8));
     ZDWB_TRY(shas.alloc(ctx, (size_t)nstrips * U));
     const size_t smem_sum = (size_t)U * 4 + 16;
-    ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_strip_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
       KernelScope _ks(ctx, "k_dec_strip_summary");
-      k_dec_strip_summary<<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R, opts->validate_only,
-                                                               d_counts.as<unsigned long long>(), sval.as<unsigned long long>(),
-                                                               shas.as<uint8_t>(), meta);
+#define ZDWB_SUMMARY(G_)                                                                                                  \
+  do {                                                                                                                    \
+    ZDWB_CUDA_TRY(ctx, (cudaFuncSetAttribute(k_dec_strip_summary<G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))); \
+    k_dec_strip_summary<G_><<<nstrips, DEC_THREADS, smem_sum, st>>>(P, row_off.as<uint32_t>(), R, opts->validate_only,     \
+                                                                   d_counts.as<unsigned long long>(),                     \
+                                                                   sval.as<unsigned long long>(), shas.as<uint8_t>(), meta); \
+  } while (0)
+      if (GL == 8) ZDWB_SUMMARY(8);
+      else if (GL == 16) ZDWB_SUMMARY(16);
+      else ZDWB_SUMMARY(32);
+#undef ZDWB_SUMMARY
     }
     ZDWB_LAUNCH_CHECK(ctx);
     if (opts->validate_only || opts->want_flag_counts) {
