@@ -11,11 +11,14 @@
 //                      inside?  Row length at a byte position is a popcount over 4 size bit-planes.
 //   k_dec_compose      composes those maps group by group (function composition is associative) ...
 //   k_dec_descend      ... and hands every tile its true entry offset and first row number.
-//   k_dec_row_starts   one warp per tile walks the true chain and records row_off[r].
+//   k_dec_row_starts   one group of lanes per tile walks the true chain and records row_off[r].
 //   k_dec_strip_summary / k_carry_*   last explicit value per (strip of rows, used column) and its
 //                      propagation across strips: the value a column holds where a strip begins.
-//   k_dec_format       per strip: scatter explicit values, fill forward down the rows, measure every
-//                      field, decoupled look-back for the strip's output offset, write the TSV bytes.
+//   k_dec_rows<false>  (k_dec_row_lens) one group of lanes per strip walks its rows keeping the text length of every
+//                      output item: row lengths -> exclusive scan -> row offsets and the exact output size.
+//   k_dec_rows<true>   (k_dec_write_rows) the same walk with the rendered texts kept in shared memory; every row is
+//                      assembled straight in global memory from a static template and the items' texts.
+// The row-walking kernels give a row to 32 lanes, or to 16 / 8 when the schema is narrow (several rows per warp).
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -28,7 +31,6 @@ namespace {
 
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
-constexpr uint64_t LB_AGG = 1ull << 62, LB_PFX = 2ull << 62, LB_MASK = (1ull << 62) - 1ull;
 
 struct DecMeta {
   uint32_t err;            // 1 = dictionary offset out of range (CORRUPTED_DATA_ERROR)

@@ -6,13 +6,15 @@
 //                                 (getnextrow.cpp:26-84, ConvertToZDW.cpp:1048-1067)
 //   k_find_cut                    block cut after max_rows rows (explicit block policy)
 //   k_pass1                       parseInput (ConvertToZDW.cpp:329-414) + Dictionary::insert (dictionary.cpp:31-51):
-//                                 one warp per tile, no CTA barrier; every non-empty field is classified (short text /
-//                                 long text / numeric) into warp-private queues and processed 32 at a time with
-//                                 convergent code; a compact RECORD (column, dictionary slot or number) per non-empty
-//                                 field is written in row order, so pass 2 never re-reads or re-parses the TSV
+//                                 one warp per tile, no CTA barrier; the non-empty fields of a 512-byte step go to a
+//                                 warp-private queue (slot = ordinal) and are worked off 32 at a time: numbers and CHAR
+//                                 cells at once from registers, texts parked in two side queues by length and inserted
+//                                 into the hash set 32 of a kind at a time; a compact RECORD (column, dictionary slot or
+//                                 number) per non-empty field is written in row order, so pass 2 never re-reads or
+//                                 re-parses the TSV
 //   k_ht_compact, sort_strings, k_sorted_lens, k_dict_slots, k_dict_emit
 //                                 Dictionary::write              dictionary.cpp:76-111
-//   k_col_stats, k_block_header   writeLookupColumnStats         ConvertToZDW.cpp:417-483, :839-842
+//   k_col_stats, k_col_info, k_block_header   writeLookupColumnStats         ConvertToZDW.cpp:417-483, :839-842
 //   k_pass2, k_gather_tiles       writeBlockRows                 ConvertToZDW.cpp:486-606 + Dictionary::getOffset :53-59
 //
 // Data layout in HBM: the TSV block is read twice (census, pass 1); records are 12 B per NON-EMPTY field (most
@@ -33,7 +35,6 @@ constexpr uint32_t TILE = 16384;          // bytes per warp tile
 constexpr uint32_t STEP = 512;            // bytes per warp step (32 lanes x 16 B)
 constexpr uint32_t HT_MAX_PROBE = 2048;
 constexpr uint32_t SHORT_MAX = 16;        // texts up to this length are hashed / compared by one lane, straight-line
-constexpr uint32_t QCAP = 64;             // entries per warp queue (at most 31 waiting + 32 pushed per round)
 constexpr uint32_t REC_EMPTY = 0xffffffffu;
 
 struct EncMeta {
@@ -644,20 +645,8 @@ __device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, 
 // parked in a small per-warp ring and worked off 32 at a time, one lane each; the rare longer texts are handled in
 // place by the octets of the warp.
 // ---------------------------------------------------------------------------------------------
-#ifndef P1_SQ
-#define P1_SQ 64
-#endif
-#ifndef P1_MINB
-#define P1_MINB 4
-#endif
-#ifndef P1_BAL
-#define P1_BAL 1
-#endif
-#ifndef P1_LDCG
-#define P1_LDCG 0
-#endif
-constexpr uint32_t MID_MAX = 128;  // longest text handled by a single lane
-constexpr uint32_t SQ = P1_SQ;     // entries of the side queue (at most 31 waiting + 32 pushed)
+constexpr uint32_t MID_MAX = 128;  // longest text handled by a single lane (measured: 32 -> 1.66, 64 -> 1.53, 128 -> 1.51 ms)
+constexpr uint32_t SQ = 64;        // entries of a side queue (at most 31 waiting + 32 pushed)
 
 struct P1Side {  // a ring; `end` = entries ever pushed, `done` = entries ever taken (warp-uniform, kept here)
   uint32_t start[SQ], len[SQ], col[SQ], ord[SQ];
@@ -689,11 +678,7 @@ __device__ __forceinline__ void note_new_string(P1Stats& st, uint32_t len) {
 
 // Column statistics.  The loads that filter the atomics may come from a stale L1 line: the three arrays only move one
 // way (set 0 -> 1, min down, max up), so a stale value can cost a redundant atomic but never skips a needed one.
-#if P1_LDCG
-#define P1_LD(p) __ldcg(p)
-#else
 #define P1_LD(p) (*(p))
-#endif
 __device__ __forceinline__ void note_column_set(const P1Args& A, uint32_t col) {
   if (P1_LD(A.colset + col) == 0u) A.colset[col] = 1u;
 }
@@ -898,7 +883,7 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
   }
 }
 
-__global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) {
+__global__ void __launch_bounds__(ENC_THREADS, 4) k_pass1(const P1Args A) {
   __shared__ P1Warp sw[ENC_WARPS];
   __shared__ P1Side s_side[ENC_WARPS][2];
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -939,7 +924,6 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
         st.max_line = max(st.max_line, (uint32_t)(L.p0 + i - row_start + 1));
         A.row_rec[R + 1u] = L.nes + (uint32_t)__popc(L.ne & ((2u << i) - 1u));
       }
-#if P1_BAL
       // ---- non-empty fields go to the warp's queue, slot = ordinal.  Two phases, so that a lane that scanned a run of
       // short fields does not hold up the warp: every lane first drops the bit position (lane * 16 + bit) of each of
       // its closing delimiters into the field's slot; then the step's fields are dealt out evenly, field k to lane
@@ -984,32 +968,6 @@ __global__ void __launch_bounds__(ENC_THREADS, P1_MINB) k_pass1(const P1Args A) 
           }
         }
       }
-#else
-      // ---- non-empty fields go to the warp's queue; the slot is the field's ordinal, so no coordination is needed
-      uint32_t rem = L.ne;
-      const uint32_t bound = L.tab | L.term | L.skip;
-      while (rem) {
-        const int i = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const uint32_t below = (1u << i) - 1u;
-        const uint32_t R = L.rows + (uint32_t)__popc(L.term & below);
-        const uint32_t T = L.tabs + (uint32_t)__popc(L.tab & below);
-        uint32_t col = T - R * tabs_per_row;
-        const uint32_t lowb = bound & below;
-        const uint32_t start = (uint32_t)((lowb ? L.p0 + (31 - __clz(lowb)) : L.pb) + 1);
-        uint32_t len = (uint32_t)(L.p0 + i) - start;
-        const uint32_t q = L.nes + (uint32_t)__popc(L.ne & below) - qbase;
-        if (col >= A.ncols) {  // (a malformed row is reported through bad_row)
-          col = 0;
-          len = 0;
-        } else if (A.trim) {
-          len = trimmed_len(A.buf, start, len);
-        }
-        W.start[q] = start;
-        W.len[q] = len;
-        W.col[q] = col;
-      }
-#endif
       __syncwarp();
     }
     // ---- work off full batches (in the extra round: whatever is left, and the side queue)
