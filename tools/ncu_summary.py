@@ -37,7 +37,11 @@ def main():
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tr = {}
         for name, r in last.items():
-            key = {"k_dec_rows<0>": "k_dec_row_lens", "k_dec_rows<1>": "k_dec_write_rows"}.get(name, name)
+            key = name
+            if name.startswith("k_dec_rows<0"):
+                key = "k_dec_row_lens"
+            elif name.startswith("k_dec_rows<1"):
+                key = "k_dec_write_rows"
             tr[key] = int(float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]])
         json.dump(tr, open(sys.argv[3], "w"), indent=1)
         print(json.dumps(tr))
