@@ -708,7 +708,7 @@ def main():
     ap.add_argument("--rows-per-block", type=int, default=ROWS_PER_BLOCK)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-decode-blocks", type=int, default=48)
-    ap.add_argument("--lanes", type=int, default=2, help="contexts (host thread + stream) that share the rank's blocks in the device-resident leg")
+    ap.add_argument("--lanes", type=int, default=4, help="contexts (host thread + stream) that share the rank's blocks in the device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="contexts (host thread + stream) that overlap copies and kernels in the e2e leg")
     ap.add_argument("--cpu-rows", type=int, default=131072, help="rows of the bounded cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")
