@@ -374,6 +374,130 @@ __host__ __device__ __forceinline__ uint32_t fmt_i64(int64_t sv, uint8_t* end) {
   return (uint32_t)(end - p);
 }
 
+// four decimal digits of x (< 10000) as ASCII, most significant digit in the lowest byte: two 2-digit fields are split
+// into tens and ones side by side (x / 100 = x * 5243 >> 19 for x < 43699, y / 10 = y * 103 >> 10 for y < 179)
+__host__ __device__ __forceinline__ uint32_t ascii4(uint32_t x) {
+  const uint32_t hi = (x * 5243u) >> 19;
+  const uint32_t p = hi | ((x - hi * 100u) << 16);
+  const uint32_t tens = ((p * 103u) >> 10) & 0x000f000fu;
+  const uint32_t ones = p - tens * 10u;
+  return (tens | (ones << 8)) + 0x30303030u;
+}
+
+#ifdef __CUDA_ARCH__
+#define ZDWB_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
+#else
+#define ZDWB_FUNNEL_R(lo, hi, sh) ((uint32_t)((((uint64_t)(hi) << 32) | (uint64_t)(lo)) >> ((sh) & 31u)))
+#endif
+
+// Decimal text of `full` as llutoa / lltoa print it (UnconvertFromZDW.cpp:318-356), exactly len characters, left-aligned
+// in w[0..4] (the first character is the lowest byte of w[0]); bytes past len are unspecified.  Straight-line: the 20
+// zero-padded digits are produced four at a time and the leading zeros shifted out.  `neg` = the value prints with a
+// minus sign (len counts it); INT64_MIN keeps the reference's digits 0x30 - d.
+__host__ __device__ __forceinline__ void render_int(unsigned long long full, bool neg, uint32_t len, uint32_t w[5]) {
+  const unsigned long long mag = neg ? 0ull - full : full;
+  uint32_t a, b, c;
+  if (mag <= 0xffffffffull) {
+    const uint32_t x = (uint32_t)mag;
+    a = 0;
+    b = x / 100000000u;
+    c = x - b * 100000000u;
+  } else {
+    const unsigned long long q = mag / 100000000ull;
+    c = (uint32_t)(mag - q * 100000000ull);
+    const unsigned long long q2 = q / 100000000ull;
+    b = (uint32_t)(q - q2 * 100000000ull);
+    a = (uint32_t)q2;
+  }
+  const uint32_t bh = b / 10000u, ch = c / 10000u;
+  uint32_t e0 = ascii4(a), e1 = ascii4(bh), e2 = ascii4(b - bh * 10000u), e3 = ascii4(ch), e4 = ascii4(c - ch * 10000u);
+  if (neg && full == 0x8000000000000000ull) {  // every remainder is negative: digit byte = 0x30 - d
+    e0 = 0x60606060u - e0;
+    e1 = 0x60606060u - e1;
+    e2 = 0x60606060u - e2;
+    e3 = 0x60606060u - e3;
+    e4 = 0x60606060u - e4;
+  }
+  const uint32_t nd = len - (neg ? 1u : 0u);  // digits
+  const uint32_t s = 20u - nd, ws = s >> 2, bs = (s & 3u) * 8u;
+  if (ws & 4u) e0 = e4;
+  if (ws & 2u) {
+    e0 = e2;
+    e1 = e3;
+    e2 = e4;
+  }
+  if (ws & 1u) {
+    e0 = e1;
+    e1 = e2;
+    e2 = e3;
+    e3 = e4;
+  }
+  uint32_t x0 = ZDWB_FUNNEL_R(e0, e1, bs), x1 = ZDWB_FUNNEL_R(e1, e2, bs), x2 = ZDWB_FUNNEL_R(e2, e3, bs),
+           x3 = ZDWB_FUNNEL_R(e3, e4, bs), x4 = e4 >> bs;
+  if (neg) {  // make room for the sign
+    x4 = (x4 << 8) | (x3 >> 24);
+    x3 = (x3 << 8) | (x2 >> 24);
+    x2 = (x2 << 8) | (x1 >> 24);
+    x1 = (x1 << 8) | (x0 >> 24);
+    x0 = (x0 << 8) | (uint32_t)'-';
+  }
+  w[0] = x0;
+  w[1] = x1;
+  w[2] = x2;
+  w[3] = x3;
+  w[4] = x4;
+}
+
+// strtoull of a field of 1..20 bytes that consists of decimal digits only, from its masked words - the common case;
+// everything else (whitespace, signs, junk, 21+ characters) takes parse_u64_field.  Twenty digits can exceed 2^64 - 1:
+// strtoull then saturates.  Returns false when the field is not all digits.
+constexpr uint32_t NUM_FAST_MAX = 20;
+__host__ __device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, unsigned long long* out) {
+  unsigned long long v = 0;
+  bool ok = true, ovf = false;
+#pragma unroll
+  for (uint32_t k = 0; k < 5; ++k) {
+    if (4u * k < len) {
+      const uint32_t nd = len - 4u * k < 4u ? len - 4u * k : 4u;
+      const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
+      const uint32_t w = (x[k] & keep) | (0x30303030u & ~keep);       // pad with '0'
+      const uint32_t d = w - 0x30303030u;
+      ok = ok && (((w + 0x46464646u) | d) & 0x80808080u) == 0u;        // every byte in '0'..'9'
+      const uint32_t al = nd >= 4u ? d : (d << (8u * (4u - nd)));      // right-align: leading zero digits
+      const uint32_t pairs = (al & 0x00ff00ffu) * 10u + ((al >> 8) & 0x00ff00ffu);
+      const uint32_t v4 = (pairs & 0xffffu) * 100u + (pairs >> 16);
+      const uint32_t scale = nd == 4u ? 10000u : nd == 3u ? 1000u : nd == 2u ? 100u : 10u;
+      if (k == 4u && nd == 4u)  // the 17th..20th digit: v * 10^4 + v4 > 2^64 - 1 ?
+        ovf = v > 1844674407370955ull || (v == 1844674407370955ull && v4 > 1615u);
+      v = v * scale + v4;
+    }
+  }
+  *out = ovf ? ~0ull : v;
+  return ok;
+}
+
+// strtoull of a field of 1..20 bytes held in five masked little-endian words (bytes past `len` are zero): an optional
+// sign in front of the digits ('-' negates modulo 2^64; with a sign at most 19 digits are left, which cannot overflow).
+// Returns false for anything else - white space, junk, a lone sign - which takes the exact byte walk parse_u64_field.
+__host__ __device__ __forceinline__ bool fast_number(const uint32_t x[5], uint32_t len, unsigned long long* out) {
+  const uint32_t c0 = x[0] & 0xffu;
+  const bool sign = c0 == (uint32_t)'-' || c0 == (uint32_t)'+';
+  uint32_t y[5] = {x[0], x[1], x[2], x[3], x[4]};
+  uint32_t dl = len;
+  if (sign) {
+    y[0] = ZDWB_FUNNEL_R(x[0], x[1], 8u);
+    y[1] = ZDWB_FUNNEL_R(x[1], x[2], 8u);
+    y[2] = ZDWB_FUNNEL_R(x[2], x[3], 8u);
+    y[3] = ZDWB_FUNNEL_R(x[3], x[4], 8u);
+    y[4] = x[4] >> 8;
+    dl = len - 1u;
+  }
+  unsigned long long v;
+  if (dl == 0u || !digits_value(y, dl, &v)) return false;
+  *out = c0 == (uint32_t)'-' ? 0ull - v : v;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------

@@ -407,80 +407,6 @@ __device__ __forceinline__ uint32_t digits_u64(unsigned long long v) {
          : v < 1000000000000000000ull ? 18u : v < 10000000000000000000ull ? 19u : 20u;
 }
 
-// four decimal digits of x (< 10000) as ASCII, most significant digit in the lowest byte: two 2-digit fields are split
-// into tens and ones side by side (x / 100 = x * 5243 >> 19 for x < 43699, y / 10 = y * 103 >> 10 for y < 179)
-__host__ __device__ __forceinline__ uint32_t ascii4(uint32_t x) {
-  const uint32_t hi = (x * 5243u) >> 19;
-  const uint32_t p = hi | ((x - hi * 100u) << 16);
-  const uint32_t tens = ((p * 103u) >> 10) & 0x000f000fu;
-  const uint32_t ones = p - tens * 10u;
-  return (tens | (ones << 8)) + 0x30303030u;
-}
-
-#ifdef __CUDA_ARCH__
-#define ZDWB_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
-#else
-#define ZDWB_FUNNEL_R(lo, hi, sh) ((uint32_t)((((uint64_t)(hi) << 32) | (uint64_t)(lo)) >> ((sh) & 31u)))
-#endif
-
-// Decimal text of `full` as llutoa / lltoa print it (UnconvertFromZDW.cpp:318-356), exactly len characters, left-aligned
-// in w[0..4] (the first character is the lowest byte of w[0]); bytes past len are unspecified.  Straight-line: the 20
-// zero-padded digits are produced four at a time and the leading zeros shifted out.  `neg` = the value prints with a
-// minus sign (len counts it); INT64_MIN keeps the reference's digits 0x30 - d.
-__host__ __device__ __forceinline__ void render_int(unsigned long long full, bool neg, uint32_t len, uint32_t w[5]) {
-  const unsigned long long mag = neg ? 0ull - full : full;
-  uint32_t a, b, c;
-  if (mag <= 0xffffffffull) {
-    const uint32_t x = (uint32_t)mag;
-    a = 0;
-    b = x / 100000000u;
-    c = x - b * 100000000u;
-  } else {
-    const unsigned long long q = mag / 100000000ull;
-    c = (uint32_t)(mag - q * 100000000ull);
-    const unsigned long long q2 = q / 100000000ull;
-    b = (uint32_t)(q - q2 * 100000000ull);
-    a = (uint32_t)q2;
-  }
-  const uint32_t bh = b / 10000u, ch = c / 10000u;
-  uint32_t e0 = ascii4(a), e1 = ascii4(bh), e2 = ascii4(b - bh * 10000u), e3 = ascii4(ch), e4 = ascii4(c - ch * 10000u);
-  if (neg && full == 0x8000000000000000ull) {  // every remainder is negative: digit byte = 0x30 - d
-    e0 = 0x60606060u - e0;
-    e1 = 0x60606060u - e1;
-    e2 = 0x60606060u - e2;
-    e3 = 0x60606060u - e3;
-    e4 = 0x60606060u - e4;
-  }
-  const uint32_t nd = len - (neg ? 1u : 0u);  // digits
-  const uint32_t s = 20u - nd, ws = s >> 2, bs = (s & 3u) * 8u;
-  if (ws & 4u) e0 = e4;
-  if (ws & 2u) {
-    e0 = e2;
-    e1 = e3;
-    e2 = e4;
-  }
-  if (ws & 1u) {
-    e0 = e1;
-    e1 = e2;
-    e2 = e3;
-    e3 = e4;
-  }
-  uint32_t x0 = ZDWB_FUNNEL_R(e0, e1, bs), x1 = ZDWB_FUNNEL_R(e1, e2, bs), x2 = ZDWB_FUNNEL_R(e2, e3, bs),
-           x3 = ZDWB_FUNNEL_R(e3, e4, bs), x4 = e4 >> bs;
-  if (neg) {  // make room for the sign
-    x4 = (x4 << 8) | (x3 >> 24);
-    x3 = (x3 << 8) | (x2 >> 24);
-    x2 = (x2 << 8) | (x1 >> 24);
-    x1 = (x1 << 8) | (x0 >> 24);
-    x0 = (x0 << 8) | (uint32_t)'-';
-  }
-  w[0] = x0;
-  w[1] = x1;
-  w[2] = x2;
-  w[3] = x3;
-  w[4] = x4;
-}
-
 // Length of the text of used column u holding stored value v.  Mirrors the switch in readNextRow
 // (UnconvertFromZDW.cpp:1349-1453).
 __device__ __forceinline__ uint32_t value_len(const DecParams& P, uint32_t u, uint8_t t, unsigned long long v, DecMeta* meta) {

@@ -610,34 +610,6 @@ __device__ __forceinline__ uint32_t trimmed_len(const uint8_t* __restrict__ buf,
   return len;
 }
 
-// strtoull of a field of 1..20 bytes that consists of decimal digits only, from its masked words - the common case;
-// everything else (whitespace, signs, junk, 21+ characters) takes parse_u64_field.  Twenty digits can exceed 2^64 - 1:
-// strtoull then saturates.  Returns false when the field is not all digits.
-constexpr uint32_t NUM_FAST_MAX = 20;
-__device__ __forceinline__ bool digits_value(const uint32_t x[5], uint32_t len, unsigned long long* out) {
-  unsigned long long v = 0;
-  bool ok = true, ovf = false;
-#pragma unroll
-  for (uint32_t k = 0; k < 5; ++k) {
-    if (4u * k < len) {
-      const uint32_t nd = min(4u, len - 4u * k);
-      const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
-      const uint32_t w = (x[k] & keep) | (0x30303030u & ~keep);       // pad with '0'
-      const uint32_t d = w - 0x30303030u;
-      ok = ok && (((w + 0x46464646u) | d) & 0x80808080u) == 0u;        // every byte in '0'..'9'
-      const uint32_t al = nd >= 4u ? d : (d << (8u * (4u - nd)));      // right-align: leading zero digits
-      const uint32_t pairs = (al & 0x00ff00ffu) * 10u + ((al >> 8) & 0x00ff00ffu);
-      const uint32_t v4 = (pairs & 0xffffu) * 100u + (pairs >> 16);
-      const uint32_t scale = nd == 4u ? 10000u : nd == 3u ? 1000u : nd == 2u ? 100u : 10u;
-      if (k == 4u && nd == 4u)  // the 17th..20th digit: v * 10^4 + v4 > 2^64 - 1 ?
-        ovf = v > 1844674407370955ull || (v == 1844674407370955ull && v4 > 1615u);
-      v = v * scale + v4;
-    }
-  }
-  *out = ovf ? ~0ull : v;
-  return ok;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Field processing.  The warp's main queue holds every non-empty field in row order (slot = ordinal).  In a batch of
 // 32, everything that fits 20 bytes - numbers, CHAR cells and texts of up to SHORT_MAX bytes, the bulk of
@@ -810,22 +782,7 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
       } else {
         // strtoull (:385,564): an optional sign in front of the digits ('-' negates modulo 2^64; with a sign at most
         // 19 digits are left, which cannot overflow); anything else - white space, junk - takes the exact byte walk
-        const uint32_t c0 = x[0] & 0xffu;
-        const bool sign = c0 == (uint32_t)'-' || c0 == (uint32_t)'+';
-        uint32_t dl = len;
-        if (sign) {
-          x[0] = __funnelshift_r(x[0], x[1], 8);
-          x[1] = __funnelshift_r(x[1], x[2], 8);
-          x[2] = __funnelshift_r(x[2], x[3], 8);
-          x[3] = __funnelshift_r(x[3], x[4], 8);
-          x[4] >>= 8;
-          dl = len - 1u;
-        }
-        if (dl != 0u && digits_value(x, dl, &v1)) {
-          if (c0 == (uint32_t)'-') v1 = 0ull - v1;
-        } else {
-          v1 = parse_u64_field(A.buf + start, len);
-        }
+        if (!fast_number(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);
         v2 = v1;
       }
     } else {  // a number of more than 20 characters
