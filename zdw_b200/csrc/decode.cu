@@ -1332,7 +1332,14 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
       ctx->out_host_cap = cap;
     }
   }
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, out_len, cudaMemcpyDeviceToHost, st));
+  if (ctx->copy_gate && out_len >= COPY_GATE_MIN) {
+    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // the rows are written: now wait for the link, not with it
+    std::lock_guard<std::mutex> turn(copy_gate(ctx->device, 1));
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, out_len, cudaMemcpyDeviceToHost, st));
+    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  } else {
+    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, out_len, cudaMemcpyDeviceToHost, st));
+  }
   if (opts->want_row_offsets) {
     const size_t rb = ((size_t)nrows + 1) * 8;
     if (ctx->out_host2_cap < rb) {

@@ -1372,7 +1372,13 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     buf = static_cast<const uint8_t*>(tsv);
   } else {
     ZDWB_TRY(tsv_dev.alloc(ctx, n + 64));
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(tsv_dev.p, tsv, n, cudaMemcpyHostToDevice, st));
+    if (ctx->copy_gate && n >= COPY_GATE_MIN) {
+      std::lock_guard<std::mutex> turn(copy_gate(ctx->device, 0));
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(tsv_dev.p, tsv, n, cudaMemcpyHostToDevice, st));
+      ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    } else {
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(tsv_dev.p, tsv, n, cudaMemcpyHostToDevice, st));
+    }
     buf = tsv_dev.as<uint8_t>();
   }
   const int64_t lo = -(int64_t)(reinterpret_cast<uintptr_t>(buf) & 15u);
