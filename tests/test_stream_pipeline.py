@@ -1,0 +1,15 @@
+"""The read-ahead input window and the writer thread of convertDWfile (zdw_b200/host/stream_pipeline.h) against the
+sequential window they replaced, compiled for the CPU with g++ and malloc as the allocator - no GPU involved."""
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_read_ahead_window_matches_sequential_window(tmp_path):
+    exe = tmp_path / "stream_pipeline_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", str(ROOT / "zdw_b200" / "host"),
+                    str(ROOT / "tests" / "stream_pipeline_test.cpp"), "-o", str(exe)], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert " 0 mismatches" in p.stdout

@@ -1,13 +1,17 @@
 // ConvertToZDW.cpp -- see ConvertToZDW.h.  Reference behaviour cited as cplusplus/ConvertToZDW.cpp:<line>.
 #include "ConvertToZDW.h"
 
+#include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <fstream>
 #include <new>
+
+#include "stream_pipeline.h"
 
 using std::map;
 using std::string;
@@ -33,42 +37,13 @@ const size_t MAX_WINDOW_BYTES = 0xff000000ull;         // zdwb_encode_block take
 
 bool startsWith(const char* s, const char* prefix) { return strncmp(s, prefix, strlen(prefix)) == 0; }
 
-// Pinned host window over the input stream: [data, data + len) always starts at a row boundary.
-class InputWindow {
- public:
-  InputWindow() : buf(NULL), cap(0), len(0), eof(false) {}
-  ~InputWindow() { zdwb_host_free(buf); }
-  bool reserve(size_t want) {
-    if (want <= cap) return true;
-    char* nb = static_cast<char*>(zdwb_host_alloc(want + 64));
-    if (!nb) return false;
-    if (len) memcpy(nb, buf, len);
-    zdwb_host_free(buf);
-    buf = nb;
-    cap = want;
-    return true;
-  }
-  // tops the window up from `in`; `tee` (may be NULL) receives a copy of everything read
-  void fill(FILE* in, FILE* tee) {
-    while (!eof && len < cap) {
-      const size_t got = fread(buf + len, 1, cap - len, in);
-      if (got && tee) fwrite(buf + len, 1, got, tee);
-      len += got;
-      if (got == 0) eof = true;
-    }
-  }
-  void consume(size_t n) {
-    if (n >= len) {
-      len = 0;
-    } else {
-      memmove(buf, buf + n, len - n);
-      len -= n;
-    }
-  }
-  char* buf;
-  size_t cap, len;
-  bool eof;
-};
+// the window's buffers: pinned memory of the C ABI (copies at the rate of the link) ...
+void* pinnedAlloc(size_t n) { return zdwb_host_alloc(n); }
+void pinnedFree(void* p) { zdwb_host_free(p); }
+// ... or plain memory for an input that fits one window: pinning a buffer costs about as much as copying out of it
+// unpinned once, and plain memory can be filled while CUDA is still starting up
+void* plainAlloc(size_t n) { return malloc(n); }
+void plainFree(void* p) { free(p); }
 
 }  // namespace
 
@@ -227,10 +202,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     statusOutput(ERROR, "Invalid metadata parameter\n");
     return BAD_METADATA_PARAM;
   }
-  if (!gpu.open(gpuDevice)) {
-    statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n", exeName, gpu.lastError().c_str());
-    return UNKNOWN_ERROR;
-  }
+  gpu.prefetch(gpuDevice);  // CUDA start-up (a few hundred milliseconds) runs beside the first read
 
   // <outputDir or source dir>/<base>.zdw<ext>, written as <base>.creating.zdw<ext> and renamed on success (:629-657)
   string basePath;
@@ -243,35 +215,72 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   const string finalName = basePath + ".zdw" + compressorExtension();
   const string tempName = basePath + ".creating.zdw" + compressorExtension();
 
-  string cmd = compressorCommand();
-  if (zArgs) cmd += string(" ") + zArgs;
-  cmd += " > " + tempName;
-  FILE* out = popen(cmd.c_str(), "w");
-  if (!out) {
-    statusOutput(ERROR, "Could not open the process '%s' for writing!\n", cmd.c_str());
-    return FILE_CREATION_ERR;
-  }
-  writeFileHeader(out, schema, metadata);
-
   ERR_CODE res = OK;
   vector<string> srcFiles;  // what validation compares against
   FILE* tee = NULL;
+  FILE* out = NULL;
   string teeName;
   if (bStreamingInput) {
     // streamed input is kept (gzipped) for validation, like the reference's per-block temp files (:786-799)
     if (bValidate) {
       teeName = basePath + ".tmp.0.gz";
       tee = popen(("gzip > " + teeName).c_str(), "w");
-      if (!tee) {
-        pclose(out);
-        unlink(tempName.c_str());
-        return CANT_OPEN_TEMP_FILE;
-      }
+      if (!tee) return CANT_OPEN_TEMP_FILE;
       srcFiles.push_back(teeName);
     }
   } else {
     srcFiles.push_back(string(filestub) + "." + getInputFileExtension());
   }
+
+  // The input window.  A regular file that fits one window is read into plain memory while the CUDA context comes up;
+  // a longer one goes through two pinned buffers: while the GPU encodes one window a helper thread reads the next.
+  ReadAheadInput win;
+  AsyncWriter writer;
+  size_t windowBytes = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
+  bool oneWindow = false;
+  bool regularInput = false;  // reads of a regular file always come back; a pipe may keep a helper thread waiting for good
+  if (!bStreamingInput) {
+    struct stat st;
+    regularInput = fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode);
+    if (regularInput && (unsigned long long)st.st_size < windowBytes) {
+      oneWindow = true;
+      windowBytes = std::max((size_t)st.st_size + 1, (size_t)4096);  // + 1: the read that finds the end of the file
+    }
+  }
+  if (oneWindow) {
+    if (!win.open(in, tee, windowBytes, plainAlloc, plainFree)) return OUT_OF_MEMORY;
+    win.fill();
+  }
+  if (!gpu.open(gpuDevice)) {
+    statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n", exeName, gpu.lastError().c_str());
+    if (tee) {
+      pclose(tee);
+      unlink(teeName.c_str());
+    }
+    return UNKNOWN_ERROR;
+  }
+  if (!oneWindow && !win.open(in, tee, windowBytes, pinnedAlloc, pinnedFree)) {
+    if (tee) {
+      pclose(tee);
+      unlink(teeName.c_str());
+    }
+    return OUT_OF_MEMORY;
+  }
+
+  string cmd = compressorCommand();
+  if (zArgs) cmd += string(" ") + zArgs;
+  cmd += " > " + tempName;
+  out = popen(cmd.c_str(), "w");
+  if (!out) {
+    statusOutput(ERROR, "Could not open the process '%s' for writing!\n", cmd.c_str());
+    if (tee) {
+      pclose(tee);
+      unlink(teeName.c_str());
+    }
+    return FILE_CREATION_ERR;
+  }
+  writeFileHeader(out, schema, metadata);
+  writer.start(out);  // from here on the pipe belongs to the writer thread until writer.finish()
 
   zdwb_schema sch;
   sch.ncols = (uint32_t)schema.types.size();
@@ -282,15 +291,9 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   int blocks = 0;
   bool wrongColumns = false;
   vector<unsigned char> pending;  // the previous block, held back until we know whether another one follows
-  InputWindow win;
-  size_t windowBytes = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
-  if (!win.reserve(windowBytes)) {
-    res = OUT_OF_MEMORY;
-    goto Done;
-  }
   for (;;) {
-    win.fill(in, tee);
-    if (win.len == 0 && win.eof) break;
+    win.fill();
+    if (win.len() == 0 && win.eof()) break;
     ++blocks;
     if (!bQuiet) {
       if (blocks == 1) statusOutput(INFO, "\nProcessing %s\n", filestub);
@@ -300,7 +303,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     zdwb_encode_opts eo;
     memset(&eo, 0, sizeof(eo));
     eo.trim_trailing_spaces = bTrimTrailingSpaces ? 1 : 0;
-    eo.more_input_follows = win.eof ? 0 : 1;
+    eo.more_input_follows = win.eof() ? 0 : 1;
     eo.prev_longest_line = longestLine;
     eo.max_rows = rowsPerBlock;
     const bool planned = (size_t)(blocks - 1) < blockPlan.size();
@@ -308,9 +311,12 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       eo.max_rows = blockPlan[blocks - 1].first;
       eo.spill_cols = blockPlan[blocks - 1].second;
     }
+    // a block cut by the window (not by a row count) uses the window up to its last row break: read ahead.  (Not from
+    // a pipe: its producer runs on anyway, and an error path must not wait for a read that may never return.)
+    if (eo.max_rows == 0 && regularInput) win.prefetch();
     zdwb_block_out blk;
-    const int rc = zdwb_encode_block(gpu.get(), &sch, win.buf, win.len, &eo, &blk);
-    if (rc == ZDWB_OK && planned && !win.eof && blk.rows_in_buffer <= eo.max_rows) {
+    const int rc = zdwb_encode_block(gpu.get(), &sch, win.data(), win.len(), &eo, &blk);
+    if (rc == ZDWB_OK && planned && !win.eof() && blk.rows_in_buffer <= eo.max_rows) {
       // the window must hold the planned rows and the complete row after them: widen it and try again
       if (windowBytes >= MAX_WINDOW_BYTES) {
         statusOutput(ERROR, "%s: block %d of the plan does not fit %zu bytes\n", exeName, blocks, (size_t)MAX_WINDOW_BYTES);
@@ -318,7 +324,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
         goto Done;
       }
       windowBytes = std::min(windowBytes * 2, MAX_WINDOW_BYTES);
-      if (!win.reserve(windowBytes)) {
+      if (!win.widen(windowBytes)) {
         res = OUT_OF_MEMORY;
         goto Done;
       }
@@ -341,7 +347,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       goto Done;
     }
     if (blk.nrows == 0) {
-      if (!win.eof) {
+      if (!win.eof()) {
         // not one complete row in the window: widen it and try again
         if (windowBytes >= MAX_WINDOW_BYTES) {
           statusOutput(ERROR, "%s: a single row exceeds %zu bytes\n", exeName, (size_t)MAX_WINDOW_BYTES);
@@ -349,7 +355,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
           goto Done;
         }
         windowBytes = std::min(windowBytes * 2, MAX_WINDOW_BYTES);
-        if (!win.reserve(windowBytes)) {
+        if (!win.widen(windowBytes)) {
           res = OUT_OF_MEMORY;
           goto Done;
         }
@@ -367,7 +373,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     }
     if (!pending.empty()) {
       pending[8] = 0;  // another block follows (:841-842)
-      fwrite(pending.data(), 1, pending.size(), out);
+      writer.push(pending);  // the compressor works on it while the next block is read and encoded
     }
     pending.assign(blk.bytes, blk.bytes + blk.len);
     longestLine = blk.longest_line;
@@ -378,16 +384,20 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   if (wrongColumns) {
     // the reference returns straight out of processFile here: the pipe is left to the process exit and the
     // .creating file stays on disk (:810-812).  We close the pipe but keep the file.
+    win.close();
+    writer.finish();
     if (tee) pclose(tee);
     pclose(out);
     return WRONG_NUM_OF_COLUMNS_ON_A_ROW;
   }
   if (!pending.empty()) {
     pending[8] = 1;
-    fwrite(pending.data(), 1, pending.size(), out);
+    writer.push(pending);
   } else {
     statusOutput(ERROR, "Empty data file -- nothing to process\n");  // :824-835, result stays OK
   }
+  win.close();  // no reader left on `in` / `tee`
+  writer.finish();
   if (tee) {
     pclose(tee);
     tee = NULL;
@@ -406,6 +416,8 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   }
 
 Done:
+  win.close();
+  writer.finish();
   if (tee) pclose(tee);
   if (out) pclose(out);
   if (!teeName.empty()) unlink(teeName.c_str());
