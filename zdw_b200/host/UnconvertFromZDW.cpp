@@ -141,6 +141,55 @@ void ZdwInput::finalDummyRead() {
 }  // namespace internal
 
 // ---------------------------------------------------------------------------------------------------------------
+// output
+// ---------------------------------------------------------------------------------------------------------------
+BufferedOutput::~BufferedOutput() {
+  {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this]() { return !busy; });
+    stop = true;
+  }
+  cv.notify_all();
+  if (started) worker.join();
+}
+
+void BufferedOutput::writeLater(const void* data, size_t size) {
+  std::unique_lock<std::mutex> lk(m);
+  cv.wait(lk, [this]() { return !busy; });
+  if (!size) return;
+  if (!started) {
+    started = true;
+    worker = std::thread([this]() { run(); });
+  }
+  jobData = data;
+  jobSize = size;
+  busy = true;
+  cv.notify_all();
+}
+
+bool BufferedOutput::waitIdle() {
+  std::unique_lock<std::mutex> lk(m);
+  cv.wait(lk, [this]() { return !busy; });
+  return !failed;
+}
+
+void BufferedOutput::run() {
+  std::unique_lock<std::mutex> lk(m);
+  for (;;) {
+    cv.wait(lk, [this]() { return busy || stop; });
+    if (!busy) return;  // stop is only raised while idle
+    const void* data = jobData;
+    const size_t size = jobSize;
+    lk.unlock();
+    const bool ok = fwrite(data, 1, size, fp) == size;
+    lk.lock();
+    if (!ok) failed = true;
+    busy = false;
+    cv.notify_all();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // base
 // ---------------------------------------------------------------------------------------------------------------
 UnconvertFromZDW_Base::UnconvertFromZDW_Base(const string& fileName, const bool showStatus, const bool quiet, const bool testOnly,
@@ -151,7 +200,7 @@ UnconvertFromZDW_Base::UnconvertFromZDW_Base(const string& fileName, const bool 
       bOutputNonEmptyColumnHeader(false), bShowBasicStatisticsOnly(false), bFailOnInvalidColumns(true),
       bExcludeSpecifiedColumns(false), bOutputEmptyMissingColumns(false), indexForVirtualBaseNameColumn(IGNORE_COLUMN),
       indexForVirtualRowColumn(IGNORE_COLUMN), rowsRead(0), rowsBeforeBlock(0), statusOutput(NULL), eState(ZDW_BEGIN),
-      gpuDevice(-1) {
+      gpuDevice(-1), blocksToSink(0) {
   if (inFileName.empty()) {
     input = new internal::ZdwInput();
     input->openStdin();
@@ -572,7 +621,8 @@ ERR_CODE UnconvertFromZDW_Base::peekBlock(BlockInfo& info) {
 }
 
 ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
-                                            bool wantFlagCounts, zdwb_rows_out* out) {
+                                            bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session) {
+  GpuSession& gpu = session ? *session : this->gpu;
   const double tOpen0 = nowSeconds();
   const bool opened = gpu.open(gpuDevice);
   if (hostTiming()) fprintf(stderr, "[zdw host] gpu.open %.3f s\n", nowSeconds() - tOpen0);
@@ -653,9 +703,13 @@ ERR_CODE UnconvertFromZDW<T>::parseNextBlock(T& sink) {
     this->rowsRead = this->numLines;
     this->input->consume((size_t)rows.consumed);
   } else if (!this->bShowBasicStatisticsOnly) {
-    rc = this->decodeBlock(info, '\t', false, false, false, &rows);
+    // Blocks alternate between two GPU contexts: the rows of this block stay valid in theirs while the sink's writer
+    // thread puts them out and the next block is read (the decompressor pipe drains meanwhile) and decoded in the
+    // other context.  The sink has one block in flight, so a context's rows are on disk before it is used again.
+    GpuSession* session = (this->blocksToSink++ & 1) ? &this->gpu2 : &this->gpu;
+    rc = this->decodeBlock(info, '\t', false, false, false, &rows, session);
     if (rc != OK) return rc;
-    sink.write(rows.tsv, rows.len);
+    sink.writeLater(rows.tsv, rows.len);
     this->rowsRead = this->numLines;
     this->input->consume((size_t)rows.consumed);
     if (this->bShowStatus) this->statusOutput(INFO, "\r%u\n", this->rowsRead);

@@ -12,11 +12,14 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <ostream>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -97,13 +100,31 @@ class ZdwInput {
 
 // Output policies of the reference (BufferedOutput.h:23-196).  Column selection and ordering happen on the GPU, so
 // both are thin FILE* writers here; the two names are kept because callers spell them as template arguments.
+// writeLater() hands a whole block of rows to a writer thread: the caller goes on to read and decode the next block
+// while this one is written (one block in flight; every call on the object first waits for it).
 class BufferedOutput {
  public:
-  explicit BufferedOutput(FILE* f) : fp(f) {}
-  bool write(const void* data, size_t size) { return !size || fwrite(data, 1, size, fp) == size; }
+  explicit BufferedOutput(FILE* f) : fp(f), jobData(NULL), jobSize(0), busy(false), stop(false), started(false), failed(false) {}
+  ~BufferedOutput();
+  bool write(const void* data, size_t size) {
+    waitIdle();
+    return !size || fwrite(data, 1, size, fp) == size;
+  }
+  // `data` must stay untouched until the next call on this object returns
+  void writeLater(const void* data, size_t size);
+  bool waitIdle();  // false once a deferred write came up short
 
  private:
+  BufferedOutput(const BufferedOutput&);
+  BufferedOutput& operator=(const BufferedOutput&);
+  void run();
   FILE* fp;
+  std::mutex m;
+  std::condition_variable cv;
+  const void* jobData;
+  size_t jobSize;
+  bool busy, stop, started, failed;
+  std::thread worker;
 };
 class BufferedOrderedOutput : public BufferedOutput {
  public:
@@ -162,7 +183,7 @@ class UnconvertFromZDW_Base {
   ERR_CODE peekBlock(BlockInfo& info);
   // Decodes that block on the GPU.  separator '\t' (files) or '\0' (in-memory rows).
   ERR_CODE decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
-                       bool wantFlagCounts, zdwb_rows_out* out);
+                       bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session = NULL);
   std::string getBlockHeaderString(const BlockInfo& info) const;
 
   ERR_CODE outputDescToFile(const std::vector<std::string>& names, const std::string& outputDir, const char* filestub,
@@ -218,6 +239,8 @@ class UnconvertFromZDW_Base {
 
   int gpuDevice;
   GpuSession gpu;
+  GpuSession gpu2;            // file output only: blocks alternate between two contexts (see parseNextBlock)
+  unsigned blocksToSink;      // blocks decoded for a file sink so far
 
  private:
   std::vector<std::string> getDesc(const std::vector<std::string>& names, const std::string& nameTypeSeparator,
