@@ -73,10 +73,13 @@ const char* zdwb_last_error(const zdwb_ctx* ctx);
  * harness time the kernels with events recorded on its own stream. */
 int zdwb_ctx_set_stream(zdwb_ctx* ctx, void* cuda_stream);
 
-/* Tuning / test knobs (name = value).  Known names: "small_sort_max" (largest dictionary sorted by the
- * single-CTA path), "ht_initial_log2" (first-try size of the string hash set), "dec_tile_bytes" (row-stream bytes
- * per CTA in the decoder's row-boundary discovery), "kernel_timing" (0/1).  Returns ZDWB_ERR_BAD_ARG
- * for unknown names. */
+/* Tuning / test knobs (name = value).  Known names: "small_sort_max" (largest dictionary ranked by the tile-sort
+ * path instead of the radix sort), "ht_initial_log2" (first-try size of the string hash set), "dec_tile_bytes"
+ * (row-stream bytes per CTA in the decoder's row-boundary discovery), "dec_strip_rows" (rows per strip of the
+ * decoder's row kernels, 0 = automatic), "dec_group_lanes" (lanes per row in those kernels: 8, 16, 32, 0 = by schema
+ * width), "copy_gate" (0/1, default 1: host<->device copies of 8 MiB and more take turns with those of the
+ * process's other contexts on the same device instead of sharing the link), "kernel_timing" (0/1).  Returns
+ * ZDWB_ERR_BAD_ARG for unknown names. */
 int zdwb_ctx_set_tuning(zdwb_ctx* ctx, const char* name, long long value);
 
 /* Number of kernels this context has launched so far (bench.py reports the delta as gpu_launches). */
