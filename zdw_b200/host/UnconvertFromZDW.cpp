@@ -97,23 +97,21 @@ void ZdwInput::openStdin() {
 size_t ZdwInput::ensure(size_t n) {
   if (len - pos >= n || ended || !fp) return len - pos;
   if (pos && pos == len) pos = len = 0;
-  if (pos + n > cap) {
-    // compact, then grow geometrically
-    if (pos) {
-      memmove(buf, buf + pos, len - pos);
-      len -= pos;
-      pos = 0;
-    }
-    if (n > cap) {
-      size_t want = cap ? cap : ((size_t)1 << 20);
-      while (want < n) want *= 2;
+  if (pos && pos + n > cap) {  // the request does not fit behind the read position: compact first
+    memmove(buf, buf + pos, len - pos);
+    len -= pos;
+    pos = 0;
+  }
+  // The buffer grows as the bytes arrive, not to `n` up front: `n` comes out of a block header, and a corrupt one must
+  // not be able to ask for more memory than the file is long.
+  while (len - pos < n && !ended) {
+    if (len == cap) {
+      const size_t want = cap ? cap * 2 : ((size_t)1 << 20);
       char* nb = static_cast<char*>(realloc(buf, want + 64));
       if (!nb) throw std::bad_alloc();
       buf = nb;
       cap = want;
     }
-  }
-  while (len - pos < n && !ended) {
     const size_t got = fread(buf + len, 1, cap - len, fp);
     len += got;
     if (got == 0) ended = true;
