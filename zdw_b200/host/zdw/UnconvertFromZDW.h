@@ -63,8 +63,8 @@ struct MetadataOptions {
   MetadataOptions() : bOutputOnlyMetadata(false), bOnlyMetadataKeys(false), bAllowMissingKeys(false) {}
 };
 
-// Byte source: `popen(<decompressor> file)` or stdin, buffered ahead in pinned memory so that a whole block can be
-// handed to the GPU in one piece.
+// Byte source: `popen(<decompressor> file)`, the file itself when it is not compressed, or stdin; buffered ahead (plain
+// memory that grows as the bytes arrive) so that a whole block can be handed to the GPU in one piece.
 class ZdwInput {
  public:
   ZdwInput();
