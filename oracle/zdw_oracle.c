@@ -292,8 +292,9 @@ static dent* dict_find(const dict* d, const char* s) {
   return NULL;
 }
 
-static void dict_insert(dict* d, const char* s) { /* Dictionary::insert, dictionary.cpp:31-51 */
-  if (dict_find(d, s)) return;
+/* returns strlen+1 when the string is new (it then goes to the string heap), 0 when it was known */
+static size_t dict_insert(dict* d, const char* s) { /* Dictionary::insert, dictionary.cpp:31-51 */
+  if (dict_find(d, s)) return 0;
   if ((d->n + 1) * 2 > d->nslots) dict_rehash(d, d->nslots ? d->nslots * 2 : 1024);
   if (d->n == d->cap) {
     d->cap = d->cap ? d->cap * 2 : 1024;
@@ -306,6 +307,26 @@ static void dict_insert(dict* d, const char* s) { /* Dictionary::insert, diction
   while (d->slots[h]) h = (h + 1) & (d->nslots - 1);
   d->slots[h] = (uint32_t)d->n + 1;
   d->n++;
+  return strlen(s) + 1;
+}
+
+/* StringHeap as far as it decides where a block ends: stringheap.cpp:23,31-59,75-86 */
+#define ZO_HEAP_BLOCK_SIZE ((size_t)64 * 1024 * 1024)
+typedef struct {
+  size_t free_bytes;   /* freeBytesInCurrentBlock */
+  uint32_t allocs;     /* heap blocks opened for the current ZDW block */
+  uint32_t limit;      /* the allocation that finds the process over --mem-limit (0 = never) */
+} heapsim;
+
+/* copyToHeap: returns 1 when this insert flagged low memory */
+static int heap_copy(heapsim* h, size_t len) {
+  if (h->free_bytes >= len) {
+    h->free_bytes -= len;
+    return 0;
+  }
+  h->free_bytes = (len > ZO_HEAP_BLOCK_SIZE ? len : ZO_HEAP_BLOCK_SIZE) - len; /* residual of the old block is wasted */
+  h->allocs++;
+  return h->limit && h->allocs >= h->limit;
 }
 
 static int dent_cmp(const void* a, const void* b) { /* cstringComp, dictionary.h:30-33 */
@@ -375,15 +396,18 @@ int zo_write_file_header(const zo_schema* s, const zo_encode_opts* o, uint8_t** 
 static uint64_t sx(char ch) { return (uint64_t)(int64_t)(signed char)ch; }
 
 /* one row (its first ncols_todo columns) through the per-column part of parseInput, ConvertToZDW.cpp:338-401 */
-static void pass1_fields(const zo_schema* s, const fieldvec* cols, uint32_t ncols_todo, uint8_t* minmaxset, uint64_t* cmin,
-                         uint64_t* cmax, dict* uniq) {
+/* Returns -1, or the column whose insert ran the string heap out of memory (hadEnoughMemory = false, :334-355): the
+   columns behind it have not been looked at. */
+static int pass1_fields(const zo_schema* s, const fieldvec* cols, uint32_t ncols_todo, uint8_t* minmaxset, uint64_t* cmin,
+                        uint64_t* cmax, dict* uniq, heapsim* heap) {
   for (uint32_t c = 0; c < ncols_todo; ++c) {
     const char* f = cols->v[c];
     if (!f[0]) continue;
     const uint8_t t = s->types[c];
     if (is_text_like(t)) {
       minmaxset[c] = 1;
-      dict_insert(uniq, f);
+      const size_t fresh = dict_insert(uniq, f);
+      if (fresh && heap && heap_copy(heap, fresh)) return (int)c;
     } else {
       uint64_t val;
       if (t == ZO_CHAR) {
@@ -403,6 +427,7 @@ static void pass1_fields(const zo_schema* s, const fieldvec* cols, uint32_t ncol
       }
     }
   }
+  return -1;
 }
 
 int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_encode_opts* o,
@@ -411,6 +436,7 @@ int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_en
   const int trim = o ? o->trim_trailing_spaces : 0;
   const uint32_t nplan = o ? o->nplan : 0;
   const uint32_t rpb = (o && !nplan) ? o->rows_per_block : 0;
+  heapsim heap = {0, 0, (o && !nplan && !rpb) ? o->heap_blocks : 0};
   obuf out = {0};
   zo_encode_info inf;
   memset(&inf, 0, sizeof(inf));
@@ -459,14 +485,31 @@ int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_en
       last = 0;
     }
     size_t k;
+    heap.free_bytes = 0; /* uniques.clear() -> StringHeap::FreeMemory, stringheap.cpp:88-100 */
+    heap.allocs = 0;
+    int out_of_memory = 0;
+    size_t row_start = in.pos;
     while ((!limit || numRows < limit) && (k = get_data_row(&in, &row, &rowSize, &cols, trim))) {
       if (k != nc) {
         inf.bad_row = numRows + 1; /* :811 */
         rc = ZO_ENC_WRONG_NUM_OF_COLUMNS_ON_A_ROW;
         goto done;
       }
-      pass1_fields(s, &cols, nc, minmaxset, cmin, cmax, &uniq);
+      if (pass1_fields(s, &cols, nc, minmaxset, cmin, cmax, &uniq, heap.limit ? &heap : NULL) >= 0) {
+        /* IS_NOT_ENOUGH_MEMORY: the row is not counted (:404-406) and is read again for the next block (fsetpos, :867) */
+        out_of_memory = 1;
+        in.pos = row_start;
+        break;
+      }
       ++numRows;
+      row_start = in.pos;
+    }
+    if (out_of_memory) {
+      if (!numRows) { /* low on memory before a single row fit: :824-834 */
+        rc = ZO_ENC_OUT_OF_MEMORY;
+        goto done;
+      }
+      last = 0;
     }
     if (limit && numRows == limit && !last) {
       /* the interrupted row: read in full (the row buffer grows with it, getnextrow.cpp:57-65), its leading columns
@@ -478,7 +521,7 @@ int zo_encode_file(const zo_schema* s, const uint8_t* tsv, size_t n, const zo_en
         rc = ZO_ENC_WRONG_NUM_OF_COLUMNS_ON_A_ROW;
         goto done;
       }
-      if (k) pass1_fields(s, &cols, spill < nc ? spill : nc, minmaxset, cmin, cmax, &uniq);
+      if (k) pass1_fields(s, &cols, spill < nc ? spill : nc, minmaxset, cmin, cmax, &uniq, NULL);
       in.pos = keep;
     }
     if (!numRows) break; /* :824-835 "Empty data file -- nothing to process" (only possible on block 1) */

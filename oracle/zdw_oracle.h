@@ -70,6 +70,16 @@ typedef struct {
   uint32_t nplan;
   const uint32_t* plan_rows;
   const uint32_t* plan_spill;
+  /* The reference's OWN block cut as a function of the input and one number (used when nplan == 0 and rows_per_block
+     == 0; 0 = off).  New strings are packed in first-occurrence order into heap blocks of 64 MiB - a block of
+     max(len+1, 64 MiB) is opened whenever the current one has fewer than len+1 bytes free, the rest of the old one is
+     wasted (StringHeap::copyToHeap, stringheap.cpp:31-59) - and the insert that opens the heap_blocks-th heap block of
+     a ZDW block finds the process over its --mem-limit (allocBlock, stringheap.cpp:75-86): pass 1 stops inside that
+     row, after that column (ConvertToZDW.cpp:334-355,404-413).  Which allocation is the first one over the limit
+     depends on the virtual size of the reference's process, i.e. on --mem-limit, the allocator and the machine;
+     everything else is a pure function of the input.  The same number is applied to every block of
+     the file (the 64 MiB blocks are mmap'd, so a finished block gives its memory back). */
+  uint32_t heap_blocks;
 } zo_encode_opts;
 
 typedef struct {

@@ -38,7 +38,8 @@ class _Schema(C.Structure):
 class _EncOpts(C.Structure):
     _fields_ = [("trim", C.c_int), ("rows_per_block", C.c_uint32), ("nmeta", C.c_uint32),
                 ("keys", C.POINTER(C.c_char_p)), ("vals", C.POINTER(C.c_char_p)),
-                ("nplan", C.c_uint32), ("plan_rows", C.POINTER(C.c_uint32)), ("plan_spill", C.POINTER(C.c_uint32))]
+                ("nplan", C.c_uint32), ("plan_rows", C.POINTER(C.c_uint32)), ("plan_spill", C.POINTER(C.c_uint32)),
+                ("heap_blocks", C.c_uint32)]
 
 
 class _EncInfo(C.Structure):
@@ -121,8 +122,9 @@ class EncodeResult:
 
 
 def encode(sch: Schema, tsv: bytes, trim: bool = False, rows_per_block: int = 0, metadata: dict | None = None,
-           plan=None) -> EncodeResult:
-    """plan: [(rows, spill_columns), ...] - explicit block boundaries with the reference's interrupted-row spill."""
+           plan=None, heap_blocks: int = 0) -> EncodeResult:
+    """plan: [(rows, spill_columns), ...] - explicit block boundaries with the reference's interrupted-row spill.
+    heap_blocks: K - the reference's own cut: a block ends on the insert that opens its K-th 64 MiB string-heap block."""
     s = _c_schema(sch)
     md = sorted((metadata or {}).items())
     keys = (C.c_char_p * max(len(md), 1))(*[k.encode() for k, _ in md])
@@ -131,7 +133,7 @@ def encode(sch: Schema, tsv: bytes, trim: bool = False, rows_per_block: int = 0,
     prow = (C.c_uint32 * max(len(plan), 1))(*[int(r) for r, _ in plan])
     pspill = (C.c_uint32 * max(len(plan), 1))(*[int(c) for _, c in plan])
     o = _EncOpts(int(trim), rows_per_block, len(md), C.cast(keys, C.POINTER(C.c_char_p)), C.cast(vals, C.POINTER(C.c_char_p)),
-                 len(plan), C.cast(prow, C.POINTER(C.c_uint32)), C.cast(pspill, C.POINTER(C.c_uint32)))
+                 len(plan), C.cast(prow, C.POINTER(C.c_uint32)), C.cast(pspill, C.POINTER(C.c_uint32)), int(heap_blocks))
     out = C.c_void_p()
     n = C.c_size_t()
     info = _EncInfo()
