@@ -786,6 +786,9 @@ int zo_decode_file(const uint8_t* zdw, size_t n, const zo_decode_opts* o, uint8_
     uint32_t nused = 0;
     for (uint32_t c = 0; c < nc; ++c) {
       if (csize[c]) {
+        /* the reference reads columnSize[c] bytes into an 8-byte columnVal (:1299-1308) whatever the size says: undefined
+           behaviour for a size above 8, which only a corrupt file has.  Reported, not restated. */
+        if (csize[c] > 8) { rc = ZO_DEC_CORRUPTED_DATA_ERROR; goto done; }
         if (!rd_bytes(&r, &cbase[c], 8)) { rc = ZO_DEC_GZREAD_FAILED; goto done; }
         ++nused;
       } else cbase[c] = 0;
