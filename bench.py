@@ -501,10 +501,22 @@ def run_cuda(args):
     def e2e_encode_pass():
         return _run_lanes(lambda c, it: L_encode_host(c, types, it[0], it[1]), list(zip(host_ptrs, host_lens)))
 
-    host_zdw_bufs = [(C.c_uint8 * len(zb)).from_buffer_copy(zb) for zb in host_zdw]
+    # the ZDW blocks the e2e decode reads: pinned like the TSV inputs (a pageable source makes the driver stage the copy
+    # under its own lock, which holds up the other contexts' copies); plain buffers only if pinning fails
+    e2e_dec_blocks, dec_keep, dec_pinned = [], [], []
+    for zb in host_zdw[:max(1, args.e2e_decode_blocks)]:
+        p = L.zdwb_host_alloc(len(zb)) if pinned else None
+        if p:
+            C.memmove(p, zb, len(zb))
+            dec_pinned.append(p)
+        else:
+            buf = (C.c_uint8 * len(zb)).from_buffer_copy(zb)
+            dec_keep.append(buf)
+            p = C.addressof(buf)
+        e2e_dec_blocks.append((p, len(zb)))
 
     def e2e_decode_pass(items):
-        return _run_lanes(lambda c, it: L_decode_host(c, types, C.addressof(it), len(it)), items)
+        return _run_lanes(lambda c, it: L_decode_host(c, types, it[0], it[1]), items)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_encode_pass()
@@ -515,7 +527,6 @@ def run_cuda(args):
         d2h_enc = e2e_encode_pass()
     torch.cuda.synchronize(dev)
     t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
-    e2e_dec_blocks = host_zdw_bufs[:max(1, args.e2e_decode_blocks)]
     e2e_decode_pass(e2e_dec_blocks[:2 * len(lanes)])  # two blocks per lane: the second call settles on a pinned output buffer
     barrier()
     t0 = time.perf_counter()
@@ -544,6 +555,8 @@ def run_cuda(args):
     pool.shutdown()
     for c in lanes:
         c.close()
+    for p in dec_pinned:
+        L.zdwb_host_free(p)
 
     # ---- instrumented step: per-kernel CUDA-event times for the roofline
     # (one context walks every block of the rank, so the launch count per kernel equals the number of blocks)
@@ -607,7 +620,7 @@ def run_cuda(args):
             "roofline": roof(kt_enc, "encode"),
             "e2e": {"value": tot_tsv / t_e2e_enc / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(tot_tsv),
                     "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "cpu_affinity": affinity, "lanes": args.e2e_lanes, "pcie_copy_gbs": pcie,
-                    "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks),
+                    "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks), "pinned_decode_input": bool(dec_pinned) and not dec_keep,
                     "decode_d2h_bytes": int(d2h_dec_all)},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
