@@ -256,6 +256,36 @@ def test_multi_block_files_and_statistics():
     assert back[0][1] == back[1][1] == tsv[: 1 << 20].rsplit(b"\n", 1)[0] + b"\n"
 
 
+def _window_plan(tsv: bytes, window: int):
+    """[(rows, 0)] for every block but the last when blocks are cut by an input window of `window` bytes: a block
+    holds the complete rows of its window, the next window starts behind them (data without escapes)."""
+    plan, pos = [], 0
+    while pos + window <= len(tsv):
+        cut = tsv[pos:pos + window].rfind(b"\n") + 1
+        assert cut > 0
+        if pos + cut == len(tsv):
+            break  # the rows end with this window: it is the last block
+        plan.append((tsv[pos:pos + cut].count(b"\n"), 0))
+        pos += cut
+    return plan
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window", [70000, 131072])
+def test_block_bytes_windows_cut_like_the_sequential_loop(window):
+    """--block-bytes on a file of many windows: the read-ahead thread, the pinned double buffer and the writer thread
+    of convertDWfile must leave the cuts where a plain fill-encode-consume loop puts them; the file must be the one
+    the restatement writes for those cuts."""
+    tsv = O.golden("movie_tickets.sql")[: 1 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    desc = O.golden("movie_tickets.desc.sql")
+    ours = encode_both(tsv, desc, [f"--block-bytes={window}"])[0]
+    assert ours[0] == 0, ours[2]
+    plan = _window_plan(tsv, window)
+    want = O.encode(O.parse_desc(desc), tsv, plan=plan)
+    assert want.nblocks == len(plan) + 1 >= 8
+    assert ours[1] == want.data
+
+
 @pytest.mark.gpu
 def test_truncated_and_trailing_garbage():
     z = O.golden_to_v11(O.golden("movie_tickets.zdw"))
