@@ -94,31 +94,36 @@ size_t zdwb_ctx_kernel_times(zdwb_ctx* c, char* buf, size_t cap) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  std::map<std::string, std::pair<unsigned long long, double>> agg;
-  for (auto& t : c->timed) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
-      auto& a = agg[t.name];
-      a.first += 1;
-      a.second += ms;
+  try {
+    std::map<std::string, std::pair<unsigned long long, double>> agg;
+    for (auto& t : c->timed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+        auto& a = agg[t.name];
+        a.first += 1;
+        a.second += ms;
+      }
+      cudaEventDestroy(t.e0);
+      cudaEventDestroy(t.e1);
     }
-    cudaEventDestroy(t.e0);
-    cudaEventDestroy(t.e1);
+    c->timed.clear();
+    (void)cudaGetLastError();
+    std::string out;
+    for (auto& kv : agg) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+      out += line;
+    }
+    if (buf && cap) {
+      const size_t k = out.size() < cap - 1 ? out.size() : cap - 1;
+      memcpy(buf, out.data(), k);
+      buf[k] = 0;
+    }
+    return out.size();
+  } catch (...) {  // out of host memory while formatting: report nothing rather than throw through the C ABI
+    if (buf && cap) buf[0] = 0;
+    return 0;
   }
-  c->timed.clear();
-  (void)cudaGetLastError();
-  std::string out;
-  for (auto& kv : agg) {
-    char line[256];
-    snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
-    out += line;
-  }
-  if (buf && cap) {
-    const size_t k = out.size() < cap - 1 ? out.size() : cap - 1;
-    memcpy(buf, out.data(), k);
-    buf[k] = 0;
-  }
-  return out.size();
 }
 
 int zdwb_encode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
@@ -133,7 +138,16 @@ int zdwb_encode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* tsv, s
     c->err = "cudaSetDevice failed";
     return ZDWB_ERR_NO_DEVICE;
   }
-  return zdwb::encode_block_impl(c, schema, tsv, n, opts, out);
+  // the implementation uses std::vector / std::string on the host side: nothing of that may leave through the C ABI
+  try {
+    return zdwb::encode_block_impl(c, schema, tsv, n, opts, out);
+  } catch (const std::bad_alloc&) {
+    c->err = "zdwb_encode_block: out of host memory";
+    return ZDWB_ERR_OOM;
+  } catch (...) {
+    c->err = "zdwb_encode_block: unexpected C++ exception";
+    return ZDWB_ERR_CUDA;
+  }
 }
 
 int zdwb_decode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* zdw, size_t avail, const zdwb_decode_opts* opts,
@@ -148,7 +162,15 @@ int zdwb_decode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* zdw, s
     c->err = "cudaSetDevice failed";
     return ZDWB_ERR_NO_DEVICE;
   }
-  return zdwb::decode_block_impl(c, schema, zdw, avail, opts, out);
+  try {
+    return zdwb::decode_block_impl(c, schema, zdw, avail, opts, out);
+  } catch (const std::bad_alloc&) {
+    c->err = "zdwb_decode_block: out of host memory";
+    return ZDWB_ERR_OOM;
+  } catch (...) {
+    c->err = "zdwb_decode_block: unexpected C++ exception";
+    return ZDWB_ERR_CUDA;
+  }
 }
 
 void* zdwb_host_alloc(size_t bytes) {
