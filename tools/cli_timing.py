@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""cli_timing.py -- wall clock of the host tools (zdw_b200/bin/convertDWfile, unconvertDWfile) on a C4-shaped file of
+several blocks, beside the compiled reference on one block of the same data.  What it is for: DESIGN.md section 5a -
+the input read-ahead, the writer thread in front of the compressor and the two-context decode only show in the
+wall clock of the tools, not in bench.py (which calls the C ABI directly).
+
+    python tools/cli_timing.py [--blocks 8] [--rows 131072] [--compressors cat,gzip] [--dir /dev/shm]
+
+Prints one JSON line per (tool, compressor).  `cat` = the pass-through stand-in of oracle/_ref/nocomp (the compressor
+stage excluded, as in bench.py's reference arm); `gzip` = the real one.  Needs a GPU for our tools; the reference leg is
+CPU only and is skipped with --no-reference."""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402  (the synthetic C4 generator and the reference environment)
+
+BIN = ROOT / "zdw_b200" / "bin"
+REF = ROOT / "oracle" / "_ref"
+
+
+def env_for(compressor: str):
+    env = dict(os.environ)
+    if compressor == "cat":
+        env["PATH"] = f"{REF / 'nocomp'}:{env.get('PATH', '')}"
+    return env
+
+
+def timed(cmd, cwd, env):
+    t0 = time.perf_counter()
+    p = subprocess.run(cmd, cwd=cwd, env=env, capture_output=True)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError(f"{cmd[0]} failed ({p.returncode}): {p.stderr[-400:].decode('latin1')}")
+    return dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--blocks", type=int, default=8)
+    ap.add_argument("--rows", type=int, default=bench.ROWS_PER_BLOCK)
+    ap.add_argument("--compressors", default="cat,gzip")
+    ap.add_argument("--dir", default="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    ap.add_argument("--block-bytes", type=int, default=0, help="--block-bytes for convertDWfile (0 = its default, 1 GiB)")
+    ap.add_argument("--no-reference", action="store_true")
+    args = ap.parse_args()
+
+    synth = bench.Synth()
+    work = Path(tempfile.mkdtemp(prefix="zdw_cli_", dir=args.dir))
+    try:
+        # ---- the input: `blocks` C4 blocks back to back in one file
+        cap = synth.cap_for(args.rows)
+        buf = (C.c_uint8 * cap)()
+        src = work / "x.sql"
+        one_block = 0
+        with open(src, "wb") as f:
+            for b in range(args.blocks):
+                n = synth.block_into(b, args.rows, C.addressof(buf), cap)
+                one_block = one_block or n
+                f.write(memoryview(buf)[:n])
+        (work / "x.desc.sql").write_bytes(synth.desc)
+        tsv_bytes = src.stat().st_size
+        extra = [f"--block-bytes={args.block_bytes}"] if args.block_bytes else []
+
+        for comp in args.compressors.split(","):
+            if not comp:
+                continue
+            env = env_for(comp)
+            for f in work.glob("x.zdw*"):
+                f.unlink()
+            t_enc = timed([str(BIN / "convertDWfile"), "-q", *extra, "x.sql"], work, env)
+            zdw = work / "x.zdw.gz"
+            out = work / "out"
+            shutil.rmtree(out, ignore_errors=True)
+            out.mkdir()
+            t_dec = timed([str(BIN / "unconvertDWfile"), "-q", "-d", "out", "x.zdw.gz"], work, env)
+            same = (out / "x.sql").stat().st_size == tsv_bytes and \
+                subprocess.run(["cmp", "-s", str(out / "x.sql"), str(src)]).returncode == 0
+            print(json.dumps({"tool": "zdw_b200", "compressor": comp, "blocks": args.blocks, "tsv_bytes": tsv_bytes,
+                              "zdw_file_bytes": zdw.stat().st_size, "encode_s": round(t_enc, 3), "decode_s": round(t_dec, 3),
+                              "encode_gbs": tsv_bytes / t_enc / 1e9, "decode_gbs": tsv_bytes / t_dec / 1e9,
+                              "round_trip_identical": same}), flush=True)
+            shutil.rmtree(out, ignore_errors=True)
+
+        # ---- the reference on the first block of the same file (single-threaded; the whole file would take minutes)
+        if not args.no_reference and bench.have_ref():
+            rd = work / "ref"
+            rd.mkdir()
+            with open(src, "rb") as f, open(rd / "x.sql", "wb") as g:
+                g.write(f.read(one_block))
+            t_enc, t_dec, nbytes = bench._ref_roundtrip(rd, rd / "x.sql", synth.desc)
+            print(json.dumps({"tool": "reference", "compressor": "cat", "blocks": 1, "tsv_bytes": nbytes,
+                              "encode_s": round(t_enc, 3), "decode_s": round(t_dec, 3),
+                              "encode_gbs": nbytes / t_enc / 1e9, "decode_gbs": nbytes / t_dec / 1e9}), flush=True)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
