@@ -620,13 +620,13 @@ ERR_CODE UnconvertFromZDW_Base::peekBlock(BlockInfo& info) {
 
 ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
                                             bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session) {
-  GpuSession& gpu = session ? *session : this->gpu;
+  GpuSession& g = session ? *session : gpu;
   const double tOpen0 = nowSeconds();
-  const bool opened = gpu.open(gpuDevice);
+  const bool opened = g.open(gpuDevice);
   if (hostTiming()) fprintf(stderr, "[zdw host] gpu.open %.3f s\n", nowSeconds() - tOpen0);
   if (!opened) {
     statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n",
-                 exeName.empty() ? "UnconvertFromZDW" : exeName.c_str(), gpu.lastError().c_str());
+                 exeName.empty() ? "UnconvertFromZDW" : exeName.c_str(), g.lastError().c_str());
     return PROCESSING_ERROR;
   }
   zdwb_schema sch;
@@ -660,7 +660,7 @@ ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char
       o.rownum_pos = outputColumns[indexForVirtualRowColumn];
   }
   const double tDec0 = nowSeconds();
-  const int rc = zdwb_decode_block(gpu.get(), &sch, input->data(), input->available(), &o, out);
+  const int rc = zdwb_decode_block(g.get(), &sch, input->data(), input->available(), &o, out);
   if (hostTiming())
     fprintf(stderr, "[zdw host] zdwb_decode_block %.3f s (%zu bytes available, %llu bytes out)\n", nowSeconds() - tDec0,
             input->available(), (unsigned long long)out->len);
@@ -674,7 +674,7 @@ ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char
       return ROW_COUNT_ERR;
     default:
       statusOutput(ERROR, "%s: GPU decode failed: %s\n", exeName.empty() ? "UnconvertFromZDW" : exeName.c_str(),
-                   zdwb_last_error(gpu.get()));
+                   zdwb_last_error(g.get()));
       return PROCESSING_ERROR;
   }
 }
