@@ -78,7 +78,8 @@ int zdwb_ctx_set_stream(zdwb_ctx* ctx, void* cuda_stream);
  * (row-stream bytes per CTA in the decoder's row-boundary discovery), "dec_strip_rows" (rows per strip of the
  * decoder's row kernels, 0 = automatic), "dec_group_lanes" (lanes per row in those kernels: 8, 16, 32, 0 = by schema
  * width), "copy_gate" (0/1, default 1: host<->device copies of 8 MiB and more take turns with those of the
- * process's other contexts on the same device instead of sharing the link), "kernel_timing" (0/1).  Returns
+ * process's other contexts on the same device instead of sharing the link), "dec_emit_words" (0/1, default 0:
+ * experimental store pattern of the decoder's row writer, not yet measured), "kernel_timing" (0/1).  Returns
  * ZDWB_ERR_BAD_ARG for unknown names. */
 int zdwb_ctx_set_tuning(zdwb_ctx* ctx, const char* name, long long value);
 

@@ -1,4 +1,5 @@
 """GPU parity tests of the decoder: product (CUDA, through the C ABI) vs oracle, bit-exact."""
+import os
 import random
 
 import pytest
@@ -190,6 +191,29 @@ def test_roundtrip_property_large_random(ctx):
     got, _, _ = G.decode_file_with_product(ctx, img)
     assert got == tsv  # canonical numerics: lossless
     assert img == O.encode(sch, tsv).data
+
+
+@pytest.mark.skipif(not os.environ.get("ZDW_EXPERIMENTS"), reason="unmeasured kernel variants: set ZDW_EXPERIMENTS=1")
+@pytest.mark.parametrize("lanes", [0, 8, 16])
+def test_experimental_word_emit(ctx, lanes):
+    """k_dec_rows<.., WORDS = true> (knob dec_emit_words, off by default): cached texts stored as aligned words.
+    Written after the round's GPU minutes were spent - parity and timing are the first thing to check next session
+    (ZDW_EXPERIMENTS=1 pytest tests/test_gpu_decode.py -m gpu -k word_emit; tools/profile_one.py --sweep dec_emit_words=0,1)."""
+    ctx.set_tuning("dec_emit_words", 1)
+    ctx.set_tuning("dec_group_lanes", lanes)
+    try:
+        for case in FAST:
+            _check_case(ctx, case)
+        for name in ("analytics-hits", "movie_tickets"):
+            img = O.golden(f"{name}.zdw")
+            want = O.decode(img)
+            got, _, _ = G.decode_file_with_product(ctx, img)
+            assert got == want.tsv, f"{name}: {G.first_diff(got, want.tsv)}"
+        test_column_projection(ctx)
+        test_in_memory_layout_and_row_offsets(ctx)
+    finally:
+        ctx.set_tuning("dec_emit_words", 0)
+        ctx.set_tuning("dec_group_lanes", 0)
 
 
 @pytest.mark.parametrize("lanes", [8, 16, 32])

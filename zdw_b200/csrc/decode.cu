@@ -584,7 +584,10 @@ __device__ __forceinline__ WarpState warp_state(uint8_t* dsm, const WarpLayout& 
 // One group of G lanes per strip of RS rows.  WRITE = false: lengths only -> row_len[r].  WRITE = true: rows -> out.
 // G = 32 for wide schemas; with at most 8 (16) output items and flag bytes a warp walks 4 (2) strips side by side, so
 // that narrow tables do not leave three quarters of every warp idle.
-template <bool WRITE, int G>
+// WORDS (experiment, knob "dec_emit_words", off by default and not yet measured): a cached text goes out as head bytes
+// up to the next 4-byte boundary of the destination, aligned words funnel-shifted out of the cache, then tail bytes,
+// instead of byte by byte.
+template <bool WRITE, int G, bool WORDS = false>
 __global__ void __launch_bounds__(128, 10)
     k_dec_rows(const DecParams P, const FmtTables FT, const int32_t* __restrict__ u_item, const uint32_t* __restrict__ row_off,
                uint32_t RS, const WarpLayout L, const unsigned long long* __restrict__ cin, unsigned long long* __restrict__ row_len,
@@ -708,12 +711,33 @@ __global__ void __launch_bounds__(128, 10)
       // rendered text: 16 bytes in the cache, numbers up to 4 more in aux
       uint8_t* d = dst + __ldg(FT.item_pos + i) + S.ioff[i];
       const uint32_t* tw = S.textc + 4 * (size_t)i;
-      for (uint32_t k = 0; k < l; k += 4) {
-        const uint32_t x = k < 16u ? tw[k >> 2] : S.aux[i], nb = l - k;
-        d[k] = (uint8_t)x;
-        if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
-        if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
-        if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
+      if constexpr (WORDS) {
+        const uint32_t x4 = S.aux[i];  // characters 17..20 of a number (not read as text for anything shorter)
+        auto X = [&](uint32_t j) { return j < 4u ? tw[j] : x4; };
+        const uint32_t head = min(l, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u)) & 3u);
+        const uint32_t x0 = tw[0];
+        if (head > 0) d[0] = (uint8_t)x0;
+        if (head > 1) d[1] = (uint8_t)(x0 >> 8);
+        if (head > 2) d[2] = (uint8_t)(x0 >> 16);
+        const uint32_t rest = l - head, nw = rest >> 2, sh = head * 8u;
+        uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);  // 4-byte aligned by construction
+        for (uint32_t m = 0; m < nw; ++m) dw[m] = __funnelshift_r(X(m), X(min(m + 1u, 4u)), sh);
+        const uint32_t tail = rest & 3u;
+        if (tail) {
+          const uint32_t t = __funnelshift_r(X(nw), X(min(nw + 1u, 4u)), sh);
+          uint8_t* dt = d + head + 4u * nw;
+          dt[0] = (uint8_t)t;
+          if (tail > 1) dt[1] = (uint8_t)(t >> 8);
+          if (tail > 2) dt[2] = (uint8_t)(t >> 16);
+        }
+      } else {
+        for (uint32_t k = 0; k < l; k += 4) {
+          const uint32_t x = k < 16u ? tw[k >> 2] : S.aux[i], nb = l - k;
+          d[k] = (uint8_t)x;
+          if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
+          if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
+          if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
+        }
       }
     }
     __syncwarp(gm);
@@ -1255,13 +1279,17 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     const uint32_t per_cta = L.warps * GPW;
     const unsigned grid = (nstrips + per_cta - 1) / per_cta, block = 32 * L.warps;
     const size_t smem = (size_t)L.stride * per_cta;
-#define ZDWB_ROWS(W_, G_)                                                                                                  \
-  do {                                                                                                                     \
-    ZDWB_CUDA_TRY(ctx, (cudaFuncSetAttribute(k_dec_rows<W_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024))); \
-    k_dec_rows<W_, G_><<<grid, block, smem, st>>>(P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L,              \
-                                                  cin.as<unsigned long long>(), lens, offs, dst, meta);                    \
+#define ZDWB_ROWS(...)                                                                                                      \
+  do {                                                                                                                      \
+    ZDWB_CUDA_TRY(ctx, (cudaFuncSetAttribute(k_dec_rows<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024))); \
+    k_dec_rows<__VA_ARGS__><<<grid, block, smem, st>>>(P, FT, d_u_item.as<int32_t>(), row_off.as<uint32_t>(), R, L,          \
+                                                       cin.as<unsigned long long>(), lens, offs, dst, meta);                \
   } while (0)
-    if (write) {
+    if (write && ctx->dec_emit_words) {
+      if (G == 8) ZDWB_ROWS(true, 8, true);
+      else if (G == 16) ZDWB_ROWS(true, 16, true);
+      else ZDWB_ROWS(true, 32, true);
+    } else if (write) {
       if (G == 8) ZDWB_ROWS(true, 8);
       else if (G == 16) ZDWB_ROWS(true, 16);
       else ZDWB_ROWS(true, 32);
