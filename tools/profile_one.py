@@ -52,10 +52,11 @@ def main():
         name, vals = args.sweep.split("=")
         ctx.set_tuning("kernel_timing", 1)
         ref = None
+        ref_rows = None
         for v in [int(x) for x in vals.split(",")]:
             ctx.set_tuning(name, v)
             best = {}
-            for _ in range(3):
+            for it in range(3):
                 blk = ctx.encode_block(types, t.data_ptr(), n, input_on_device=True, output_on_device=True)
                 for k, (cnt, ms) in ctx.kernel_times().items():
                     best[k] = min(best.get(k, 1e9), ms)
@@ -65,9 +66,16 @@ def main():
                     ref = z[:blk.length].clone()
                 else:
                     assert ref.numel() == blk.length and bool((ref == z[:blk.length]).all()), "encoded block differs between knob values"
-                ctx.decode_block(types, z.data_ptr(), blk.length, input_on_device=True, output_on_device=True)
+                dec = ctx.decode_block(types, z.data_ptr(), blk.length, input_on_device=True, output_on_device=True)
                 for k, (cnt, ms) in ctx.kernel_times().items():
                     best[k] = min(best.get(k, 1e9), ms)
+                if it == 0:  # the decoded rows must not depend on the knob either
+                    rows_out = torch.empty(dec.length, dtype=torch.uint8, device=dev)
+                    bench._d2d(torch, rows_out, dec.dev_ptr, dec.length)
+                    if ref_rows is None:
+                        ref_rows = rows_out
+                    else:
+                        assert ref_rows.numel() == dec.length and bool((ref_rows == rows_out).all()), "decoded rows differ between knob values"
             enc = sum(ms for k, ms in best.items() if not k.startswith(("k_dec", "k_carry", "k_dict_nulmap")))
             top = sorted(best.items(), key=lambda kv: -kv[1])[:6]
             print(f"{name}={v}: sum_ms={sum(best.values()):.3f} " + " ".join(f"{k}={ms:.3f}" for k, ms in top), flush=True)
