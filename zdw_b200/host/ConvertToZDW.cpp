@@ -242,14 +242,19 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   if (!bStreamingInput) {
     struct stat st;
     regularInput = fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode);
-    if (regularInput && (unsigned long long)st.st_size < windowBytes) {
+    if (regularInput && st.st_size > 0 && (unsigned long long)st.st_size < windowBytes) {
       oneWindow = true;
       windowBytes = std::max((size_t)st.st_size + 1, (size_t)4096);  // + 1: the read that finds the end of the file
     }
   }
   if (oneWindow) {
+    const size_t configured = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
     if (!win.open(in, tee, windowBytes, plainAlloc, plainFree)) return OUT_OF_MEMORY;
     win.fill();
+    if (!win.eof()) {  // longer than stat() said (it grew, or the file system does not report sizes): the usual window
+      windowBytes = configured;
+      if (!win.widen(windowBytes)) return OUT_OF_MEMORY;
+    }
   }
   if (!gpu.open(gpuDevice)) {
     statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n", exeName, gpu.lastError().c_str());
