@@ -242,7 +242,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   if (!bStreamingInput) {
     struct stat st;
     regularInput = fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode);
-    if (regularInput && st.st_size > 0 && (unsigned long long)st.st_size < windowBytes) {
+    if (regularInput && (unsigned long long)st.st_size < windowBytes) {  // (0 = empty, or a file system without sizes)
       oneWindow = true;
       windowBytes = std::max((size_t)st.st_size + 1, (size_t)4096);  // + 1: the read that finds the end of the file
     }
