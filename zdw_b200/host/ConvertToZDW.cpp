@@ -1,6 +1,7 @@
 // ConvertToZDW.cpp -- see ConvertToZDW.h.  Reference behaviour cited as cplusplus/ConvertToZDW.cpp:<line>.
 #include "ConvertToZDW.h"
 
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
@@ -242,6 +243,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   if (!bStreamingInput) {
     struct stat st;
     regularInput = fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode);
+    if (regularInput) posix_fadvise(fileno(in), 0, 0, POSIX_FADV_SEQUENTIAL);  // read front to back, once per byte
     if (regularInput && (unsigned long long)st.st_size < windowBytes) {  // (0 = empty, or a file system without sizes)
       oneWindow = true;
       windowBytes = std::max((size_t)st.st_size + 1, (size_t)4096);  // + 1: the read that finds the end of the file
