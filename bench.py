@@ -183,6 +183,61 @@ def have_ref() -> bool:
     return (ref / "convertDWfile").exists() and (ref / "unconvertDWfile").exists() and (ref / "nocomp" / "gzip").exists()
 
 
+
+# --------------------------------------------------------------------------------------- parity gate
+def file_header_bytes(schema) -> bytes:
+    """v11 file header without metadata: version, metadata length, names, types, char sizes (ConvertToZDW.cpp:673-737)."""
+    hdr = (11).to_bytes(2, "little") + (0).to_bytes(4, "little")
+    for nme in schema.names:
+        hdr += (nme if isinstance(nme, bytes) else nme.encode("latin1")) + b"\0"
+    return hdr + b"\0" + bytes(schema.types) + b"".join(int(c).to_bytes(2, "little") for c in schema.charsize)
+
+
+def ref_encode_block(tsv_view, desc: bytes) -> bytes:
+    """The unmodified compiled reference (oracle/_ref/convertDWfile, compressor stage = cat) on one block of rows.
+    Returns its whole .zdw file (file header + one block)."""
+    scratch = scratch_dir()
+    try:
+        with open(scratch / "x.sql", "wb") as f:
+            f.write(tsv_view)
+        (scratch / "x.desc.sql").write_bytes(desc)
+        subprocess.run([str(ROOT / "oracle" / "_ref" / "convertDWfile"), "-q", "x.sql"], cwd=scratch, env=_ref_env(), check=True,
+                       capture_output=True)
+        return (scratch / "x.zdw.gz").read_bytes()
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
+def ref_decode_matches(image: bytes, expected_chunks) -> bool:
+    """oracle/_ref/unconvertDWfile of `image` to a pipe, compared on the fly with the expected rows (an iterable of
+    bytes-like chunks), so that no multi-GB TSV is ever held twice."""
+    scratch = scratch_dir()
+    try:
+        (scratch / "x.zdw").write_bytes(image)
+        p = subprocess.Popen([str(ROOT / "oracle" / "_ref" / "unconvertDWfile"), "-q", "-", "x.zdw"], cwd=scratch, env=_ref_env(),
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        ok = True
+        for chunk in expected_chunks:
+            mv = memoryview(chunk).cast("B")
+            pos = 0
+            while ok and pos < len(mv):
+                got = p.stdout.read(min(1 << 24, len(mv) - pos))
+                if not got or got != mv[pos:pos + len(got)]:
+                    ok = False
+                pos += len(got)
+            if not ok:
+                break
+        if ok and p.stdout.read(1):
+            ok = False
+        p.stdout.close()
+        if not ok:
+            p.kill()
+        rc = p.wait()
+        return ok and rc == 0
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
 def ref_parallel_step(synth: Synth, shard_rows: int, nproc: int, scratch: Path, inputs: list):
     """nproc independent reference processes, one shard each (the reference is single-threaded).
     Returns (enc_wall, dec_wall, total_tsv_bytes) with wall = slowest process."""
@@ -441,12 +496,65 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- parity gate: the first block must round-trip bit-exactly (every timing counts only if parity holds)
+    # ---- parity gate (SURVEY 8(d) "parity gate for every timing"): no number is printed unless it holds.
+    #  (0) decode(encode(block 0)) == block 0 on the device;
+    #  (a) every rank: the CUDA-encoded bytes of its first and last block == what the unmodified compiled reference
+    #      (oracle/_ref/convertDWfile) writes for the same rows;
+    #  (b) those blocks of ALL ranks, gathered on rank 0 and stitched in file order (isLast, cumulative longestLine:
+    #      ConvertToZDW.cpp:841-842,965), go through the reference's unconvertDWfile and must come back as the source rows.
     rt = ctx.decode_block(types, dev_zdw[0].data_ptr(), zdw_lens[0], input_on_device=True, output_on_device=True)
     back = torch.empty(rt.length, dtype=torch.uint8, device=dev)
     _d2d(torch, back, rt.dev_ptr, rt.length)
     if rt.length != host_lens[0] or not torch.equal(back, dev_tsv[0][:host_lens[0]]):
         raise SystemExit("parity gate failed: decode(encode(block 0)) != block 0")
+    del back
+    parity = {"zdw_vs_ref": None, "tsv_vs_ref": None, "blocks": 0, "self_roundtrip": True}
+    if args.no_parity:
+        parity["note"] = "--no-parity: reference comparison skipped (diagnostic run, not a bench value)"
+    elif not have_ref():
+        parity["note"] = "oracle/_ref missing on this box: only the device round trip was checked"
+    else:
+        from zdw_b200.shard import stitch_blocks
+        hdr = file_header_bytes(synth.schema)
+        check = sorted({0, len(my_blocks) - 1})
+
+        def _vs_ref(k):
+            view = (C.c_uint8 * host_lens[k]).from_address(host_ptrs[k])
+            ref_file = ref_encode_block(view, synth.desc)
+            return ref_file[:len(hdr)] == hdr and ref_file[len(hdr):] == host_zdw[k]
+        with ThreadPoolExecutor(max_workers=len(check)) as ex:
+            zdw_ok = all(ex.map(_vs_ref, check))
+        mine = [(my_blocks[k], host_zdw[k]) for k in check]
+        gathered = [mine]
+        if world > 1:
+            import torch.distributed as dist
+            gloo = dist.new_group(backend="gloo")
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(mine, gathered, dst=0, group=gloo)
+            flag = torch.tensor([1 if zdw_ok else 0], dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=gloo)
+            zdw_ok = bool(flag.item())
+        tsv_ok = True
+        if rank == 0:
+            allb = sorted(x for part in gathered for x in part)
+            image = stitch_blocks(hdr, [b for _, b in allb])
+
+            def _expected():
+                scratch_buf = (C.c_uint8 * cap)()
+                for bid, _ in allb:
+                    m = synth.block_into(bid, rows, C.addressof(scratch_buf), cap)
+                    yield memoryview(scratch_buf)[:m]
+            tsv_ok = ref_decode_matches(image, _expected())
+            parity.update({"zdw_vs_ref": zdw_ok, "tsv_vs_ref": tsv_ok, "blocks": len(allb),
+                           "checked": ("first and last block of every rank: CUDA bytes == oracle/_ref/convertDWfile bytes; the "
+                                       f"{len(allb)} blocks stitched in file order on rank 0 -> oracle/_ref/unconvertDWfile == source rows")})
+        if world > 1:
+            flag = torch.tensor([1 if (zdw_ok and tsv_ok) else 0], dtype=torch.int32)
+            dist.broadcast(flag, src=0, group=gloo)
+            if not flag.item():
+                raise SystemExit("parity gate failed: CUDA output differs from the reference (see rank 0)")
+        elif not (zdw_ok and tsv_ok):
+            raise SystemExit(f"parity gate failed: zdw_vs_ref={zdw_ok} tsv_vs_ref={tsv_ok}")
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -623,6 +731,7 @@ def run_cuda(args):
                     "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks), "pinned_decode_input": bool(dec_pinned) and not dec_keep,
                     "decode_d2h_bytes": int(d2h_dec_all)},
             "gpu_launches": int(launches_all),
+            "parity": parity,
             "clocks": clocks,
             "tsv_bytes": int(tot_tsv), "zdw_bytes": int(tot_zdw),
             "wall_s_timed_region": t_wall,
@@ -731,6 +840,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")
     ap.add_argument("--ref-procs", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the comparison with oracle/_ref (diagnostic runs only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
