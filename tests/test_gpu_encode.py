@@ -161,3 +161,58 @@ def test_reproduces_a_file_the_reference_cut_on_its_own(ctx):
     assert plan and any(spill for _, spill in plan)
     got = G.encode_file_with_product(ctx, sch, tsv, plan=plan)
     assert got == image, G.first_diff(got, image)
+
+
+@pytest.mark.parametrize("variant,p2_rows", [(1, 0), (1, 3), (1, 1), (0, 0)])
+def test_pass1_variants_forced(ctx, variant, p2_rows):
+    """Pass 1 has a row-delta variant (wide rows: only fields that differ from the row before are parsed and recorded)
+    and a general one; `enc_delta` forces either, `enc_p2_rows` the rows per pass-2 tile (small tiles: the carried-in
+    column values cross many tile borders).  Both must write the reference's bytes for every corpus case, the goldens,
+    multi-block cuts and block plans with spilled columns."""
+    ctx.set_tuning("enc_delta", variant)
+    ctx.set_tuning("enc_p2_rows", p2_rows)
+    try:
+        for case in CASES:
+            _check_case(ctx, case)
+        for name in ("test", "analytics-hits", "movie_tickets"):
+            if name == "movie_tickets" and p2_rows == 1:
+                continue  # 524 160 one-row tiles: covered by the other tile sizes
+            sch = O.parse_desc(O.golden(f"{name}.desc.sql"))
+            want = O.golden_to_v11(O.golden(f"{name}.zdw"))
+            got = G.encode_file_with_product(ctx, sch, O.golden(f"{name}.sql"))
+            assert got == want, f"{name}: {G.first_diff(got, want)}"
+        case = next(c for c in CASES if c[0] == "mixed_3000")
+        sch = O.parse_desc(case[1])
+        for rpb in (1, 7, 1000):
+            want = O.encode(sch, case[2], rows_per_block=rpb).data
+            got = G.encode_file_with_product(ctx, sch, case[2], rows_per_block=rpb)
+            assert got == want, f"rows_per_block {rpb}: {G.first_diff(got, want)}"
+        for plan in ([(1000, 3), (500, 1)], [(7, 8)], [(1, 1), (1, 9), (1, 4)]):
+            want = O.encode(sch, case[2], plan=plan).data
+            got = G.encode_file_with_product(ctx, sch, case[2], plan=plan)
+            assert got == want, f"plan {plan}: {G.first_diff(got, want)}"
+    finally:
+        ctx.set_tuning("enc_delta", -1)
+        ctx.set_tuning("enc_p2_rows", 0)
+
+
+def test_row_delta_falls_back_when_a_row_does_not_fit(ctx):
+    """A row with more non-empty fields than a warp's lists hold (and one longer than 64 KiB): the row-delta pass gives
+    the block back and the general pass encodes it - same bytes either way."""
+    ncols = 700
+    sch = O.parse_desc(corpus.desc([(f"c{i}", "varchar(8)" if i % 3 else "int(11)") for i in range(ncols)]))
+    rows = [b"\t".join(b"%d" % ((r * 7 + i) % 13 + 1) for i in range(ncols)) for r in range(40)]
+    tsv = b"\n".join(rows) + b"\n"
+    want = O.encode(sch, tsv).data
+    ctx.set_tuning("enc_delta", 1)
+    try:
+        got = G.encode_file_with_product(ctx, sch, tsv)
+        assert got == want, G.first_diff(got, want)
+        sch2 = O.parse_desc(corpus.desc([("a", "text"), ("b", "int(11)")]))
+        long_rows = b"x" * 70000 + b"\t5\n" + b"y\t6\n" * 10 + b"z" * 66000 + b"\t7\n"
+        want2 = O.encode(sch2, long_rows).data
+        ctx.set_tuning("enc_delta", 1)
+        got2 = G.encode_file_with_product(ctx, sch2, long_rows)
+        assert got2 == want2, G.first_diff(got2, want2)
+    finally:
+        ctx.set_tuning("enc_delta", -1)

@@ -42,6 +42,11 @@ struct Ctx {
   long long dec_tile_bytes = 8192;   // row-stream bytes per CTA in the decoder's row-boundary discovery
   unsigned long long last_out_per_row = 0;  // decoded bytes per row of the previous block (sizes the next output)
   unsigned long long last_unique = 0;  // dictionary size of the previous block (seeds the next hash set)
+  long long enc_delta = -1;            // pass 1 variant: 1 = row-delta, 0 = general, -1 = by row width (encode.cu)
+  long long enc_p2_rows = 0;           // rows per pass-2 tile (0 = automatic)
+  bool delta_bailed = false;           // a block of this context did not fit the row-delta pass: stop trying
+  unsigned long long last_row_bytes = 0;  // mean row length of the previous block
+  unsigned long long last_records = 0;    // records the previous block's row-delta pass 1 produced (sizes the next arrays)
   // outputs owned by the context (valid until the next call)
   void* out_dev = nullptr;     // device output buffer
   void* out_dev2 = nullptr;    // second device output (row offsets)

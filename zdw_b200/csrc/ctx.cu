@@ -84,6 +84,10 @@ int zdwb_ctx_set_tuning(zdwb_ctx* c, const char* name, long long value) {
   else if (!strcmp(name, "dec_emit_words")) c->dec_emit_words = value;
   else if (!strcmp(name, "dec_strip_rows")) c->dec_strip_rows = value;
   else if (!strcmp(name, "dec_group_lanes")) c->dec_group_lanes = value;
+  else if (!strcmp(name, "enc_delta")) {
+    c->enc_delta = value;
+    c->delta_bailed = false;
+  } else if (!strcmp(name, "enc_p2_rows")) c->enc_p2_rows = value;
   else if (!strcmp(name, "kernel_timing")) c->timing = value != 0;
   else return ZDWB_ERR_BAD_ARG;
   return ZDWB_OK;

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "carry.cuh"
 
 namespace zdwb {
 
@@ -284,51 +285,6 @@ __global__ void __launch_bounds__(DEC_THREADS)
     });
   }
   for (uint32_t u = threadIdx.x; u < P.U; u += DEC_THREADS) shas[(size_t)blockIdx.x * P.U + u] = last_row[u] >= 0 ? 1 : 0;
-}
-
-// carry propagation over strips, per used column: "select the last explicit value" is associative
-__global__ void k_carry_reduce(const unsigned long long* __restrict__ sval, const uint8_t* __restrict__ shas,
-                               uint32_t nstrips, uint32_t U, uint32_t S, unsigned long long* __restrict__ seg_val,
-                               uint8_t* __restrict__ seg_has) {
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
-  if (u >= U) return;
-  const uint32_t sb = seg * S, se = min(nstrips, sb + S);
-  unsigned long long v = 0;
-  uint8_t h = 0;
-  for (uint32_t s = sb; s < se; ++s) {
-    if (shas[(size_t)s * U + u]) {
-      v = sval[(size_t)s * U + u];
-      h = 1;
-    }
-  }
-  seg_val[(size_t)seg * U + u] = v;
-  seg_has[(size_t)seg * U + u] = h;
-}
-
-__global__ void k_carry_scan(unsigned long long* __restrict__ seg_val, const uint8_t* __restrict__ seg_has, uint32_t nseg,
-                             uint32_t U) {
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  unsigned long long v = 0;  // columnVal starts at 0 in every block: UnconvertFromZDW.cpp:985-986
-  for (uint32_t s = 0; s < nseg; ++s) {
-    const unsigned long long mine = seg_val[(size_t)s * U + u];
-    const uint8_t h = seg_has[(size_t)s * U + u];
-    seg_val[(size_t)s * U + u] = v;  // becomes the carry-in of the segment
-    if (h) v = mine;
-  }
-}
-
-__global__ void k_carry_apply(const unsigned long long* __restrict__ sval, const uint8_t* __restrict__ shas,
-                              const unsigned long long* __restrict__ seg_cin, uint32_t nstrips, uint32_t U, uint32_t S,
-                              unsigned long long* __restrict__ cin) {
-  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
-  if (u >= U) return;
-  const uint32_t sb = seg * S, se = min(nstrips, sb + S);
-  unsigned long long v = seg_cin[(size_t)seg * U + u];
-  for (uint32_t s = sb; s < se; ++s) {
-    cin[(size_t)s * U + u] = v;
-    if (shas[(size_t)s * U + u]) v = sval[(size_t)s * U + u];
-  }
 }
 
 // ---------------------------------------------------------------------------------------------

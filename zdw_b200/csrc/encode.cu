@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "carry.cuh"
 
 namespace zdwb {
 
@@ -56,7 +57,9 @@ struct EncMeta {
   uint64_t rows_base;
   unsigned long long rows_bytes;
   uint32_t compact_count;
-  uint32_t pad;
+  uint32_t rec_count;      // delta path: records handed out so far (atomic bump allocator)
+  uint32_t rec_overflow;   // ... the record arrays were too small: retry with larger ones
+  uint32_t delta_bail;     // ... a row does not fit the warp's lists: the block goes through the general pass 1
   // census totals
   uint32_t tot_rows, tot_tabs, tot_ne, last_break_p1;
   // block cut (max_rows)
@@ -71,6 +74,8 @@ struct TileAgg {
   uint32_t rows, tabs, ne;
   uint32_t bound_p1;   // position + 1 of the last boundary (separator, terminator, blank-line newline); 0 = none
   uint32_t break_p1;   // position + 1 of the last row break (terminator or blank-line newline); 0 = none
+  uint32_t rs_p1;      // position + 1 of the last row START (first byte of a non-blank line); 0 = none.  Only the
+                       // row census of the delta path (k_row_census) fills it in
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
     a.ne = ne;
     a.bound_p1 = last_b >= 0 ? (uint32_t)(t0 + last_b + 1) : 0u;
     a.break_p1 = last_r >= 0 ? (uint32_t)(t0 + last_r + 1) : 0u;
+    a.rs_p1 = 0u;
     agg[tile] = a;
   }
 }
@@ -294,6 +300,7 @@ __device__ __forceinline__ TileAgg agg_join(const TileAgg& a, const TileAgg& b) 
   r.ne = a.ne + b.ne;
   r.bound_p1 = max(a.bound_p1, b.bound_p1);
   r.break_p1 = max(a.break_p1, b.break_p1);
+  r.rs_p1 = max(a.rs_p1, b.rs_p1);
   return r;
 }
 __device__ __forceinline__ TileAgg agg_shfl_up(const TileAgg& a, int o) {
@@ -303,12 +310,13 @@ __device__ __forceinline__ TileAgg agg_shfl_up(const TileAgg& a, int o) {
   r.ne = __shfl_up_sync(0xffffffffu, a.ne, o);
   r.bound_p1 = __shfl_up_sync(0xffffffffu, a.bound_p1, o);
   r.break_p1 = __shfl_up_sync(0xffffffffu, a.break_p1, o);
+  r.rs_p1 = __shfl_up_sync(0xffffffffu, a.rs_p1, o);
   return r;
 }
 __global__ void __launch_bounds__(TS_THREADS) k_tile_scan(TileAgg* __restrict__ agg, uint32_t ntiles, EncMeta* __restrict__ meta) {
   __shared__ TileAgg wsum[32];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const TileAgg zero = {0u, 0u, 0u, 0u, 0u};
+  const TileAgg zero = {0u, 0u, 0u, 0u, 0u, 0u};
   TileAgg carry = zero;  // everything in front of the current round of 1024 tiles
   for (uint32_t base = 0; base < ntiles; base += TS_THREADS) {
     const uint32_t t = base + threadIdx.x;
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(TS_THREADS) k_tile_scan(TileAgg* __restrict__ 
 __global__ void __launch_bounds__(TS_THREADS) k_tile_scan_local(TileAgg* __restrict__ agg, uint32_t ntiles, TileAgg* __restrict__ part) {
   __shared__ TileAgg wsum[32];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const TileAgg zero = {0u, 0u, 0u, 0u, 0u};
+  const TileAgg zero = {0u, 0u, 0u, 0u, 0u, 0u};
   const uint32_t t = blockIdx.x * TS_THREADS + threadIdx.x;
   const TileAgg mine = t < ntiles ? agg[t] : zero;
   TileAgg inc = mine;
@@ -386,8 +394,8 @@ __global__ void __launch_bounds__(TS_THREADS) k_tile_scan_add(TileAgg* __restric
 }
 
 // one warp: terminator of row `want` (0-based) -> meta->cut_end_p1, first byte of the next row -> meta->next_start
-__global__ void k_find_cut(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, const TileAgg* __restrict__ pre,
-                           uint32_t want, EncMeta* __restrict__ meta) {
+__global__ void k_find_cut(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, uint32_t tile_bytes,
+                           const TileAgg* __restrict__ pre, uint32_t want, EncMeta* __restrict__ meta) {
   // largest tile whose exclusive row prefix is <= want
   uint32_t a = 0, b = ntiles;
   while (b - a > 1) {
@@ -395,10 +403,10 @@ __global__ void k_find_cut(const uint8_t* __restrict__ buf, uint64_t n, int64_t 
     if (pre[m].rows <= want) a = m;
     else b = m;
   }
-  const int64_t t0 = lo + (int64_t)a * TILE;
+  const int64_t t0 = lo + (int64_t)a * tile_bytes;
   WarpCarry c;
   carry_init(buf, t0, pre[a], c);
-  for (uint32_t s = 0; s < TILE; s += STEP) {
+  for (uint32_t s = 0; s < tile_bytes; s += STEP) {
     const LaneStep L = scan_step(buf, (int64_t)n, t0 + s, c);
     uint32_t t = L.term;
     while (t) {
@@ -662,7 +670,9 @@ __device__ __forceinline__ void note_column_value(const P1Args& A, uint32_t col,
   }
 }
 
-// one text, any length, by a single lane: words streamed four at a time through a funnel shift
+// one text, any length, by a single lane: words streamed four at a time through a funnel shift.  The record's value is
+// the string's hash-set slot + BIAS (the delta path uses BIAS = 1 so that 0 can mean "the field became empty")
+template <uint32_t BIAS = 0>
 __device__ __forceinline__ void text_one(const P1Args& A, const uint32_t* wlast, uint32_t start, uint32_t len, uint32_t col,
                                             uint32_t ord, P1Stats& st) {
   const uint32_t nw = (len + 3u) >> 2;
@@ -744,7 +754,7 @@ __device__ __forceinline__ void text_one(const P1Args& A, const uint32_t* wlast,
     i = 0;
   }
   A.rec_col[ord] = col;
-  A.rec_val[ord] = i;
+  A.rec_val[ord] = (unsigned long long)i + BIAS;
   note_column_set(A, col);
   if (is_new) note_new_string(st, len);
 }
@@ -969,6 +979,523 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_pass1(const P1Args A) {
       atomicAdd(&A.meta->n_unique, (unsigned long long)st.new_count);
       atomicAdd(&A.meta->dict_str_bytes, st.new_bytes);
       atomicMax(&A.meta->max_str_len, st.max_len);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1, row-delta variant (wide rows)
+//
+// The reference parses every field of every row twice (parseInput ConvertToZDW.cpp:329-414, writeBlockRows :486-606).
+// What its output depends on is much less: a field whose bytes equal the bytes of the same column in the row before
+// has the same value as that row - it is in the dictionary already, inside the column's min/max already, and pass 2 will
+// find it equal to the previous value (:532,548,567) and emit nothing.  On analytics-shaped rows (config C3/C4) 84 % of
+// the non-empty cells are such repeats.  This variant therefore works on ROWS: a warp owns the rows that start inside
+// its tile, reads the row in front of its first one as a reference, and for every row compares each non-empty field with
+// the same column of the previous row (column -> field through a non-empty bitmap and its rank prefix).  Only fields that
+// CHANGED are parsed / inserted into the hash set, and only they - plus columns that went from a value to empty - leave
+// a record (column, value) for pass 2.  A block starts from all-empty columns (:504-505), so the first row is compared
+// with an empty row and every distinct field of the block is seen as "changed" at least once.
+//
+// Byte classification is the same as scan_step's (escape parity, blank lines); positions of the non-empty fields come
+// out of it without any search: the k-th field START (a content byte behind a boundary) pairs with the k-th CLOSING
+// delimiter behind a content byte, so both are dropped into per-row lists at their ordinals.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t DTILE = 32768;       // bytes of TSV whose row starts one warp owns
+constexpr uint32_t DCAP = 288;          // non-empty fields of a row a warp can hold (else: delta_bail)
+constexpr uint32_t DBW = 128;           // bitmap words per row: up to 4096 columns
+constexpr uint32_t DELTA_MAX_COLS = DBW * 32;
+constexpr int D1_WARPS = 4;
+constexpr int D1_THREADS = D1_WARPS * 32;
+
+struct D1Warp {
+  uint16_t S[2][DCAP];   // first byte of the k-th non-empty field, relative to the row start
+  uint16_t E[2][DCAP];   // its closing delimiter, relative to the row start
+  uint16_t C[DCAP];      // its column (current row only)
+  uint16_t PF[2][DBW];   // fields in front of bitmap word w
+  uint32_t BM[2][DBW];   // bit c = column c of the row is non-empty
+  P1Side Q[2];           // changed fields waiting for the full treatment: [0] numbers / CHAR cells, [1] texts
+};
+
+struct D1Args {
+  P1Args P;              // buf, n, lo, limit, ncols, types, trim, hash set, column statistics, rec_col / rec_val, meta
+  uint32_t ntiles;       // tiles of DTILE bytes
+  uint32_t nrows;        // rows of the block: records of rows beyond it (the spilled row) are dropped
+  uint32_t rec_cap;      // capacity of rec_col / rec_val; slot rec_cap itself takes the dropped records
+  uint32_t* row_cnt;     // [nrows] records of row r; they start at P.row_rec[r]
+};
+
+// Row census of the delta path: per tile the number of row terminators, the last row break and the last row start.
+// Only newlines (and a backslash in front of one) matter, so the pass runs at the speed of the read.
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_row_census(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, uint32_t tile_bytes, TileAgg* __restrict__ agg) {
+  const uint32_t tile = blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+  if (tile >= ntiles) return;
+  const unsigned lane = lane_id();
+  const int64_t t0 = lo + (int64_t)tile * tile_bytes, limit = (int64_t)n;
+  uint32_t c_nl = t0 <= 0 ? 1u : (is_unescaped_newline(buf, t0 - 1) ? 1u : 0u);
+  uint32_t rows = 0;
+  int32_t last_r = -1, last_s = -1;
+  for (uint32_t s = 0; s < tile_bytes; s += STEP) {
+    const int64_t p0 = t0 + s + 16 * (int64_t)lane;
+    uint32_t nl = 0, in = 0;
+    if (p0 < limit && p0 + 16 > 0) {
+      const uint4 v = ldg_stream_u4(buf + p0);
+      const int64_t ia = p0 < 0 ? -p0 : 0;
+      const int64_t ib = p0 + 16 > limit ? limit - p0 : 16;
+      in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
+      if (chunk_has(v, '\n')) {
+        nl = chunk_mask(v, '\n') & in;
+        uint32_t m = nl;
+        while (m) {  // escape parity (getnextrow.cpp:44-53): rare, walked byte by byte
+          const int i = __ffs(m) - 1;
+          m &= m - 1;
+          if (odd_backslashes_before(buf, p0 + i)) nl &= ~(1u << i);
+        }
+      }
+    }
+    uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
+    if (lane == 0) prevnl = c_nl;
+    uint32_t after_nl = ((nl << 1) | prevnl) & 0xffffu;
+    if (p0 <= 0 && p0 + 16 > 0) after_nl |= 1u << (-p0);
+    const uint32_t skip = nl & after_nl, term = nl & ~skip, rs = after_nl & ~nl & in;
+    rows += (uint32_t)__popc(term);
+    if (nl) last_r = (int32_t)(s + 16u * lane) + (31 - __clz(nl));
+    if (rs) last_s = (int32_t)(s + 16u * lane) + (31 - __clz(rs));
+    c_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
+  }
+  rows = __reduce_add_sync(0xffffffffu, rows);
+  last_r = __reduce_max_sync(0xffffffffu, last_r);
+  last_s = __reduce_max_sync(0xffffffffu, last_s);
+  if (lane == 0) {
+    TileAgg a;
+    a.rows = rows;
+    a.tabs = 0;
+    a.ne = 0;
+    a.break_p1 = last_r >= 0 ? (uint32_t)(t0 + last_r + 1) : 0u;
+    a.bound_p1 = a.break_p1;
+    a.rs_p1 = last_s >= 0 ? (uint32_t)(t0 + last_s + 1) : 0u;
+    agg[tile] = a;
+  }
+}
+
+// lane's 16-bit mask of the step's bit positions >= a / <= b (positions 0..511, lane l holds 16 l .. 16 l + 15)
+__device__ __forceinline__ uint32_t lane_bits_ge(int32_t a, unsigned lane) {
+  const int32_t lo = a - (int32_t)(lane * 16u);
+  return lo <= 0 ? 0xffffu : (lo >= 16 ? 0u : ((0xffffu << lo) & 0xffffu));
+}
+__device__ __forceinline__ uint32_t lane_bits_le(int32_t b, unsigned lane) {
+  const int32_t hi = b - (int32_t)(lane * 16u);
+  return hi < 0 ? 0u : (hi >= 15 ? 0xffffu : ((2u << hi) - 1u));
+}
+
+// do the `len` bytes at a and b differ?  (aligned word loads + funnel shifts; nothing past *wlast is read)
+__device__ __forceinline__ bool bytes_differ(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len,
+                                             const uint32_t* wlast) {
+  const uintptr_t ua = reinterpret_cast<uintptr_t>(a), ub = reinterpret_cast<uintptr_t>(b);
+  const uint32_t* wa = reinterpret_cast<const uint32_t*>(ua & ~(uintptr_t)3);
+  const uint32_t* wb = reinterpret_cast<const uint32_t*>(ub & ~(uintptr_t)3);
+  const uint32_t sa = (uint32_t)(ua & 3u) * 8u, sb = (uint32_t)(ub & 3u) * 8u;
+  uint32_t pa = __ldg(wa), pb = __ldg(wb);
+  const uint32_t nw = (len + 3u) >> 2;
+  uint32_t diff = 0;
+  for (uint32_t k = 0; k < nw && diff == 0u; ++k) {
+    const uint32_t* qa = wa + k + 1;
+    const uint32_t* qb = wb + k + 1;
+    const uint32_t na = __ldg(qa <= wlast ? qa : wlast), nb = __ldg(qb <= wlast ? qb : wlast);
+    uint32_t x = __funnelshift_r(pa, na, sa) ^ __funnelshift_r(pb, nb, sb);
+    pa = na;
+    pb = nb;
+    const uint32_t rem = len - 4u * k;
+    if (rem < 4u) x &= (1u << (8u * rem)) - 1u;
+    diff = x;
+  }
+  return diff != 0u;
+}
+
+// changed numbers / CHAR cells, `take` <= 32 of them from the ring: value, record, column range (the numeric branch of
+// p1_process)
+__device__ __forceinline__ void d1_numbers(const P1Args& A, const uint32_t* wlast, P1Side& S, uint32_t take) {
+  const unsigned lane = lane_id();
+  const uint32_t head = S.done;
+  if (lane < take) {
+    const uint32_t e = (head + lane) & (SQ - 1u);
+    const uint32_t start = S.start[e], len = S.len[e], col = S.col[e], ord = S.ord[e];
+    const uint8_t t = __ldg(A.types + col);
+    unsigned long long v1, v2;
+    if (len <= NUM_FAST_MAX || t == ZDWB_CHAR) {
+      uint32_t x[5];
+      short_words<5>(A.buf + start, len, wlast, x);
+      if (t == ZDWB_CHAR) {  // ConvertToZDW.cpp:358-361 (range), :543-547 (stored value)
+        const long long b0 = (long long)(int8_t)(x[0] & 0xffu);
+        const long long b1 = len > 1 ? (long long)((int32_t)(int8_t)((x[0] >> 8) & 0xffu) * 256) : 0ll;
+        v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
+        v2 = (unsigned long long)(b0 + b1);
+      } else {
+        if (!fast_number(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);
+        v2 = v1;
+      }
+    } else {
+      v1 = v2 = parse_u64_field(A.buf + start, len);
+    }
+    A.rec_col[ord] = col;
+    A.rec_val[ord] = v2;
+    note_column_value(A, col, v1);
+  }
+  __syncwarp();
+  if (lane == 0) S.done = head + take;
+  __syncwarp();
+}
+__device__ __forceinline__ void d1_texts(const P1Args& A, const uint32_t* wlast, P1Side& S, uint32_t take, P1Stats& st) {
+  const unsigned lane = lane_id();
+  const uint32_t head = S.done;
+  if (lane < take) {
+    const uint32_t e = (head + lane) & (SQ - 1u);
+    text_one<1>(A, wlast, S.start[e], S.len[e], S.col[e], S.ord[e], st);
+  }
+  __syncwarp();
+  if (lane == 0) S.done = head + take;
+  __syncwarp();
+}
+
+// The open row is complete (n fields in the lists of `cur`): bitmap + rank prefix; unless it is the reference row,
+// compare with the row before (lists of cur ^ 1), hand out the records and queue the changed fields.
+// r = row number, or >= A.nrows for the spilled row (its records are dropped, its strings and numbers still count).
+__device__ __forceinline__ void d1_finish_row(const D1Args& A, const uint32_t* wlast, D1Warp& W, uint32_t cur, uint32_t n,
+                                              int64_t row_start, int64_t prev_start, bool reference, uint32_t r, P1Stats& st) {
+  const P1Args& P = A.P;
+  const unsigned lane = lane_id();
+  const uint32_t BW = (P.ncols + 31u) >> 5, prv = cur ^ 1u;
+  // ---- -t: trailing spaces do not belong to a field; a field of spaces only is an empty one (ConvertToZDW.cpp:295-313)
+  if (P.trim) {
+    uint32_t kept = 0;
+    for (uint32_t k0 = 0; k0 < n; k0 += 32u) {
+      const uint32_t k = k0 + lane;
+      uint32_t s = 0, e = 0, c = 0;
+      if (k < n) {
+        s = W.S[cur][k];
+        e = W.E[cur][k];
+        c = W.C[k];
+        while (e > s && __ldg(P.buf + row_start + e - 1) == (uint8_t)' ') --e;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, e > s);
+      __syncwarp();
+      if (e > s) {
+        const uint32_t d = kept + (uint32_t)__popc(m & lanemask_lt());
+        W.S[cur][d] = (uint16_t)s;
+        W.E[cur][d] = (uint16_t)e;
+        W.C[d] = (uint16_t)c;
+      }
+      kept += (uint32_t)__popc(m);
+      __syncwarp();
+    }
+    n = kept;
+  }
+  // ---- bitmap of the non-empty columns: the fields are in column order, so fields of one bitmap word sit side by
+  // side; a segmented OR along the lanes leaves the word's bits in the last lane of its run
+  for (uint32_t w = lane; w < BW; w += 32u) W.BM[cur][w] = 0u;
+  __syncwarp();
+  for (uint32_t k0 = 0; k0 < n; k0 += 32u) {
+    const uint32_t k = k0 + lane;
+    const bool valid = k < n;
+    const uint32_t col = valid ? (uint32_t)W.C[k] : 0xffffffffu;
+    const uint32_t w = col >> 5;
+    uint32_t v = valid ? 1u << (col & 31u) : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t uv = __shfl_up_sync(0xffffffffu, v, o), uw = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= (unsigned)o && uw == w) v |= uv;
+    }
+    const uint32_t nw = __shfl_down_sync(0xffffffffu, w, 1);
+    if (valid && (lane == 31u || nw != w)) W.BM[cur][w] |= v;  // one lane per word and batch; batches run in turn
+    __syncwarp();
+  }
+  // ---- rank prefix: fields in front of every bitmap word
+  {
+    uint32_t run = 0;
+    for (uint32_t w0 = 0; w0 < BW; w0 += 32u) {
+      const uint32_t w = w0 + lane;
+      const uint32_t c = w < BW ? (uint32_t)__popc(W.BM[cur][w]) : 0u;
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      if (w < BW) W.PF[cur][w] = (uint16_t)(run + inc - c);
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncwarp();
+  if (reference) return;
+
+  // ---- which fields changed?  batch b's verdicts are kept by lane b
+  uint32_t my_mask = 0, nchg = 0;
+  for (uint32_t k0 = 0, b = 0; k0 < n; k0 += 32u, ++b) {
+    const uint32_t k = k0 + lane;
+    bool changed = false;
+    if (k < n) {
+      const uint32_t s = W.S[cur][k], len = (uint32_t)W.E[cur][k] - s, col = W.C[k];
+      const uint32_t pw = W.BM[prv][col >> 5], bit = col & 31u;
+      changed = true;
+      if ((pw >> bit) & 1u) {
+        const uint32_t j = (uint32_t)W.PF[prv][col >> 5] + (uint32_t)__popc(pw & ((1u << bit) - 1u));
+        const uint32_t ps = W.S[prv][j], pl = (uint32_t)W.E[prv][j] - ps;
+        if (pl == len) changed = bytes_differ(P.buf + row_start + s, P.buf + prev_start + ps, len, wlast);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, changed);
+    if (lane == b) my_mask = m;
+    nchg += (uint32_t)__popc(m);
+  }
+  // ---- columns that had a value in the row before and are empty now
+  uint32_t nte = 0;
+  for (uint32_t w = lane; w < BW; w += 32u) nte += (uint32_t)__popc(W.BM[prv][w] & ~W.BM[cur][w]);
+  nte = __reduce_add_sync(0xffffffffu, nte);
+  const uint32_t cnt = nchg + nte;
+  // ---- records of the row: one bump allocation
+  uint32_t base = 0;
+  if (lane == 0 && cnt && r < A.nrows) base = atomicAdd(&P.meta->rec_count, cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  bool drop = r >= A.nrows;
+  if (!drop && cnt && (base > A.rec_cap || cnt > A.rec_cap - base)) {
+    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&P.meta->rec_overflow) = 1u;
+    drop = true;
+  }
+  if (r < A.nrows && lane == 0) {
+    P.row_rec[r] = base;
+    A.row_cnt[r] = drop ? 0u : cnt;
+  }
+  // ---- "became empty" records: (column, 0)
+  if (nte && !drop) {
+    uint32_t run = 0;
+    for (uint32_t w0 = 0; w0 < BW; w0 += 32u) {
+      const uint32_t w = w0 + lane;
+      uint32_t x = w < BW ? (W.BM[prv][w] & ~W.BM[cur][w]) : 0u;
+      const uint32_t c = (uint32_t)__popc(x);
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      uint32_t at = base + run + inc - c;
+      while (x) {
+        const uint32_t bit = (uint32_t)__ffs(x) - 1u;
+        x &= x - 1u;
+        P.rec_col[at] = w * 32u + bit;
+        P.rec_val[at] = 0ull;
+        ++at;
+      }
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  // ---- changed fields: to the number / text rings, each with the record it fills; full batches are worked off
+  uint32_t at = base + nte;
+  for (uint32_t k0 = 0, b = 0; k0 < n; k0 += 32u, ++b) {
+    const unsigned m = __shfl_sync(0xffffffffu, my_mask, (int)b);
+    if (!m) continue;
+    const uint32_t k = k0 + lane;
+    const bool mine = (m >> lane) & 1u;
+    uint32_t start = 0, len = 0, col = 0;
+    bool text = false;
+    if (mine) {
+      const uint32_t s = W.S[cur][k];
+      start = (uint32_t)(row_start + s);
+      len = (uint32_t)W.E[cur][k] - s;
+      col = W.C[k];
+      text = is_text_like(__ldg(P.types + col));
+    }
+    const uint32_t ord = drop ? A.rec_cap : at + (uint32_t)__popc(m & lanemask_lt());
+    at += (uint32_t)__popc(m);
+    const uint32_t wn = side_push(W.Q[0], mine && !text, start, len, col, ord);
+    if (wn >= 32u) d1_numbers(P, wlast, W.Q[0], 32u);
+    const uint32_t wt = side_push(W.Q[1], mine && text, start, len, col, ord);
+    if (wt >= 32u) d1_texts(P, wlast, W.Q[1], 32u, st);
+  }
+}
+
+__global__ void __launch_bounds__(D1_THREADS, 8) k_pass1d(const D1Args A) {
+  __shared__ D1Warp sw[D1_WARPS];
+  const P1Args& P = A.P;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x * D1_WARPS + warp;
+  if (tile >= A.ntiles) return;
+  const int64_t t0 = P.lo + (int64_t)tile * DTILE;
+  if (t0 >= P.limit) return;
+  const int64_t tile_end = t0 + DTILE;
+  D1Warp& W = sw[warp];
+  const uint32_t* wlast = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.buf + P.n - 1) & ~(uintptr_t)3);
+  const TileAgg pre = P.pre[tile];
+  const uint32_t BW = (P.ncols + 31u) >> 5;
+  // the row in front of the tile's first row (if there is one) is read as the reference the first row is compared with
+  const bool have_prev = pre.rs_p1 != 0u;
+  const int64_t scan_from = have_prev ? (int64_t)pre.rs_p1 - 1 : (t0 > 0 ? t0 : 0);
+  for (uint32_t w = lane; w < BW; w += 32u) W.BM[0][w] = W.BM[1][w] = 0u;  // "the row before" of a block's first row is empty
+  if (lane < 2) W.Q[lane].end = W.Q[lane].done = 0u;
+  __syncwarp();
+  P1Stats st = {0u, 0u, 0u, 0ull};
+  const uint32_t tabs_per_row = P.ncols - 1u;
+
+  uint32_t cur = 0;
+  bool row_open = false, reference = false;
+  int64_t row_start = 0, prev_start = 0;
+  uint32_t n_st = 0, n_ne = 0, tabs = 0, row_no = 0, rows_seen = 0;
+  uint32_t c_bs = 0, c_nl = 1, c_bd = 1;  // the scan starts at a row start: behind a row break, no backslash pending
+  bool bail = false;
+
+  int64_t sb = scan_from - ((scan_from - P.lo) & 15);  // step positions are 16-byte aligned in memory
+  for (bool first = true; sb < P.limit && !bail; sb += STEP, first = false) {
+    if (!row_open && sb >= tile_end) break;
+    const int64_t p0 = sb + 16 * (int64_t)lane;
+    uint32_t tab = 0, nl = 0, bs = 0, in = 0;
+    if (p0 < P.limit && p0 + 16 > scan_from) {
+      const uint4 v = ldg_stream_u4(P.buf + p0);
+      const int64_t ia = p0 < scan_from ? scan_from - p0 : 0;
+      const int64_t ib = p0 + 16 > P.limit ? P.limit - p0 : 16;
+      in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
+      tab = chunk_mask(v, '\t') & in;
+      if (chunk_has(v, '\n')) nl = chunk_mask(v, '\n') & in;
+      if (chunk_has(v, '\\')) bs = chunk_mask(v, '\\') & in;
+    }
+    {  // escape parity: only delimiters that directly follow a backslash need the backward walk
+      uint32_t prev = __shfl_up_sync(0xffffffffu, bs >> 15, 1);
+      if (lane == 0) prev = c_bs;
+      uint32_t sus = (tab | nl) & ((bs << 1) | prev);
+      while (sus) {
+        const int i = __ffs(sus) - 1;
+        sus &= sus - 1;
+        if (odd_backslashes_before(P.buf, p0 + i)) {
+          tab &= ~(1u << i);
+          nl &= ~(1u << i);
+        }
+      }
+    }
+    const uint32_t fix = (first && p0 <= scan_from && p0 + 16 > scan_from) ? 1u << (scan_from - p0) : 0u;
+    uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
+    if (lane == 0) prevnl = first ? 0u : c_nl;
+    const uint32_t after_nl = (((nl << 1) | prevnl) & 0xffffu) | fix;
+    const uint32_t skip = nl & after_nl, term = nl & ~skip, bound = tab | nl;
+    uint32_t prevbd = __shfl_up_sync(0xffffffffu, bound >> 15, 1);
+    if (lane == 0) prevbd = first ? 0u : c_bd;
+    const uint32_t after_bound = (((bound << 1) | prevbd) & 0xffffu) | fix;
+    const uint32_t ne = (tab | term) & ~after_bound;   // closing delimiters of non-empty fields
+    const uint32_t fs = after_bound & ~bound & in;      // first bytes of non-empty fields
+    const uint32_t rs = after_nl & ~nl & in;            // first bytes of rows
+    c_bs = __shfl_sync(0xffffffffu, bs >> 15, 31);
+    c_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
+    c_bd = __shfl_sync(0xffffffffu, bound >> 15, 31);
+
+    // ---- walk the step's events in order: a row start opens a row, a terminator completes it
+    const bool plain = row_open && __ballot_sync(0xffffffffu, nl != 0u) == 0u;  // the usual step of a wide row
+    int32_t cursor = 0;
+    for (;;) {
+      if (!row_open) {
+        const uint32_t m = rs & lane_bits_ge(cursor, lane);
+        const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+        if (!b) break;
+        const int src = __ffs(b) - 1;
+        const int32_t pos = src * 16 + (__ffs(__shfl_sync(0xffffffffu, m, src)) - 1);
+        const int64_t start_abs = sb + pos;
+        if (start_abs >= tile_end) {  // the next warp's row: done
+          sb = P.limit;
+          break;
+        }
+        row_open = true;
+        reference = start_abs < t0;
+        row_start = start_abs;
+        row_no = pre.rows + rows_seen;
+        n_st = n_ne = tabs = 0;
+        cursor = pos;
+      }
+      int32_t seg_end = 511;
+      bool ends = false;
+      if (!plain) {
+        const uint32_t m = term & lane_bits_ge(cursor, lane);
+        const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+        if (b) {
+          const int src = __ffs(b) - 1;
+          seg_end = src * 16 + (__ffs(__shfl_sync(0xffffffffu, m, src)) - 1);
+          ends = true;
+        }
+      }
+      // ---- the fields of [cursor, seg_end] go to the row's lists at their ordinals
+      {
+        const uint32_t seg = plain ? 0xffffu : (lane_bits_ge(cursor, lane) & lane_bits_le(seg_end, lane));
+        uint32_t s_ = fs & seg, e_ = ne & seg;
+        const uint32_t t_ = tab & seg;
+        const uint32_t mine = (uint32_t)__popc(s_) | ((uint32_t)__popc(e_) << 10) | ((uint32_t)__popc(t_) << 20);
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= (unsigned)o) inc += t;
+        }
+        const uint32_t ex = inc - mine, tot = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t os = n_st + (ex & 1023u), oe = n_ne + ((ex >> 10) & 1023u);
+        const uint32_t tb = tabs + (ex >> 20);
+        // does everything fit?  (field positions are 16-bit, relative to the row start)
+        if (n_st + (tot & 1023u) > DCAP || sb + 512 - row_start > 65535) {
+          bail = true;
+          break;
+        }
+        const uint32_t rel0 = (uint32_t)(p0 - row_start);
+        while (s_) {
+          const uint32_t i = (uint32_t)__ffs(s_) - 1u;
+          s_ &= s_ - 1u;
+          W.S[cur][os++] = (uint16_t)(rel0 + i);
+        }
+        while (e_) {
+          const uint32_t i = (uint32_t)__ffs(e_) - 1u;
+          e_ &= e_ - 1u;
+          W.E[cur][oe] = (uint16_t)(rel0 + i);
+          W.C[oe] = (uint16_t)min(tb + (uint32_t)__popc(t_ & ((1u << i) - 1u)), P.ncols - 1u);
+          ++oe;
+        }
+        n_st += tot & 1023u;
+        n_ne += (tot >> 10) & 1023u;
+        tabs += tot >> 20;
+      }
+      __syncwarp();
+      if (!ends) break;
+      // ---- the row is complete
+      const int64_t term_abs = sb + seg_end;
+      if (!reference) {
+        if (tabs != tabs_per_row) atomicMin(&P.meta->bad_row, row_no);  // ConvertToZDW.cpp:336-337
+        st.max_line = max(st.max_line, (uint32_t)(term_abs - row_start + 1));
+      }
+      if (term_abs >= t0) ++rows_seen;
+      d1_finish_row(A, wlast, W, cur, n_ne, row_start, prev_start, reference, row_no, st);
+      prev_start = row_start;
+      cur ^= 1u;
+      row_open = false;
+      cursor = seg_end + 1;
+    }
+  }
+  if (bail) {
+    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&P.meta->delta_bail) = 1u;
+    return;
+  }
+  // a row the block's limit cut short (the reference's interrupted row): the columns in front of the
+  // limit count for the dictionary and the column ranges, the row itself is not part of the block
+  if (row_open && !reference && n_ne) d1_finish_row(A, wlast, W, cur, n_ne, row_start, prev_start, false, 0xffffffffu, st);
+  {
+    const uint32_t wn = W.Q[0].end - W.Q[0].done;
+    if (wn) d1_numbers(P, wlast, W.Q[0], wn);
+    const uint32_t wt = W.Q[1].end - W.Q[1].done;
+    if (wt) d1_texts(P, wlast, W.Q[1], wt, st);
+  }
+  st.max_line = __reduce_max_sync(0xffffffffu, st.max_line);
+  st.max_len = __reduce_max_sync(0xffffffffu, st.max_len);
+  st.new_count = __reduce_add_sync(0xffffffffu, st.new_count);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) st.new_bytes += __shfl_xor_sync(0xffffffffu, st.new_bytes, o);
+  if (lane == 0) {
+    if (st.max_line) atomicMax(&P.meta->max_line, st.max_line);
+    if (st.new_count) {
+      atomicAdd(&P.meta->n_unique, (unsigned long long)st.new_count);
+      atomicAdd(&P.meta->dict_str_bytes, st.new_bytes);
+      atomicMax(&P.meta->max_str_len, st.max_len);
     }
   }
 }
@@ -1279,6 +1806,230 @@ __global__ void __launch_bounds__(ENC_THREADS)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// pass 2, row-delta variant: the records of a row name only the columns whose field changed against the row before
+// (value 0 = the field became empty; a text's value is its hash-set slot + 1).  A tile of R rows therefore needs the
+// value every used column has where the tile begins: k_p2d_summary reports the last record of every column inside a
+// tile, the k_carry_* kernels (carry.cuh) turn that into the carried-in values, and k_pass2d fills the value matrix
+// forward row by row before flags and value bytes are produced exactly as in k_pass2 (ConvertToZDW.cpp:486-606).
+// ---------------------------------------------------------------------------------------------
+struct P2DArgs {
+  const uint32_t* rec_col;
+  const unsigned long long* rec_val;
+  const uint32_t* row_rec;   // [nrows] first record of the row
+  const uint32_t* row_cnt;   // [nrows]
+  uint32_t nrows, R, U, nflag;
+  const ColInfo* cinfo;
+  const uint32_t* slot_off;
+  const uint32_t* used_cols;
+  const uint8_t* csize;
+};
+
+// value a record stands for in the row stream: dictionary offset / number minus the column's base (0 stays 0)
+__device__ __forceinline__ unsigned long long record_value(const P2DArgs& A, const ColInfo& ci, unsigned long long v) {
+  if (v == 0ull) return 0ull;
+  return ci.text ? (unsigned long long)__ldg(A.slot_off + (uint32_t)(v - 1ull)) : v - ci.base;  // :548,566; Dictionary::getOffset
+}
+
+// shared by both kernels: record ranges of the tile's rows; roff[j] = records in front of row j of the tile
+__device__ __forceinline__ void p2d_load_ranges(const P2DArgs& A, uint32_t r0, uint32_t Rn, uint32_t* rstart, uint32_t* roff) {
+  for (uint32_t j = threadIdx.x; j < Rn; j += ENC_THREADS) {
+    rstart[j] = A.row_rec[r0 + j];
+    roff[j + 1] = A.row_cnt[r0 + j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    roff[0] = 0;
+    for (uint32_t j = 0; j < Rn; ++j) {
+      run += roff[j + 1];
+      roff[j + 1] = run;
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ uint32_t p2d_row_of(const uint32_t* roff, uint32_t Rn, uint32_t idx) {
+  uint32_t a = 0, b = Rn;  // last a with roff[a] <= idx
+  while (b - a > 1) {
+    const uint32_t m = (a + b) >> 1;
+    if (roff[m] <= idx) a = m;
+    else b = m;
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_p2d_summary(const P2DArgs A, unsigned long long* __restrict__ sval, uint8_t* __restrict__ shas) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  int32_t* last_row = reinterpret_cast<int32_t*>(dsm);          // [U]
+  uint32_t* rstart = reinterpret_cast<uint32_t*>(last_row + A.U);  // [R]
+  uint32_t* roff = rstart + A.R;                                 // [R + 1]
+  const uint32_t tile = blockIdx.x, r0 = tile * A.R, Rn = min(A.nrows - r0, A.R);
+  for (uint32_t u = threadIdx.x; u < A.U; u += ENC_THREADS) last_row[u] = -1;
+  p2d_load_ranges(A, r0, Rn, rstart, roff);
+  const uint32_t tot = roff[Rn];
+  for (uint32_t idx = threadIdx.x; idx < tot; idx += ENC_THREADS) {
+    const uint32_t j = p2d_row_of(roff, Rn, idx);
+    const uint32_t col = A.rec_col[rstart[j] + (idx - roff[j])];
+    const int32_t u = __ldg(&A.cinfo[col].u);
+    if (u >= 0) atomicMax(&last_row[u], (int32_t)j);
+  }
+  __syncthreads();
+  for (uint32_t idx = threadIdx.x; idx < tot; idx += ENC_THREADS) {
+    const uint32_t j = p2d_row_of(roff, Rn, idx);
+    const uint32_t k = rstart[j] + (idx - roff[j]);
+    const uint32_t col = A.rec_col[k];
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(A.cinfo + col));
+    ColInfo ci;
+    ci.base = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+    ci.u = (int32_t)q.z;
+    ci.text = q.w;
+    if (ci.u >= 0 && last_row[ci.u] == (int32_t)j) sval[(size_t)tile * A.U + (uint32_t)ci.u] = record_value(A, ci, A.rec_val[k]);
+  }
+  for (uint32_t u = threadIdx.x; u < A.U; u += ENC_THREADS) shas[(size_t)tile * A.U + u] = last_row[u] >= 0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_pass2d(const P2DArgs A, const unsigned long long* __restrict__ cin, uint64_t tile_cap, uint8_t* __restrict__ staging,
+             uint64_t* __restrict__ tile_bytes) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  // dynamic smem: nval[(R+1)*U] u64 | mark[(R+1)*MW] u32 | rowoff[R+1] | rstart[R] | roff[R+1] | usz[U] u8
+  const uint32_t U = A.U, R = A.R, MW = (U + 31u) >> 5, nflag = A.nflag;
+  unsigned long long* nval = reinterpret_cast<unsigned long long*>(dsm);
+  uint32_t* mark = reinterpret_cast<uint32_t*>(nval + (size_t)(R + 1) * U);
+  uint32_t* rowoff = mark + (size_t)(R + 1) * MW;
+  uint32_t* rstart = rowoff + R + 1;
+  uint32_t* roff = rstart + R;
+  uint8_t* usz = reinterpret_cast<uint8_t*>(roff + R + 1);
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.x, r0 = tile * R, Rn = min(A.nrows - r0, R);
+
+  for (uint32_t u = tid; u < U; u += ENC_THREADS) {
+    nval[u] = cin ? cin[(size_t)tile * U + u] : 0ull;  // the row in front of the tile (all empty at block start, :504-505)
+    usz[u] = A.csize[A.used_cols[u]];
+  }
+  for (uint32_t k = tid; k < (R + 1) * MW; k += ENC_THREADS) mark[k] = 0u;
+  p2d_load_ranges(A, r0, Rn, rstart, roff);
+
+  // ---- the records of the tile's rows: value into the matrix, mark bit set
+  {
+    const uint32_t tot = roff[Rn];
+    constexpr int NR = 4;
+    for (uint32_t ib = tid; ib < tot; ib += NR * ENC_THREADS) {
+      uint32_t row[NR], col[NR];
+      unsigned long long v[NR];
+      ColInfo ci[NR];
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        const uint32_t idx = ib + (uint32_t)q * ENC_THREADS;
+        row[q] = 0;
+        col[q] = REC_EMPTY;
+        v[q] = 0ull;
+        if (idx < tot) {
+          row[q] = p2d_row_of(roff, Rn, idx);
+          const uint32_t k = rstart[row[q]] + (idx - roff[row[q]]);
+          col[q] = A.rec_col[k];
+          v[q] = A.rec_val[k];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        ci[q].u = -1;
+        ci[q].text = 0;
+        ci[q].base = 0;
+        if (col[q] != REC_EMPTY) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(A.cinfo + col[q]));
+          ci[q].base = (unsigned long long)w.x | ((unsigned long long)w.y << 32);
+          ci[q].u = (int32_t)w.z;
+          ci[q].text = w.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        if (ci[q].u < 0) continue;
+        const uint32_t u = (uint32_t)ci[q].u;
+        nval[(size_t)(row[q] + 1) * U + u] = record_value(A, ci[q], v[q]);
+        atomicOr(&mark[(size_t)(row[q] + 1) * MW + (u >> 5)], 1u << (u & 31u));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- a column without a record keeps the value of the row before
+  for (uint32_t u = tid; u < U; u += ENC_THREADS) {
+    unsigned long long v = nval[u];
+    for (uint32_t j = 1; j <= Rn; ++j) {
+      if ((mark[(size_t)j * MW + (u >> 5)] >> (u & 31u)) & 1u) v = nval[(size_t)j * U + u];
+      else nval[(size_t)j * U + u] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- encoded length of every row: nflag + sum of the sizes of the changed columns
+  for (uint32_t j = warp; j < Rn; j += ENC_WARPS) {
+    const unsigned long long* cur = nval + (size_t)(j + 1) * U;
+    const unsigned long long* prv = nval + (size_t)j * U;
+    uint32_t acc = 0;
+    for (uint32_t u = lane; u < U; u += 32)
+      if (cur[u] != prv[u]) acc += usz[u];
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if (lane == 0) rowoff[j] = nflag + acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t run = 0;
+    for (uint32_t j0 = 0; j0 < Rn; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      const uint32_t v = j < Rn ? rowoff[j] : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      if (j < Rn) rowoff[j] = run + inc - v;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+      rowoff[Rn] = run;
+      tile_bytes[tile] = run;
+    }
+  }
+  __syncthreads();
+  uint8_t* tile_out = staging + (uint64_t)tile * tile_cap;
+
+  // ---- emit: flag bytes, then the low columnSize bytes of every changed value (little-endian)
+  for (uint32_t j = warp; j < Rn; j += ENC_WARPS) {
+    const unsigned long long* cur = nval + (size_t)(j + 1) * U;
+    const unsigned long long* prv = nval + (size_t)j * U;
+    uint8_t* orow = tile_out + rowoff[j];
+    uint32_t voff = nflag;
+    for (uint32_t ub = 0; ub < U; ub += 32) {
+      const uint32_t u = ub + lane;
+      unsigned long long v = 0;
+      bool flag = false;
+      if (u < U) {
+        v = cur[u];
+        flag = v != prv[u];
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      if (lane < 4 && (ub >> 3) + lane < nflag) orow[(ub >> 3) + lane] = (uint8_t)(bal >> (8 * lane));
+      const uint32_t sz = flag ? usz[u] : 0u;
+      uint32_t inc = sz;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+      if (flag) {
+        uint8_t* d = orow + voff + inc - sz;
+        for (uint32_t b = 0; b < sz; ++b) d[b] = (uint8_t)(v >> (8 * b));
+      }
+      voff += tot;
+    }
+  }
+}
+
 // Little-endian 32-bit words of the byte string that starts at an arbitrary address: aligned loads + funnel shift.
 struct WordStream {
   const uint32_t* w;
@@ -1400,158 +2151,219 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(types_d.p, pinned, ncols, cudaMemcpyHostToDevice, st));
   }
 
-  // ---- census: per-tile counts and their prefix
-  const uint64_t span = (uint64_t)(-lo) + n;
-  const uint32_t ntiles = (uint32_t)((span + TILE - 1) / TILE);
-  const uint32_t tile_ctas = (ntiles + ENC_WARPS - 1) / ENC_WARPS;
-  DevBuf agg;
-  ZDWB_TRY(agg.alloc(ctx, (size_t)ntiles * sizeof(TileAgg)));
-  {
-    KernelScope _ks(ctx, "k_tile_count");
-    k_tile_count<<<tile_ctas, ENC_THREADS, 0, st>>>(buf, n, lo, ntiles, agg.as<TileAgg>());
-  }
-  ZDWB_LAUNCH_CHECK(ctx);
-  {
-    const uint32_t nparts = (ntiles + TS_THREADS - 1) / TS_THREADS;
-    DevBuf part;
-    ZDWB_TRY(part.alloc(ctx, (size_t)nparts * sizeof(TileAgg)));
-    KernelScope _ks(ctx, "k_tile_scan");
-    k_tile_scan_local<<<nparts, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, part.as<TileAgg>());
-    ZDWB_LAUNCH_CHECK(ctx);
-    k_tile_scan<<<1, TS_THREADS, 0, st>>>(part.as<TileAgg>(), nparts, meta);
-    ZDWB_LAUNCH_CHECK(ctx);
-    k_tile_scan_add<<<nparts, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, part.as<TileAgg>());
-    ZDWB_LAUNCH_CHECK(ctx);
-  }
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
-  ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-  const uint64_t rows_total = hmeta->tot_rows;
-  const uint64_t ne_total = hmeta->tot_ne;
-  const uint64_t tail_start = hmeta->last_break_p1;  // first byte after the last row break
-  out->rows_in_buffer = rows_total;
-  if (rows_total == 0) {
-    out->tsv_consumed = opts->more_input_follows ? 0 : n;  // a window without a complete row: the caller widens it
-    return ZDWB_OK;  // "Empty data file -- nothing to process", ConvertToZDW.cpp:824-835
-  }
+  // ---- which pass 1?  The row-delta variant (k_pass1d) pays on wide rows; narrow rows - and rows that do not fit its
+  // per-warp lists - go through the general one (k_pass1).  Both leave records for their own pass 2.
+  const uint64_t DELTA_MIN_ROW_BYTES = 512;
+  bool delta = ctx->enc_delta != 0 && ncols <= DELTA_MAX_COLS && n >= 64 &&
+               (ctx->enc_delta == 1 || (!ctx->delta_bailed && (ctx->last_row_bytes == 0 || ctx->last_row_bytes >= DELTA_MIN_ROW_BYTES)));
 
-  const uint64_t nrows64 = (opts->max_rows && opts->max_rows < rows_total) ? opts->max_rows : rows_total;
-  const uint32_t nrows = (uint32_t)nrows64;
-  const bool took_all = nrows64 == rows_total;
-  const bool is_last = took_all && !opts->more_input_follows;
-
-  // ---- block extent
-  uint64_t limit;  // bytes that belong to the block
-  uint32_t spill_row_len = 0;  // the interrupted row was read in full before it was dropped: it counts for longestLine
-  uint32_t tail_bytes = 0;
-  if (took_all) {
-    // the terminator of the last row is the last row break unless blank lines follow it; either way every
-    // delimiter in front of tail_start belongs to the block
-    limit = tail_start;
-    if (is_last) {
-      out->tsv_consumed = n;
-      tail_bytes = (uint32_t)(n - tail_start);
+  DevBuf agg, colset, colmin, colmax, slots, rec_col, rec_val, row_rec, row_cnt;
+  HashTable ht{nullptr, 0};
+  uint32_t nrows = 0;
+  bool is_last = false;
+  uint32_t spill_row_len = 0, tail_bytes = 0;
+  uint64_t rows_total = 0, ne_total = 0;
+  for (;;) {  // at most twice: the delta variant may hand the block over to the general one
+    // ---- census: per-tile counts and their prefix
+    const uint32_t tile_bytes = delta ? DTILE : TILE;
+    const uint64_t span = (uint64_t)(-lo) + n;
+    const uint32_t ntiles = (uint32_t)((span + tile_bytes - 1) / tile_bytes);
+    const uint32_t tile_ctas = (ntiles + ENC_WARPS - 1) / ENC_WARPS;
+    ZDWB_TRY(agg.alloc(ctx, (size_t)ntiles * sizeof(TileAgg)));
+    if (delta) {
+      KernelScope _ks(ctx, "k_row_census");
+      k_row_census<<<tile_ctas, ENC_THREADS, 0, st>>>(buf, n, lo, ntiles, tile_bytes, agg.as<TileAgg>());
     } else {
-      out->tsv_consumed = tail_start;  // the unterminated tail belongs to the next window
-    }
-  } else {
-    {
-      KernelScope _ks(ctx, "k_find_cut");
-      k_find_cut<<<1, 32, 0, st>>>(buf, n, lo, ntiles, agg.as<TileAgg>(), nrows - 1, meta);
+      KernelScope _ks(ctx, "k_tile_count");
+      k_tile_count<<<tile_ctas, ENC_THREADS, 0, st>>>(buf, n, lo, ntiles, agg.as<TileAgg>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
+    {
+      const uint32_t nparts = (ntiles + TS_THREADS - 1) / TS_THREADS;
+      DevBuf part;
+      ZDWB_TRY(part.alloc(ctx, (size_t)nparts * sizeof(TileAgg)));
+      KernelScope _ks(ctx, "k_tile_scan");
+      k_tile_scan_local<<<nparts, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, part.as<TileAgg>());
+      ZDWB_LAUNCH_CHECK(ctx);
+      k_tile_scan<<<1, TS_THREADS, 0, st>>>(part.as<TileAgg>(), nparts, meta);
+      ZDWB_LAUNCH_CHECK(ctx);
+      k_tile_scan_add<<<nparts, TS_THREADS, 0, st>>>(agg.as<TileAgg>(), ntiles, part.as<TileAgg>());
+      ZDWB_LAUNCH_CHECK(ctx);
+    }
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    limit = hmeta->cut_end_p1;
-    out->tsv_consumed = hmeta->next_start;
-    if (opts->spill_cols) {
+    rows_total = hmeta->tot_rows;
+    const uint64_t tail_start = hmeta->last_break_p1;  // first byte after the last row break
+    out->rows_in_buffer = rows_total;
+    if (rows_total == 0) {
+      out->tsv_consumed = opts->more_input_follows ? 0 : n;  // a window without a complete row: the caller widens it
+      return ZDWB_OK;  // "Empty data file -- nothing to process", ConvertToZDW.cpp:824-835
+    }
+    ctx->last_row_bytes = std::max<uint64_t>(1, tail_start / rows_total);
+    if (delta && ctx->enc_delta != 1 && ctx->last_row_bytes < DELTA_MIN_ROW_BYTES) {
+      delta = false;  // narrow rows: the general pass 1 (and its census)
+      continue;
+    }
+
+    const uint64_t nrows64 = (opts->max_rows && opts->max_rows < rows_total) ? opts->max_rows : rows_total;
+    nrows = (uint32_t)nrows64;
+    const bool took_all = nrows64 == rows_total;
+    is_last = took_all && !opts->more_input_follows;
+
+    // ---- block extent
+    uint64_t limit;  // bytes that belong to the block
+    spill_row_len = 0;  // the interrupted row was read in full before it was dropped: it counts for longestLine
+    tail_bytes = 0;
+    if (took_all) {
+      // the terminator of the last row is the last row break unless blank lines follow it; either way every
+      // delimiter in front of tail_start belongs to the block
+      limit = tail_start;
+      if (is_last) {
+        out->tsv_consumed = n;
+        tail_bytes = (uint32_t)(n - tail_start);
+      } else {
+        out->tsv_consumed = tail_start;  // the unterminated tail belongs to the next window
+      }
+    } else {
       {
-        KernelScope _ks(ctx, "k_find_spill");
-        k_find_spill<<<1, 1, 0, st>>>(buf, n, hmeta->next_start, opts->spill_cols, meta);
+        KernelScope _ks(ctx, "k_find_cut");
+        k_find_cut<<<1, 32, 0, st>>>(buf, n, lo, ntiles, tile_bytes, agg.as<TileAgg>(), nrows - 1, meta);
       }
       ZDWB_LAUNCH_CHECK(ctx);
       ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
       ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-      if (hmeta->spill_row_len) {
-        limit = hmeta->spill_end;  // pass 1 takes every field whose closing delimiter lies in front of this
-        spill_row_len = hmeta->spill_row_len;
+      limit = hmeta->cut_end_p1;
+      out->tsv_consumed = hmeta->next_start;
+      if (opts->spill_cols) {
+        {
+          KernelScope _ks(ctx, "k_find_spill");
+          k_find_spill<<<1, 1, 0, st>>>(buf, n, hmeta->next_start, opts->spill_cols, meta);
+        }
+        ZDWB_LAUNCH_CHECK(ctx);
+        ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
+        ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (hmeta->spill_row_len) {
+          limit = hmeta->spill_end;  // pass 1 takes every field whose closing delimiter lies in front of this
+          spill_row_len = hmeta->spill_row_len;
+        }
       }
     }
-  }
-  out->nrows = nrows;
+    out->nrows = nrows;
 
-  // ---- pass 1 (retry with a larger hash set when it fills up)
-  const uint64_t block_bytes = limit;
-  DevBuf colset, colmin, colmax, slots, rec_col, rec_val, row_rec;
-  ZDWB_TRY(colset.alloc(ctx, (size_t)ncols * 4));
-  ZDWB_TRY(colmin.alloc(ctx, (size_t)ncols * 8));
-  ZDWB_TRY(colmax.alloc(ctx, (size_t)ncols * 8));
-  ZDWB_TRY(rec_col.alloc(ctx, (size_t)(ne_total + 1) * 4));
-  ZDWB_TRY(rec_val.alloc(ctx, (size_t)(ne_total + 1) * 8));
-  ZDWB_TRY(row_rec.alloc(ctx, (size_t)(rows_total + 2) * 4));
-  uint32_t cap_log2 = (uint32_t)std::max<long long>(10, std::min<long long>(ctx->ht_initial_log2, 31));
-  while (cap_log2 < 31 && (1ull << cap_log2) < ctx->last_unique * 4) ++cap_log2;  // blocks of one file look alike
-  {
-    // a block cannot hold more distinct non-empty strings than non-empty fields
-    uint32_t need = 10;
-    while (need < 31 && (1ull << need) < ne_total * 2) ++need;
-    if (cap_log2 > need) cap_log2 = need;
-  }
-  HashTable ht{nullptr, 0};
-  const uint32_t p1_tiles = (uint32_t)(((uint64_t)(-lo) + limit + TILE - 1) / TILE);
-  for (;;) {
-    const uint64_t cap = 1ull << cap_log2;
-    ZDWB_TRY(slots.alloc(ctx, cap * 8));
-    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(slots.p, 0, cap * 8, st));
-    ht.slots = slots.as<unsigned long long>();
-    ht.mask = (uint32_t)(cap - 1);
-    {
-      KernelScope _ks(ctx, "k_init_minmax");
-      k_init_minmax<<<(ncols + 255) / 256, 256, 0, st>>>(colmin.as<unsigned long long>(), colmax.as<unsigned long long>(),
-                                                       colset.as<uint32_t>(), ncols);
+    // ---- pass 1 (retry with a larger hash set / larger record arrays when they fill up)
+    ZDWB_TRY(colset.alloc(ctx, (size_t)ncols * 4));
+    ZDWB_TRY(colmin.alloc(ctx, (size_t)ncols * 8));
+    ZDWB_TRY(colmax.alloc(ctx, (size_t)ncols * 8));
+    ne_total = hmeta->tot_ne;  // (general variant only: the delta census does not count fields)
+    uint64_t rec_cap = 0;
+    if (delta) {
+      // a row's records = its changed fields + the columns that became empty; sized from the previous block of the
+      // file (blocks look alike) or from the bytes, and grown on overflow
+      rec_cap = std::max<uint64_t>({ctx->last_records + ctx->last_records / 2, limit / 16, (uint64_t)1 << 16});
+      rec_cap = std::min<uint64_t>(rec_cap, limit + 64);
+      ZDWB_TRY(row_rec.alloc(ctx, (size_t)(nrows + 2) * 4));
+      ZDWB_TRY(row_cnt.alloc(ctx, (size_t)(nrows + 2) * 4));
+    } else {
+      rec_cap = ne_total;
+      ZDWB_TRY(row_rec.alloc(ctx, (size_t)(rows_total + 2) * 4));
     }
-    ZDWB_LAUNCH_CHECK(ctx);
-    P1Args A;
-    A.buf = buf;
-    A.n = n;
-    A.lo = lo;
-    A.limit = (int64_t)limit;
-    A.ntiles = p1_tiles;
-    A.ncols = ncols;
-    A.pre = agg.as<TileAgg>();
-    A.types = types_d.as<uint8_t>();
-    A.trim = opts->trim_trailing_spaces;
-    A.ht = ht;
-    A.colset = colset.as<uint32_t>();
-    A.colmin = colmin.as<unsigned long long>();
-    A.colmax = colmax.as<unsigned long long>();
-    A.rec_col = rec_col.as<uint32_t>();
-    A.rec_val = rec_val.as<unsigned long long>();
-    A.row_rec = row_rec.as<uint32_t>();
-    A.meta = meta;
-    {
-      KernelScope _ks(ctx, "k_pass1");
-      k_pass1<<<(p1_tiles + ENC_WARPS - 1) / ENC_WARPS, ENC_THREADS, 0, st>>>(A);
+    ZDWB_TRY(rec_col.alloc(ctx, (size_t)(rec_cap + 1) * 4));
+    ZDWB_TRY(rec_val.alloc(ctx, (size_t)(rec_cap + 1) * 8));
+    uint32_t cap_log2 = (uint32_t)std::max<long long>(10, std::min<long long>(ctx->ht_initial_log2, 31));
+    while (cap_log2 < 31 && (1ull << cap_log2) < ctx->last_unique * 4) ++cap_log2;  // blocks of one file look alike
+    if (!delta) {
+      // a block cannot hold more distinct non-empty strings than non-empty fields
+      uint32_t need = 10;
+      while (need < 31 && (1ull << need) < ne_total * 2) ++need;
+      if (cap_log2 > need) cap_log2 = need;
     }
-    ZDWB_LAUNCH_CHECK(ctx);
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
-    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    if (hmeta->bad_row < nrows) break;
-    if (!hmeta->ht_overflow && hmeta->n_unique * 2 <= cap) break;
-    if (cap_log2 >= 31) {
-      ctx->err = "encode: dictionary hash set exceeds 2^31 slots";
-      return ZDWB_ERR_UNSUPPORTED;
+    const uint32_t p1_tiles = (uint32_t)(((uint64_t)(-lo) + limit + tile_bytes - 1) / tile_bytes);
+    bool bailed = false;
+    for (;;) {
+      const uint64_t cap = 1ull << cap_log2;
+      ZDWB_TRY(slots.alloc(ctx, cap * 8));
+      ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(slots.p, 0, cap * 8, st));
+      ht.slots = slots.as<unsigned long long>();
+      ht.mask = (uint32_t)(cap - 1);
+      {
+        KernelScope _ks(ctx, "k_init_minmax");
+        k_init_minmax<<<(ncols + 255) / 256, 256, 0, st>>>(colmin.as<unsigned long long>(), colmax.as<unsigned long long>(),
+                                                         colset.as<uint32_t>(), ncols);
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      P1Args A;
+      A.buf = buf;
+      A.n = n;
+      A.lo = lo;
+      A.limit = (int64_t)limit;
+      A.ntiles = p1_tiles;
+      A.ncols = ncols;
+      A.pre = agg.as<TileAgg>();
+      A.types = types_d.as<uint8_t>();
+      A.trim = opts->trim_trailing_spaces;
+      A.ht = ht;
+      A.colset = colset.as<uint32_t>();
+      A.colmin = colmin.as<unsigned long long>();
+      A.colmax = colmax.as<unsigned long long>();
+      A.rec_col = rec_col.as<uint32_t>();
+      A.rec_val = rec_val.as<unsigned long long>();
+      A.row_rec = row_rec.as<uint32_t>();
+      A.meta = meta;
+      if (delta) {
+        D1Args D;
+        D.P = A;
+        D.ntiles = p1_tiles;
+        D.nrows = nrows;
+        D.rec_cap = (uint32_t)rec_cap;
+        D.row_cnt = row_cnt.as<uint32_t>();
+        KernelScope _ks(ctx, "k_pass1d");
+        k_pass1d<<<(p1_tiles + D1_WARPS - 1) / D1_WARPS, D1_THREADS, 0, st>>>(D);
+      } else {
+        KernelScope _ks(ctx, "k_pass1");
+        k_pass1<<<(p1_tiles + ENC_WARPS - 1) / ENC_WARPS, ENC_THREADS, 0, st>>>(A);
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
+      ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (hmeta->delta_bail) {
+        bailed = true;
+        break;
+      }
+      if (hmeta->bad_row < nrows) break;
+      const bool ht_full = hmeta->ht_overflow || hmeta->n_unique * 2 > cap;
+      const bool rec_full = hmeta->rec_overflow != 0;
+      if (!ht_full && !rec_full) break;
+      if (ht_full) {
+        if (cap_log2 >= 31) {
+          ctx->err = "encode: dictionary hash set exceeds 2^31 slots";
+          return ZDWB_ERR_UNSUPPORTED;
+        }
+        cap_log2 = std::min<uint32_t>(31, cap_log2 + 3);
+      }
+      if (rec_full) {
+        rec_cap = std::min<uint64_t>(std::max<uint64_t>(rec_cap * 4, (uint64_t)hmeta->rec_count + 64), limit + 64);
+        ZDWB_TRY(rec_col.alloc(ctx, (size_t)(rec_cap + 1) * 4));
+        ZDWB_TRY(rec_val.alloc(ctx, (size_t)(rec_cap + 1) * 8));
+      }
+      // reset the counters pass 1 accumulates
+      EncMeta z = *hmeta;
+      z.ht_overflow = 0;
+      z.rec_overflow = 0;
+      z.rec_count = 0;
+      z.n_unique = 0;
+      z.dict_str_bytes = 0;
+      z.max_str_len = 0;
+      z.max_line = 0;
+      *hmeta = z;
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(meta, hmeta, sizeof(EncMeta), cudaMemcpyHostToDevice, st));
+      ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
-    cap_log2 = std::min<uint32_t>(31, cap_log2 + 3);
-    // reset the counters pass 1 accumulates
-    EncMeta z = *hmeta;
-    z.ht_overflow = 0;
-    z.n_unique = 0;
-    z.dict_str_bytes = 0;
-    z.max_str_len = 0;
-    z.max_line = 0;
-    *hmeta = z;
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(meta, hmeta, sizeof(EncMeta), cudaMemcpyHostToDevice, st));
-    ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (!bailed) break;
+    // a row with more non-empty fields (or bytes) than a warp's lists hold: the whole block takes the general path
+    delta = false;
+    ctx->delta_bailed = true;
+    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(meta, 0, sizeof(EncMeta), st));
+    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(&meta->bad_row, 0xff, 4, st));
   }
   if (hmeta->bad_row < nrows) {
     out->bad_row = hmeta->bad_row + 1;  // "Row %u had the problem": one past the last good row, ConvertToZDW.cpp:811
@@ -1560,6 +2372,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   }
   const uint64_t n_unique = hmeta->n_unique;
   ctx->last_unique = n_unique;
+  if (delta) ctx->last_records = hmeta->rec_count;
   const uint64_t dict_total = hmeta->dict_str_bytes + 1;
   if (dict_total >= 0xffffffffull) {
     ctx->err = "encode: block dictionary would reach 4 GiB (Dictionary::size is 32-bit, dictionary.h:62); use smaller blocks";
@@ -1633,12 +2446,14 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
       return ZDWB_ERR_UNSUPPORTED;
     }
     const uint64_t smem_budget = 64 * 1024;
-    const uint64_t by_smem = std::max<uint64_t>(2, smem_budget / ((uint64_t)U * 8));
-    const uint64_t rec_per_row = std::max<uint64_t>(1, ne_total / std::max<uint64_t>(rows_total, 1));
+    const uint32_t MW = (U + 31) / 32;
+    const uint64_t row_smem = (uint64_t)U * 8 + (delta ? (uint64_t)MW * 4 : 0);
+    const uint64_t by_smem = std::max<uint64_t>(2, smem_budget / row_smem);
+    const uint64_t recs = delta ? hmeta->rec_count : ne_total;
+    const uint64_t rec_per_row = std::max<uint64_t>(1, recs / std::max<uint64_t>(delta ? nrows : rows_total, 1));
     uint32_t rpc2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 4096 / rec_per_row), 1024);
     rpc2 = (uint32_t)std::min<uint64_t>(rpc2, by_smem - 1);
-    const size_t smem = (size_t)(rpc2 + 1) * U * 8 + (size_t)(rpc2 + 1) * 4 + (size_t)(rpc2 + 2) * 4 + U + 16;
-    ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    if (ctx->enc_p2_rows > 0) rpc2 = (uint32_t)std::min<uint64_t>((uint64_t)ctx->enc_p2_rows, by_smem - 1);
     tiles2 = (nrows + rpc2 - 1) / rpc2;
     tile_cap = (((uint64_t)rpc2 * hmeta->max_row_bytes) + 15) & ~15ull;
     ZDWB_TRY(staging.alloc(ctx, (size_t)tiles2 * tile_cap + 64));
@@ -1652,14 +2467,76 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
                                                     colinfo.as<ColInfo>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
-    {
-      KernelScope _ks(ctx, "k_pass2");
-      k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(rec_col.as<uint32_t>(), rec_val.as<unsigned long long>(), row_rec.as<uint32_t>(),
-                                               nrows, rpc2, colinfo.as<ColInfo>(), slot_off.as<uint32_t>(),
-                                               used_cols.as<uint32_t>(), csize.as<uint8_t>(), U,
-                                               nflag, tile_cap, staging.as<uint8_t>(), tile_bytes.as<uint64_t>());
+    if (delta) {
+      P2DArgs A2;
+      A2.rec_col = rec_col.as<uint32_t>();
+      A2.rec_val = rec_val.as<unsigned long long>();
+      A2.row_rec = row_rec.as<uint32_t>();
+      A2.row_cnt = row_cnt.as<uint32_t>();
+      A2.nrows = nrows;
+      A2.R = rpc2;
+      A2.U = U;
+      A2.nflag = nflag;
+      A2.cinfo = colinfo.as<ColInfo>();
+      A2.slot_off = slot_off.as<uint32_t>();
+      A2.used_cols = used_cols.as<uint32_t>();
+      A2.csize = csize.as<uint8_t>();
+      // the value every used column has where a tile begins
+      DevBuf cin, sval, shas, seg_val, seg_has;
+      if (tiles2 > 1) {
+        ZDWB_TRY(cin.alloc(ctx, (size_t)tiles2 * U * 8));
+        ZDWB_TRY(sval.alloc(ctx, (size_t)tiles2 * U * 8));
+        ZDWB_TRY(shas.alloc(ctx, (size_t)tiles2 * U));
+        const size_t smem_sum = (size_t)U * 4 + (size_t)(2 * rpc2 + 1) * 4 + 16;
+        ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_p2d_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+        {
+          KernelScope _ks(ctx, "k_p2d_summary");
+          k_p2d_summary<<<tiles2, ENC_THREADS, smem_sum, st>>>(A2, sval.as<unsigned long long>(), shas.as<uint8_t>());
+        }
+        ZDWB_LAUNCH_CHECK(ctx);
+        const uint32_t S = (tiles2 + 255) / 256;
+        const uint32_t nseg = (tiles2 + S - 1) / S;
+        ZDWB_TRY(seg_val.alloc(ctx, (size_t)nseg * U * 8));
+        ZDWB_TRY(seg_has.alloc(ctx, (size_t)nseg * U));
+        dim3 g2((U + 127) / 128, nseg);
+        {
+          KernelScope _ks(ctx, "k_carry_reduce");
+          k_carry_reduce<<<g2, 128, 0, st>>>(sval.as<unsigned long long>(), shas.as<uint8_t>(), tiles2, U, S,
+                                           seg_val.as<unsigned long long>(), seg_has.as<uint8_t>());
+        }
+        ZDWB_LAUNCH_CHECK(ctx);
+        {
+          KernelScope _ks(ctx, "k_carry_scan");
+          k_carry_scan<<<(U + 127) / 128, 128, 0, st>>>(seg_val.as<unsigned long long>(), seg_has.as<uint8_t>(), nseg, U);
+        }
+        ZDWB_LAUNCH_CHECK(ctx);
+        {
+          KernelScope _ks(ctx, "k_carry_apply");
+          k_carry_apply<<<g2, 128, 0, st>>>(sval.as<unsigned long long>(), shas.as<uint8_t>(), seg_val.as<unsigned long long>(),
+                                          tiles2, U, S, cin.as<unsigned long long>());
+        }
+        ZDWB_LAUNCH_CHECK(ctx);
+      }
+      const size_t smem = (size_t)(rpc2 + 1) * U * 8 + (size_t)(rpc2 + 1) * MW * 4 + (size_t)(3 * rpc2 + 3) * 4 + U + 16;
+      ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pass2d, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+      {
+        KernelScope _ks(ctx, "k_pass2d");
+        k_pass2d<<<tiles2, ENC_THREADS, smem, st>>>(A2, tiles2 > 1 ? cin.as<unsigned long long>() : nullptr, tile_cap,
+                                                  staging.as<uint8_t>(), tile_bytes.as<uint64_t>());
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+    } else {
+      const size_t smem = (size_t)(rpc2 + 1) * U * 8 + (size_t)(rpc2 + 1) * 4 + (size_t)(rpc2 + 2) * 4 + U + 16;
+      ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+      {
+        KernelScope _ks(ctx, "k_pass2");
+        k_pass2<<<tiles2, ENC_THREADS, smem, st>>>(rec_col.as<uint32_t>(), rec_val.as<unsigned long long>(), row_rec.as<uint32_t>(),
+                                                 nrows, rpc2, colinfo.as<ColInfo>(), slot_off.as<uint32_t>(),
+                                                 used_cols.as<uint32_t>(), csize.as<uint8_t>(), U,
+                                                 nflag, tile_cap, staging.as<uint8_t>(), tile_bytes.as<uint64_t>());
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
     }
-    ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u64(ctx, tile_bytes.as<uint64_t>(), tile_off.as<uint64_t>(), tiles2, rows_total_d.as<uint64_t>()));
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->meta_host) + 1024, rows_total_d.p, 8, cudaMemcpyDeviceToHost, st));
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -1703,7 +2580,6 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   out->dict_entries = n_unique;
   out->dict_bytes = dict_total;
   out->dict_index_size = bytes_needed(dict_total);
-  (void)block_bytes;
   if (opts->output_on_device) {
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     out->bytes = outp;
