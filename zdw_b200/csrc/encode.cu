@@ -761,8 +761,11 @@ __device__ __forceinline__ void text_one(const P1Args& A, const uint32_t* wlast,
 
 // Processes the queued fields [off, off + count) of the warp's main queue (count <= 32): lane l takes field off + l.
 // Q[0] parks texts of up to SHORT_MAX bytes, Q[1] texts of up to MID_MAX bytes; longer ones go to the octets at once.
-__device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, const P1Warp& W, uint32_t off, uint32_t count,
-                                           uint32_t ord0, P1Stats& st, P1Side* Q, bool flush) {
+// QT = the queue's arrays (start / len / col); `ords` (may be null) = the record every field fills, else ord0 + lane.
+// BIAS is added to the hash-set slot a text's record holds (the delta path keeps 0 for "became empty").
+template <uint32_t BIAS, class QT>
+__device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlast, const QT& W, uint32_t off, uint32_t count,
+                                           uint32_t ord0, const uint32_t* ords, P1Stats& st, P1Side* Q, bool flush) {
   const unsigned lane = lane_id();
   const bool valid = lane < count;
   uint32_t start = 0, len = 0, col = 0;
@@ -773,10 +776,11 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
     col = W.col[off + lane];
     t = __ldg(A.types + col);
   }
-  const uint32_t ord = ord0 + lane;
+  const uint32_t ord = ords ? (valid ? ords[off + lane] : 0u) : ord0 + lane;
+  const uint32_t ord_src = ord;  // (long texts below fetch the source lane's record by shuffle)
   const bool live = valid && len != 0u;
   const bool text = is_text_like(t);
-  if (valid && len == 0u) A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one (or the row is malformed)
+  if (BIAS == 0u && valid && len == 0u) A.rec_col[ord] = REC_EMPTY;  // -t turned the field into an empty one (or the row is malformed)
   if (live && !text) {
     unsigned long long v1, v2;
     if (len <= NUM_FAST_MAX || t == ZDWB_CHAR) {
@@ -820,10 +824,10 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
                      c2 = __shfl_sync(0xffffffffu, col, src);
       bool is_new;
       const uint32_t slot = ht_upsert_long(A, wlast, s2, l2, gl, om, active, &is_new);
+      const uint32_t o2 = __shfl_sync(0xffffffffu, ord_src, src);
       if (active && gl == 0) {
-        const uint32_t o2 = ord0 + (uint32_t)src;
         A.rec_col[o2] = c2;
-        A.rec_val[o2] = slot;
+        A.rec_val[o2] = (unsigned long long)slot + BIAS;
         note_column_set(A, c2);
         if (is_new) note_new_string(st, l2);
       }
@@ -840,7 +844,7 @@ __device__ __forceinline__ void p1_process(const P1Args& A, const uint32_t* wlas
       const uint32_t take = min(n, 32u), head = S.done;
       if (lane < take) {
         const uint32_t e = (head + lane) & (SQ - 1u);
-        text_one(A, wlast, S.start[e], S.len[e], S.col[e], S.ord[e], st);
+        text_one<BIAS>(A, wlast, S.start[e], S.len[e], S.col[e], S.ord[e], st);
       }
       __syncwarp();
       if (lane == 0) S.done = head + take;
@@ -944,7 +948,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_pass1(const P1Args A) {
     while (off + 32u <= have || (last && !flushed)) {
       const uint32_t cnt = min(32u, have - off);
       flushed = last && off + cnt == have;
-      p1_process(A, wlast, W, off, cnt, qbase + off, st, Q, flushed);
+      p1_process<0>(A, wlast, W, off, cnt, qbase + off, nullptr, st, Q, flushed);
       off += cnt;
     }
     if (last) break;
@@ -1002,9 +1006,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_pass1(const P1Args A) {
 // delimiter behind a content byte, so both are dropped into per-row lists at their ordinals.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t DTILE = 32768;       // bytes of TSV whose row starts one warp owns
-constexpr uint32_t DCAP = 288;          // non-empty fields of a row a warp can hold (else: delta_bail)
+constexpr uint32_t DSTEP = 1024;        // bytes per warp step: 32 lanes x 32 bytes
+constexpr uint32_t DCAP = 280;          // non-empty fields of a row a warp can hold (else: delta_bail)
 constexpr uint32_t DBW = 128;           // bitmap words per row: up to 4096 columns
 constexpr uint32_t DELTA_MAX_COLS = DBW * 32;
+constexpr uint32_t DQN = 64;            // changed fields waiting for the full treatment (31 left over + 32 new)
+constexpr uint32_t CMP_INLINE = 16;     // fields up to this length are compared straight-line by their lane
 constexpr int D1_WARPS = 4;
 constexpr int D1_THREADS = D1_WARPS * 32;
 
@@ -1012,17 +1019,20 @@ struct D1Warp {
   uint16_t S[2][DCAP];   // first byte of the k-th non-empty field, relative to the row start
   uint16_t E[2][DCAP];   // its closing delimiter, relative to the row start
   uint16_t C[DCAP];      // its column (current row only)
+  uint16_t PD[DCAP];     // fields whose comparison needs more than CMP_INLINE bytes (worked off together per row)
   uint16_t PF[2][DBW];   // fields in front of bitmap word w
   uint32_t BM[2][DBW];   // bit c = column c of the row is non-empty
-  P1Side Q[2];           // changed fields waiting for the full treatment: [0] numbers / CHAR cells, [1] texts
+  uint32_t CM[(DCAP + 31) / 32];  // bit k & 31 of word k >> 5 = field k changed
 };
 
 struct D1Args {
   P1Args P;              // buf, n, lo, limit, ncols, types, trim, hash set, column statistics, rec_col / rec_val, meta
   uint32_t ntiles;       // tiles of DTILE bytes
-  uint32_t nrows;        // rows of the block: records of rows beyond it (the spilled row) are dropped
-  uint32_t rec_cap;      // capacity of rec_col / rec_val; slot rec_cap itself takes the dropped records
+  uint32_t nrows;        // rows of the block: the spilled row beyond it has records but no row entry
+  uint32_t rec_cap;      // capacity of the record arrays
   uint32_t* row_cnt;     // [nrows] records of row r; they start at P.row_rec[r]
+  uint32_t* chg_start;   // [rec_cap] where the changed field of record k starts in the TSV ...
+  uint32_t* chg_len;     // ... and its length; 0 = the record of a column that became empty (value 0)
 };
 
 // Row census of the delta path: per tile the number of row terminators, the last row break and the last row start.
@@ -1079,17 +1089,63 @@ __global__ void __launch_bounds__(ENC_THREADS)
   }
 }
 
-// lane's 16-bit mask of the step's bit positions >= a / <= b (positions 0..511, lane l holds 16 l .. 16 l + 15)
-__device__ __forceinline__ uint32_t lane_bits_ge(int32_t a, unsigned lane) {
-  const int32_t lo = a - (int32_t)(lane * 16u);
-  return lo <= 0 ? 0xffffu : (lo >= 16 ? 0u : ((0xffffu << lo) & 0xffffu));
+// 32-bit masks of a lane's 32 bytes: bit i = byte i equals `ch`.  bytes_eq leaves 0x80 in every matching byte; a dot
+// product with the byte weights 1, 2, 4, ... gathers the four flags of a word, two words per accumulator.
+__device__ __forceinline__ uint32_t mask16_dp(const uint4& v, uint32_t rep) {
+  const uint32_t lo = __dp4a(bytes_eq(v.x, rep), 0x08040201u, __dp4a(bytes_eq(v.y, rep), 0x80402010u, 0u));
+  const uint32_t hi = __dp4a(bytes_eq(v.z, rep), 0x08040201u, __dp4a(bytes_eq(v.w, rep), 0x80402010u, 0u));
+  return (lo >> 7) | (hi << 1);  // both sums carry the factor 0x80
 }
-__device__ __forceinline__ uint32_t lane_bits_le(int32_t b, unsigned lane) {
-  const int32_t hi = b - (int32_t)(lane * 16u);
-  return hi < 0 ? 0u : (hi >= 15 ? 0xffffu : ((2u << hi) - 1u));
+__device__ __forceinline__ uint32_t mask32(const uint4& a, const uint4& b, uint8_t ch) {
+  const uint32_t rep = 0x01010101u * ch;
+  return mask16_dp(a, rep) | (mask16_dp(b, rep) << 16);
 }
 
-// do the `len` bytes at a and b differ?  (aligned word loads + funnel shifts; nothing past *wlast is read)
+// lane's 32-bit mask of the step's bit positions >= a / <= b (positions 0..1023, lane l holds 32 l .. 32 l + 31)
+__device__ __forceinline__ uint32_t lane_bits_ge(int32_t a, unsigned lane) {
+  const int32_t lo = a - (int32_t)(lane * 32u);
+  return lo <= 0 ? 0xffffffffu : (lo >= 32 ? 0u : (0xffffffffu << lo));
+}
+__device__ __forceinline__ uint32_t lane_bits_le(int32_t b, unsigned lane) {
+  const int32_t hi = b - (int32_t)(lane * 32u);
+  return hi < 0 ? 0u : (hi >= 31 ? 0xffffffffu : ((2u << hi) - 1u));
+}
+__device__ __forceinline__ uint32_t bits_below(uint32_t i) { return (1u << i) - 1u; }  // i < 32
+
+// do the `len` (1..16) bytes at a and b differ?  Straight-line: five aligned words a side, funnel shifts, one mask.
+// SAFE = both fields lie at least 20 bytes in front of the end of the buffer: no load needs clamping.
+template <bool SAFE>
+__device__ __forceinline__ bool short_differ(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len,
+                                             const uint32_t* wlast) {
+  const uintptr_t ua = reinterpret_cast<uintptr_t>(a), ub = reinterpret_cast<uintptr_t>(b);
+  const uint32_t* wa = reinterpret_cast<const uint32_t*>(ua & ~(uintptr_t)3);
+  const uint32_t* wb = reinterpret_cast<const uint32_t*>(ub & ~(uintptr_t)3);
+  const uint32_t sa = (uint32_t)(ua & 3u) * 8u, sb = (uint32_t)(ub & 3u) * 8u;
+  uint32_t a0, a1, a2, a3, a4, b0, b1, b2, b3, b4;
+  if (SAFE) {
+    a0 = __ldg(wa), a1 = __ldg(wa + 1), a2 = __ldg(wa + 2), a3 = __ldg(wa + 3), a4 = __ldg(wa + 4);
+    b0 = __ldg(wb), b1 = __ldg(wb + 1), b2 = __ldg(wb + 2), b3 = __ldg(wb + 3), b4 = __ldg(wb + 4);
+  } else {
+    const uint32_t ra = (uint32_t)min((ptrdiff_t)4, wlast - wa), rb = (uint32_t)min((ptrdiff_t)4, wlast - wb);
+    a0 = __ldg(wa), a1 = __ldg(wa + min(1u, ra)), a2 = __ldg(wa + min(2u, ra)), a3 = __ldg(wa + min(3u, ra)), a4 = __ldg(wa + min(4u, ra));
+    b0 = __ldg(wb), b1 = __ldg(wb + min(1u, rb)), b2 = __ldg(wb + min(2u, rb)), b3 = __ldg(wb + min(3u, rb)), b4 = __ldg(wb + min(4u, rb));
+  }
+  const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+  const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+  const uint32_t x2 = __funnelshift_r(a2, a3, sa) ^ __funnelshift_r(b2, b3, sb);
+  const uint32_t x3 = __funnelshift_r(a3, a4, sa) ^ __funnelshift_r(b3, b4, sb);
+  // keep the first len bytes: word w keeps min(4, len - 4 w) of them
+  const uint32_t tail = len & 3u, tm = tail ? ((1u << (8u * tail)) - 1u) : 0xffffffffu, nw = (len + 3u) >> 2;
+  uint32_t d = x0 & (nw == 1u ? tm : 0xffffffffu);
+  if (nw > 1u) d |= x1 & (nw == 2u ? tm : 0xffffffffu);
+  if (nw > 2u) d |= x2 & (nw == 3u ? tm : 0xffffffffu);
+  if (nw > 3u) d |= x3 & tm;
+  return d != 0u;
+}
+
+// the same for any length, one lane, 16 bytes a round (used for 17 .. MID_MAX bytes, a row's worth of them side by
+// side).  SAFE = both fields end at least 20 bytes in front of the end of the buffer.
+template <bool SAFE>
 __device__ __forceinline__ bool bytes_differ(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len,
                                              const uint32_t* wlast) {
   const uintptr_t ua = reinterpret_cast<uintptr_t>(a), ub = reinterpret_cast<uintptr_t>(b);
@@ -1098,6 +1154,26 @@ __device__ __forceinline__ bool bytes_differ(const uint8_t* __restrict__ a, cons
   const uint32_t sa = (uint32_t)(ua & 3u) * 8u, sb = (uint32_t)(ub & 3u) * 8u;
   uint32_t pa = __ldg(wa), pb = __ldg(wb);
   const uint32_t nw = (len + 3u) >> 2;
+  const uint32_t tail = len & 3u, tm = tail ? ((1u << (8u * tail)) - 1u) : 0xffffffffu;
+  if (SAFE) {
+    for (uint32_t k = 0; k < nw; k += 4u) {
+      const uint32_t a1 = __ldg(wa + k + 1), a2 = __ldg(wa + k + 2), a3 = __ldg(wa + k + 3), a4 = __ldg(wa + k + 4);
+      const uint32_t b1 = __ldg(wb + k + 1), b2 = __ldg(wb + k + 2), b3 = __ldg(wb + k + 3), b4 = __ldg(wb + k + 4);
+      const uint32_t x0 = __funnelshift_r(pa, a1, sa) ^ __funnelshift_r(pb, b1, sb);
+      const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+      const uint32_t x2 = __funnelshift_r(a2, a3, sa) ^ __funnelshift_r(b2, b3, sb);
+      const uint32_t x3 = __funnelshift_r(a3, a4, sa) ^ __funnelshift_r(b3, b4, sb);
+      pa = a4;
+      pb = b4;
+      const uint32_t left = nw - k;  // words of the field in this round (>= 1)
+      uint32_t d = x0 & (left == 1u ? tm : 0xffffffffu);
+      if (left > 1u) d |= x1 & (left == 2u ? tm : 0xffffffffu);
+      if (left > 2u) d |= x2 & (left == 3u ? tm : 0xffffffffu);
+      if (left > 3u) d |= x3 & (left == 4u ? tm : 0xffffffffu);
+      if (d) return true;
+    }
+    return false;
+  }
   uint32_t diff = 0;
   for (uint32_t k = 0; k < nw && diff == 0u; ++k) {
     const uint32_t* qa = wa + k + 1;
@@ -1106,63 +1182,43 @@ __device__ __forceinline__ bool bytes_differ(const uint8_t* __restrict__ a, cons
     uint32_t x = __funnelshift_r(pa, na, sa) ^ __funnelshift_r(pb, nb, sb);
     pa = na;
     pb = nb;
-    const uint32_t rem = len - 4u * k;
-    if (rem < 4u) x &= (1u << (8u * rem)) - 1u;
+    if (k + 1u == nw) x &= tm;
     diff = x;
   }
   return diff != 0u;
 }
 
-// changed numbers / CHAR cells, `take` <= 32 of them from the ring: value, record, column range (the numeric branch of
-// p1_process)
-__device__ __forceinline__ void d1_numbers(const P1Args& A, const uint32_t* wlast, P1Side& S, uint32_t take) {
-  const unsigned lane = lane_id();
-  const uint32_t head = S.done;
-  if (lane < take) {
-    const uint32_t e = (head + lane) & (SQ - 1u);
-    const uint32_t start = S.start[e], len = S.len[e], col = S.col[e], ord = S.ord[e];
-    const uint8_t t = __ldg(A.types + col);
-    unsigned long long v1, v2;
-    if (len <= NUM_FAST_MAX || t == ZDWB_CHAR) {
-      uint32_t x[5];
-      short_words<5>(A.buf + start, len, wlast, x);
-      if (t == ZDWB_CHAR) {  // ConvertToZDW.cpp:358-361 (range), :543-547 (stored value)
-        const long long b0 = (long long)(int8_t)(x[0] & 0xffu);
-        const long long b1 = len > 1 ? (long long)((int32_t)(int8_t)((x[0] >> 8) & 0xffu) * 256) : 0ll;
-        v1 = (unsigned long long)(b0 + ((x[0] & 0xffu) == (uint32_t)'\\' ? b1 : 0ll));
-        v2 = (unsigned long long)(b0 + b1);
-      } else {
-        if (!fast_number(x, len, &v1)) v1 = parse_u64_field(A.buf + start, len);
-        v2 = v1;
-      }
-    } else {
-      v1 = v2 = parse_u64_field(A.buf + start, len);
+// ... and by the whole warp, 128 bytes a round, for the rare long field (all lanes call, all get the verdict)
+__device__ __forceinline__ bool warp_differ(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len,
+                                            const uint32_t* wlast) {
+  const uintptr_t ua = reinterpret_cast<uintptr_t>(a), ub = reinterpret_cast<uintptr_t>(b);
+  const uint32_t* wa = reinterpret_cast<const uint32_t*>(ua & ~(uintptr_t)3);
+  const uint32_t* wb = reinterpret_cast<const uint32_t*>(ub & ~(uintptr_t)3);
+  const uint32_t sa = (uint32_t)(ua & 3u) * 8u, sb = (uint32_t)(ub & 3u) * 8u;
+  const uint32_t nw = (len + 3u) >> 2;
+  for (uint32_t k0 = 0; k0 < nw; k0 += 32u) {
+    const uint32_t k = k0 + lane_id();
+    uint32_t x = 0;
+    if (k < nw) {
+      const uint32_t* qa = wa + k;
+      const uint32_t* qb = wb + k;
+      x = __funnelshift_r(__ldg(qa), __ldg(qa + 1 <= wlast ? qa + 1 : wlast), sa) ^
+          __funnelshift_r(__ldg(qb), __ldg(qb + 1 <= wlast ? qb + 1 : wlast), sb);
+      const uint32_t rem = len - 4u * k;
+      if (rem < 4u) x &= (1u << (8u * rem)) - 1u;
     }
-    A.rec_col[ord] = col;
-    A.rec_val[ord] = v2;
-    note_column_value(A, col, v1);
+    if (__any_sync(0xffffffffu, x != 0u)) return true;
   }
-  __syncwarp();
-  if (lane == 0) S.done = head + take;
-  __syncwarp();
-}
-__device__ __forceinline__ void d1_texts(const P1Args& A, const uint32_t* wlast, P1Side& S, uint32_t take, P1Stats& st) {
-  const unsigned lane = lane_id();
-  const uint32_t head = S.done;
-  if (lane < take) {
-    const uint32_t e = (head + lane) & (SQ - 1u);
-    text_one<1>(A, wlast, S.start[e], S.len[e], S.col[e], S.ord[e], st);
-  }
-  __syncwarp();
-  if (lane == 0) S.done = head + take;
-  __syncwarp();
+  return false;
 }
 
 // The open row is complete (n fields in the lists of `cur`): bitmap + rank prefix; unless it is the reference row,
 // compare with the row before (lists of cur ^ 1), hand out the records and queue the changed fields.
-// r = row number, or >= A.nrows for the spilled row (its records are dropped, its strings and numbers still count).
+// r = row number, or >= A.nrows for the spilled row (no row entry: its records only feed the dictionary and the column
+// ranges).  The changed fields are only LISTED here (record slot, column, position, length); k_pass1d_values works the
+// list off afterwards - two small kernels instead of one that does not fit the instruction cache.
 __device__ __forceinline__ void d1_finish_row(const D1Args& A, const uint32_t* wlast, D1Warp& W, uint32_t cur, uint32_t n,
-                                              int64_t row_start, int64_t prev_start, bool reference, uint32_t r, P1Stats& st) {
+                                              int64_t row_start, int64_t prev_start, bool reference, uint32_t r) {
   const P1Args& P = A.P;
   const unsigned lane = lane_id();
   const uint32_t BW = (P.ncols + 31u) >> 5, prv = cur ^ 1u;
@@ -1229,25 +1285,71 @@ __device__ __forceinline__ void d1_finish_row(const D1Args& A, const uint32_t* w
   __syncwarp();
   if (reference) return;
 
-  // ---- which fields changed?  batch b's verdicts are kept by lane b
-  uint32_t my_mask = 0, nchg = 0;
+  // ---- which fields changed?  Up to CMP_INLINE bytes are compared on the spot; longer fields of equal length are
+  // listed and compared together afterwards (one lane each, so that no lane drags a 100-byte loop through a batch of
+  // 8-byte fields).  CM[b] = verdicts of batch b.
+  uint32_t nchg = 0, npd = 0;
+  // both rows end far enough from the end of the buffer (a row is at most 64 KiB long): the compares need no clamping
+  const bool safe = (uint64_t)row_start + 65536u + 32u < P.n && (uint64_t)prev_start + 65536u + 32u < P.n;
   for (uint32_t k0 = 0, b = 0; k0 < n; k0 += 32u, ++b) {
     const uint32_t k = k0 + lane;
-    bool changed = false;
+    bool changed = false, pending = false;
     if (k < n) {
       const uint32_t s = W.S[cur][k], len = (uint32_t)W.E[cur][k] - s, col = W.C[k];
       const uint32_t pw = W.BM[prv][col >> 5], bit = col & 31u;
       changed = true;
       if ((pw >> bit) & 1u) {
-        const uint32_t j = (uint32_t)W.PF[prv][col >> 5] + (uint32_t)__popc(pw & ((1u << bit) - 1u));
+        const uint32_t j = (uint32_t)W.PF[prv][col >> 5] + (uint32_t)__popc(pw & bits_below(bit));
         const uint32_t ps = W.S[prv][j], pl = (uint32_t)W.E[prv][j] - ps;
-        if (pl == len) changed = bytes_differ(P.buf + row_start + s, P.buf + prev_start + ps, len, wlast);
+        if (pl == len) {
+          if (len <= CMP_INLINE) {
+            changed = safe ? short_differ<true>(P.buf + row_start + s, P.buf + prev_start + ps, len, wlast)
+                           : short_differ<false>(P.buf + row_start + s, P.buf + prev_start + ps, len, wlast);
+          } else {
+            changed = false;
+            pending = true;
+          }
+        }
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, changed);
-    if (lane == b) my_mask = m;
+    const unsigned m = __ballot_sync(0xffffffffu, changed), mp = __ballot_sync(0xffffffffu, pending);
+    if (lane == 0) W.CM[b] = m;
+    if (pending) W.PD[npd + (uint32_t)__popc(mp & lanemask_lt())] = (uint16_t)k;
     nchg += (uint32_t)__popc(m);
+    npd += (uint32_t)__popc(mp);
   }
+  __syncwarp();
+  for (uint32_t q0 = 0; q0 < npd; q0 += 32u) {
+    const uint32_t q = q0 + lane;
+    bool changed = false, big = false;
+    uint32_t k = 0, s = 0, len = 0, ps = 0;
+    if (q < npd) {
+      k = W.PD[q];
+      s = W.S[cur][k];
+      len = (uint32_t)W.E[cur][k] - s;
+      const uint32_t col = W.C[k];
+      const uint32_t pw = W.BM[prv][col >> 5], bit = col & 31u;
+      ps = W.S[prv][(uint32_t)W.PF[prv][col >> 5] + (uint32_t)__popc(pw & bits_below(bit))];
+      if (len <= MID_MAX) {
+        changed = safe ? bytes_differ<true>(P.buf + row_start + s, P.buf + prev_start + ps, len, wlast)
+                       : bytes_differ<false>(P.buf + row_start + s, P.buf + prev_start + ps, len, wlast);
+      } else {
+        big = true;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {  // the rare long field: the whole warp compares it
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t s2 = __shfl_sync(0xffffffffu, s, src), p2 = __shfl_sync(0xffffffffu, ps, src),
+                     l2 = __shfl_sync(0xffffffffu, len, src);
+      const bool d = warp_differ(P.buf + row_start + s2, P.buf + prev_start + p2, l2, wlast);
+      if ((int)lane == src) changed = d;
+    }
+    if (changed) atomicOr(&W.CM[k >> 5], 1u << (k & 31u));
+    nchg += (uint32_t)__popc(__ballot_sync(0xffffffffu, changed));
+  }
+  __syncwarp();
   // ---- columns that had a value in the row before and are empty now
   uint32_t nte = 0;
   for (uint32_t w = lane; w < BW; w += 32u) nte += (uint32_t)__popc(W.BM[prv][w] & ~W.BM[cur][w]);
@@ -1255,10 +1357,10 @@ __device__ __forceinline__ void d1_finish_row(const D1Args& A, const uint32_t* w
   const uint32_t cnt = nchg + nte;
   // ---- records of the row: one bump allocation
   uint32_t base = 0;
-  if (lane == 0 && cnt && r < A.nrows) base = atomicAdd(&P.meta->rec_count, cnt);
+  if (lane == 0 && cnt) base = atomicAdd(&P.meta->rec_count, cnt);
   base = __shfl_sync(0xffffffffu, base, 0);
-  bool drop = r >= A.nrows;
-  if (!drop && cnt && (base > A.rec_cap || cnt > A.rec_cap - base)) {
+  bool drop = false;
+  if (cnt && (base > A.rec_cap || cnt > A.rec_cap - base)) {
     if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&P.meta->rec_overflow) = 1u;
     drop = true;
   }
@@ -1266,8 +1368,9 @@ __device__ __forceinline__ void d1_finish_row(const D1Args& A, const uint32_t* w
     P.row_rec[r] = base;
     A.row_cnt[r] = drop ? 0u : cnt;
   }
-  // ---- "became empty" records: (column, 0)
-  if (nte && !drop) {
+  if (drop || !cnt) return;
+  // ---- "became empty" records: (column, value 0)
+  if (nte) {
     uint32_t run = 0;
     for (uint32_t w0 = 0; w0 < BW; w0 += 32u) {
       const uint32_t w = w0 + lane;
@@ -1285,33 +1388,25 @@ __device__ __forceinline__ void d1_finish_row(const D1Args& A, const uint32_t* w
         x &= x - 1u;
         P.rec_col[at] = w * 32u + bit;
         P.rec_val[at] = 0ull;
+        A.chg_len[at] = 0u;
         ++at;
       }
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
   }
-  // ---- changed fields: to the number / text rings, each with the record it fills; full batches are worked off
+  // ---- changed fields: listed with the record each of them fills
   uint32_t at = base + nte;
-  for (uint32_t k0 = 0, b = 0; k0 < n; k0 += 32u, ++b) {
-    const unsigned m = __shfl_sync(0xffffffffu, my_mask, (int)b);
+  for (uint32_t k0 = 0, b = 0; k0 < n && nchg; k0 += 32u, ++b) {
+    const unsigned m = W.CM[b];
     if (!m) continue;
     const uint32_t k = k0 + lane;
-    const bool mine = (m >> lane) & 1u;
-    uint32_t start = 0, len = 0, col = 0;
-    bool text = false;
-    if (mine) {
-      const uint32_t s = W.S[cur][k];
-      start = (uint32_t)(row_start + s);
-      len = (uint32_t)W.E[cur][k] - s;
-      col = W.C[k];
-      text = is_text_like(__ldg(P.types + col));
+    if ((m >> lane) & 1u) {
+      const uint32_t s = W.S[cur][k], d = at + (uint32_t)__popc(m & lanemask_lt());
+      P.rec_col[d] = W.C[k];
+      A.chg_start[d] = (uint32_t)(row_start + s);
+      A.chg_len[d] = (uint32_t)W.E[cur][k] - s;
     }
-    const uint32_t ord = drop ? A.rec_cap : at + (uint32_t)__popc(m & lanemask_lt());
     at += (uint32_t)__popc(m);
-    const uint32_t wn = side_push(W.Q[0], mine && !text, start, len, col, ord);
-    if (wn >= 32u) d1_numbers(P, wlast, W.Q[0], 32u);
-    const uint32_t wt = side_push(W.Q[1], mine && text, start, len, col, ord);
-    if (wt >= 32u) d1_texts(P, wlast, W.Q[1], 32u, st);
   }
 }
 
@@ -1332,171 +1427,253 @@ __global__ void __launch_bounds__(D1_THREADS, 8) k_pass1d(const D1Args A) {
   const bool have_prev = pre.rs_p1 != 0u;
   const int64_t scan_from = have_prev ? (int64_t)pre.rs_p1 - 1 : (t0 > 0 ? t0 : 0);
   for (uint32_t w = lane; w < BW; w += 32u) W.BM[0][w] = W.BM[1][w] = 0u;  // "the row before" of a block's first row is empty
-  if (lane < 2) W.Q[lane].end = W.Q[lane].done = 0u;
   __syncwarp();
-  P1Stats st = {0u, 0u, 0u, 0ull};
   const uint32_t tabs_per_row = P.ncols - 1u;
+  uint32_t max_line = 0;
 
   uint32_t cur = 0;
   bool row_open = false, reference = false;
   int64_t row_start = 0, prev_start = 0;
-  uint32_t n_st = 0, n_ne = 0, tabs = 0, row_no = 0, rows_seen = 0;
-  uint32_t c_bs = 0, c_nl = 1, c_bd = 1;  // the scan starts at a row start: behind a row break, no backslash pending
+  uint32_t n_ne = 0, tabs = 0, row_no = 0, rows_seen = 0;
+  uint32_t c_bs = 0, c_nl = 0, c_bd = 0;
   bool bail = false;
 
   int64_t sb = scan_from - ((scan_from - P.lo) & 15);  // step positions are 16-byte aligned in memory
-  for (bool first = true; sb < P.limit && !bail; sb += STEP, first = false) {
-    if (!row_open && sb >= tile_end) break;
-    const int64_t p0 = sb + 16 * (int64_t)lane;
-    uint32_t tab = 0, nl = 0, bs = 0, in = 0;
-    if (p0 < P.limit && p0 + 16 > scan_from) {
-      const uint4 v = ldg_stream_u4(P.buf + p0);
-      const int64_t ia = p0 < scan_from ? scan_from - p0 : 0;
-      const int64_t ib = p0 + 16 > P.limit ? P.limit - p0 : 16;
-      in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
-      tab = chunk_mask(v, '\t') & in;
-      if (chunk_has(v, '\n')) nl = chunk_mask(v, '\n') & in;
-      if (chunk_has(v, '\\')) bs = chunk_mask(v, '\\') & in;
-    }
-    {  // escape parity: only delimiters that directly follow a backslash need the backward walk
-      uint32_t prev = __shfl_up_sync(0xffffffffu, bs >> 15, 1);
-      if (lane == 0) prev = c_bs;
-      uint32_t sus = (tab | nl) & ((bs << 1) | prev);
-      while (sus) {
-        const int i = __ffs(sus) - 1;
-        sus &= sus - 1;
-        if (odd_backslashes_before(P.buf, p0 + i)) {
-          tab &= ~(1u << i);
-          nl &= ~(1u << i);
-        }
-      }
-    }
-    const uint32_t fix = (first && p0 <= scan_from && p0 + 16 > scan_from) ? 1u << (scan_from - p0) : 0u;
-    uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
-    if (lane == 0) prevnl = first ? 0u : c_nl;
-    const uint32_t after_nl = (((nl << 1) | prevnl) & 0xffffu) | fix;
-    const uint32_t skip = nl & after_nl, term = nl & ~skip, bound = tab | nl;
-    uint32_t prevbd = __shfl_up_sync(0xffffffffu, bound >> 15, 1);
-    if (lane == 0) prevbd = first ? 0u : c_bd;
-    const uint32_t after_bound = (((bound << 1) | prevbd) & 0xffffu) | fix;
-    const uint32_t ne = (tab | term) & ~after_bound;   // closing delimiters of non-empty fields
-    const uint32_t fs = after_bound & ~bound & in;      // first bytes of non-empty fields
-    const uint32_t rs = after_nl & ~nl & in;            // first bytes of rows
-    c_bs = __shfl_sync(0xffffffffu, bs >> 15, 31);
-    c_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
-    c_bd = __shfl_sync(0xffffffffu, bound >> 15, 31);
-
-    // ---- walk the step's events in order: a row start opens a row, a terminator completes it
-    const bool plain = row_open && __ballot_sync(0xffffffffu, nl != 0u) == 0u;  // the usual step of a wide row
-    int32_t cursor = 0;
-    for (;;) {
-      if (!row_open) {
-        const uint32_t m = rs & lane_bits_ge(cursor, lane);
-        const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
-        if (!b) break;
-        const int src = __ffs(b) - 1;
-        const int32_t pos = src * 16 + (__ffs(__shfl_sync(0xffffffffu, m, src)) - 1);
-        const int64_t start_abs = sb + pos;
-        if (start_abs >= tile_end) {  // the next warp's row: done
-          sb = P.limit;
-          break;
-        }
-        row_open = true;
-        reference = start_abs < t0;
-        row_start = start_abs;
-        row_no = pre.rows + rows_seen;
-        n_st = n_ne = tabs = 0;
-        cursor = pos;
-      }
-      int32_t seg_end = 511;
-      bool ends = false;
-      if (!plain) {
-        const uint32_t m = term & lane_bits_ge(cursor, lane);
-        const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
-        if (b) {
-          const int src = __ffs(b) - 1;
-          seg_end = src * 16 + (__ffs(__shfl_sync(0xffffffffu, m, src)) - 1);
-          ends = true;
-        }
-      }
-      // ---- the fields of [cursor, seg_end] go to the row's lists at their ordinals
-      {
-        const uint32_t seg = plain ? 0xffffu : (lane_bits_ge(cursor, lane) & lane_bits_le(seg_end, lane));
-        uint32_t s_ = fs & seg, e_ = ne & seg;
-        const uint32_t t_ = tab & seg;
-        const uint32_t mine = (uint32_t)__popc(s_) | ((uint32_t)__popc(e_) << 10) | ((uint32_t)__popc(t_) << 20);
-        uint32_t inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= (unsigned)o) inc += t;
-        }
-        const uint32_t ex = inc - mine, tot = __shfl_sync(0xffffffffu, inc, 31);
-        uint32_t os = n_st + (ex & 1023u), oe = n_ne + ((ex >> 10) & 1023u);
-        const uint32_t tb = tabs + (ex >> 20);
-        // does everything fit?  (field positions are 16-bit, relative to the row start)
-        if (n_st + (tot & 1023u) > DCAP || sb + 512 - row_start > 65535) {
-          bail = true;
-          break;
-        }
-        const uint32_t rel0 = (uint32_t)(p0 - row_start);
-        while (s_) {
-          const uint32_t i = (uint32_t)__ffs(s_) - 1u;
-          s_ &= s_ - 1u;
-          W.S[cur][os++] = (uint16_t)(rel0 + i);
-        }
-        while (e_) {
-          const uint32_t i = (uint32_t)__ffs(e_) - 1u;
-          e_ &= e_ - 1u;
-          W.E[cur][oe] = (uint16_t)(rel0 + i);
-          W.C[oe] = (uint16_t)min(tb + (uint32_t)__popc(t_ & ((1u << i) - 1u)), P.ncols - 1u);
-          ++oe;
-        }
-        n_st += tot & 1023u;
-        n_ne += (tot >> 10) & 1023u;
-        tabs += tot >> 20;
-      }
-      __syncwarp();
-      if (!ends) break;
-      // ---- the row is complete
-      const int64_t term_abs = sb + seg_end;
-      if (!reference) {
-        if (tabs != tabs_per_row) atomicMin(&P.meta->bad_row, row_no);  // ConvertToZDW.cpp:336-337
-        st.max_line = max(st.max_line, (uint32_t)(term_abs - row_start + 1));
-      }
-      if (term_abs >= t0) ++rows_seen;
-      d1_finish_row(A, wlast, W, cur, n_ne, row_start, prev_start, reference, row_no, st);
+  int64_t c_lastb = scan_from - 1;                     // the last boundary in front of the step (the scan starts behind a row break)
+  // One loop, one call site for the row work (the kernel must stay small: it is instruction-cache sensitive).  Every
+  // round either completes a row (need_finish), fetches the next 1 KiB step, or handles the step's next event.
+  bool have_step = false, need_finish = false, final = false, stop = false, first = true, plain = false;
+  uint32_t fin_row = 0;
+  uint32_t tab = 0, term = 0, bound = 0, ne = 0, rs = 0;
+  int32_t lb_in = 0, cursor = 0;
+  for (;;) {
+    if (need_finish) {
+      d1_finish_row(A, wlast, W, cur, n_ne, row_start, prev_start, reference, fin_row);
+      need_finish = false;
+      if (final) break;
       prev_start = row_start;
       cur ^= 1u;
       row_open = false;
-      cursor = seg_end + 1;
     }
+    if (!have_step) {
+      if (bail) break;
+      if (stop || sb >= P.limit || (!row_open && sb >= tile_end)) {
+        // a row the block's limit cut short (the reference's interrupted row): the columns in front
+        // of the limit count for the dictionary and the column ranges, the row itself is not part of the block
+        if (row_open && !reference && n_ne) {
+          need_finish = final = true;
+          fin_row = 0xffffffffu;
+          continue;
+        }
+        break;
+      }
+      const int64_t p0 = sb + 32 * (int64_t)lane;
+      uint32_t nl = 0, bs = 0, in = 0;
+      tab = 0;
+      if (p0 < P.limit && p0 + 32 > scan_from) {
+        const uint4 v0 = ldg_stream_u4(P.buf + p0);
+        const uint4 v1 = p0 + 16 < P.limit ? ldg_stream_u4(P.buf + p0 + 16) : make_uint4(0u, 0u, 0u, 0u);
+        in = 0xffffffffu;
+        if (sb < scan_from || sb + (int64_t)DSTEP > P.limit) {  // (warp-uniform: only the first and the last step)
+          const int64_t ia = p0 < scan_from ? scan_from - p0 : 0;
+          const int64_t ib = p0 + 32 > P.limit ? P.limit - p0 : 32;
+          in = (ib >= 32 ? 0xffffffffu : ((1u << ib) - 1u)) & ~((1u << ia) - 1u);
+        }
+        tab = mask32(v0, v1, '\t') & in;
+        if (chunk_has(v0, '\n') || chunk_has(v1, '\n')) nl = mask32(v0, v1, '\n') & in;
+        if (chunk_has(v0, '\\') || chunk_has(v1, '\\')) bs = mask32(v0, v1, '\\') & in;
+      }
+      {  // escape parity: only delimiters that directly follow a backslash need the backward walk
+        uint32_t prev = __shfl_up_sync(0xffffffffu, bs >> 31, 1);
+        if (lane == 0) prev = c_bs;
+        uint32_t sus = (tab | nl) & ((bs << 1) | prev);
+        while (sus) {
+          const int i = __ffs(sus) - 1;
+          sus &= sus - 1;
+          if (odd_backslashes_before(P.buf, p0 + i)) {
+            tab &= ~(1u << i);
+            nl &= ~(1u << i);
+          }
+        }
+      }
+      const uint32_t fix = (first && p0 <= scan_from && p0 + 32 > scan_from) ? 1u << (scan_from - p0) : 0u;
+      uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 31, 1);
+      if (lane == 0) prevnl = c_nl;
+      const uint32_t after_nl = ((nl << 1) | prevnl) | fix;
+      const uint32_t skip = nl & after_nl;
+      term = nl & ~skip;
+      bound = tab | nl;
+      uint32_t prevbd = __shfl_up_sync(0xffffffffu, bound >> 31, 1);
+      if (lane == 0) prevbd = c_bd;
+      const uint32_t after_bound = ((bound << 1) | prevbd) | fix;
+      ne = (tab | term) & ~after_bound;   // closing delimiters of non-empty fields
+      rs = after_nl & ~nl & in;           // first bytes of rows
+      c_bs = __shfl_sync(0xffffffffu, bs >> 31, 31);
+      c_nl = __shfl_sync(0xffffffffu, nl >> 31, 31);
+      c_bd = __shfl_sync(0xffffffffu, bound >> 31, 31);
+      {  // the last boundary in front of every lane's bytes, as a step position (negative: in an earlier step)
+        const int32_t mine = bound ? (int32_t)(lane * 32u) + (31 - __clz(bound)) : INT32_MIN;
+        int32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= (unsigned)o) inc = max(inc, t);
+        }
+        lb_in = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) lb_in = INT32_MIN;
+        lb_in = max(lb_in, (int32_t)(c_lastb - sb));
+        const int32_t top = __shfl_sync(0xffffffffu, inc, 31);
+        if (top != INT32_MIN) c_lastb = sb + top;
+      }
+      plain = row_open && __ballot_sync(0xffffffffu, nl != 0u) == 0u;  // the usual step of a wide row
+      cursor = 0;
+      have_step = true;
+      first = false;
+    }
+    // ---- the step's next event: a row start opens a row, a terminator completes it
+    if (!row_open) {
+      const uint32_t m = rs & lane_bits_ge(cursor, lane);
+      const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+      if (!b) {
+        have_step = false;
+        sb += DSTEP;
+        continue;
+      }
+      const int src = __ffs(b) - 1;
+      const int32_t pos = src * 32 + (__ffs(__shfl_sync(0xffffffffu, m, src)) - 1);
+      const int64_t start_abs = sb + pos;
+      if (start_abs >= tile_end) {  // the next warp's row: done
+        stop = true;
+        have_step = false;
+        continue;
+      }
+      row_open = true;
+      reference = start_abs < t0;
+      row_start = start_abs;
+      row_no = pre.rows + rows_seen;
+      n_ne = tabs = 0;
+      cursor = pos;
+    }
+    int32_t seg_end = (int32_t)DSTEP - 1;
+    bool ends = false;
+    if (!plain) {
+      const uint32_t m = term & lane_bits_ge(cursor, lane);
+      const unsigned b = __ballot_sync(0xffffffffu, m != 0u);
+      if (b) {
+        const int src = __ffs(b) - 1;
+        seg_end = src * 32 + (__ffs(__shfl_sync(0xffffffffu, m, src)) - 1);
+        ends = true;
+      }
+    }
+    // ---- the fields that close in [cursor, seg_end]: every lane drops the positions of its closing delimiters into
+    // the row's list at their ordinals; then field k is worked out by lane k & 31 - column from the tabs in front of
+    // it, first byte from the last boundary in front of it
+    {
+      const uint32_t seg = plain ? 0xffffffffu : (lane_bits_ge(cursor, lane) & lane_bits_le(seg_end, lane));
+      uint32_t e_ = ne & seg;
+      const uint32_t t_ = tab & seg;
+      const uint32_t mine = (uint32_t)__popc(e_) | ((uint32_t)__popc(t_) << 16);
+      uint32_t inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      const uint32_t ex = inc - mine, tot = __shfl_sync(0xffffffffu, inc, 31);
+      const uint32_t nf = tot & 0xffffu;
+      // does everything fit?  (field positions are 16-bit, relative to the row start)
+      if (n_ne + nf > DCAP || sb + (int64_t)DSTEP - row_start > 65535) {
+        bail = true;
+        have_step = false;
+        continue;
+      }
+      const int32_t rel_sb = (int32_t)(sb - row_start);  // step position -> row-relative position
+      uint32_t oe = n_ne + (ex & 0xffffu);
+      while (e_) {
+        const uint32_t i = (uint32_t)__ffs(e_) - 1u;
+        e_ &= e_ - 1u;
+        W.E[cur][oe++] = (uint16_t)(rel_sb + (int32_t)(lane * 32u + i));
+      }
+      __syncwarp();
+      const uint32_t tb = tabs + (ex >> 16);
+      for (uint32_t k0 = 0; k0 < nf; k0 += 32u) {
+        const uint32_t k = n_ne + k0 + lane;
+        const bool mine_f = k0 + lane < nf;
+        const int32_t pos = mine_f ? (int32_t)W.E[cur][k] - rel_sb : 0;
+        const int j = pos >> 5;
+        const uint32_t i = (uint32_t)pos & 31u;
+        const uint32_t tj = __shfl_sync(0xffffffffu, t_, j), bj = __shfl_sync(0xffffffffu, bound, j);
+        const uint32_t tbj = __shfl_sync(0xffffffffu, tb, j);
+        const int32_t lbj = __shfl_sync(0xffffffffu, lb_in, j);
+        if (mine_f) {
+          const uint32_t lowb = bj & bits_below(i);
+          const int32_t fs = (lowb ? j * 32 + (31 - __clz(lowb)) : lbj) + 1;
+          W.S[cur][k] = (uint16_t)(rel_sb + fs);
+          W.C[k] = (uint16_t)min(tbj + (uint32_t)__popc(tj & bits_below(i)), P.ncols - 1u);
+        }
+      }
+      n_ne += nf;
+      tabs += tot >> 16;
+    }
+    __syncwarp();
+    if (!ends) {
+      have_step = false;
+      sb += DSTEP;
+      continue;
+    }
+    // ---- the row is complete
+    const int64_t term_abs = sb + seg_end;
+    if (!reference) {
+      if (tabs != tabs_per_row) atomicMin(&P.meta->bad_row, row_no);  // ConvertToZDW.cpp:336-337
+      max_line = max(max_line, (uint32_t)(term_abs - row_start + 1));
+    }
+    if (term_abs >= t0) ++rows_seen;
+    need_finish = true;
+    fin_row = row_no;
+    cursor = seg_end + 1;
   }
   if (bail) {
     if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&P.meta->delta_bail) = 1u;
     return;
   }
-  // a row the block's limit cut short (the reference's interrupted row): the columns in front of the
-  // limit count for the dictionary and the column ranges, the row itself is not part of the block
-  if (row_open && !reference && n_ne) d1_finish_row(A, wlast, W, cur, n_ne, row_start, prev_start, false, 0xffffffffu, st);
-  {
-    const uint32_t wn = W.Q[0].end - W.Q[0].done;
-    if (wn) d1_numbers(P, wlast, W.Q[0], wn);
-    const uint32_t wt = W.Q[1].end - W.Q[1].done;
-    if (wt) d1_texts(P, wlast, W.Q[1], wt, st);
+  if (lane == 0 && max_line) atomicMax(&P.meta->max_line, max_line);
+}
+
+// Second half of the row-delta pass 1: the value of every listed field (parseInput's strtoull / CHAR tuple /
+// Dictionary::insert, ConvertToZDW.cpp:345-402) - p1_process over a flat list, 32 fields a batch, texts parked by
+// length class as in k_pass1.  Persistent warps: batch b goes to warp b mod (warps of the grid).
+struct D1List {
+  const uint32_t* start;
+  const uint32_t* len;
+  const uint32_t* col;
+};
+__global__ void __launch_bounds__(ENC_THREADS, 4) k_pass1d_values(const P1Args A, const D1List L, uint32_t rec_cap) {
+  __shared__ P1Side s_side[ENC_WARPS][2];
+  const EncMeta* meta = A.meta;
+  if (meta->delta_bail || meta->rec_overflow) return;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t total = min(meta->rec_count, rec_cap);
+  const uint32_t* wlast = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(A.buf + A.n - 1) & ~(uintptr_t)3);
+  P1Side* Q = s_side[warp];
+  if (lane < 2) Q[lane].end = Q[lane].done = 0u;
+  __syncwarp();
+  P1Stats st = {0u, 0u, 0u, 0ull};
+  const uint32_t stride = gridDim.x * ENC_WARPS * 32u;
+  // one call site: the round after the last batch flushes the parked texts
+  for (uint32_t base = (blockIdx.x * ENC_WARPS + warp) * 32u;; base += stride) {
+    const bool last = base >= total;
+    const uint32_t count = last ? 0u : min(32u, total - base);
+    p1_process<1>(A, wlast, L, last ? 0u : base, count, base, nullptr, st, Q, last);
+    if (last) break;
   }
-  st.max_line = __reduce_max_sync(0xffffffffu, st.max_line);
   st.max_len = __reduce_max_sync(0xffffffffu, st.max_len);
   st.new_count = __reduce_add_sync(0xffffffffu, st.new_count);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) st.new_bytes += __shfl_xor_sync(0xffffffffu, st.new_bytes, o);
-  if (lane == 0) {
-    if (st.max_line) atomicMax(&P.meta->max_line, st.max_line);
-    if (st.new_count) {
-      atomicAdd(&P.meta->n_unique, (unsigned long long)st.new_count);
-      atomicAdd(&P.meta->dict_str_bytes, st.new_bytes);
-      atomicMax(&P.meta->max_str_len, st.max_len);
-    }
+  if (lane == 0 && st.new_count) {
+    atomicAdd(&A.meta->n_unique, (unsigned long long)st.new_count);
+    atomicAdd(&A.meta->dict_str_bytes, st.new_bytes);
+    atomicMax(&A.meta->max_str_len, st.max_len);
   }
 }
 
@@ -2157,7 +2334,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   bool delta = ctx->enc_delta != 0 && ncols <= DELTA_MAX_COLS && n >= 64 &&
                (ctx->enc_delta == 1 || (!ctx->delta_bailed && (ctx->last_row_bytes == 0 || ctx->last_row_bytes >= DELTA_MIN_ROW_BYTES)));
 
-  DevBuf agg, colset, colmin, colmax, slots, rec_col, rec_val, row_rec, row_cnt;
+  DevBuf agg, colset, colmin, colmax, slots, rec_col, rec_val, row_rec, row_cnt, chg_start, chg_len;
   HashTable ht{nullptr, 0};
   uint32_t nrows = 0;
   bool is_last = false;
@@ -2269,6 +2446,10 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     }
     ZDWB_TRY(rec_col.alloc(ctx, (size_t)(rec_cap + 1) * 4));
     ZDWB_TRY(rec_val.alloc(ctx, (size_t)(rec_cap + 1) * 8));
+    if (delta) {
+      ZDWB_TRY(chg_start.alloc(ctx, (size_t)(rec_cap + 1) * 4));
+      ZDWB_TRY(chg_len.alloc(ctx, (size_t)(rec_cap + 1) * 4));
+    }
     uint32_t cap_log2 = (uint32_t)std::max<long long>(10, std::min<long long>(ctx->ht_initial_log2, 31));
     while (cap_log2 < 31 && (1ull << cap_log2) < ctx->last_unique * 4) ++cap_log2;  // blocks of one file look alike
     if (!delta) {
@@ -2316,8 +2497,19 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
         D.nrows = nrows;
         D.rec_cap = (uint32_t)rec_cap;
         D.row_cnt = row_cnt.as<uint32_t>();
-        KernelScope _ks(ctx, "k_pass1d");
-        k_pass1d<<<(p1_tiles + D1_WARPS - 1) / D1_WARPS, D1_THREADS, 0, st>>>(D);
+        D.chg_start = chg_start.as<uint32_t>();
+        D.chg_len = chg_len.as<uint32_t>();
+        {
+          KernelScope _ks(ctx, "k_pass1d");
+          k_pass1d<<<(p1_tiles + D1_WARPS - 1) / D1_WARPS, D1_THREADS, 0, st>>>(D);
+        }
+        ZDWB_LAUNCH_CHECK(ctx);
+        D1List L;
+        L.start = chg_start.as<uint32_t>();
+        L.len = chg_len.as<uint32_t>();
+        L.col = rec_col.as<uint32_t>();
+        KernelScope _ks(ctx, "k_pass1d_values");
+        k_pass1d_values<<<ctx->sm_count * 4, ENC_THREADS, 0, st>>>(A, L, (uint32_t)rec_cap);
       } else {
         KernelScope _ks(ctx, "k_pass1");
         k_pass1<<<(p1_tiles + ENC_WARPS - 1) / ENC_WARPS, ENC_THREADS, 0, st>>>(A);
@@ -2344,6 +2536,8 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
         rec_cap = std::min<uint64_t>(std::max<uint64_t>(rec_cap * 4, (uint64_t)hmeta->rec_count + 64), limit + 64);
         ZDWB_TRY(rec_col.alloc(ctx, (size_t)(rec_cap + 1) * 4));
         ZDWB_TRY(rec_val.alloc(ctx, (size_t)(rec_cap + 1) * 8));
+        ZDWB_TRY(chg_start.alloc(ctx, (size_t)(rec_cap + 1) * 4));
+        ZDWB_TRY(chg_len.alloc(ctx, (size_t)(rec_cap + 1) * 4));
       }
       // reset the counters pass 1 accumulates
       EncMeta z = *hmeta;
@@ -2453,6 +2647,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     const uint64_t rec_per_row = std::max<uint64_t>(1, recs / std::max<uint64_t>(delta ? nrows : rows_total, 1));
     uint32_t rpc2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, 4096 / rec_per_row), 1024);
     rpc2 = (uint32_t)std::min<uint64_t>(rpc2, by_smem - 1);
+    if (delta) rpc2 = std::min<uint32_t>(rpc2, 16);  // measured on C4: 16-row tiles (6 CTAs per SM) beat 30-row ones
     if (ctx->enc_p2_rows > 0) rpc2 = (uint32_t)std::min<uint64_t>((uint64_t)ctx->enc_p2_rows, by_smem - 1);
     tiles2 = (nrows + rpc2 - 1) / rpc2;
     tile_cap = (((uint64_t)rpc2 * hmeta->max_row_bytes) + 15) & ~15ull;
