@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ZDWB_ABI_VERSION 2
+#define ZDWB_ABI_VERSION 3
 
 /* status codes (mapped to the reference's ERR_CODE enums by the host classes) */
 enum {
@@ -92,6 +92,9 @@ unsigned long long zdwb_ctx_kernel_launches(const zdwb_ctx* ctx);
 size_t zdwb_ctx_kernel_times(zdwb_ctx* ctx, char* buf, size_t cap);
 
 int zdwb_abi_version(void);
+
+/* Number of CUDA devices this process can use (0 = none; the host tools spread whole ZDW blocks over them). */
+int zdwb_device_count(void);
 
 /* ---- schema ---------------------------------------------------------------------------------- */
 
@@ -174,7 +177,9 @@ typedef struct {
   int32_t validate_only;     /* -t: walk every row, bounds-check dictionary offsets, produce no text (:1488-1572) */
   uint64_t first_row_number; /* number of the block's first row (1-based, runs on across blocks) */
   int32_t want_flag_counts;  /* -s: also return out->flag_counts[ncols_used] = rows in which the column's bit is set */
-  int32_t reserved3;
+  int32_t skim_only;         /* only find where the block ends: out->consumed (and the header fields) are filled in, no row is
+                                formatted.  The file has no block length (UnconvertFromZDW.cpp:782-810,1577-1589): a host that
+                                spreads blocks over several GPUs skims block k to learn where block k+1 starts */
 } zdwb_decode_opts;
 
 typedef struct {
@@ -198,7 +203,7 @@ int zdwb_decode_block(zdwb_ctx* ctx, const zdwb_schema* schema, const void* zdw,
                       const zdwb_decode_opts* opts, zdwb_rows_out* out);
 
 /* ---- pinned host staging (used by the host classes and the end-to-end bench) ------------------ */
-void* zdwb_host_alloc(size_t bytes);   /* cudaHostAlloc'd (pinned) memory, NULL on failure */
+void* zdwb_host_alloc(size_t bytes);   /* cudaHostAlloc'd (pinned, usable from every device) memory, NULL on failure */
 void zdwb_host_free(void* p);
 
 #ifdef __cplusplus

@@ -335,3 +335,134 @@ def test_block_plan_flag_reproduces_the_references_memory_cut():
         rc, out, err = run(BIN, "convertDWfile", ["-q", flag, "--block-bytes=16777216", "x.sql"], d, timeout=600)
         assert rc == 0, (out + err)[-500:]
         assert (d / "x.zdw.gz").read_bytes() == image
+
+
+# ------------------------------------------------------------------------------------------------ block fan-out
+def _gpu_count():
+    try:
+        from zdw_b200.capi import load_library
+        return load_library().zdwb_device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [["--lanes-per-gpu=1"], ["--gpus=0,0", "--lanes-per-gpu=3"], ["--gpus=0,0,0"]])
+def test_encode_workers_write_the_sequential_file(flags):
+    """Whole blocks dealt out to several encode workers (here: several contexts on device 0): the windows are cut on the
+    host before any block is encoded, the blocks leave in file order - same bytes as the one-context loop
+    (--lanes-per-gpu=1) and as the restatement for those cuts."""
+    tsv = O.golden("movie_tickets.sql")[: 3 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    desc = O.golden("movie_tickets.desc.sql")
+    ours = encode_both(tsv, desc, ["--block-bytes=131072", *flags])[0]
+    assert ours[0] == 0, ours[2]
+    plan = _window_plan(tsv, 131072)
+    want = O.encode(O.parse_desc(desc), tsv, plan=plan)
+    assert want.nblocks == len(plan) + 1 >= 20
+    assert ours[1] == want.data
+    assert "Rows=%d" % want.total_rows in ours[2]
+
+
+@pytest.mark.gpu
+def test_encode_workers_report_the_first_bad_row():
+    """A malformed row in a later window: exit code 2, the reference's message, the .creating file stays (App. B-19)."""
+    rows = [b"%d\tabc\t%d" % (i, i * 3) for i in range(40000)]
+    rows[31000] = b"1\t2"
+    tsv = b"\n".join(rows) + b"\n"
+    desc = corpus.desc([("a", "int(11)"), ("b", "varchar(8)"), ("c", "int(11)")])
+    for flags in (["--lanes-per-gpu=1"], ["--gpus=0,0"]):
+        ours = encode_both(tsv, desc, ["--block-bytes=65536", *flags])[0]
+        assert ours[0] == 2, ours[2]
+        assert "had the problem" in ours[2] and "WRONG_NUM_OF_COLUMNS_ON_A_ROW" in ours[2]
+        assert "x.creating.zdw.gz" in ours[3] and "x.zdw.gz" not in ours[3]
+
+
+@pytest.mark.gpu
+def test_c4_file_on_two_gpus_equals_one_gpu_and_the_oracle():
+    """>= 16 blocks of C4-shaped rows: --gpus=2 (two real devices; below two GPUs the second worker group shares device
+    0) writes the bytes of --gpus=1 and of the restatement, and the reference decodes them to the source rows."""
+    import ctypes as C
+
+    import bench
+    synth = bench.Synth()
+    rows = 1024
+    cap = synth.cap_for(rows)
+    buf = (C.c_uint8 * cap)()
+    parts = []
+    for b in range(18):
+        n = synth.block_into(40 + b, rows, C.addressof(buf), cap)
+        parts.append(bytes(memoryview(buf)[:n]))
+    tsv = b"".join(parts)
+    window = len(tsv) // 17
+    two = "--gpus=2" if _gpu_count() >= 2 else "--gpus=0,0"
+    one = encode_both(tsv, synth.desc, [f"--block-bytes={window}", "--gpus=1", "--lanes-per-gpu=1"])[0]
+    par = encode_both(tsv, synth.desc, [f"--block-bytes={window}", two])[0]
+    assert one[0] == 0 and par[0] == 0, one[2] + par[2]
+    assert one[1] == par[1]
+    plan = _window_plan(tsv, window)
+    want = O.encode(O.parse_desc(synth.desc), tsv, plan=plan)
+    assert want.nblocks >= 16 and par[1] == want.data
+    rc, ref_tsv, err = O.ref_decode(par[1], timeout=600)
+    assert rc == 0 and ref_tsv == tsv, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [["--lanes-per-gpu=1"], ["--gpus=0,0", "--lanes-per-gpu=2"], ["--lanes-per-gpu=3"]])
+def test_decode_workers_write_the_sequential_rows(flags):
+    """Blocks skimmed for their length by the calling thread and decoded by several workers: to a regular file (blocks
+    written side by side at their offsets) and to stdout (in order through the pipe) - the rows of the one-context
+    loop, the reference's rows, column selection and the block header lines included."""
+    tsv = O.golden("movie_tickets.sql")[: 3 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    desc = O.golden("movie_tickets.desc.sql")
+    img = O.encode(O.parse_desc(desc), tsv, rows_per_block=2500)
+    assert img.nblocks >= 15
+    a, b = decode_both(img.data, ["-q", *flags])
+    assert a[0] == b[0] == 0, a[2]
+    assert a[3]["x.sql"] == b[3]["x.sql"] == tsv
+    with Work() as d:
+        (d / "x.zdw").write_bytes(img.data)
+        rc, out, err = run(BIN, "unconvertDWfile", ["-q", *flags, "-", "x.zdw"], d)
+        assert rc == 0 and out == tsv, err
+        rc, out, err = run(BIN, "unconvertDWfile", ["-q", *flags, "-c", "price,virtual_export_row,title", "--non-empty-column-header", "-", "x.zdw"], d)
+        rc2, out2, err2 = run(REF, "unconvertDWfile", ["-q", "-c", "price,virtual_export_row,title", "--non-empty-column-header", "-", "x.zdw"], d)
+        assert rc == rc2 == 0 and out == out2, err
+
+
+@pytest.mark.gpu
+def test_decode_workers_stop_at_a_corrupt_block():
+    """A block cut short in the middle of a multi-block file: same exit code and message as the one-context loop; the
+    rows in front of the bad block are written, nothing behind it."""
+    tsv = O.golden("movie_tickets.sql")[: 1 << 20].rsplit(b"\n", 1)[0] + b"\n"
+    desc = O.golden("movie_tickets.desc.sql")
+    img = O.encode(O.parse_desc(desc), tsv, rows_per_block=2500).data
+    cut = img[: len(img) * 2 // 3]
+    res = []
+    for flags in (["--lanes-per-gpu=1"], ["--gpus=0,0"]):
+        with Work() as d:
+            (d / "x.zdw").write_bytes(cut)
+            rc, out, err = run(BIN, "unconvertDWfile", ["-q", *flags, "x.zdw"], d)
+            res.append((rc, (d / "x.sql").read_bytes() if (d / "x.sql").exists() else None))
+    assert res[0][0] == res[1][0] != 0
+    assert res[0][1] == res[1][1] and tsv.startswith(res[1][1])
+
+
+@pytest.mark.gpu
+def test_c4_file_decodes_on_two_gpus():
+    import ctypes as C
+
+    import bench
+    synth = bench.Synth()
+    rows = 1024
+    cap = synth.cap_for(rows)
+    buf = (C.c_uint8 * cap)()
+    parts = []
+    for b in range(17):
+        n = synth.block_into(70 + b, rows, C.addressof(buf), cap)
+        parts.append(bytes(memoryview(buf)[:n]))
+    tsv = b"".join(parts)
+    img = O.encode(O.parse_desc(synth.desc), tsv, rows_per_block=rows)
+    assert img.nblocks == 17
+    two = "--gpus=2" if _gpu_count() >= 2 else "--gpus=0,0"
+    a, b = decode_both(img.data, ["-q", two])
+    assert a[0] == 0, a[2]
+    assert a[3]["x.sql"] == tsv == b[3]["x.sql"]

@@ -16,7 +16,7 @@ STATUS_NAMES = {0: "OK", 1: "ERR_CUDA", 2: "ERR_OOM", 3: "ERR_WRONG_COLUMNS", 4:
                 6: "ERR_CORRUPT", 7: "ERR_TRUNCATED", 8: "ERR_ROW_COUNT", 9: "ERR_NO_DEVICE"}
 
 EXPORTED_SYMBOLS = [
-    "zdwb_abi_version", "zdwb_ctx_create", "zdwb_ctx_destroy", "zdwb_last_error", "zdwb_ctx_set_stream",
+    "zdwb_abi_version", "zdwb_device_count", "zdwb_ctx_create", "zdwb_ctx_destroy", "zdwb_last_error", "zdwb_ctx_set_stream",
     "zdwb_ctx_set_tuning", "zdwb_ctx_kernel_launches", "zdwb_ctx_kernel_times", "zdwb_encode_block", "zdwb_decode_block", "zdwb_host_alloc",
     "zdwb_host_free",
 ]
@@ -61,7 +61,7 @@ class _DecOpts(C.Structure):
                 ("at_end_of_file", C.c_int32), ("separator", C.c_uint8), ("reserved", C.c_uint8 * 7),
                 ("out_col", C.POINTER(C.c_int32)), ("n_out", C.c_uint32), ("n_fills", C.c_uint32),
                 ("fills", C.POINTER(_Fill)), ("rownum_pos", C.c_int32), ("validate_only", C.c_int32),
-                ("first_row_number", C.c_uint64), ("want_flag_counts", C.c_int32), ("reserved3", C.c_int32)]
+                ("first_row_number", C.c_uint64), ("want_flag_counts", C.c_int32), ("skim_only", C.c_int32)]
 
 
 class _RowsOut(C.Structure):
@@ -85,6 +85,7 @@ def load_library():
                           "(zdw_b200 has no CPU fallback)")
     L = C.CDLL(str(p))
     L.zdwb_abi_version.restype = C.c_int
+    L.zdwb_device_count.restype = C.c_int
     L.zdwb_ctx_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
     L.zdwb_ctx_destroy.argtypes = [C.c_void_p]
     L.zdwb_ctx_destroy.restype = None
@@ -223,7 +224,8 @@ class Context:
     # ------------------------------------------------------------------ decode
     def decode_block(self, types, zdw, avail: int | None = None, *, input_on_device=False, output_on_device=False,
                      want_row_offsets=False, at_end_of_file=True, separator=b"\t", out_col=None, n_out=0, fills=None,
-                     rownum_pos=-1, first_row_number=1, validate_only=False, want_flag_counts=False) -> DecodedBlock:
+                     rownum_pos=-1, first_row_number=1, validate_only=False, want_flag_counts=False,
+                     skim_only=False) -> DecodedBlock:
         """fills: {output position: bytes} constant texts for positions no file column maps to."""
         tarr = (C.c_uint8 * max(len(types), 1))(*types)
         sch = _Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
@@ -243,7 +245,7 @@ class Context:
         o = _DecOpts(int(input_on_device), int(output_on_device), int(want_row_offsets), int(at_end_of_file),
                      separator[0], (C.c_uint8 * 7)(), C.cast(oc, C.POINTER(C.c_int32)) if oc is not None else None,
                      n_out, len(fills) if fills else 0, C.cast(fl, C.POINTER(_Fill)) if fl is not None else None,
-                     rownum_pos, int(validate_only), first_row_number, int(want_flag_counts), 0)
+                     rownum_pos, int(validate_only), first_row_number, int(want_flag_counts), int(skim_only))
         out = _RowsOut()
         rc = self._L.zdwb_decode_block(self._h, C.byref(sch), ptr, avail, C.byref(o), C.byref(out))
         if rc:

@@ -19,6 +19,15 @@ extern "C" {
 
 int zdwb_abi_version(void) { return ZDWB_ABI_VERSION; }
 
+int zdwb_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
 int zdwb_ctx_create(int device, size_t workspace_hint, zdwb_ctx** out) {
   if (!out) return ZDWB_ERR_BAD_ARG;
   *out = nullptr;
@@ -180,7 +189,7 @@ int zdwb_decode_block(zdwb_ctx* c, const zdwb_schema* schema, const void* zdw, s
 
 void* zdwb_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
     (void)cudaGetLastError();
     return nullptr;
   }

@@ -1110,6 +1110,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
     consumed_stream = h_end;
   }
   out->consumed = rows_base + consumed_stream;
+  if (opts->skim_only) return ZDWB_OK;  // the caller only wanted to know where the next block starts
 
   // ---- strips: one warp walks RS consecutive rows (k_dec_rows); about four waves of warps over the GPU
   if (U >= (1u << 24) || NI >= (1u << 24)) {

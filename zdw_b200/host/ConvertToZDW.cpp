@@ -12,7 +12,11 @@
 #include <fstream>
 #include <new>
 
+#include "block_pipeline.h"
 #include "stream_pipeline.h"
+
+#include <atomic>
+#include <thread>
 
 using std::map;
 using std::string;
@@ -50,7 +54,7 @@ void plainFree(void* p) { free(p); }
 
 ConvertToZDW::ConvertToZDW(const bool quiet, const bool streamingInput)
     : compressor(GZIP), statusOutput(defaultStatusOutputCallback), bQuiet(quiet), bTrimTrailingSpaces(false),
-      bStreamingInput(streamingInput), rowsPerBlock(0), blockBytes(DEFAULT_BLOCK_BYTES), gpuDevice(-1) {}
+      bStreamingInput(streamingInput), rowsPerBlock(0), blockBytes(DEFAULT_BLOCK_BYTES), gpuDevice(-1), lanesPerGpu(2) {}
 
 ConvertToZDW::~ConvertToZDW() {}
 
@@ -196,6 +200,188 @@ ConvertToZDW::ERR_CODE ConvertToZDW::validate(const char* zdwFile, const vector<
   return system(cmd.c_str()) == 0 ? OK : FILES_DIFFER;
 }
 
+// ---- several encode workers (the reference's block loop is ConvertToZDW.cpp:765-894) ----------------
+// The windows of the file are cut on the host first (block_pipeline.h), then dealt out: worker w takes the next window
+// that nobody has, reads it straight from the file into its own pinned buffer (so the reads run side by side too),
+// encodes it on its GPU and hands the block to the calling thread, which puts the blocks out in file order with isLast
+// and the cumulative longestLine patched (:841-842, :965).
+struct ConvertToZDW::ParallelOutcome {
+  uint64_t totalRows;
+  int blocks;
+  bool wrongColumns;
+  uint32_t badRow;
+  ParallelOutcome() : totalRows(0), blocks(0), wrongColumns(false), badRow(0) {}
+};
+
+namespace {
+struct EncodedBlock {
+  int rc;
+  std::string err;
+  vector<unsigned char> bytes;
+  uint32_t nrows, longest, badRow, idxSize;
+  uint64_t dictBytes, dictEntries;
+  bool skipped;
+  EncodedBlock() : rc(ZDWB_OK), nrows(0), longest(0), badRow(0), idxSize(0), dictBytes(0), dictEntries(0), skipped(false) {}
+};
+uint32_t readU32(const unsigned char* p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+}  // namespace
+
+ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t windowBytes, const DescSchema& schema,
+                                                           const char* filestub, const char* exeName, AsyncWriter& writer,
+                                                           ParallelOutcome& outcome) {
+  const int fd = fileno(in);
+  struct stat st;
+  if (fstat(fd, &st) != 0) return MISSING_SQL_FILE;
+  vector<FileWindow> wins;
+  size_t cap = windowBytes;
+  if (!planFileWindows(fd, (uint64_t)st.st_size, windowBytes, MAX_WINDOW_BYTES, wins, &cap)) {
+    statusOutput(ERROR, "%s: a single row exceeds %zu bytes (or the input could not be read)\n", exeName, (size_t)MAX_WINDOW_BYTES);
+    return UNKNOWN_ERROR;
+  }
+  size_t maxLen = 0;
+  for (size_t k = 0; k < wins.size(); ++k) maxLen = std::max(maxLen, wins[k].len);
+
+  vector<int> workers;  // CUDA device of every worker
+  {
+    vector<int> devices = gpuList;
+    if (devices.empty()) devices.push_back(GpuSession::resolve(gpuDevice));
+    const int lanes = std::max(1, lanesPerGpu);
+    for (int l = 0; l < lanes; ++l)  // lane-major: the first windows go to different devices
+      for (size_t d = 0; d < devices.size(); ++d) workers.push_back(devices[d]);
+    if (workers.size() > wins.size()) workers.resize(std::max<size_t>(1, wins.size()));
+  }
+  zdwb_schema sch;
+  sch.ncols = (uint32_t)schema.types.size();
+  sch.types = schema.types.data();
+
+  OrderedResults<EncodedBlock> results(wins.size());
+  std::atomic<size_t> next(0);
+  std::atomic<bool> cancel(false);
+  const size_t ahead = workers.size() + 2;
+  const bool trim = bTrimTrailingSpaces;
+  auto work = [&](int device) {
+    GpuSession session;
+    char* buf = NULL;
+    std::string fatal;
+    int fatalRc = ZDWB_OK;
+    if (!session.open(device)) {
+      fatal = "no usable CUDA device (" + session.lastError() + "); this build has no CPU path";
+      fatalRc = ZDWB_ERR_NO_DEVICE;
+    } else if (!(buf = static_cast<char*>(zdwb_host_alloc(maxLen + 64)))) {
+      fatal = "pinned window allocation failed";
+      fatalRc = ZDWB_ERR_OOM;
+    }
+    for (;;) {
+      const size_t k = next.fetch_add(1);
+      if (k >= wins.size()) break;
+      results.waitTurn(k, ahead);
+      EncodedBlock r;
+      if (fatalRc != ZDWB_OK) {
+        r.rc = fatalRc;
+        r.err = fatal;
+        cancel = true;
+      } else if (cancel) {
+        r.skipped = true;
+      } else {
+        const FileWindow& w = wins[k];
+        size_t got = 0;
+        while (got < w.len) {
+          const ssize_t n = pread(fd, buf + got, w.len - got, (off_t)(w.offset + got));
+          if (n <= 0) break;
+          got += (size_t)n;
+        }
+        zdwb_encode_opts eo;
+        memset(&eo, 0, sizeof(eo));
+        eo.trim_trailing_spaces = trim ? 1 : 0;
+        eo.more_input_follows = w.more ? 1 : 0;
+        zdwb_block_out blk;
+        memset(&blk, 0, sizeof(blk));
+        if (got != w.len) {
+          r.rc = ZDWB_ERR_BAD_ARG;
+          r.err = "short read of the input file";
+        } else {
+          r.rc = zdwb_encode_block(session.get(), &sch, buf, w.len, &eo, &blk);
+          if (r.rc != ZDWB_OK) r.err = zdwb_last_error(session.get());
+        }
+        r.badRow = blk.bad_row;
+        if (r.rc == ZDWB_OK && blk.nrows && w.more && blk.tsv_consumed != w.consumed) {
+          r.rc = ZDWB_ERR_BAD_ARG;  // the host's cut and the GPU's disagree: never write such a file
+          r.err = "internal error: window cut mismatch (host " + std::to_string(w.consumed) + ", GPU " +
+                  std::to_string((unsigned long long)blk.tsv_consumed) + ")";
+        }
+        if (r.rc == ZDWB_OK) {
+          r.bytes.assign(blk.bytes, blk.bytes + blk.len);
+          r.nrows = blk.nrows;
+          r.longest = blk.longest_line;
+          r.idxSize = blk.dict_index_size;
+          r.dictBytes = blk.dict_bytes;
+          r.dictEntries = blk.dict_entries;
+        } else {
+          cancel = true;
+        }
+      }
+      results.put(k, std::move(r));
+    }
+    if (buf) zdwb_host_free(buf);
+  };
+  vector<std::thread> threads;
+  for (size_t w = 0; w < workers.size(); ++w) threads.push_back(std::thread(work, workers[w]));
+
+  ERR_CODE res = OK;
+  uint32_t longestLine = 0;
+  vector<unsigned char> pending;  // the previous block, held back until we know whether another one follows
+  for (size_t k = 0; k < wins.size(); ++k) {
+    EncodedBlock r = results.take(k);
+    if (res != OK || outcome.wrongColumns || r.skipped) continue;  // (drain: the workers must get their turns)
+    if (r.rc == ZDWB_ERR_WRONG_COLUMNS) {
+      outcome.wrongColumns = true;
+      outcome.badRow = r.badRow;
+      continue;
+    }
+    if (r.rc == ZDWB_ERR_OOM) {
+      statusOutput(ERROR, "Not enough memory to run %s\n", exeName);
+      res = OUT_OF_MEMORY;
+      continue;
+    }
+    if (r.rc != ZDWB_OK) {
+      statusOutput(ERROR, "%s: GPU encode failed: %s\n", exeName, r.err.c_str());
+      res = UNKNOWN_ERROR;
+      continue;
+    }
+    if (r.nrows == 0) continue;  // only blank lines / an unterminated tail
+    ++outcome.blocks;
+    if (!bQuiet) {
+      if (outcome.blocks == 1) statusOutput(INFO, "\nProcessing %s\n", filestub);
+      else statusOutput(INFO, "\nProcessing block %d of %s (%llu rows so far)\n", outcome.blocks, filestub, (unsigned long long)outcome.totalRows);
+      statusOutput(INFO, "Compiling unique values\n");
+      statusOutput(INFO, "\r%u rows\n", r.nrows);
+      statusOutput(INFO, "\nWriting dictionary:\n%u bytes being stored for %u unique entries.  Generating %d-byte offsets...\n",
+                   (unsigned)r.dictBytes, (unsigned)r.dictEntries, (int)r.idxSize);
+      statusOutput(INFO, "\nWriting rows\n");
+    }
+    if (!pending.empty()) {
+      pending[8] = 0;  // another block follows (:841-842)
+      writer.push(pending);
+    }
+    // every block was encoded on its own (prev_longest_line = 0): longestLine is cumulative over the file (:965)
+    longestLine = std::max(longestLine, readU32(r.bytes.data() + 4));
+    memcpy(r.bytes.data() + 4, &longestLine, 4);
+    pending.swap(r.bytes);
+    outcome.totalRows += r.nrows;
+    if (!bQuiet) statusOutput(INFO, "\r%u\nDone with block %d -- cleaning up...\n", r.nrows, outcome.blocks);
+  }
+  for (size_t w = 0; w < threads.size(); ++w) threads[w].join();
+  if (res == OK && !outcome.wrongColumns && !pending.empty()) {
+    pending[8] = 1;
+    writer.push(pending);
+  }
+  return res;
+}
+
 ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub, const DescSchema& schema,
                                                  const bool bValidate, const char* exeName, const char* outputDir,
                                                  const char* zArgs, const map<string, string>& metadata) {
@@ -203,7 +389,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     statusOutput(ERROR, "Invalid metadata parameter\n");
     return BAD_METADATA_PARAM;
   }
-  gpu.prefetch(gpuDevice);  // CUDA start-up (a few hundred milliseconds) runs beside the first read
+  gpu.prefetch(gpuList.empty() ? gpuDevice : gpuList[0]);  // CUDA start-up (a few hundred milliseconds) runs beside the first read
 
   // <outputDir or source dir>/<base>.zdw<ext>, written as <base>.creating.zdw<ext> and renamed on success (:629-657)
   string basePath;
@@ -249,6 +435,9 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       windowBytes = std::max((size_t)st.st_size + 1, (size_t)4096);  // + 1: the read that finds the end of the file
     }
   }
+  // Several windows of a regular file, cut by their size only: whole blocks go to several encode workers (and GPUs).
+  const size_t nWorkers = std::max<size_t>(1, gpuList.size()) * (size_t)std::max(1, lanesPerGpu);
+  const bool parallel = regularInput && !oneWindow && rowsPerBlock == 0 && blockPlan.empty() && nWorkers > 1;
   if (oneWindow) {
     const size_t configured = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
     if (!win.open(in, tee, windowBytes, plainAlloc, plainFree)) return OUT_OF_MEMORY;
@@ -258,7 +447,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       if (!win.widen(windowBytes)) return OUT_OF_MEMORY;
     }
   }
-  if (!gpu.open(gpuDevice)) {
+  if (!parallel && !gpu.open(gpuDevice)) {
     statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n", exeName, gpu.lastError().c_str());
     if (tee) {
       pclose(tee);
@@ -266,7 +455,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     }
     return UNKNOWN_ERROR;
   }
-  if (!oneWindow && !win.open(in, tee, windowBytes, pinnedAlloc, pinnedFree)) {
+  if (!parallel && !oneWindow && !win.open(in, tee, windowBytes, pinnedAlloc, pinnedFree)) {
     if (tee) {
       pclose(tee);
       unlink(teeName.c_str());
@@ -298,7 +487,19 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   int blocks = 0;
   bool wrongColumns = false;
   vector<unsigned char> pending;  // the previous block, held back until we know whether another one follows
-  for (;;) {
+  if (parallel) {
+    ParallelOutcome po;
+    res = encodeWindowsParallel(in, windowBytes, schema, filestub, exeName, writer, po);
+    totalRows = po.totalRows;
+    blocks = po.blocks;
+    if (po.wrongColumns) {
+      statusOutput(ERROR, "\nRow %u had the problem\n", po.badRow);
+      wrongColumns = true;
+    }
+    if (res != OK) goto Done;
+    if (!wrongColumns && blocks == 0) statusOutput(ERROR, "Empty data file -- nothing to process\n");
+  }
+  for (; !parallel;) {
     win.fill();
     if (win.len() == 0 && win.eof()) break;
     ++blocks;
@@ -400,7 +601,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   if (!pending.empty()) {
     pending[8] = 1;
     writer.push(pending);
-  } else {
+  } else if (!parallel) {
     statusOutput(ERROR, "Empty data file -- nothing to process\n");  // :824-835, result stays OK
   }
   win.close();  // no reader left on `in` / `tee`

@@ -66,6 +66,12 @@ class ConvertToZDW {
   // for its dictionary and column ranges (the reference's interrupted row); rows left form a last block
   void setBlockPlan(const std::vector<std::pair<uint64_t, uint32_t> >& plan) { blockPlan = plan; }
   void setGpuDevice(int device) { gpuDevice = device; }
+  // Whole blocks are dealt out to several GPUs: `devices` lists the CUDA device of every encode worker
+  // group (a device may appear more than once), `lanes` = workers (context + pinned window + host thread) per entry.
+  // The output is the same as with one worker; blocks are written in file order.  Applies to regular input files cut
+  // by --block-bytes windows (the default); streamed input, --rows-per-block and --block-plan run on one context.
+  void setGpus(const std::vector<int>& devices) { gpuList = devices; }
+  void setLanesPerGpu(int lanes) { lanesPerGpu = lanes; }
 
  private:
   struct DescSchema {
@@ -92,7 +98,12 @@ class ConvertToZDW {
   std::vector<std::pair<uint64_t, uint32_t> > blockPlan;
   size_t blockBytes;
   int gpuDevice;
+  std::vector<int> gpuList;
+  int lanesPerGpu;
   GpuSession gpu;
+  struct ParallelOutcome;
+  ERR_CODE encodeWindowsParallel(FILE* in, size_t windowBytes, const DescSchema& schema, const char* filestub, const char* exeName,
+                                 class AsyncWriter& writer, ParallelOutcome& outcome);
 };
 
 }  // namespace zdw

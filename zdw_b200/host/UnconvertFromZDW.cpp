@@ -9,7 +9,11 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
+#include <deque>
 #include <sstream>
+
+#include <unistd.h>
 
 using std::map;
 using std::set;
@@ -198,7 +202,7 @@ UnconvertFromZDW_Base::UnconvertFromZDW_Base(const string& fileName, const bool 
       bOutputNonEmptyColumnHeader(false), bShowBasicStatisticsOnly(false), bFailOnInvalidColumns(true),
       bExcludeSpecifiedColumns(false), bOutputEmptyMissingColumns(false), indexForVirtualBaseNameColumn(IGNORE_COLUMN),
       indexForVirtualRowColumn(IGNORE_COLUMN), rowsRead(0), rowsBeforeBlock(0), statusOutput(NULL), eState(ZDW_BEGIN),
-      gpuDevice(-1), blocksToSink(0) {
+      gpuDevice(-1), lanesPerGpu(2), lastBlockBytes(0), blocksToSink(0) {
   if (inFileName.empty()) {
     input = new internal::ZdwInput();
     input->openStdin();
@@ -611,37 +615,35 @@ ERR_CODE UnconvertFromZDW_Base::peekBlock(BlockInfo& info) {
   info.numSetColumns = (used + 7) / 8;
   info.maxRowBytes = info.numSetColumns + valueBytes;
   info.rowsOffset = statsAt + nc + 8 * used;
-  // buffer the whole block: its rows cannot take more than numLines * maxRowBytes
+  // Buffer what the block will probably need - its rows cannot take more than numLines * maxRowBytes, but delta-coded
+  // rows are usually several times smaller, so that bound would pull the following blocks (often the rest of the file)
+  // into memory.  The first guess is the size of the previous block plus a quarter (blocks of a file look alike), or a
+  // quarter of the bound; decodeBlock asks for more when the GPU reports the block as cut short.
   const double tRead0 = nowSeconds();
-  input->ensure(info.rowsOffset + (size_t)info.numLines * info.maxRowBytes + 1);
+  const size_t upper = info.rowsOffset + (size_t)info.numLines * info.maxRowBytes + 1;
+  size_t guess = lastBlockBytes ? lastBlockBytes + lastBlockBytes / 4 + 4096
+                                : info.rowsOffset + (size_t)info.numLines * info.maxRowBytes / 4 + 65536;
+  input->ensure(std::min(upper, std::max(guess, info.rowsOffset + 1)));
   if (hostTiming()) fprintf(stderr, "[zdw host] input buffered %.3f s (%zu bytes)\n", nowSeconds() - tRead0, input->available());
   return OK;
 }
 
-ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
-                                            bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session) {
-  GpuSession& g = session ? *session : gpu;
-  const double tOpen0 = nowSeconds();
-  const bool opened = g.open(gpuDevice);
-  if (hostTiming()) fprintf(stderr, "[zdw host] gpu.open %.3f s\n", nowSeconds() - tOpen0);
-  if (!opened) {
-    statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n",
-                 exeName.empty() ? "UnconvertFromZDW" : exeName.c_str(), g.lastError().c_str());
-    return PROCESSING_ERROR;
-  }
+int UnconvertFromZDW_Base::decodeBytes(GpuSession& g, const void* data, size_t avail, bool atEnd, unsigned long long firstRow,
+                                       unsigned char separator, bool wantRowOffsets, bool validateOnly, bool wantFlagCounts,
+                                       bool skimOnly, zdwb_rows_out* out) const {
   zdwb_schema sch;
   sch.ncols = numColumnsInExportFile;
   sch.types = columnType.data();
   zdwb_decode_opts o;
   memset(&o, 0, sizeof(o));
   o.want_row_offsets = wantRowOffsets ? 1 : 0;
-  const size_t upper = info.rowsOffset + (size_t)info.numLines * info.maxRowBytes;
-  o.at_end_of_file = (input->sourceEnded() && input->available() <= upper) ? 1 : 0;
+  o.at_end_of_file = atEnd ? 1 : 0;
   o.separator = separator;
   o.rownum_pos = -1;
   o.validate_only = validateOnly ? 1 : 0;
   o.want_flag_counts = wantFlagCounts ? 1 : 0;
-  o.first_row_number = rowsBeforeBlock + 1;
+  o.skim_only = skimOnly ? 1 : 0;
+  o.first_row_number = firstRow;
   vector<int32_t> map32;
   zdwb_fill fill;
   if (!namesOfColumnsToOutput.empty()) {
@@ -659,17 +661,44 @@ ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char
     if (UseVirtualExportRowColumn() && outputColumns[indexForVirtualRowColumn] != IGNORE_COLUMN)
       o.rownum_pos = outputColumns[indexForVirtualRowColumn];
   }
-  const double tDec0 = nowSeconds();
-  const int rc = zdwb_decode_block(g.get(), &sch, input->data(), input->available(), &o, out);
-  if (hostTiming())
-    fprintf(stderr, "[zdw host] zdwb_decode_block %.3f s (%zu bytes available, %llu bytes out)\n", nowSeconds() - tDec0,
-            input->available(), (unsigned long long)out->len);
+  return zdwb_decode_block(g.get(), &sch, data, avail, &o, out);
+}
+
+ERR_CODE UnconvertFromZDW_Base::decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
+                                            bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session, bool skimOnly) {
+  GpuSession& g = session ? *session : gpu;
+  const double tOpen0 = nowSeconds();
+  const bool opened = g.open(gpuList.empty() ? gpuDevice : gpuList[0]);
+  if (hostTiming()) fprintf(stderr, "[zdw host] gpu.open %.3f s\n", nowSeconds() - tOpen0);
+  if (!opened) {
+    statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n",
+                 exeName.empty() ? "UnconvertFromZDW" : exeName.c_str(), g.lastError().c_str());
+    return PROCESSING_ERROR;
+  }
+  int rc;
+  for (;;) {
+    const double tDec0 = nowSeconds();
+    rc = decodeBytes(g, input->data(), input->available(), input->sourceEnded(), rowsBeforeBlock + 1, separator, wantRowOffsets,
+                     validateOnly, wantFlagCounts, skimOnly, out);
+    if (hostTiming())
+      fprintf(stderr, "[zdw host] zdwb_decode_block%s %.3f s (%zu bytes available, %llu bytes out)\n", skimOnly ? " (skim)" : "",
+              nowSeconds() - tDec0, input->available(), (unsigned long long)out->len);
+    if (rc != ZDWB_ERR_TRUNCATED || input->sourceEnded()) break;
+    // the block is longer than what was buffered for it: read on (at least as much again) and try once more
+    const size_t have = input->available();
+    if (input->ensure(have + std::max<size_t>(have, (size_t)1 << 20)) == have && !input->sourceEnded()) break;
+  }
+  (void)info;
   switch (rc) {
-    case ZDWB_OK: return OK;
+    case ZDWB_OK:
+      if (out->consumed) lastBlockBytes = (size_t)out->consumed;
+      return OK;
     case ZDWB_ERR_CORRUPT: return CORRUPTED_DATA_ERROR;  // reference :1364-1365
     case ZDWB_ERR_ROW_COUNT:
     case ZDWB_ERR_TRUNCATED:
       printError(exeName, displayName(inFileName));
+      // (the reference prints the rows it had unpacked when the data ran out; here a block is decoded as a whole or not
+      // at all, so the count of a block that is cut short is always 0 and none of its rows are written)
       statusOutput(INFO, "Rows unpacked (%u) does not match expected (%u)\n\n", 0u, numLines);  // :1597-1605
       return ROW_COUNT_ERR;
     default:
@@ -731,6 +760,227 @@ ERR_CODE UnconvertFromZDW<T>::parseNextBlock(T& sink) {
   if (this->isLastBlock() && !this->bQuiet && !this->bShowBasicStatisticsOnly)
     this->statusOutput(INFO, "%s %s\n\n", displayName(this->inFileName).c_str(), this->bTestOnly ? "tested good" : "uncompressed");
   return OK;
+}
+
+// ---- several decode workers (SURVEY 8(e) "Decode"; the reference's block loop is :1814-1820) -------------------------
+// The calling thread walks the file: block header, then a SKIM of the block on its own context - the row-boundary
+// kernels only - which yields the block's length, i.e. where the next block starts.  The block's bytes go to a worker
+// (own context, any device), which decodes them and puts the rows out when it is the block's turn: in order through the
+// FILE* for pipes, or side by side with pwrite() at the block's offset when the sink is a regular file (a block's offset
+// is known as soon as the blocks in front of it have been decoded, not written).
+namespace {
+
+class OrderedSink {
+ public:
+  explicit OrderedSink(FILE* f) : fp_(f), fd_(fileno(f)), seekable_(false), base_(0), nextSeq_(0), total_(0), failed_(false) {
+    struct stat st;
+    fflush(fp_);
+    if (fstat(fd_, &st) == 0 && S_ISREG(st.st_mode)) {
+      const off_t at = lseek(fd_, 0, SEEK_CUR);
+      if (at >= 0) {
+        seekable_ = true;
+        base_ = (uint64_t)at;
+      }
+    }
+  }
+  // rows of block `seq` (with the optional line that precedes them); returns false once anything failed to be written
+  bool deliver(size_t seq, const string& prefix, const void* rows, size_t len) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
+    bool ok = !failed_;
+    if (!seekable_) {
+      if (ok && !prefix.empty()) ok = fwrite(prefix.data(), 1, prefix.size(), fp_) == prefix.size();
+      if (ok && len) ok = fwrite(rows, 1, len, fp_) == len;
+      if (!ok) failed_ = true;
+      ++nextSeq_;
+      cv_.notify_all();
+      return ok;
+    }
+    const uint64_t at = base_ + total_;
+    total_ += prefix.size() + len;
+    ++nextSeq_;  // the next block may take its offset: the writes themselves run side by side
+    cv_.notify_all();
+    lk.unlock();
+    ok = ok && writeAt(prefix.data(), prefix.size(), at) && writeAt(rows, len, at + prefix.size());
+    if (!ok) {
+      std::lock_guard<std::mutex> g(m_);
+      failed_ = true;
+    }
+    return ok;
+  }
+  // a block that produced nothing (its worker failed): later blocks must not wait for it for ever
+  // (nothing behind it is written either: the output ends where the reference's would, in front of the bad block)
+  void skip(size_t seq) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
+    failed_ = true;
+    ++nextSeq_;
+    cv_.notify_all();
+  }
+  // after every worker is done: leaves the FILE* positioned behind the rows
+  bool finish() {
+    if (seekable_ && lseek(fd_, (off_t)(base_ + total_), SEEK_SET) < 0) return false;
+    return !failed_;
+  }
+
+ private:
+  bool writeAt(const void* p, size_t n, uint64_t at) {
+    const char* c = static_cast<const char*>(p);
+    while (n) {
+      const ssize_t w = pwrite(fd_, c, n, (off_t)at);
+      if (w <= 0) return false;
+      c += w;
+      n -= (size_t)w;
+      at += (uint64_t)w;
+    }
+    return true;
+  }
+  FILE* fp_;
+  int fd_;
+  bool seekable_;
+  uint64_t base_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  size_t nextSeq_;
+  uint64_t total_;
+  bool failed_;
+};
+
+struct DecodeJob {
+  size_t seq;
+  vector<char> bytes;  // the whole block
+  unsigned long long firstRow;
+  ULONG numLines;
+  string prefix;       // --non-empty-column-header line
+};
+
+}  // namespace
+
+template <typename T>
+ERR_CODE UnconvertFromZDW<T>::decodeBlocksFanOut(T& sink) {
+  sink.waitIdle();
+  OrderedSink ordered(sink.file());
+  vector<int> workers;
+  {
+    vector<int> devices = this->gpuList;
+    if (devices.empty()) devices.push_back(GpuSession::resolve(this->gpuDevice));
+    for (int l = 0; l < std::max(1, this->lanesPerGpu); ++l)
+      for (size_t d = 0; d < devices.size(); ++d) workers.push_back(devices[d]);
+  }
+  std::mutex qm;
+  std::condition_variable qcv;
+  std::deque<DecodeJob> queue;
+  bool closed = false;
+  std::atomic<int> firstError(OK);
+  string workerErr;
+  const size_t maxQueued = workers.size() + 1;
+
+  auto work = [&](int device) {
+    GpuSession session;
+    const bool opened = session.open(device);
+    for (;;) {
+      DecodeJob job;
+      {
+        std::unique_lock<std::mutex> lk(qm);
+        qcv.wait(lk, [&]() { return closed || !queue.empty(); });
+        if (queue.empty()) return;
+        job = std::move(queue.front());
+        queue.pop_front();
+      }
+      qcv.notify_all();
+      ERR_CODE rc = OK;
+      bool handedOver = false;  // deliver() was called: the sink has moved on to the next block
+      if (!opened) {
+        rc = PROCESSING_ERROR;
+        std::lock_guard<std::mutex> lk(qm);
+        if (workerErr.empty()) workerErr = "no usable CUDA device (" + session.lastError() + "); this build has no CPU path";
+      } else if (firstError.load() == OK) {  // (after a failure nothing more is written)
+        zdwb_rows_out rows;
+        memset(&rows, 0, sizeof(rows));
+        const int zrc = this->decodeBytes(session, job.bytes.data(), job.bytes.size(), true, job.firstRow, '\t', false, false, false,
+                                          false, &rows);
+        if (zrc == ZDWB_OK) {
+          handedOver = true;
+          if (!ordered.deliver(job.seq, job.prefix, rows.tsv, rows.len)) rc = FILE_CREATION_ERR;
+        } else {
+          rc = zrc == ZDWB_ERR_CORRUPT ? CORRUPTED_DATA_ERROR
+               : (zrc == ZDWB_ERR_ROW_COUNT || zrc == ZDWB_ERR_TRUNCATED) ? ROW_COUNT_ERR : PROCESSING_ERROR;
+          std::lock_guard<std::mutex> lk(qm);
+          if (workerErr.empty()) workerErr = zdwb_last_error(session.get());
+        }
+      }
+      if (!handedOver) ordered.skip(job.seq);
+      if (rc != OK) {
+        int expected = OK;
+        firstError.compare_exchange_strong(expected, (int)rc);
+      }
+    }
+  };
+  vector<std::thread> threads;
+  for (size_t w = 0; w < workers.size(); ++w) threads.push_back(std::thread(work, workers[w]));
+
+  ERR_CODE rc = OK;
+  size_t seq = 0;
+  try {
+    do {
+      typename UnconvertFromZDW_Base::BlockInfo info;
+      rc = this->peekBlock(info);
+      if (rc != OK) break;
+      this->rowsRead = 0;
+      if (!this->bQuiet) this->statusOutput(INFO, "Reading %u rows\n", this->numLines);
+      zdwb_rows_out sk;
+      memset(&sk, 0, sizeof(sk));
+      rc = this->decodeBlock(info, '\t', false, false, false, &sk, NULL, true);  // skim: where does the block end?
+      if (rc != OK) break;
+      if (firstError.load() != OK) break;
+      DecodeJob job;
+      job.seq = seq++;
+      job.bytes.assign(this->input->data(), this->input->data() + (size_t)sk.consumed);
+      job.firstRow = this->rowsBeforeBlock + 1;
+      job.numLines = this->numLines;
+      if (this->bOutputNonEmptyColumnHeader) job.prefix = this->getBlockHeaderString(info);
+      {
+        std::unique_lock<std::mutex> lk(qm);
+        qcv.wait(lk, [&]() { return queue.size() < maxQueued; });
+        queue.push_back(std::move(job));
+      }
+      qcv.notify_all();
+      this->rowsRead = this->numLines;
+      this->input->consume((size_t)sk.consumed);
+      if (this->bShowStatus) this->statusOutput(INFO, "\r%u\n", this->rowsRead);
+      this->rowsBeforeBlock += this->numLines;
+      if (this->isLastBlock() && !this->bQuiet)
+        this->statusOutput(INFO, "%s %s\n\n", displayName(this->inFileName).c_str(), "uncompressed");
+    } while (!this->isLastBlock());
+  } catch (...) {
+    {
+      std::lock_guard<std::mutex> lk(qm);
+      closed = true;
+    }
+    qcv.notify_all();
+    for (size_t w = 0; w < threads.size(); ++w) threads[w].join();
+    ordered.finish();
+    throw;
+  }
+  {
+    std::lock_guard<std::mutex> lk(qm);
+    closed = true;
+  }
+  qcv.notify_all();
+  for (size_t w = 0; w < threads.size(); ++w) threads[w].join();
+  const bool written = ordered.finish();
+  if (rc == OK && firstError.load() != OK) {
+    rc = (ERR_CODE)firstError.load();
+    if (rc == ROW_COUNT_ERR) {
+      this->printError(this->exeName, displayName(this->inFileName));
+      this->statusOutput(INFO, "Rows unpacked (%u) does not match expected (%u)\n\n", 0u, this->numLines);
+    } else if (rc == PROCESSING_ERROR) {
+      this->statusOutput(ERROR, "%s: GPU decode failed: %s\n", this->exeName.empty() ? "UnconvertFromZDW" : this->exeName.c_str(),
+                         workerErr.c_str());
+    }
+  }
+  if (rc == OK && !written) rc = FILE_CREATION_ERR;
+  return rc;
 }
 
 // Whole file to disk / stdout (reference :1656-1844).
@@ -818,10 +1068,17 @@ ERR_CODE UnconvertFromZDWToFile<BufferedOutput_T>::unconvert(const char* binaryN
 
   {
     BufferedOutput_T sink(this->out ? this->out : stdout);
-    do {
-      rc = this->parseNextBlock(sink);
+    const size_t nWorkers = std::max<size_t>(1, this->gpuList.size()) * (size_t)std::max(1, this->lanesPerGpu);
+    if (producesRows && nWorkers > 1) {
+      rc = this->decodeBlocksFanOut(sink);
       if (rc != OK) return rc;
-    } while (!this->isLastBlock());
+    } else {
+      do {
+        rc = this->parseNextBlock(sink);
+        if (rc != OK) return rc;
+      } while (!this->isLastBlock());
+      if (!sink.waitIdle()) return FILE_CREATION_ERR;  // a deferred write came up short (disk full, closed pipe)
+    }
   }
   if (!this->bShowBasicStatisticsOnly) {
     this->input->finalDummyRead();

@@ -49,6 +49,9 @@ void printUsage(const char* exe) {
         "\t                      (B200 build) were already parsed when the reference closed the block (reproduces its memory-driven cuts)\n"
         "\t--block-bytes=<N>     (B200 build) TSV bytes per block window [default=1 GiB]\n"
         "\t--gpu=<N>             (B200 build) CUDA device to use [default=$ZDW_GPU or 0]\n"
+        "\t--gpus=<N|all|a,b,..> (B200 build) spread the blocks of a file over N GPUs / all GPUs / the listed devices\n"
+        "\t                      (B200 build) [default=$ZDW_GPUS or the one device]; the output does not depend on it\n"
+        "\t--lanes-per-gpu=<N>   (B200 build) encode workers (context + pinned window + host thread) per GPU [default=2]\n"
         "\n"
         "\t--help     show this help\n"
         "\t--version  show the version number\n"
@@ -79,10 +82,12 @@ struct Options {
   std::vector<std::pair<uint64_t, uint32_t> > blockPlan;
   unsigned long long blockBytes;
   int gpu;
+  std::string gpus;
+  int lanes;
   std::vector<const char*> files;
   Options()
       : streaming(false), removeOld(false), trim(false), validate(false), quiet(false), compressor(ConvertToZDW::GZIP),
-        outputDir(NULL), zArgs(NULL), rowsPerBlock(0), blockBytes(0), gpu(-1) {}
+        outputDir(NULL), zArgs(NULL), rowsPerBlock(0), blockBytes(0), gpu(-1), lanes(0) {}
 };
 
 }  // namespace
@@ -182,6 +187,15 @@ int main(int argc, char* argv[]) {
           opt.gpu = atoi(flag + 4);
           break;
         }
+        if (!strncmp(flag, "gpus=", 5)) {
+          opt.gpus = flag + 5;
+          break;
+        }
+        if (!strncmp(flag, "lanes-per-gpu=", 14)) {
+          opt.lanes = atoi(flag + 14);
+          if (opt.lanes < 1) return reportFailure(ConvertToZDW::BAD_PARAMETER);
+          break;
+        }
         printUsage(exe);
         return unknownParameter(exe, a);
       }
@@ -191,6 +205,14 @@ int main(int argc, char* argv[]) {
   }
   if (opt.files.empty()) return reportFailure(ConvertToZDW::NO_INPUT_FILES);
   if (opt.streaming && isatty(0)) return reportFailure(ConvertToZDW::NO_INPUT_FILES);  // nothing is piped in
+
+  // --gpus: a count, "all", or a list of devices (a device may be named more than once)
+  std::vector<int> gpuList;
+  {
+    std::string spec = opt.gpus;
+    if (spec.empty() && getenv("ZDW_GPUS")) spec = getenv("ZDW_GPUS");
+    if (!adobe::zdw::parseGpuSpec(spec, opt.gpu, gpuList)) return reportFailure(ConvertToZDW::BAD_PARAMETER);
+  }
 
   int exitCode = ConvertToZDW::OK;
   for (size_t f = 0; f < opt.files.size(); ++f) {
@@ -202,6 +224,8 @@ int main(int argc, char* argv[]) {
     if (!opt.blockPlan.empty()) conv.setBlockPlan(opt.blockPlan);
     if (opt.blockBytes) conv.setBlockBytes((size_t)opt.blockBytes);
     conv.setGpuDevice(opt.gpu);
+    if (!gpuList.empty()) conv.setGpus(gpuList);
+    if (opt.lanes) conv.setLanesPerGpu(opt.lanes);
     const ConvertToZDW::ERR_CODE res =
       conv.convertFile(opt.files[f], exe, opt.validate, stub.data(), opt.outputDir, opt.zArgs, opt.metadata);
     if (res != ConvertToZDW::OK) {

@@ -5,11 +5,41 @@
 #include <cstdlib>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "zdw_b200.h"
 
 namespace adobe {
 namespace zdw {
+
+// --gpus=<N | all | a,b,...> (and $ZDW_GPUS): the CUDA device of every worker group.  A count means the devices
+// first, first + 1, ...; a device may be listed more than once.  Returns false for a malformed spec.
+inline bool parseGpuSpec(const std::string& spec, int first, std::vector<int>& out) {
+  out.clear();
+  if (spec.empty()) return true;
+  if (spec == "all") {
+    const int n = zdwb_device_count();
+    for (int d = 0; d < n; ++d) out.push_back(d);
+    return true;
+  }
+  if (spec.find_first_not_of("0123456789,") != std::string::npos) return false;
+  if (spec.find(',') == std::string::npos) {
+    const int n = atoi(spec.c_str());
+    if (n < 1) return false;
+    for (int d = 0; d < n; ++d) out.push_back((first >= 0 ? first : 0) + d);
+    return true;
+  }
+  size_t at = 0;
+  for (;;) {
+    const size_t comma = spec.find(',', at);
+    const std::string item = spec.substr(at, comma == std::string::npos ? std::string::npos : comma - at);
+    if (item.empty()) return false;
+    out.push_back(atoi(item.c_str()));
+    if (comma == std::string::npos) break;
+    at = comma + 1;
+  }
+  return true;
+}
 
 class GpuSession {
  public:

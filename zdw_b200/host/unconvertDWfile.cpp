@@ -15,6 +15,9 @@ using std::string;
 namespace {
 
 int g_gpu = -1;
+int g_lanes = 0;
+std::string g_gpusSpec;
+std::vector<int> g_gpuList;
 
 const char* baseName(const char* path) {
   const char* s = strrchr(path, '/');
@@ -60,6 +63,8 @@ void printUsage(const char* exe) {
         "\n"
         "\t--non-empty-column-header   output a header line listing non-empty columns in the next file block\n"
         "\t--gpu=<N>   (B200 build) CUDA device to use [default=$ZDW_GPU or 0]\n"
+        "\t--gpus=<N|all|a,b,..>  (B200 build) spread the blocks over N GPUs / all GPUs / the listed devices [default=$ZDW_GPUS or one]\n"
+        "\t--lanes-per-gpu=<N>    (B200 build) decode workers per GPU [default=2]; the output does not depend on either\n"
         "\n"
         "\t--help     show this help\n"
         "\t--version  show the version number\n"
@@ -98,6 +103,8 @@ struct Job {
 template <class Decoder>
 ERR_CODE drive(Decoder& d, const Job& job, const char* exe, const char* outputBasename, const string& ext) {
   d.setGpuDevice(g_gpu);
+  if (!g_gpuList.empty()) d.setGpus(g_gpuList);
+  if (g_lanes) d.setLanesPerGpu(g_lanes);
   d.setMetadataOptions(job.meta);
   if (job.statsOnly) d.showBasicStatisticsOnly();
   d.outputNonEmptyColumnHeader(job.blockHeaders);
@@ -194,6 +201,15 @@ int main(int argc, char* argv[]) {
           g_gpu = atoi(flag + 4);
           break;
         }
+        if (!strncmp(flag, "gpus=", 5)) {
+          g_gpusSpec = flag + 5;
+          break;
+        }
+        if (!strncmp(flag, "lanes-per-gpu=", 14)) {
+          g_lanes = atoi(flag + 14);
+          if (g_lanes < 1) g_lanes = 1;
+          break;
+        }
         const bool strict = !strncmp(flag, "metadata-values=", 16);
         const bool lenient = !strncmp(flag, "metadata-values-allow-missing=", 30);
         if (strict || lenient) {
@@ -219,6 +235,15 @@ int main(int argc, char* argv[]) {
   if (job.descOnly && job.meta.bOutputOnlyMetadata) {
     fprintf(stderr, "-o and --metadata options are incompatible.  Aborting.\n");
     return BAD_PARAMETER;
+  }
+
+  {
+    std::string spec = g_gpusSpec;
+    if (spec.empty() && getenv("ZDW_GPUS")) spec = getenv("ZDW_GPUS");
+    if (!adobe::zdw::parseGpuSpec(spec, g_gpu, g_gpuList)) {
+      fprintf(stderr, "%s: bad --gpus value '%s'\n", exe, spec.c_str());
+      return BAD_PARAMETER;
+    }
   }
 
   // pass 2: the files

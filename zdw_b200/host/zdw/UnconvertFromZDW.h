@@ -113,6 +113,7 @@ class BufferedOutput {
   // `data` must stay untouched until the next call on this object returns
   void writeLater(const void* data, size_t size);
   bool waitIdle();  // false once a deferred write came up short
+  FILE* file() const { return fp; }
 
  private:
   BufferedOutput(const BufferedOutput&);
@@ -163,6 +164,11 @@ class UnconvertFromZDW_Base {
   void setMetadataOptions(const internal::MetadataOptions& options) { metadataOptions = options; }
 
   void setGpuDevice(int device) { gpuDevice = device; }  // addition of this build
+  // Whole blocks are decoded by several workers (a device may be listed more than once; `lanes` workers per entry):
+  // the calling thread skims every block for its length (the file has none, reference :782-810,1577-1589), the
+  // workers decode, the rows leave in file order.  File / stdout output only; the output does not depend on it.
+  void setGpus(const std::vector<int>& devices) { gpuList = devices; }
+  void setLanesPerGpu(int lanes) { lanesPerGpu = lanes; }
 
  protected:
   enum { IGNORE_COLUMN = -1, USE_VIRTUAL_COLUMN = -2 };
@@ -183,7 +189,11 @@ class UnconvertFromZDW_Base {
   ERR_CODE peekBlock(BlockInfo& info);
   // Decodes that block on the GPU.  separator '\t' (files) or '\0' (in-memory rows).
   ERR_CODE decodeBlock(const BlockInfo& info, unsigned char separator, bool wantRowOffsets, bool validateOnly,
-                       bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session = NULL);
+                       bool wantFlagCounts, zdwb_rows_out* out, GpuSession* session = NULL, bool skimOnly = false);
+  // the same on explicit bytes (a complete block when atEnd): what the decode workers call.  Reads only members that
+  // do not change after readHeader(); error texts go to *errText instead of the status callback.
+  int decodeBytes(GpuSession& g, const void* data, size_t avail, bool atEnd, unsigned long long firstRow, unsigned char separator,
+                  bool wantRowOffsets, bool validateOnly, bool wantFlagCounts, bool skimOnly, zdwb_rows_out* out) const;
   std::string getBlockHeaderString(const BlockInfo& info) const;
 
   ERR_CODE outputDescToFile(const std::vector<std::string>& names, const std::string& outputDir, const char* filestub,
@@ -238,6 +248,9 @@ class UnconvertFromZDW_Base {
   STATE eState;
 
   int gpuDevice;
+  std::vector<int> gpuList;
+  int lanesPerGpu;
+  size_t lastBlockBytes;      // size of the previous block: how much of the next one is buffered before the first try
   GpuSession gpu;
   GpuSession gpu2;            // file output only: blocks alternate between two contexts (see parseNextBlock)
   unsigned blocksToSink;      // blocks decoded for a file sink so far
@@ -260,6 +273,8 @@ class UnconvertFromZDW : public UnconvertFromZDW_Base {
 
  protected:
   ERR_CODE parseNextBlock(T& buffer);
+  // every remaining block, decoded by several workers (see setGpus); file-like sinks only
+  ERR_CODE decodeBlocksFanOut(T& sink);
 };
 
 template <typename BufferedOutput_T>
