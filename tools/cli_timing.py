@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--dir", default="/dev/shm" if os.path.isdir("/dev/shm") else None)
     ap.add_argument("--block-bytes", type=int, default=0, help="--block-bytes for convertDWfile (0 = its default, 1 GiB)")
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--gpus", default="", help="comma separated list of --gpus values to time, e.g. 1,2,4,8 (default: the tools' default)")
+    ap.add_argument("--lanes", type=int, default=0, help="--lanes-per-gpu for our tools (0 = their default)")
     args = ap.parse_args()
 
     synth = bench.Synth()
@@ -73,21 +75,21 @@ def main():
         tsv_bytes = src.stat().st_size
         extra = [f"--block-bytes={args.block_bytes}"] if args.block_bytes else []
 
-        for comp in args.compressors.split(","):
-            if not comp:
-                continue
+        runs = [(comp, g) for comp in args.compressors.split(",") if comp for g in (args.gpus.split(",") if args.gpus else [""])]
+        for comp, g in runs:
+            extra_g = ([f"--gpus={g}"] if g else []) + ([f"--lanes-per-gpu={args.lanes}"] if args.lanes else [])
             env = env_for(comp)
             for f in work.glob("x.zdw*"):
                 f.unlink()
-            t_enc = timed([str(BIN / "convertDWfile"), "-q", *extra, "x.sql"], work, env)
+            t_enc = timed([str(BIN / "convertDWfile"), "-q", *extra, *extra_g, "x.sql"], work, env)
             zdw = work / "x.zdw.gz"
             out = work / "out"
             shutil.rmtree(out, ignore_errors=True)
             out.mkdir()
-            t_dec = timed([str(BIN / "unconvertDWfile"), "-q", "-d", "out", "x.zdw.gz"], work, env)
+            t_dec = timed([str(BIN / "unconvertDWfile"), "-q", *extra_g, "-d", "out", "x.zdw.gz"], work, env)
             same = (out / "x.sql").stat().st_size == tsv_bytes and \
                 subprocess.run(["cmp", "-s", str(out / "x.sql"), str(src)]).returncode == 0
-            print(json.dumps({"tool": "zdw_b200", "compressor": comp, "blocks": args.blocks, "tsv_bytes": tsv_bytes,
+            print(json.dumps({"tool": "zdw_b200", "compressor": comp, "gpus": g or "default", "blocks": args.blocks, "tsv_bytes": tsv_bytes,
                               "zdw_file_bytes": zdw.stat().st_size, "encode_s": round(t_enc, 3), "decode_s": round(t_dec, 3),
                               "encode_gbs": tsv_bytes / t_enc / 1e9, "decode_gbs": tsv_bytes / t_dec / 1e9,
                               "round_trip_identical": same}), flush=True)

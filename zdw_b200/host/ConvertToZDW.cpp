@@ -6,6 +6,7 @@
 #include <string.h>
 #include <strings.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -42,6 +43,17 @@ const size_t MAX_WINDOW_BYTES = 0xff000000ull;         // zdwb_encode_block take
 
 bool startsWith(const char* s, const char* prefix) { return strncmp(s, prefix, strlen(prefix)) == 0; }
 
+// ZDW_HOST_TIMING=1: wall-clock of the host-side stages on stderr (diagnostics)
+bool hostTiming() {
+  static const bool on = getenv("ZDW_HOST_TIMING") != NULL;
+  return on;
+}
+double nowSeconds() {
+  timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
 // the window's buffers: pinned memory of the C ABI (copies at the rate of the link) ...
 void* pinnedAlloc(size_t n) { return zdwb_host_alloc(n); }
 void pinnedFree(void* p) { zdwb_host_free(p); }
@@ -49,6 +61,67 @@ void pinnedFree(void* p) { zdwb_host_free(p); }
 // unpinned once, and plain memory can be filled while CUDA is still starting up
 void* plainAlloc(size_t n) { return malloc(n); }
 void plainFree(void* p) { free(p); }
+
+// What the reference keeps of a streamed input for validation (GetDataRow, ConvertToZDW.cpp:274-283,316-319): the
+// rows as GetNextRow returns them - blank lines skipped, an unterminated last line dropped (getnextrow.cpp:39-43,67-69)
+// - and with -t every field without its trailing spaces (dump_trimmed_row_to_temp_file, :1069-1090).  p[0..n) are the
+// bytes one block covered; it starts at a row boundary.
+bool writeRowsForValidation(FILE* to, const char* p, size_t n, bool trim) {
+  size_t at = 0;
+  while (at < n) {
+    // end of the logical line: a newline behind an even number of backslashes
+    size_t e = at;
+    bool found = false;
+    while (e < n) {
+      const void* hit = memchr(p + e, '\n', n - e);
+      if (!hit) break;
+      e = (size_t)(static_cast<const char*>(hit) - p);
+      size_t k = e, slashes = 0;
+      while (k > at && p[k - 1] == '\\') {
+        --k;
+        ++slashes;
+      }
+      if ((slashes & 1u) == 0) {
+        found = true;
+        break;
+      }
+      ++e;
+    }
+    if (!found) break;       // an unterminated last line is not a row
+    if (e == at) {           // blank line
+      ++at;
+      continue;
+    }
+    if (!trim) {
+      if (fwrite(p + at, 1, e - at + 1, to) != e - at + 1) return false;
+    } else {
+      size_t f = at;
+      for (;;) {
+        // end of the field: a tab behind an even number of backslashes (get_next_column, :1048-1067)
+        size_t t = f;
+        while (t < e) {
+          if (p[t] == '\t') {
+            size_t k = t, slashes = 0;
+            while (k > f && p[k - 1] == '\\') {
+              --k;
+              ++slashes;
+            }
+            if ((slashes & 1u) == 0) break;
+          }
+          ++t;
+        }
+        size_t end = t;
+        while (end > f && p[end - 1] == ' ') --end;
+        if (end > f && fwrite(p + f, 1, end - f, to) != end - f) return false;
+        if (fputc(t < e ? '\t' : '\n', to) == EOF) return false;
+        if (t >= e) break;
+        f = t + 1;
+      }
+    }
+    at = e + 1;
+  }
+  return true;
+}
 
 }  // namespace
 
@@ -244,6 +317,8 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
   }
   size_t maxLen = 0;
   for (size_t k = 0; k < wins.size(); ++k) maxLen = std::max(maxLen, wins[k].len);
+  const double tStart = nowSeconds();
+  if (hostTiming()) fprintf(stderr, "[zdw host] %zu windows planned (window %zu bytes)\n", wins.size(), cap);
 
   vector<int> workers;  // CUDA device of every worker
   {
@@ -266,20 +341,57 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
   auto work = [&](int device) {
     GpuSession session;
     char* buf = NULL;
+    bool pinned = false;
     std::string fatal;
     int fatalRc = ZDWB_OK;
-    if (!session.open(device)) {
-      fatal = "no usable CUDA device (" + session.lastError() + "); this build has no CPU path";
-      fatalRc = ZDWB_ERR_NO_DEVICE;
-    } else if (!(buf = static_cast<char*>(zdwb_host_alloc(maxLen + 64)))) {
-      fatal = "pinned window allocation failed";
+    const double tw0 = nowSeconds();
+    double tOpen = 0, tAlloc = 0, tRead = 0, tEnc = 0, tCopy = 0;
+    // Pinning a window-sized buffer takes about as long as four copies out of pageable memory (measured: 0.45 s per
+    // GiB, and the driver serialises it with every other context's calls): only worth it for a worker that will see
+    // more than a few windows.  A plain buffer also needs no CUDA: the first window is read while the context comes up.
+    pinned = wins.size() > 4 * workers.size();
+    bool opened = false;
+    if (pinned) {
+      opened = session.open(device);
+      tOpen = nowSeconds() - tw0;
+      const double ta = nowSeconds();
+      if (opened) buf = static_cast<char*>(zdwb_host_alloc(maxLen + 64));
+      tAlloc = nowSeconds() - ta;
+    } else {
+      session.prefetch(device);
+      buf = static_cast<char*>(malloc(maxLen + 64));
+    }
+    if (!buf && (opened || !pinned)) {
+      fatal = "window allocation failed";
       fatalRc = ZDWB_ERR_OOM;
     }
+    bool sessionReady = pinned;
     for (;;) {
       const size_t k = next.fetch_add(1);
       if (k >= wins.size()) break;
       results.waitTurn(k, ahead);
       EncodedBlock r;
+      size_t preRead = 0;
+      if (!sessionReady && fatalRc == ZDWB_OK && !cancel) {  // the read of the first window overlaps the CUDA start-up
+        const FileWindow& w = wins[k];
+        const double tr = nowSeconds();
+        while (preRead < w.len) {
+          const ssize_t n = pread(fd, buf + preRead, w.len - preRead, (off_t)(w.offset + preRead));
+          if (n <= 0) break;
+          preRead += (size_t)n;
+        }
+        tRead += nowSeconds() - tr;
+      }
+      if (!sessionReady) {
+        const double to = nowSeconds();
+        opened = session.open(device);
+        tOpen = nowSeconds() - to;
+        sessionReady = true;
+      }
+      if (!opened && fatalRc == ZDWB_OK) {
+        fatal = "no usable CUDA device (" + session.lastError() + "); this build has no CPU path";
+        fatalRc = ZDWB_ERR_NO_DEVICE;
+      }
       if (fatalRc != ZDWB_OK) {
         r.rc = fatalRc;
         r.err = fatal;
@@ -288,18 +400,21 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
         r.skipped = true;
       } else {
         const FileWindow& w = wins[k];
-        size_t got = 0;
+        size_t got = preRead;
+        const double tr = nowSeconds();
         while (got < w.len) {
           const ssize_t n = pread(fd, buf + got, w.len - got, (off_t)(w.offset + got));
           if (n <= 0) break;
           got += (size_t)n;
         }
+        tRead += nowSeconds() - tr;
         zdwb_encode_opts eo;
         memset(&eo, 0, sizeof(eo));
         eo.trim_trailing_spaces = trim ? 1 : 0;
         eo.more_input_follows = w.more ? 1 : 0;
         zdwb_block_out blk;
         memset(&blk, 0, sizeof(blk));
+        const double te = nowSeconds();
         if (got != w.len) {
           r.rc = ZDWB_ERR_BAD_ARG;
           r.err = "short read of the input file";
@@ -307,6 +422,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
           r.rc = zdwb_encode_block(session.get(), &sch, buf, w.len, &eo, &blk);
           if (r.rc != ZDWB_OK) r.err = zdwb_last_error(session.get());
         }
+        tEnc += nowSeconds() - te;
         r.badRow = blk.bad_row;
         if (r.rc == ZDWB_OK && blk.nrows && w.more && blk.tsv_consumed != w.consumed) {
           r.rc = ZDWB_ERR_BAD_ARG;  // the host's cut and the GPU's disagree: never write such a file
@@ -326,7 +442,13 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
       }
       results.put(k, std::move(r));
     }
-    if (buf) zdwb_host_free(buf);
+    const double tf = nowSeconds();
+    if (buf && pinned) zdwb_host_free(buf);
+    else free(buf);
+    (void)tCopy;
+    if (hostTiming())
+      fprintf(stderr, "[zdw host] encode worker on device %d: open %.3f s, pinned alloc %.3f s, read %.3f s, encode %.3f s, free %.3f s, total %.3f s\n",
+              device, tOpen, tAlloc, tRead, tEnc, nowSeconds() - tf, nowSeconds() - tw0);
   };
   vector<std::thread> threads;
   for (size_t w = 0; w < workers.size(); ++w) threads.push_back(std::thread(work, workers[w]));
@@ -375,6 +497,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
     if (!bQuiet) statusOutput(INFO, "\r%u\nDone with block %d -- cleaning up...\n", r.nrows, outcome.blocks);
   }
   for (size_t w = 0; w < threads.size(); ++w) threads[w].join();
+  if (hostTiming()) fprintf(stderr, "[zdw host] all blocks encoded after %.3f s\n", nowSeconds() - tStart);
   if (res == OK && !outcome.wrongColumns && !pending.empty()) {
     pending[8] = 1;
     writer.push(pending);
@@ -440,7 +563,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   const bool parallel = regularInput && !oneWindow && rowsPerBlock == 0 && blockPlan.empty() && nWorkers > 1;
   if (oneWindow) {
     const size_t configured = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
-    if (!win.open(in, tee, windowBytes, plainAlloc, plainFree)) return OUT_OF_MEMORY;
+    if (!win.open(in, NULL, windowBytes, plainAlloc, plainFree)) return OUT_OF_MEMORY;
     win.fill();
     if (!win.eof()) {  // longer than stat() said (it grew, or the file system does not report sizes): the usual window
       windowBytes = configured;
@@ -455,7 +578,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     }
     return UNKNOWN_ERROR;
   }
-  if (!parallel && !oneWindow && !win.open(in, tee, windowBytes, pinnedAlloc, pinnedFree)) {
+  if (!parallel && !oneWindow && !win.open(in, NULL, windowBytes, pinnedAlloc, pinnedFree)) {
     if (tee) {
       pclose(tee);
       unlink(teeName.c_str());
@@ -499,6 +622,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     if (res != OK) goto Done;
     if (!wrongColumns && blocks == 0) statusOutput(ERROR, "Empty data file -- nothing to process\n");
   }
+  try {
   for (; !parallel;) {
     win.fill();
     if (win.len() == 0 && win.eof()) break;
@@ -584,17 +708,26 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       writer.push(pending);  // the compressor works on it while the next block is read and encoded
     }
     pending.assign(blk.bytes, blk.bytes + blk.len);
+    if (tee && !writeRowsForValidation(tee, win.data(), (size_t)blk.tsv_consumed, bTrimTrailingSpaces)) {
+      res = CANT_OPEN_TEMP_FILE;
+      goto Done;
+    }
     longestLine = blk.longest_line;
     totalRows += blk.nrows;
     if (!bQuiet) statusOutput(INFO, "\r%u\nDone with block %d -- cleaning up...\n", blk.nrows, blocks);
     win.consume((size_t)blk.tsv_consumed);
   }
+  } catch (const std::bad_alloc&) {  // (the window could not grow): clean up like any other failure
+    res = OUT_OF_MEMORY;
+  }
+  if (res != OK) goto Done;
   if (wrongColumns) {
     // the reference returns straight out of processFile here: the pipe is left to the process exit and the
     // .creating file stays on disk (:810-812).  We close the pipe but keep the file.
     win.close();
     writer.finish();
     if (tee) pclose(tee);
+    if (!teeName.empty()) unlink(teeName.c_str());
     pclose(out);
     return WRONG_NUM_OF_COLUMNS_ON_A_ROW;
   }
@@ -610,8 +743,17 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     pclose(tee);
     tee = NULL;
   }
-  pclose(out);
-  out = NULL;
+  {
+    // a compressor that died or a full disk must not end in a rename of a truncated file
+    const bool flushed = fflush(out) == 0;
+    const int status = pclose(out);
+    out = NULL;
+    if (!writer.ok() || !flushed || status != 0) {
+      statusOutput(ERROR, "%s: writing %s failed (compressor exit status %d)\n", exeName, tempName.c_str(), status);
+      res = FILE_CREATION_ERR;
+      goto Done;
+    }
+  }
 
   if (bValidate) {
     const ERR_CODE v = validate(tempName.c_str(), srcFiles, exeName, outputDir);

@@ -216,6 +216,7 @@ int main(int argc, char* argv[]) {
 
   int exitCode = ConvertToZDW::OK;
   for (size_t f = 0; f < opt.files.size(); ++f) {
+    if (f + 1 == opt.files.size()) adobe::zdw::GpuSession::processExiting() = true;
     std::vector<char> stub(strlen(opt.files[f]) + 1024);
     ConvertToZDW conv(opt.quiet, opt.streaming);
     conv.compressor = opt.compressor;
@@ -242,5 +243,6 @@ int main(int argc, char* argv[]) {
       }
     }
   }
-  return exitCode;
+  fflush(NULL);
+  _exit(exitCode);  // (no CUDA teardown: see GpuSession::processExiting)
 }

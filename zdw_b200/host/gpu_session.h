@@ -75,8 +75,15 @@ class GpuSession {
       worker_.join();
       pending_ = false;
     }
-    if (ctx_) zdwb_ctx_destroy(ctx_);
+    // (tearing a context down - unpinning its buffers, freeing its arena - takes tenths of a second; a command line tool
+    // that is about to exit leaves that to the process exit)
+    if (ctx_ && !processExiting()) zdwb_ctx_destroy(ctx_);
     ctx_ = NULL;
+  }
+  // set by the command line tools before their last file: contexts are no longer torn down one by one
+  static bool& processExiting() {
+    static bool flag = false;
+    return flag;
   }
   zdwb_ctx* get() const { return ctx_; }
   int status() const { return rc_; }

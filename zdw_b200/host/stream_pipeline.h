@@ -212,7 +212,7 @@ class ReadAheadInput {
 
 class AsyncWriter {
  public:
-  AsyncWriter() : out_(NULL), done_(false), started_(false) {}
+  AsyncWriter() : out_(NULL), done_(false), started_(false), failed_(false) {}
   ~AsyncWriter() { finish(); }
 
   void start(FILE* out) {
@@ -229,6 +229,12 @@ class AsyncWriter {
     queue_.emplace_back();
     queue_.back().swap(block);
     workCv_.notify_one();
+  }
+
+  // false once a write to the pipe came up short (the compressor died, the disk is full)
+  bool ok() {
+    std::lock_guard<std::mutex> lk(m_);
+    return !failed_;
   }
 
   // everything pushed so far has been written when this returns; the FILE* is the caller's to close
@@ -253,9 +259,10 @@ class AsyncWriter {
         if (queue_.empty()) return;
         blk.swap(queue_.front());
       }
-      fwrite(blk.data(), 1, blk.size(), out_);
+      const bool wrote = fwrite(blk.data(), 1, blk.size(), out_) == blk.size();
       {
         std::lock_guard<std::mutex> lk(m_);
+        if (!wrote) failed_ = true;
         queue_.pop_front();  // only now: "queued" counts the block being written
       }
       roomCv_.notify_one();
@@ -266,7 +273,7 @@ class AsyncWriter {
   std::mutex m_;
   std::condition_variable workCv_, roomCv_;
   std::deque<std::vector<unsigned char> > queue_;
-  bool done_, started_;
+  bool done_, started_, failed_;
   std::thread worker_;
 };
 

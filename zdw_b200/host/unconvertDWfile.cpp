@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <string>
 
@@ -132,6 +133,13 @@ ERR_CODE unconvertOne(const string& file, const Job& job, const char* exe, const
 
 }  // namespace
 
+// leaves without the CUDA teardown once the contexts were left standing (GpuSession::processExiting)
+static int finish(int code) {
+  if (!adobe::zdw::GpuSession::processExiting()) return code;
+  fflush(NULL);
+  _exit(code);
+}
+
 int main(int argc, char* argv[]) {
   const char* exe = argv[0];
   Job job;
@@ -248,12 +256,21 @@ int main(int argc, char* argv[]) {
 
   // pass 2: the files
   const char* stdinOutputName = NULL;
+  int lastFileArg = 0;  // the last file is decoded without tearing its CUDA contexts down (the process exits next)
+  for (int i = 1; i < argc; ++i) {
+    if (argv[i][0] == '-') {
+      if (argv[i][1] == 'a' || argv[i][1] == 'c' || argv[i][1] == 'd') ++i;
+      continue;
+    }
+    lastFileArg = i;
+  }
   for (int i = 1; i < argc; ++i) {
     const char* a = argv[i];
     if (a[0] == '-') {
       if (a[1] == 'a' || a[1] == 'c' || a[1] == 'd') ++i;
       continue;
     }
+    if (i == lastFileArg && !fromStdin) adobe::zdw::GpuSession::processExiting() = true;
     if (a[0] == '\0') {
       fprintf(stderr, "%s: Empty filename not allowed\n\n", exe);
       fprintf(stderr, "    Run with --help for usage info.\n");
@@ -264,11 +281,12 @@ int main(int argc, char* argv[]) {
       continue;
     }
     const ERR_CODE rc = unconvertOne(a, job, exe, NULL, defaultExt + (appendText ? appendText : ""));
-    if (rc != OK) return rc;
+    if (rc != OK) return finish(rc);
   }
   if (fromStdin) {
+    adobe::zdw::GpuSession::processExiting() = true;
     const ERR_CODE rc = unconvertOne("", job, exe, stdinOutputName, appendText ? string(appendText) : defaultExt);
-    if (rc != OK) return rc;
+    if (rc != OK) return finish(rc);
   }
-  return OK;
+  return finish(OK);
 }
