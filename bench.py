@@ -815,7 +815,7 @@ def L_encode_host(ctx, types, ptr: int, n: int) -> int:
     from zdw_b200 import capi
     tarr = (C.c_uint8 * len(types))(*types)
     sch = capi._Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
-    o = capi._EncOpts(0, 0, 0, 0, 0, 0, 0)
+    o = capi._EncOpts(0, 0, 0, 0, 0, 0, 0, 0, 0)
     out = capi._BlockOut()
     rc = ctx._L.zdwb_encode_block(ctx._h, C.byref(sch), C.c_void_p(ptr), n, C.byref(o), C.byref(out))
     if rc:

@@ -122,6 +122,15 @@ typedef struct {
                                    (max_rows, spill_cols) per block any file the reference cut on its own can be
                                    reproduced byte for byte.  0 = none. */
   uint64_t max_rows;            /* 0 = every row in the buffer; else close the block after this many rows */
+  uint32_t heap_blocks;         /* K > 0 (and max_rows == 0): close the block where the REFERENCE would when its process is found
+                                   over --mem-limit at the K-th allocation of a 64 MiB string-heap block: new strings are packed
+                                   in first-occurrence order like StringHeap::copyToHeap (stringheap.cpp:31-59,75-86), the block
+                                   ends in front of the row - and behind the column - whose insert opens heap block K
+                                   (ConvertToZDW.cpp:334-355,404-413).  K is the one number of that cut which
+                                   depends on the reference's process instead of the input.  If the buffer ends before heap
+                                   block K opens and more input follows, nothing is encoded (nrows = 0, tsv_consumed = 0): the
+                                   caller widens the window.  K = 1 is the reference's OUT_OF_MEMORY (ZDWB_ERR_OOM). */
+  uint32_t reserved_e;
 } zdwb_encode_opts;
 
 typedef struct {

@@ -201,6 +201,42 @@ def _cases():
     return out
 
 
+def _big_cases():
+    """Cases too large for the loops that walk the whole corpus: run once each by dedicated tests."""
+    out = []
+    d1c = desc([("s", "varchar(255)")])
+    # d9 (SURVEY App. D): dictionary total at 2^24 - 1 / 2^24 / 2^24 + 1 bytes: 3- vs 4-byte offsets (dictionary.cpp:62-73)
+    for target in (16777215, 16777216, 16777217):
+        n = (target - 1 - 16) // 11            # 11 bytes per "k%09d" + NUL; the last string takes up the slack
+        total = 1 + 11 * n
+        rem = target - total
+        strings = [b"k%09d" % i for i in range(n)]
+        if rem >= 2:
+            strings.append(b"z" * (rem - 1))
+        assert 1 + sum(len(x) + 1 for x in strings) == target
+        out.append((f"d9_dict{target}", d1c, b"\n".join(strings) + b"\n", {}))
+    return out
+
+
+_BIG = None
+
+
+def big_cases():
+    global _BIG
+    if _BIG is None:
+        _BIG = _big_cases()
+    return _BIG
+
+
+def later_block_long_line():
+    """d4: the long lines sit in LATER blocks (2 rows per block): longestLine is cumulative over the file,
+    32768 (the interrupted row behind block 0 is read in full) -> 32768 -> 131072 -> 131072 (getnextrow.cpp:57-65,
+    ConvertToZDW.cpp:965)."""
+    two_text = desc([("a", "text"), ("b", "text")])
+    r = [b"s\tt", b"u\tv", b"x" * 20000 + b"\ty", b"p\tq", b"m\tn", b"z" * 70000 + b"\tw", b"e\tf", b"g\th"]
+    return two_text, b"\n".join(r) + b"\n", 2
+
+
 _CACHE = None
 
 

@@ -216,3 +216,62 @@ def test_row_delta_falls_back_when_a_row_does_not_fit(ctx):
         assert got2 == want2, G.first_diff(got2, want2)
     finally:
         ctx.set_tuning("enc_delta", -1)
+
+
+@pytest.mark.parametrize("case", corpus.big_cases(), ids=[c[0] for c in corpus.big_cases()])
+def test_dictionary_offset_width_edge_at_2_24(ctx, case):
+    """App. D d9: 2^24 - 1 / 2^24 / 2^24 + 1 dictionary bytes (3- vs 4-byte offsets), encode and decode."""
+    name, desc, tsv, _ = case
+    sch = O.parse_desc(desc)
+    want = O.encode(sch, tsv)
+    got = G.encode_file_with_product(ctx, sch, tsv)
+    assert got == want.data, f"{name}: {G.first_diff(got, want.data)}"
+    back, nblocks, consumed = G.decode_file_with_product(ctx, got)
+    assert back == tsv and nblocks == 1 and consumed == len(got)
+
+
+def test_longest_line_is_cumulative_over_blocks(ctx):
+    desc, tsv, rpb = corpus.later_block_long_line()
+    sch = O.parse_desc(desc)
+    want = O.encode(sch, tsv, rows_per_block=rpb).data
+    for variant in (1, 0):
+        ctx.set_tuning("enc_delta", variant)
+        try:
+            got = G.encode_file_with_product(ctx, sch, tsv, rows_per_block=rpb)
+        finally:
+            ctx.set_tuning("enc_delta", -1)
+        assert got == want, G.first_diff(got, want)
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_heap_blocks_cut_like_the_reference_model(ctx, K):
+    """zdwb_encode_opts.heap_blocks = K: the block ends where the reference's string heap would open its K-th 64 MiB
+    block - against the restatement's model of StringHeap, which test_block_plan.py pins to a file
+    the compiled reference cut on its own.  Every block of the file is cut that way."""
+    import c5_check
+    sch = O.parse_desc(c5_check.DESC)
+    tsv = c5_check.make_rows(1_300_000 if K == 2 else 1_700_000)
+    want = O.encode(sch, tsv, heap_blocks=K)
+    assert want.rc == 0 and want.nblocks >= 2
+    out = bytearray(G.split_header(want.data)[0])
+    pos, longest, blocks = 0, 0, 0
+    while pos < len(tsv):
+        blk = ctx.encode_block(sch.types, tsv[pos:], prev_longest_line=longest, heap_blocks=K)
+        assert blk.nrows > 0
+        out += blk.data
+        longest = blk.longest_line
+        pos += blk.tsv_consumed
+        blocks += 1
+        if blk.nrows == blk.rows_in_buffer:
+            break
+    assert blocks == want.nblocks
+    assert bytes(out) == want.data, G.first_diff(bytes(out), want.data)
+
+
+def test_heap_blocks_first_row_is_out_of_memory(ctx):
+    import c5_check
+    from zdw_b200 import ZdwError
+    sch = O.parse_desc(c5_check.DESC)
+    with pytest.raises(ZdwError) as ei:
+        ctx.encode_block(sch.types, c5_check.make_rows(1000), heap_blocks=1)
+    assert ei.value.code == 2  # ZDWB_ERR_OOM: the reference's OUT_OF_MEMORY (ConvertToZDW.cpp:824-834)

@@ -436,15 +436,16 @@ def test_decode_workers_stop_at_a_corrupt_block():
     tsv = O.golden("movie_tickets.sql")[: 1 << 20].rsplit(b"\n", 1)[0] + b"\n"
     desc = O.golden("movie_tickets.desc.sql")
     img = O.encode(O.parse_desc(desc), tsv, rows_per_block=2500).data
-    cut = img[: len(img) * 2 // 3]
-    res = []
+    offs = O.decode(img).block_offset
+    cut = img[: offs[4] + (offs[5] - offs[4]) * 7 // 8]  # inside the rows of block 4 (a cut inside a header ends in the
+    res = []                                             # reference's uncaught ZDWException instead)
     for flags in (["--lanes-per-gpu=1"], ["--gpus=0,0"]):
         with Work() as d:
             (d / "x.zdw").write_bytes(cut)
             rc, out, err = run(BIN, "unconvertDWfile", ["-q", *flags, "x.zdw"], d)
             res.append((rc, (d / "x.sql").read_bytes() if (d / "x.sql").exists() else None))
-    assert res[0][0] == res[1][0] != 0
-    assert res[0][1] == res[1][1] and tsv.startswith(res[1][1])
+    assert res[0][0] == res[1][0] == 8  # ROW_COUNT_ERR
+    assert res[0][1] == res[1][1] == b"".join(tsv.split(b"\n")[k] + b"\n" for k in range(4 * 2500))
 
 
 @pytest.mark.gpu
@@ -492,3 +493,24 @@ def test_streaming_validation_compares_normalised_rows(flags):
             outs.append((rc, b"GOOD" in out, sorted(p.name for p in d.iterdir()), (out + err).decode("latin1")))
     assert outs[0][:3] == outs[1][:3], outs
     assert outs[0][0] == 0 and outs[0][1], outs[0][3]
+
+
+@pytest.mark.gpu
+def test_heap_blocks_flag_reproduces_the_references_memory_cut_without_a_plan():
+    """convertDWfile --heap-blocks=2 writes the file the compiled reference cut on its own under --mem-limit=140 (K = 2 is
+    the allocation at which that process was over its limit, tests/test_block_plan.py) - no explicit plan given.
+    --mem-limit itself is accepted and changes nothing."""
+    import c5_check
+    import test_block_plan as BP
+    tsv, image = BP.reference_mem_limit_file(600_000, 140)
+    with Work() as d:
+        (d / "x.sql").write_bytes(tsv)
+        (d / "x.desc.sql").write_bytes(c5_check.DESC)
+        rc, out, err = run(BIN, "convertDWfile", ["-q", "--heap-blocks=2", "--mem-limit=140", "x.sql"], d, timeout=600)
+        assert rc == 0, (out + err)[-500:]
+        assert (d / "x.zdw.gz").read_bytes() == image
+        # a window smaller than the block: it is widened until heap block 2 opens inside it
+        os.unlink(d / "x.zdw.gz")
+        rc, out, err = run(BIN, "convertDWfile", ["-q", "--heap-blocks=2", "--block-bytes=8388608", "x.sql"], d, timeout=600)
+        assert rc == 0, (out + err)[-500:]
+        assert (d / "x.zdw.gz").read_bytes() == image

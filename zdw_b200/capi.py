@@ -42,7 +42,7 @@ class _Schema(C.Structure):
 class _EncOpts(C.Structure):
     _fields_ = [("trim", C.c_int32), ("input_on_device", C.c_int32), ("output_on_device", C.c_int32),
                 ("more_input_follows", C.c_int32), ("prev_longest_line", C.c_uint32), ("spill_cols", C.c_uint32),
-                ("max_rows", C.c_uint64)]
+                ("max_rows", C.c_uint64), ("heap_blocks", C.c_uint32), ("reserved_e", C.c_uint32)]
 
 
 class _BlockOut(C.Structure):
@@ -196,7 +196,7 @@ class Context:
     # ------------------------------------------------------------------ encode
     def encode_block(self, types, tsv, n: int | None = None, *, trim=False, input_on_device=False,
                      output_on_device=False, prev_longest_line=0, max_rows=0, more_input_follows=False,
-                     spill_cols=0) -> EncodedBlock:
+                     spill_cols=0, heap_blocks=0) -> EncodedBlock:
         """tsv: bytes-like (host) or an int device pointer (input_on_device=True, n required)."""
         tarr = (C.c_uint8 * max(len(types), 1))(*types)
         sch = _Schema(len(types), C.cast(tarr, C.POINTER(C.c_uint8)))
@@ -208,7 +208,7 @@ class Context:
             n = len(keep) if n is None else n
             ptr = C.cast(C.c_char_p(bytes(keep)), C.c_void_p) if not isinstance(keep, bytes) else C.cast(C.c_char_p(keep), C.c_void_p)
         o = _EncOpts(int(trim), int(input_on_device), int(output_on_device), int(more_input_follows), prev_longest_line,
-                     int(spill_cols), max_rows)
+                     int(spill_cols), max_rows, int(heap_blocks), 0)
         out = _BlockOut()
         rc = self._L.zdwb_encode_block(self._h, C.byref(sch), ptr, n, C.byref(o), C.byref(out))
         if rc:

@@ -2259,6 +2259,88 @@ __global__ void k_init_minmax(unsigned long long* colmin, unsigned long long* co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// where would the reference close the block?  (opts.heap_blocks = K)
+//
+// The reference copies every NEW string into 64 MiB string-heap blocks in the order it meets them - row by row, column by
+// column - and ends the ZDW block on the insert that opens heap block K (stringheap.cpp:31-59,75-86; ConvertToZDW.cpp
+// :334-355,404-413).  After the general pass 1 the records of the buffer are in exactly that order and a text record
+// holds its string's hash-set slot, so: the first record of every slot is the string's first occurrence
+// (k_heap_first_ord), its length + 1 the bytes it takes on the heap (k_heap_new_len), a prefix sum over the records
+// the heap's fill level, and K - 1 binary searches over that prefix find the record whose string does not fit the
+// current heap block any more (k_heap_cut).
+// ---------------------------------------------------------------------------------------------
+struct HeapCut {
+  uint32_t found;     // heap block K was opened inside the buffer
+  uint32_t row;       // rows in front of the row whose insert opened it (= rows of the block)
+  uint32_t col;       // column of that insert
+  uint32_t allocs;    // heap blocks opened in the whole buffer (when !found)
+};
+
+__global__ void k_heap_first_ord(const uint32_t* __restrict__ rec_col, const unsigned long long* __restrict__ rec_val,
+                                 const uint8_t* __restrict__ types, uint32_t nrec, uint32_t* __restrict__ first_ord) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrec) return;
+  const uint32_t col = rec_col[k];
+  if (col == REC_EMPTY || !is_text_like(__ldg(types + col))) return;
+  atomicMin(&first_ord[(uint32_t)rec_val[k]], k);
+}
+__global__ void k_heap_new_len(const uint32_t* __restrict__ rec_col, const unsigned long long* __restrict__ rec_val,
+                               const uint8_t* __restrict__ types, uint32_t nrec, const uint32_t* __restrict__ first_ord,
+                               const unsigned long long* __restrict__ slots, uint64_t* __restrict__ new_len) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrec) return;
+  const uint32_t col = rec_col[k];
+  uint64_t v = 0;
+  if (col != REC_EMPTY && is_text_like(__ldg(types + col))) {
+    const uint32_t slot = (uint32_t)rec_val[k];
+    if (first_ord[slot] == k) v = (uint64_t)(uint32_t)slots[slot] + 1ull;  // strlen + 1, StringHeap::copyToHeap
+  }
+  new_len[k] = v;
+}
+// one thread: pre[k] = heap bytes of the new strings in front of record k, len[k] = bytes of record k's string if new
+__global__ void k_heap_cut(const uint64_t* __restrict__ pre, const uint64_t* __restrict__ len, uint32_t nrec, uint64_t total,
+                           uint32_t K, const uint32_t* __restrict__ row_rec, uint32_t nrows, const uint32_t* __restrict__ rec_col,
+                           HeapCut* __restrict__ out) {
+  const uint64_t HEAP_BLOCK = 64ull << 20;
+  out->found = 0;
+  out->row = out->col = 0;
+  uint32_t allocs = 0, at = 0;
+  uint64_t limit = 0;  // the heap is full once the bytes up to and including a new string exceed this
+  bool have = false;
+  for (;;) {
+    // first record k >= at whose new string ends behind `limit` (pre + len is non-decreasing and only grows at new strings)
+    uint32_t a = at, b = nrec;
+    while (a < b) {
+      const uint32_t m = a + ((b - a) >> 1);
+      const uint64_t end = pre[m] + len[m];
+      if (have ? end > limit : end > 0) b = m;
+      else a = m + 1;
+    }
+    if (a >= nrec) break;  // everything else fits
+    ++allocs;
+    if (allocs >= K) {
+      // row of record a: last r with row_rec[r] <= a
+      uint32_t lo = 0, hi = nrows;
+      while (hi - lo > 1) {
+        const uint32_t m = (lo + hi) >> 1;
+        if (row_rec[m] <= a) lo = m;
+        else hi = m;
+      }
+      out->found = 1;
+      out->row = lo;
+      out->col = rec_col[a];
+      break;
+    }
+    const uint64_t l = len[a];
+    limit = pre[a] + (l > HEAP_BLOCK ? l : HEAP_BLOCK);  // the new heap block starts with this string
+    have = true;
+    at = a + 1;
+  }
+  out->allocs = allocs;
+  (void)total;
+}
+
 uint32_t longest_line_field(uint32_t prev, uint32_t max_line) {
   // smallest 16384 * 2^k >= L + 1, cumulative over the file (getnextrow.cpp:57-65)
   uint64_t cap = prev ? prev : 16384u;
@@ -2271,8 +2353,77 @@ uint32_t longest_line_field(uint32_t prev, uint32_t max_line) {
 // =================================================================================================
 // host driver
 // =================================================================================================
+namespace {
+struct HeapProbe {  // the probe run of opts.heap_blocks: K in, the cut out
+  uint32_t K;
+  bool found;
+  uint32_t row, col, allocs;
+};
+}  // namespace
+
+static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
+                            zdwb_block_out* out, HeapProbe* probe);
+
 int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
                       zdwb_block_out* out) {
+  if (!opts->heap_blocks || opts->max_rows) return encode_block_run(ctx, schema, tsv, n, opts, out, nullptr);
+  // ---- the reference's own cut: a probe run of pass 1 over the whole buffer finds the insert that opens heap block K,
+  // the block is then encoded with the (rows, spilled columns) that follow from it.  The buffer is made resident first:
+  // both runs read it.
+  memset(out, 0, sizeof(*out));
+  if (n == 0 || n >= 0xffffff00ull) return encode_block_run(ctx, schema, tsv, n, opts, out, nullptr);
+  void* resident = nullptr;
+  zdwb_encode_opts o = *opts;
+  const void* src = tsv;
+  if (!opts->input_on_device) {
+    if (cudaMalloc(&resident, n + 64) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ctx->err = "encode: device allocation of the input window failed";
+      return ZDWB_ERR_OOM;
+    }
+    if (cudaMemcpyAsync(resident, tsv, n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      (void)cudaGetLastError();
+      cudaFree(resident);
+      ctx->err = "encode: copy of the input window failed";
+      return ZDWB_ERR_CUDA;
+    }
+    src = resident;
+    o.input_on_device = 1;
+  }
+  HeapProbe probe = {opts->heap_blocks, false, 0, 0, 0};
+  zdwb_encode_opts po = o;
+  po.heap_blocks = 0;
+  po.output_on_device = 1;
+  int rc = encode_block_run(ctx, schema, src, n, &po, out, &probe);
+  if (rc == ZDWB_OK && out->rows_in_buffer) {
+    zdwb_encode_opts fo = o;
+    fo.heap_blocks = 0;
+    if (probe.found && probe.row == 0) {
+      ctx->err = "encode: string heap block " + std::to_string(opts->heap_blocks) + " opens inside the first row (the reference's OUT_OF_MEMORY)";
+      rc = ZDWB_ERR_OOM;  // ConvertToZDW.cpp:824-834
+    } else if (probe.found) {
+      fo.max_rows = probe.row;
+      fo.spill_cols = probe.col + 1;
+      rc = encode_block_run(ctx, schema, src, n, &fo, out, nullptr);
+    } else if (opts->more_input_follows) {
+      // the heap block does not open inside this window: the caller widens it (nothing is consumed)
+      const uint64_t rows = out->rows_in_buffer;
+      memset(out, 0, sizeof(*out));
+      out->rows_in_buffer = rows;
+    } else {
+      rc = encode_block_run(ctx, schema, src, n, &fo, out, nullptr);
+    }
+  }
+  if (resident) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(resident);
+  }
+  return rc;
+}
+
+static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size_t n, const zdwb_encode_opts* opts,
+                            zdwb_block_out* out, HeapProbe* probe) {
   memset(out, 0, sizeof(*out));
   ZDWB_TRY(call_begin(ctx));
   cudaStream_t st = ctx->stream;
@@ -2331,7 +2482,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
   // ---- which pass 1?  The row-delta variant (k_pass1d) pays on wide rows; narrow rows - and rows that do not fit its
   // per-warp lists - go through the general one (k_pass1).  Both leave records for their own pass 2.
   const uint64_t DELTA_MIN_ROW_BYTES = 512;
-  bool delta = ctx->enc_delta != 0 && ncols <= DELTA_MAX_COLS && n >= 64 &&
+  bool delta = !probe && ctx->enc_delta != 0 && ncols <= DELTA_MAX_COLS && n >= 64 &&
                (ctx->enc_delta == 1 || (!ctx->delta_bailed && (ctx->last_row_bytes == 0 || ctx->last_row_bytes >= DELTA_MIN_ROW_BYTES)));
 
   DevBuf agg, colset, colmin, colmax, slots, rec_col, rec_val, row_rec, row_cnt, chg_start, chg_len;
@@ -2411,7 +2562,9 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
       ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
       limit = hmeta->cut_end_p1;
       out->tsv_consumed = hmeta->next_start;
-      if (opts->spill_cols) {
+      {
+        // the row behind the block has been read in full when the block is closed - the row buffer has grown with it
+        // (getnextrow.cpp:57-65), so its length counts for longestLine - and its first spill_cols columns have been parsed
         {
           KernelScope _ks(ctx, "k_find_spill");
           k_find_spill<<<1, 1, 0, st>>>(buf, n, hmeta->next_start, opts->spill_cols, meta);
@@ -2420,7 +2573,7 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
         ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
         ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
         if (hmeta->spill_row_len) {
-          limit = hmeta->spill_end;  // pass 1 takes every field whose closing delimiter lies in front of this
+          if (opts->spill_cols) limit = hmeta->spill_end;  // pass 1 takes every field whose closing delimiter lies in front of this
           spill_row_len = hmeta->spill_row_len;
         }
       }
@@ -2563,6 +2716,48 @@ int encode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* tsv, size
     out->bad_row = hmeta->bad_row + 1;  // "Row %u had the problem": one past the last good row, ConvertToZDW.cpp:811
     ctx->err = "Row " + std::to_string(out->bad_row) + " had the problem";
     return ZDWB_ERR_WRONG_COLUMNS;
+  }
+  if (probe) {
+    // ---- the record at which the reference's string heap opens its K-th block
+    const uint32_t nrec = (uint32_t)ne_total;
+    probe->found = false;
+    if (nrec) {
+      DevBuf first_ord, new_len, pre, cut_d;
+      const size_t cap = (size_t)ht.mask + 1;
+      ZDWB_TRY(first_ord.alloc(ctx, cap * 4));
+      ZDWB_TRY(new_len.alloc(ctx, (size_t)nrec * 8));
+      ZDWB_TRY(pre.alloc(ctx, (size_t)nrec * 8));
+      ZDWB_TRY(cut_d.alloc(ctx, sizeof(HeapCut)));
+      ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(first_ord.p, 0xff, cap * 4, st));
+      {
+        KernelScope _ks(ctx, "k_heap_first_ord");
+        k_heap_first_ord<<<(nrec + 255) / 256, 256, 0, st>>>(rec_col.as<uint32_t>(), rec_val.as<unsigned long long>(),
+                                                           types_d.as<uint8_t>(), nrec, first_ord.as<uint32_t>());
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      {
+        KernelScope _ks(ctx, "k_heap_new_len");
+        k_heap_new_len<<<(nrec + 255) / 256, 256, 0, st>>>(rec_col.as<uint32_t>(), rec_val.as<unsigned long long>(),
+                                                         types_d.as<uint8_t>(), nrec, first_ord.as<uint32_t>(), ht.slots,
+                                                         new_len.as<uint64_t>());
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      ZDWB_TRY(exclusive_scan_u64(ctx, new_len.as<uint64_t>(), pre.as<uint64_t>(), nrec, nullptr));
+      {
+        KernelScope _ks(ctx, "k_heap_cut");
+        k_heap_cut<<<1, 1, 0, st>>>(pre.as<uint64_t>(), new_len.as<uint64_t>(), nrec, 0, probe->K, row_rec.as<uint32_t>(),
+                                    nrows, rec_col.as<uint32_t>(), cut_d.as<HeapCut>());
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      HeapCut* hc = reinterpret_cast<HeapCut*>(reinterpret_cast<uint8_t*>(ctx->meta_host) + 2048);
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hc, cut_d.p, sizeof(HeapCut), cudaMemcpyDeviceToHost, st));
+      ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      probe->found = hc->found != 0;
+      probe->row = hc->row;
+      probe->col = hc->col;
+      probe->allocs = hc->allocs;
+    }
+    return ZDWB_OK;
   }
   const uint64_t n_unique = hmeta->n_unique;
   ctx->last_unique = n_unique;

@@ -127,7 +127,7 @@ bool writeRowsForValidation(FILE* to, const char* p, size_t n, bool trim) {
 
 ConvertToZDW::ConvertToZDW(const bool quiet, const bool streamingInput)
     : compressor(GZIP), statusOutput(defaultStatusOutputCallback), bQuiet(quiet), bTrimTrailingSpaces(false),
-      bStreamingInput(streamingInput), rowsPerBlock(0), blockBytes(DEFAULT_BLOCK_BYTES), gpuDevice(-1), lanesPerGpu(2) {}
+      bStreamingInput(streamingInput), rowsPerBlock(0), blockBytes(DEFAULT_BLOCK_BYTES), heapBlocks(0), gpuDevice(-1), lanesPerGpu(2) {}
 
 ConvertToZDW::~ConvertToZDW() {}
 
@@ -560,7 +560,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   }
   // Several windows of a regular file, cut by their size only: whole blocks go to several encode workers (and GPUs).
   const size_t nWorkers = std::max<size_t>(1, gpuList.size()) * (size_t)std::max(1, lanesPerGpu);
-  const bool parallel = regularInput && !oneWindow && rowsPerBlock == 0 && blockPlan.empty() && nWorkers > 1;
+  const bool parallel = regularInput && !oneWindow && rowsPerBlock == 0 && blockPlan.empty() && heapBlocks == 0 && nWorkers > 1;
   if (oneWindow) {
     const size_t configured = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
     if (!win.open(in, NULL, windowBytes, plainAlloc, plainFree)) return OUT_OF_MEMORY;
@@ -642,10 +642,12 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     if (planned) {
       eo.max_rows = blockPlan[blocks - 1].first;
       eo.spill_cols = blockPlan[blocks - 1].second;
+    } else if (eo.max_rows == 0) {
+      eo.heap_blocks = heapBlocks;  // the reference's own cut (a window in which heap block K does not open is widened below)
     }
     // a block cut by the window (not by a row count) uses the window up to its last row break: read ahead.  (Not from
     // a pipe: its producer runs on anyway, and an error path must not wait for a read that may never return.)
-    if (eo.max_rows == 0 && regularInput) win.prefetch();
+    if (eo.max_rows == 0 && eo.heap_blocks == 0 && regularInput) win.prefetch();
     zdwb_block_out blk;
     const int rc = zdwb_encode_block(gpu.get(), &sch, win.data(), win.len(), &eo, &blk);
     if (rc == ZDWB_OK && planned && !win.eof() && blk.rows_in_buffer <= eo.max_rows) {

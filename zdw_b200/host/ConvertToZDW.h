@@ -66,6 +66,9 @@ class ConvertToZDW {
   // for its dictionary and column ranges (the reference's interrupted row); rows left form a last block
   void setBlockPlan(const std::vector<std::pair<uint64_t, uint32_t> >& plan) { blockPlan = plan; }
   void setGpuDevice(int device) { gpuDevice = device; }
+  // Close every block where the reference would when its process is found over --mem-limit at the K-th allocation of a
+  // 64 MiB string-heap block (zdwb_encode_opts.heap_blocks).  0 = off.
+  void setHeapBlocks(uint32_t k) { heapBlocks = k; }
   // Whole blocks are dealt out to several GPUs: `devices` lists the CUDA device of every encode worker
   // group (a device may appear more than once), `lanes` = workers (context + pinned window + host thread) per entry.
   // The output is the same as with one worker; blocks are written in file order.  Applies to regular input files cut
@@ -97,6 +100,7 @@ class ConvertToZDW {
   uint64_t rowsPerBlock;
   std::vector<std::pair<uint64_t, uint32_t> > blockPlan;
   size_t blockBytes;
+  uint32_t heapBlocks;
   int gpuDevice;
   std::vector<int> gpuList;
   int lanesPerGpu;

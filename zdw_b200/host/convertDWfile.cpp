@@ -48,6 +48,8 @@ void printUsage(const char* exe) {
         "\t--block-plan=<rows:spill,...>  (B200 build) explicit blocks: rows per block and the columns of the next row that\n"
         "\t                      (B200 build) were already parsed when the reference closed the block (reproduces its memory-driven cuts)\n"
         "\t--block-bytes=<N>     (B200 build) TSV bytes per block window [default=1 GiB]\n"
+        "\t--heap-blocks=<K>     (B200 build) close every block where the reference does when it finds itself over --mem-limit at\n"
+        "\t                      (B200 build) its K-th 64 MiB string-heap allocation; --mem-limit itself is accepted and has no effect\n"
         "\t--gpu=<N>             (B200 build) CUDA device to use [default=$ZDW_GPU or 0]\n"
         "\t--gpus=<N|all|a,b,..> (B200 build) spread the blocks of a file over N GPUs / all GPUs / the listed devices\n"
         "\t                      (B200 build) [default=$ZDW_GPUS or the one device]; the output does not depend on it\n"
@@ -84,10 +86,12 @@ struct Options {
   int gpu;
   std::string gpus;
   int lanes;
+  unsigned heapBlocks;
+  bool memLimitGiven;
   std::vector<const char*> files;
   Options()
       : streaming(false), removeOld(false), trim(false), validate(false), quiet(false), compressor(ConvertToZDW::GZIP),
-        outputDir(NULL), zArgs(NULL), rowsPerBlock(0), blockBytes(0), gpu(-1), lanes(0) {}
+        outputDir(NULL), zArgs(NULL), rowsPerBlock(0), blockBytes(0), gpu(-1), lanes(0), heapBlocks(0), memLimitGiven(false) {}
 };
 
 }  // namespace
@@ -135,11 +139,18 @@ int main(int argc, char* argv[]) {
           return ConvertToZDW::OK;
         }
         if (!strncmp(flag, "mem-limit=", 10)) {
-          // The reference compares process virtual memory with this limit to cut blocks (memory.cpp:65-81).  Here it
-          // bounds the block window instead: a third of the limit, so that window + device copy + output fit.
+          // The reference compares its process's virtual memory with this limit to decide when a block ends
+          // (memory.cpp:65-81, stringheap.cpp:75-86): a property of that process, not of the input.  The flag is
+          // accepted and has no effect here; --heap-blocks=K reproduces the cut itself (the K-th 64 MiB string-heap
+          // allocation), --block-bytes / --rows-per-block set this build's own block size.
           const double mb = atof(flag + 10);
           if (!(mb > 0.0)) return unknownParameter(exe, a);
-          if (!opt.blockBytes) opt.blockBytes = (unsigned long long)(mb * 1024.0 * 1024.0 / 3.0);
+          opt.memLimitGiven = true;
+          break;
+        }
+        if (!strncmp(flag, "heap-blocks=", 12)) {
+          opt.heapBlocks = (unsigned)strtoul(flag + 12, NULL, 10);
+          if (!opt.heapBlocks) return reportFailure(ConvertToZDW::BAD_PARAMETER);
           break;
         }
         if (!strncmp(flag, "metadata:", 9)) {
@@ -224,6 +235,9 @@ int main(int argc, char* argv[]) {
     if (opt.rowsPerBlock) conv.setRowsPerBlock(opt.rowsPerBlock);
     if (!opt.blockPlan.empty()) conv.setBlockPlan(opt.blockPlan);
     if (opt.blockBytes) conv.setBlockBytes((size_t)opt.blockBytes);
+    if (opt.heapBlocks) conv.setHeapBlocks(opt.heapBlocks);
+    if (opt.memLimitGiven && !opt.quiet && f == 0)
+      fprintf(stderr, "%s: --mem-limit has no effect in this build (blocks are cut by --block-bytes, --rows-per-block or --heap-blocks)\n", exe);
     conv.setGpuDevice(opt.gpu);
     if (!gpuList.empty()) conv.setGpus(gpuList);
     if (opt.lanes) conv.setLanesPerGpu(opt.lanes);
