@@ -193,14 +193,16 @@ def test_roundtrip_property_large_random(ctx):
     assert img == O.encode(sch, tsv).data
 
 
-@pytest.mark.skipif(not os.environ.get("ZDW_EXPERIMENTS"), reason="unmeasured kernel variants: set ZDW_EXPERIMENTS=1")
-@pytest.mark.parametrize("lanes", [0, 8, 16])
-def test_experimental_word_emit(ctx, lanes):
-    """k_dec_rows<.., WORDS = true> (knob dec_emit_words, off by default): cached texts stored as aligned words.
-    Written after the round's GPU minutes were spent - parity and timing are the first thing to check next session
-    (ZDW_EXPERIMENTS=1 pytest tests/test_gpu_decode.py -m gpu -k word_emit; tools/profile_one.py --sweep dec_emit_words=0,1)."""
-    ctx.set_tuning("dec_emit_words", 1)
+@pytest.mark.parametrize("emit_words,delta,lanes,strip", [(0, 0, 0, 0), (1, 0, 8, 0), (1, 0, 16, 0), (1, 1, 32, 0), (1, 1, 32, 3), (0, 1, 0, 1)])
+def test_row_writer_variants_forced(ctx, emit_words, delta, lanes, strip):
+    """The row writer has variants: cached texts stored byte by byte or as aligned words (dec_emit_words), and for wide
+    schemas rows assembled from the row before (dec_delta: unchanged stretches copied 16 bytes at a time, only changed
+    items rendered).  Every combination must write the oracle's rows: the whole corpus, the goldens, projections, the
+    in-memory layout; short strips make the delta writer start over often."""
+    ctx.set_tuning("dec_emit_words", emit_words)
+    ctx.set_tuning("dec_delta", delta)
     ctx.set_tuning("dec_group_lanes", lanes)
+    ctx.set_tuning("dec_strip_rows", strip)
     try:
         for case in FAST:
             _check_case(ctx, case)
@@ -212,8 +214,10 @@ def test_experimental_word_emit(ctx, lanes):
         test_column_projection(ctx)
         test_in_memory_layout_and_row_offsets(ctx)
     finally:
-        ctx.set_tuning("dec_emit_words", 0)
+        ctx.set_tuning("dec_emit_words", 1)
+        ctx.set_tuning("dec_delta", 1)
         ctx.set_tuning("dec_group_lanes", 0)
+        ctx.set_tuning("dec_strip_rows", 0)
 
 
 @pytest.mark.parametrize("lanes", [8, 16, 32])

@@ -20,7 +20,7 @@ for r in rows:
             a = agg[(cur, int(r[0]))]; a[0] += int(r[si] or 0); a[1] += int(r[ii] or 0)
         except ValueError: pass
 ti = sum(a[1] for a in agg.values()); ts = sum(a[0] for a in agg.values())
-src = (Path(__file__).resolve().parent.parent / "zdw_b200" / "csrc" / "encode.cu").read_text().split("\n")
+src = (Path(__file__).resolve().parent.parent / "zdw_b200" / "csrc" / (sys.argv[4] if len(sys.argv) > 4 else "encode.cu")).read_text().split("\n")
 marks = []
 for i, l in enumerate(src):
     t = l.strip()
@@ -30,7 +30,7 @@ for i, l in enumerate(src):
 marks.sort()
 tot = collections.defaultdict(lambda: [0, 0])
 for (f, l), a in agg.items():
-    if f != "encode.cu":
+    if f != (sys.argv[4] if len(sys.argv) > 4 else "encode.cu"):
         k = "[" + f + "]"
     else:
         k = "encode.cu:top"

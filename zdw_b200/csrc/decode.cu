@@ -710,6 +710,417 @@ __global__ void __launch_bounds__(128, 10)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// delta row writer (wide schemas): a decoded row differs from the row before only in the items whose flag bit is set -
+// 16 % of the cells of analytics-shaped data - and everything between two changed items, separators and defaults
+// included, is a byte-for-byte copy of the same stretch of the previous row, moved by the length changes so far.
+// The previous row has just been written by the same warp (it sits in L2), so row r is assembled from it: 16-byte
+// chunks whose bytes all come from one unchanged stretch are copied with one unaligned load and one aligned store,
+// only the changed items are rendered (readNextRow's per-column switch, UnconvertFromZDW.cpp:1349-1453), and the few
+// chunks that straddle a changed item go byte by byte.  The first row of a strip - and a row with more changes than
+// the warp's lists hold - is assembled in full from the column values the warp keeps.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t DLC = 128;  // changed items per row the delta path handles (more: the row is assembled in full)
+
+struct DeltaLayout {   // byte offsets inside a warp's slice of dynamic shared memory
+  uint32_t o_val, o_len, o_ioff, o_lcs, o_lce, o_lpe, o_lvoff, o_litem, o_lu, o_slow;
+  uint32_t stride, warps;
+};
+struct DeltaState {
+  unsigned long long* val;  // [NI] stored value of the item's column
+  uint32_t* len;            // [NI] length of its text
+  uint32_t* ioff;           // [NI + 1] dynamic bytes in front of the item (prefix of len)
+  uint32_t *lcs, *lce, *lpe;  // [DLC] changed item: start / end in this row, end in the previous row
+  uint32_t* lvoff;          // [DLC] offset of its value in the encoded row
+  uint16_t *litem, *lu;     // [DLC] its item / used column
+  uint16_t* slow;           // [max(2 DLC + 4, NI)] chunks that straddle a changed item or the row's ends; afterwards (lng)
+  uint16_t* lng;            // the items whose text comes straight from the dictionary, by octets (same memory)
+};
+__device__ __forceinline__ DeltaState delta_state(uint8_t* dsm, const DeltaLayout& L, unsigned warp) {
+  uint8_t* b = dsm + (size_t)warp * L.stride;
+  DeltaState S;
+  S.val = reinterpret_cast<unsigned long long*>(b + L.o_val);
+  S.len = reinterpret_cast<uint32_t*>(b + L.o_len);
+  S.ioff = reinterpret_cast<uint32_t*>(b + L.o_ioff);
+  S.lcs = reinterpret_cast<uint32_t*>(b + L.o_lcs);
+  S.lce = reinterpret_cast<uint32_t*>(b + L.o_lce);
+  S.lpe = reinterpret_cast<uint32_t*>(b + L.o_lpe);
+  S.lvoff = reinterpret_cast<uint32_t*>(b + L.o_lvoff);
+  S.litem = reinterpret_cast<uint16_t*>(b + L.o_litem);
+  S.lu = reinterpret_cast<uint16_t*>(b + L.o_lu);
+  S.slow = reinterpret_cast<uint16_t*>(b + L.o_slow);
+  S.lng = S.slow;
+  return S;
+}
+
+__device__ __forceinline__ uint32_t ld_coherent_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// 16 bytes from an arbitrary address (coherent loads: five aligned words, funnel shifts)
+__device__ __forceinline__ uint4 ld_coherent_16(const uint8_t* s) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+  const uint32_t w0 = ld_coherent_u32(w), w1 = ld_coherent_u32(w + 1), w2 = ld_coherent_u32(w + 2), w3 = ld_coherent_u32(w + 3),
+                 w4 = sh ? ld_coherent_u32(w + 4) : 0u;
+  uint4 v;
+  v.x = __funnelshift_r(w0, w1, sh);
+  v.y = __funnelshift_r(w1, w2, sh);
+  v.z = __funnelshift_r(w2, w3, sh);
+  v.w = __funnelshift_r(w3, w4, sh);
+  return v;
+}
+// word `at` .. `at` + 3 of a 16-byte chunk: the bytes [from, upto) of the chunk are taken from v, the others stay
+__device__ __forceinline__ uint32_t merge_bytes(uint32_t acc, uint32_t v, uint32_t from, uint32_t upto, uint32_t at) {
+  const uint32_t lo = from > at ? min(from - at, 4u) : 0u, hi = upto > at ? min(upto - at, 4u) : 0u;  // bytes [lo, hi) of the word
+  if (hi <= lo) return acc;
+  const uint32_t m = (hi >= 4u ? 0xffffffffu : ((1u << (8u * hi)) - 1u)) & ~((1u << (8u * lo)) - 1u);
+  return (acc & ~m) | (v & m);
+}
+
+// l (1..20) bytes held in w[0..4] (first byte = lowest byte of w[0]) to d: head bytes up to the next 4-byte boundary,
+// aligned words, tail bytes
+__device__ __forceinline__ void emit_words(uint8_t* __restrict__ d, const uint32_t w[5], uint32_t l) {
+  const uint32_t head = min(l, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u)) & 3u);
+  if (head > 0) d[0] = (uint8_t)w[0];
+  if (head > 1) d[1] = (uint8_t)(w[0] >> 8);
+  if (head > 2) d[2] = (uint8_t)(w[0] >> 16);
+  const uint32_t rest = l - head, nw = rest >> 2, sh = head * 8u;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
+  if (nw > 0) dw[0] = __funnelshift_r(w[0], w[1], sh);
+  if (nw > 1) dw[1] = __funnelshift_r(w[1], w[2], sh);
+  if (nw > 2) dw[2] = __funnelshift_r(w[2], w[3], sh);
+  if (nw > 3) dw[3] = __funnelshift_r(w[3], w[4], sh);
+  if (nw > 4) dw[4] = w[4] >> sh;
+  const uint32_t tail = rest & 3u;
+  if (tail) {
+    const uint32_t lo = nw == 0 ? w[0] : nw == 1 ? w[1] : nw == 2 ? w[2] : nw == 3 ? w[3] : w[4];
+    const uint32_t hi = nw == 0 ? w[1] : nw == 1 ? w[2] : nw == 2 ? w[3] : nw == 3 ? w[4] : 0u;
+    const uint32_t t = __funnelshift_r(lo, hi, sh);
+    uint8_t* dt = d + head + 4u * nw;
+    dt[0] = (uint8_t)t;
+    if (tail > 1) dt[1] = (uint8_t)(t >> 8);
+    if (tail > 2) dt[2] = (uint8_t)(t >> 16);
+  }
+}
+
+// Text of used column u holding stored value v (l = its length, > 0) to d.  Returns false for a dictionary text of
+// more than 16 bytes: the caller copies those with the octets of the warp.
+__device__ __forceinline__ bool emit_value(const DecParams& P, uint32_t u, unsigned long long v, uint32_t l, uint8_t* __restrict__ d) {
+  const uint8_t t = P.utype[u];
+  uint32_t w[5] = {0u, 0u, 0u, 0u, 0u};
+  if (is_text_like(t)) {
+    if (v == 0) {  // outputDefault(DECIMAL): "0.000000000000"
+      w[0] = 0x30302e30u;
+      w[1] = 0x30303030u;
+      w[2] = 0x30303030u;
+      w[3] = 0x00003030u;
+    } else {
+      if (l > 16) return false;
+      const uint32_t index = (uint32_t)(v + P.ubase[u]);
+      const uint8_t* s = P.blk + P.dict_base + index;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      const uint32_t* pend = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.blk + P.avail - 1) & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+      const uint32_t lim = (uint32_t)min((ptrdiff_t)4, pend - p);
+      const uint32_t w0 = __ldg(p), w1 = __ldg(p + min(1u, lim)), w2 = __ldg(p + min(2u, lim)), w3 = __ldg(p + min(3u, lim)),
+                     w4 = __ldg(p + min(4u, lim));
+      w[0] = __funnelshift_r(w0, w1, sh);
+      w[1] = __funnelshift_r(w1, w2, sh);
+      w[2] = __funnelshift_r(w2, w3, sh);
+      w[3] = __funnelshift_r(w3, w4, sh);
+    }
+  } else if (t == ZDWB_CHAR) {
+    w[0] = (uint32_t)(v + P.ubase[u]) & 0xffffu;
+  } else {
+    const unsigned long long full = v ? v + P.ubase[u] : 0ull;
+    render_int(full, is_signed_int_type(t) && (long long)full < 0, l, w);
+  }
+  emit_words(d, w, l);
+  return true;
+}
+
+// exclusive prefix of S.len over the items -> S.ioff (all lanes)
+__device__ __forceinline__ void delta_scan_lens(const DeltaState& S, uint32_t NI) {
+  const unsigned lane = lane_id();
+  uint32_t run = 0;
+  for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const uint32_t l = i < NI ? S.len[i] : 0u;
+    uint32_t inc = l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += t;
+    }
+    if (i < NI) S.ioff[i] = run + inc - l;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) S.ioff[NI] = run;
+}
+
+__global__ void __launch_bounds__(128, 8)
+    k_dec_write_delta(const DecParams P, const FmtTables FT, const int32_t* __restrict__ u_item, const uint8_t* __restrict__ outmask,
+                      const uint32_t* __restrict__ row_off, uint32_t RS, const DeltaLayout L, const unsigned long long* __restrict__ cin,
+                      const unsigned long long* __restrict__ out_row_off, uint8_t* __restrict__ out, DecMeta* __restrict__ meta) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t strip = blockIdx.x * L.warps + warp;
+  const uint32_t r0 = strip * RS;
+  if (warp >= L.warps || r0 >= P.nrows) return;
+  const uint32_t r1 = min(P.nrows, r0 + RS);
+  const DeltaState S = delta_state(dsm, L, warp);
+  const uint32_t U = P.U, NI = FT.n_items, F = P.F;
+  const uint8_t* rows = P.blk + P.rows_base;
+
+  // ---- the values carried into the strip
+  for (uint32_t u = lane; u < U; u += 32) {
+    const int32_t i = __ldg(u_item + u);
+    if (i < 0) continue;
+    const unsigned long long v = cin[(size_t)strip * U + u];
+    S.val[i] = v;
+    S.len[i] = value_len(P, u, P.utype[u], v, meta);
+  }
+  __syncwarp();
+  const uint8_t* prev = nullptr;  // the previous row of the strip in `out`
+  const unsigned long long strip_end = out_row_off[r1];
+
+  for (uint32_t r = r0; r < r1; ++r) {
+    const uint8_t* rp = rows + row_off[r];
+    const unsigned long long o0 = out_row_off[r];
+    uint8_t* dst = out + o0;
+    const uint32_t row_len = (uint32_t)(out_row_off[r + 1] - o0);
+    // ---- which items change?  flag byte j: bits of the used columns 8 j .. 8 j + 7; the value bytes in front of a
+    // flag byte's values come from the width bit planes like in warp_parse_row
+    uint32_t n = 0;         // changed items that are output
+    bool full = prev == nullptr;
+    if (!full) {            // more changes than the lists hold?  (then the values are applied on the spot, see below)
+      uint32_t cnt = 0;
+      for (uint32_t j = lane; j < F; j += 32) cnt += (uint32_t)__popc((uint32_t)__ldg(rp + j) & (uint32_t)__ldg(outmask + j));
+      full = __reduce_add_sync(0xffffffffu, cnt) > DLC;
+    }
+    uint32_t run = F;       // offset of the next value inside the encoded row
+    for (uint32_t j0 = 0; j0 < F; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      uint32_t fb = 0, bl = 0, ob = 0;
+      if (j < F) {
+        fb = (uint32_t)__ldg(rp + j);
+        if (fb) {
+          const uint32_t sh = (j & 3u) * 8u, w = j >> 2;
+          bl = __popc(fb & (P.planes[w] >> sh)) + 2u * __popc(fb & (P.planes[P.W + w] >> sh)) +
+               4u * __popc(fb & (P.planes[2 * P.W + w] >> sh)) + 8u * __popc(fb & (P.planes[3 * P.W + w] >> sh));
+          ob = fb & (uint32_t)__ldg(outmask + j);
+        }
+      }
+      const uint32_t mine = bl | ((uint32_t)__popc(ob) << 16);
+      uint32_t inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+      uint32_t voff = run + ((inc - mine) & 0xffffu);
+      uint32_t at = n + ((inc - mine) >> 16);
+      const uint32_t cnt_all = tot >> 16;
+      // every flagged column: the new value (and, on the delta path, its place in the list)
+      while (fb) {
+        const int b = __ffs(fb) - 1;
+        fb &= fb - 1;
+        const uint32_t u = j * 8 + b;
+        if (u >= U) break;
+        const uint32_t sz = P.usz[u];
+        if ((ob >> b) & 1u) {
+          if (!full) {
+            S.lu[at] = (uint16_t)u;
+            S.lvoff[at] = voff;
+          } else {
+            const uint32_t i = (uint32_t)__ldg(u_item + u);
+            const unsigned long long v = load_le(rp + voff, sz);
+            S.val[i] = v;
+            S.len[i] = value_len(P, u, P.utype[u], v, meta);
+          }
+          ++at;
+        }
+        voff += sz;
+      }
+      run += tot & 0xffffu;
+      n += cnt_all;
+    }
+    __syncwarp();
+    if (!full) {
+      // ---- apply the changes: value, new length; where the item ended in the previous row.  Bit 15 of litem marks a
+      // change of LENGTH: only those move the bytes behind them
+      for (uint32_t e = lane; e < n; e += 32) {
+        const uint32_t u = S.lu[e];
+        const uint32_t i = (uint32_t)__ldg(u_item + u);
+        const unsigned long long v = load_le(rp + S.lvoff[e], P.usz[u]);
+        const uint32_t oldl = S.len[i], newl = value_len(P, u, P.utype[u], v, meta);
+        S.lpe[e] = __ldg(FT.item_pos + i) + S.ioff[i] + oldl;
+        S.litem[e] = (uint16_t)(i | (oldl != newl ? 0x8000u : 0u));
+        S.val[i] = v;
+        S.len[i] = newl;
+      }
+      __syncwarp();
+    }
+    delta_scan_lens(S, NI);
+    __syncwarp();
+
+    if (full) {
+      // ---- the whole row from the template and the column values
+      warp_write_template<32>(FT, S.ioff, dst);
+      uint32_t nlong = 0;
+      for (uint32_t i0 = 0; i0 < NI; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool is_long = false;
+        if (i < NI) {
+          const uint32_t l = S.len[i];
+          if (l) is_long = !emit_value(P, __ldg(FT.item_u + i), S.val[i], l, dst + __ldg(FT.item_pos + i) + S.ioff[i]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is_long);
+        if (is_long) S.lng[nlong + __popc(m & lanemask_lt())] = (uint16_t)i;
+        nlong += __popc(m);
+      }
+      __syncwarp();
+      for (uint32_t e = lane >> 3; e < nlong; e += 4) {
+        const uint32_t i = S.lng[e];
+        const uint32_t u = __ldg(FT.item_u + i);
+        octet_copy(dst + __ldg(FT.item_pos + i) + S.ioff[i], P.blk + P.dict_base + (uint32_t)(S.val[i] + P.ubase[u]), S.len[i], lane & 7u);
+      }
+    } else {
+      // ---- the items whose length changed, in row order: start / end in this row (lcs / lce) and end in the previous
+      // row (lpe, compacted in place).  Stretch k (behind such an item k, k = -1: the row's head) holds the bytes
+      // [lce[k], lcs[k + 1]) of this row = the previous row's bytes from lpe[k] on.
+      uint32_t nb = 0;
+      for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        uint32_t li = 0, pe = 0;
+        if (e < n) {
+          li = S.litem[e];
+          pe = S.lpe[e];
+        }
+        const bool moved = (li & 0x8000u) != 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, moved);
+        __syncwarp();
+        if (moved) {
+          const uint32_t i = li & 0x7fffu, k = nb + (uint32_t)__popc(m & lanemask_lt());
+          const uint32_t cs = __ldg(FT.item_pos + i) + S.ioff[i];
+          S.lcs[k] = cs;
+          S.lce[k] = cs + S.len[i];
+          S.lpe[k] = pe;
+        }
+        nb += (uint32_t)__popc(m);
+        __syncwarp();
+      }
+      // ---- 16 aligned bytes per lane.  A chunk inside one stretch is one unaligned load; the others - the row's head
+      // (its first bytes belong to the row before), chunks that hold an item whose length changed - are merged from
+      // their sources afterwards.  Bytes of changed items are overwritten by the rendering below; a chunk may run over
+      // the end of the row into the next row of the strip (which is written later), never into another strip.
+      const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+      const uint32_t nch = (a0 + row_len + 15u) >> 4;
+      // (... of the strip: with rows shorter than a chunk the overrun could otherwise pass the rows behind it)
+      const uint32_t ext = (uint32_t)min((unsigned long long)row_len + 16ull, strip_end - o0);
+      uint32_t nslow = 0;
+      for (uint32_t c0 = 0; c0 < nch; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const int32_t x0 = (int32_t)(c * 16u) - (int32_t)a0;  // row-relative offset of the chunk
+        bool slow = false;
+        if (c < nch) {
+          const uint32_t x = x0 > 0 ? (uint32_t)x0 : 0u;
+          uint32_t lo = 0, hi = nb;  // moved items that end at or in front of x
+          while (lo < hi) {
+            const uint32_t m = (lo + hi) >> 1;
+            if (S.lce[m] <= x) lo = m + 1;
+            else hi = m;
+          }
+          const uint32_t stop = lo < nb ? S.lcs[lo] : ext;  // the stretch ends here
+          if (x0 >= 0 && (uint32_t)x0 + 16u <= stop) {
+            const uint32_t src = lo ? (uint32_t)x0 - S.lce[lo - 1] + S.lpe[lo - 1] : (uint32_t)x0;
+            *reinterpret_cast<uint4*>(dst + x0) = ld_coherent_16(prev + src);
+          } else if (!(x0 >= 0 && lo < nb && S.lcs[lo] <= x && (uint32_t)x0 + 16u <= S.lce[lo])) {
+            slow = true;  // (a chunk inside one moved item is left to the rendering: at most two listed chunks per item)
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, slow);
+        if (slow) S.slow[nslow + __popc(m & lanemask_lt())] = (uint16_t)c;
+        nslow += __popc(m);
+      }
+      __syncwarp();
+      for (uint32_t q = lane; q < nslow; q += 32) {
+        const uint32_t c = S.slow[q];
+        const int32_t x0 = (int32_t)(c * 16u) - (int32_t)a0;
+        uint8_t* at = dst + x0;  // 16-byte aligned
+        uint4 acc = x0 < 0 ? ld_coherent_16(at) : make_uint4(0u, 0u, 0u, 0u);  // the bytes in front of the row stay
+        uint32_t pos = x0 < 0 ? a0 : 0u;  // bytes of the chunk settled so far
+        uint32_t k = 0;
+        {
+          const uint32_t x = x0 > 0 ? (uint32_t)x0 : 0u;
+          uint32_t lo = 0, hi = nb;
+          while (lo < hi) {
+            const uint32_t m = (lo + hi) >> 1;
+            if (S.lce[m] <= x) lo = m + 1;
+            else hi = m;
+          }
+          k = lo;
+        }
+        // source after source: stretch k - 1 up to the start of moved item k, whose bytes are left to the rendering
+        while (pos < 16u) {
+          const uint32_t x = (uint32_t)(x0 + (int32_t)pos);
+          const uint32_t stop = k < nb ? S.lcs[k] : 0xffffffffu;
+          uint32_t upto = 16u;  // bytes [pos, upto) of the chunk come from stretch k - 1
+          if (stop != 0xffffffffu && stop < (uint32_t)(x0 + 16)) upto = stop > x ? stop - (uint32_t)x0 : pos;
+          if (upto > pos) {
+            const uint32_t src = k ? x - S.lce[k - 1] + S.lpe[k - 1] : x;
+            const uint4 v = ld_coherent_16(prev + src - pos);  // byte j of v = the chunk's byte j
+            acc.x = merge_bytes(acc.x, v.x, pos, upto, 0u);
+            acc.y = merge_bytes(acc.y, v.y, pos, upto, 4u);
+            acc.z = merge_bytes(acc.z, v.z, pos, upto, 8u);
+            acc.w = merge_bytes(acc.w, v.w, pos, upto, 12u);
+          }
+          if (k >= nb) break;
+          // skip moved item k (its bytes are rendered below) and go on behind it
+          const uint32_t end = S.lce[k];
+          pos = end > (uint32_t)(x0 + 16) ? 16u : (end > x ? end - (uint32_t)x0 : max(pos, upto));
+          if (pos < upto) pos = upto;
+          ++k;
+        }
+        if ((uint32_t)(x0 + 16) > ext) {  // the strip's last bytes: nothing behind them may be touched
+          const uint32_t w[4] = {acc.x, acc.y, acc.z, acc.w};
+          for (int32_t b = x0 < 0 ? -x0 : 0; b < 16 && (uint32_t)(x0 + b) < row_len; ++b) at[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+        } else {
+          *reinterpret_cast<uint4*>(at) = acc;
+        }
+      }
+      __syncwarp();
+      // ---- the changed items
+      uint32_t nlong = 0;
+      for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        bool is_long = false;
+        if (e < n) {
+          const uint32_t i = S.litem[e] & 0x7fffu, l = S.len[i];
+          if (l) is_long = !emit_value(P, S.lu[e], S.val[i], l, dst + __ldg(FT.item_pos + i) + S.ioff[i]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is_long);
+        if (is_long) S.lng[nlong + __popc(m & lanemask_lt())] = (uint16_t)e;
+        nlong += __popc(m);
+      }
+      __syncwarp();
+      for (uint32_t q = lane >> 3; q < nlong; q += 4) {
+        const uint32_t e = S.lng[q];
+        const uint32_t i = S.litem[e] & 0x7fffu, u = S.lu[e];
+        octet_copy(dst + __ldg(FT.item_pos + i) + S.ioff[i], P.blk + P.dict_base + (uint32_t)(S.val[i] + P.ubase[u]), S.len[i], lane & 7u);
+      }
+    }
+    __syncwarp();
+    prev = dst;
+  }
+}
+
 struct HostBlockHeader {
   uint32_t nrows = 0, line_len = 0;
   uint8_t last = 0, idx_size = 0;
@@ -1232,6 +1643,17 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   unsigned long long* d_row_off = static_cast<unsigned long long*>(ctx->out_dev2);
   DevBuf row_len;
   ZDWB_TRY(row_len.alloc(ctx, (size_t)nrows * 8));
+  // ---- the delta writer takes wide schemas whose output order follows the file order (so that the changed items of a
+  // row come out of the flag walk in output order) and no running row number
+  bool use_delta = ctx->dec_delta != 0 && GL == 32 && FT.rownum_item == ITEM_ROWNUM && NI > 0 && NI < 65536 && U < 65536;
+  {
+    int32_t last_item = -1;
+    for (uint32_t u = 0; u < U && use_delta; ++u) {
+      if (u_item[u] < 0) continue;
+      if (u_item[u] <= last_item) use_delta = false;
+      last_item = u_item[u];
+    }
+  }
   auto launch_rows = [&](bool write, const WarpLayout& L, unsigned long long* lens, const unsigned long long* offs, uint8_t* dst) -> int {
     const uint32_t per_cta = L.warps * GPW;
     const unsigned grid = (nstrips + per_cta - 1) / per_cta, block = 32 * L.warps;
@@ -1279,11 +1701,47 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   // ---- pass B: the rows
   ctx->out_dev = nullptr;
   {
+    // (64 bytes in front: the delta writer's merged chunks may read up to 15 bytes in front of the first row)
     DevBuf ob;
-    ZDWB_TRY(ob.alloc(ctx, hm->out_bytes + 64));
-    ctx->out_dev = ob.detach();
+    ZDWB_TRY(ob.alloc(ctx, hm->out_bytes + 192));
+    ctx->out_dev = static_cast<uint8_t*>(ob.detach()) + 64;
   }
-  {
+  if (use_delta) {
+    // per-warp state of the delta writer: column values, lengths, their prefix, the lists of a row's changed items
+    DeltaLayout DL;
+    size_t o = 0;
+    DL.o_val = (uint32_t)o;    o += (size_t)NI * 8;
+    DL.o_len = (uint32_t)o;    o += (size_t)NI * 4;
+    DL.o_ioff = (uint32_t)o;   o += ((size_t)NI + 1) * 4;
+    DL.o_lcs = (uint32_t)o;    o += (size_t)DLC * 4;
+    DL.o_lce = (uint32_t)o;    o += (size_t)DLC * 4;
+    DL.o_lpe = (uint32_t)o;    o += (size_t)DLC * 4;
+    DL.o_lvoff = (uint32_t)o;  o += (size_t)DLC * 4;
+    DL.o_litem = (uint32_t)o;  o += (size_t)DLC * 2;
+    DL.o_lu = (uint32_t)o;     o += (size_t)DLC * 2;
+    DL.o_slow = (uint32_t)o;   o += std::max<size_t>(2 * DLC + 4, NI) * 2;
+    o = (o + 15) & ~(size_t)15;
+    uint32_t warps = 4;
+    while (warps > 1 && o * warps > 200 * 1024) warps >>= 1;
+    if (o * warps > 200 * 1024) {
+      use_delta = false;
+    } else {
+      DL.stride = (uint32_t)o;
+      DL.warps = warps;
+      std::vector<uint8_t> outmask((size_t)F + 4, 0);
+      for (uint32_t u = 0; u < U; ++u)
+        if (u_item[u] >= 0) outmask[u >> 3] |= (uint8_t)(1u << (u & 7u));
+      DevBuf d_outmask;
+      ZDWB_TRY(upload(ctx, d_outmask, outmask));
+      ZDWB_CUDA_TRY(ctx, cudaFuncSetAttribute(k_dec_write_delta, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+      const unsigned grid = (nstrips + warps - 1) / warps;
+      KernelScope _ks(ctx, "k_dec_write_delta");
+      k_dec_write_delta<<<grid, 32 * warps, (size_t)DL.stride * warps, st>>>(P, FT, d_u_item.as<int32_t>(), d_outmask.as<uint8_t>(),
+                                                                           row_off.as<uint32_t>(), R, DL, cin.as<unsigned long long>(),
+                                                                           d_row_off, static_cast<uint8_t*>(ctx->out_dev), meta);
+    }
+  }
+  if (!use_delta) {
     KernelScope _ks(ctx, "k_dec_write_rows");
     ZDWB_TRY(launch_rows(true, L2, nullptr, d_row_off, static_cast<uint8_t*>(ctx->out_dev)));
   }
