@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(128, 8)
   }
   __syncwarp();
   const uint8_t* prev = nullptr;  // the previous row of the strip in `out`
-  const unsigned long long strip_end = out_row_off[r1];
+  const unsigned long long strip_end = out_row_off[r1], strip_begin = out_row_off[r0];
 
   for (uint32_t r = r0; r < r1; ++r) {
     const uint8_t* rp = rows + row_off[r];
@@ -1024,19 +1024,15 @@ __global__ void __launch_bounds__(128, 8)
       const uint32_t nch = (a0 + row_len + 15u) >> 4;
       // (... of the strip: with rows shorter than a chunk the overrun could otherwise pass the rows behind it)
       const uint32_t ext = (uint32_t)min((unsigned long long)row_len + 16ull, strip_end - o0);
-      uint32_t nslow = 0;
+      uint32_t nslow = 0, kb = 0;  // kb: moved items that end in front of the round's first chunk (all lanes agree)
       for (uint32_t c0 = 0; c0 < nch; c0 += 32) {
         const uint32_t c = c0 + lane;
         const int32_t x0 = (int32_t)(c * 16u) - (int32_t)a0;  // row-relative offset of the chunk
         bool slow = false;
+        uint32_t lo = kb;  // moved items that end at or in front of x: a round's 512 bytes hold few of them
         if (c < nch) {
           const uint32_t x = x0 > 0 ? (uint32_t)x0 : 0u;
-          uint32_t lo = 0, hi = nb;  // moved items that end at or in front of x
-          while (lo < hi) {
-            const uint32_t m = (lo + hi) >> 1;
-            if (S.lce[m] <= x) lo = m + 1;
-            else hi = m;
-          }
+          while (lo < nb && S.lce[lo] <= x) ++lo;
           const uint32_t stop = lo < nb ? S.lcs[lo] : ext;  // the stretch ends here
           if (x0 >= 0 && (uint32_t)x0 + 16u <= stop) {
             const uint32_t src = lo ? (uint32_t)x0 - S.lce[lo - 1] + S.lpe[lo - 1] : (uint32_t)x0;
@@ -1048,6 +1044,7 @@ __global__ void __launch_bounds__(128, 8)
         const unsigned m = __ballot_sync(0xffffffffu, slow);
         if (slow) S.slow[nslow + __popc(m & lanemask_lt())] = (uint16_t)c;
         nslow += __popc(m);
+        kb = __shfl_sync(0xffffffffu, lo, 31);  // (lanes beyond the last chunk carry the round's start value: harmless)
       }
       __syncwarp();
       for (uint32_t q = lane; q < nslow; q += 32) {
@@ -1088,7 +1085,9 @@ __global__ void __launch_bounds__(128, 8)
           if (pos < upto) pos = upto;
           ++k;
         }
-        if ((uint32_t)(x0 + 16) > ext) {  // the strip's last bytes: nothing behind them may be touched
+        // bytes of another strip - in front of this strip's first row, behind its last - belong to another warp, which may
+        // be writing them right now: such a chunk is stored byte by byte, this row's bytes only
+        if ((uint32_t)(x0 + 16) > ext || (x0 < 0 && o0 - (unsigned long long)(-x0) < strip_begin)) {
           const uint32_t w[4] = {acc.x, acc.y, acc.z, acc.w};
           for (int32_t b = x0 < 0 ? -x0 : 0; b < 16 && (uint32_t)(x0 + b) < row_len; ++b) at[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
         } else {
@@ -1534,8 +1533,21 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   // per-row step (flag bytes, output items) to fit one round of that many lanes
   const uint32_t G = GL;
   const uint32_t GPW = 32 / G;
+  // ---- the delta writer takes wide schemas whose output order follows the file order (so that the changed items of a
+  // row come out of the flag walk in output order) and no running row number
+  bool use_delta = ctx->dec_delta != 0 && GL == 32 && FT.rownum_item == ITEM_ROWNUM && NI > 0 && NI < 65536 && U < 65536;
+  {
+    int32_t last_item = -1;
+    for (uint32_t u = 0; u < U && use_delta; ++u) {
+      if (u_item[u] < 0) continue;
+      if (u_item[u] <= last_item) use_delta = false;
+      last_item = u_item[u];
+    }
+  }
   uint32_t R = 8;
-  while (R < 64 && (uint64_t)R * 2 <= nrows / ((uint64_t)ctx->sm_count * 48 * GPW)) R *= 2;
+  // (the delta writer starts every strip with a row assembled in full: it likes strips twice as long - measured on C4:
+  // 0.79 ms with 16 rows, 0.74 with 32, 1.27 with 64)
+  while (R < 64 && (uint64_t)R * 2 <= nrows / ((uint64_t)ctx->sm_count * (use_delta ? 24 : 48) * GPW)) R *= 2;
   if (ctx->dec_strip_rows > 0) R = (uint32_t)ctx->dec_strip_rows;
   const uint32_t nstrips = (nrows + R - 1) / R;
 
@@ -1643,17 +1655,6 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   unsigned long long* d_row_off = static_cast<unsigned long long*>(ctx->out_dev2);
   DevBuf row_len;
   ZDWB_TRY(row_len.alloc(ctx, (size_t)nrows * 8));
-  // ---- the delta writer takes wide schemas whose output order follows the file order (so that the changed items of a
-  // row come out of the flag walk in output order) and no running row number
-  bool use_delta = ctx->dec_delta != 0 && GL == 32 && FT.rownum_item == ITEM_ROWNUM && NI > 0 && NI < 65536 && U < 65536;
-  {
-    int32_t last_item = -1;
-    for (uint32_t u = 0; u < U && use_delta; ++u) {
-      if (u_item[u] < 0) continue;
-      if (u_item[u] <= last_item) use_delta = false;
-      last_item = u_item[u];
-    }
-  }
   auto launch_rows = [&](bool write, const WarpLayout& L, unsigned long long* lens, const unsigned long long* offs, uint8_t* dst) -> int {
     const uint32_t per_cta = L.warps * GPW;
     const unsigned grid = (nstrips + per_cta - 1) / per_cta, block = 32 * L.warps;
