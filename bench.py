@@ -346,6 +346,68 @@ def cpu_baseline_sample(synth: Synth, rows: int):
         shutil.rmtree(scratch, ignore_errors=True)
 
 
+def other_configs(torch, dev, local):
+    """BASELINE configs C2 / C3 (the reference's own fixtures) and a C5-shaped block (high-cardinality text), device
+    resident on this GPU: best-of-5 CUDA-event times of one encode and one decode call, with the parity each config
+    allows - C2 / C3: the encoded bytes equal the reference's golden .zdw; C5: the decoded rows equal the input.
+    These are parity-test cases (tests/), timed here so that the driver's record holds them too."""
+    from zdw_b200 import Context
+    from zdw_b200.desc import parse_desc
+    out = []
+    g = ROOT / "tests" / "golden"
+    ctx = Context(local)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+
+    def time_call(fn):
+        best = None
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        return best, r
+
+    def one(name, tsv, types, golden_block):
+        t = torch.empty(len(tsv) + 64, dtype=torch.uint8, device=dev)
+        t[:len(tsv)].copy_(torch.frombuffer(bytearray(tsv), dtype=torch.uint8))
+        torch.cuda.synchronize(dev)
+        enc = lambda: ctx.encode_block(types, t.data_ptr(), len(tsv), input_on_device=True, output_on_device=True)
+        blk = enc()
+        z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)
+        _d2d(torch, z, blk.dev_ptr, blk.length)
+        dec = lambda: ctx.decode_block(types, z.data_ptr(), blk.length, input_on_device=True, output_on_device=True)
+        d = dec()
+        back = torch.empty(d.length, dtype=torch.uint8, device=dev)
+        _d2d(torch, back, d.dev_ptr, d.length)
+        roundtrip = d.length == len(tsv) and bool(torch.equal(back, t[:len(tsv)]))
+        vs_golden = None
+        if golden_block is not None:
+            vs_golden = bytes(z[:blk.length].cpu().numpy().tobytes()) == golden_block
+        e_ms, _ = time_call(enc)
+        d_ms, _ = time_call(dec)
+        out.append({"config": name, "tsv_bytes": len(tsv), "zdw_bytes": int(blk.length), "rows": int(blk.nrows),
+                    "encode_ms": round(e_ms, 3), "decode_ms": round(d_ms, 3), "encode_gbs": round(len(tsv) / e_ms / 1e6, 2),
+                    "decode_gbs": round(len(tsv) / d_ms / 1e6, 2), "zdw_equals_reference_golden": vs_golden,
+                    "roundtrip_bit_exact": roundtrip, "timing": "device resident, best of 5, CUDA events"})
+
+    for label, name in (("C2 movie_tickets (reference fixture)", "movie_tickets"), ("C3 analytics-hits (reference fixture)", "analytics-hits")):
+        tsv = lzma.decompress((g / f"{name}.sql.xz").read_bytes())
+        sch = parse_desc((g / f"{name}.desc.sql").read_bytes())
+        gz = g / f"{name}.zdw"
+        golden = gz.read_bytes() if gz.exists() else lzma.decompress((g / f"{name}.zdw.xz").read_bytes())
+        # the golden files are v9 / v10: the block bytes follow their file header (no metadata section before v11)
+        hdr_len = 2 + sum(len(n.encode("latin1")) + 1 for n in sch.names) + 1 + 3 * sch.ncols
+        one(label, tsv, sch.types, golden[hdr_len:])
+    import c5_check
+    sch5 = parse_desc(c5_check.DESC)
+    one("C5 high-cardinality text, 1 000 000 rows (2 M unique 65-byte strings, one block)", c5_check.make_rows(1_000_000), sch5.types, None)
+    ctx.close()
+    return out
+
+
 def _parse_cpulist(text: str):
     cpus = set()
     for part in text.strip().split(","):
@@ -612,7 +674,7 @@ def run_cuda(args):
     # the ZDW blocks the e2e decode reads: pinned like the TSV inputs (a pageable source makes the driver stage the copy
     # under its own lock, which holds up the other contexts' copies); plain buffers only if pinning fails
     e2e_dec_blocks, dec_keep, dec_pinned = [], [], []
-    for zb in host_zdw[:max(1, args.e2e_decode_blocks)]:
+    for zb in host_zdw[:max(1, args.e2e_decode_blocks)]:  # (the rank's blocks; repeated below when it has fewer than 24)
         p = L.zdwb_host_alloc(len(zb)) if pinned else None
         if p:
             C.memmove(p, zb, len(zb))
@@ -635,31 +697,44 @@ def run_cuda(args):
         d2h_enc = e2e_encode_pass()
     torch.cuda.synchronize(dev)
     t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
-    e2e_decode_pass(e2e_dec_blocks[:2 * len(lanes)])  # two blocks per lane: the second call settles on a pinned output buffer
+    # every rank decodes at least 24 blocks (its own, over again if need be) so that the lanes have something to overlap;
+    # a context writes its first three results to pageable memory (pinning costs more than it saves for a short-lived
+    # context), so four blocks per lane are warm-up
+    reps = max(1, -(-24 // max(1, len(e2e_dec_blocks))))
+    e2e_dec_items = e2e_dec_blocks * reps
+    e2e_decode_pass((e2e_dec_blocks * 4)[:4 * len(lanes)])
     barrier()
     t0 = time.perf_counter()
-    d2h_dec = e2e_decode_pass(e2e_dec_blocks)
+    d2h_dec = e2e_decode_pass(e2e_dec_items)
     torch.cuda.synchronize(dev)
     t_e2e_dec = time.perf_counter() - t0
     launches_e2e = sum(c.kernel_launches() for c in lanes)
-    # plain pinned-host <-> device copies of one block: the PCIe ceiling the e2e numbers sit under
+    # plain pinned-host <-> device copies of one block by EVERY rank at the same time (between barriers): the link ceiling
+    # the e2e numbers sit under - at N > 1 the ranks share the host's memory and PCIe root ports, so the per-rank rate
+    # is lower than a rank's rate when it copies alone
     pcie = {}
     try:
         hp = torch.empty(host_lens[0], dtype=torch.uint8).pin_memory()
         dp = torch.empty(host_lens[0], dtype=torch.uint8, device=dev)
         for name, (dst, src) in (("h2d_gbs", (dp, hp)), ("d2h_gbs", (hp, dp))):
             dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize(dev)
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(3):
+            for _ in range(4):
                 dst.copy_(src, non_blocking=True)
             e1.record(stream)
             e1.synchronize()
-            pcie[name] = 3 * host_lens[0] / (e0.elapsed_time(e1) / 1e3) / 1e9
+            pcie[name] = 4 * host_lens[0] / (e0.elapsed_time(e1) / 1e3) / 1e9
+            barrier()
         del hp, dp
     except Exception as ex:  # noqa: BLE001
         pcie = {"error": str(ex)}
+    link = torch.tensor([pcie.get("h2d_gbs", 0.0), pcie.get("d2h_gbs", 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(link, op=dist.ReduceOp.SUM)  # the box's concurrent copy rate, all ranks together
+    link_h2d, link_d2h = [float(x) for x in link.tolist()]
     pool.shutdown()
     for c in lanes:
         c.close()
@@ -686,7 +761,7 @@ def run_cuda(args):
               file=sys.stderr, flush=True)
     vals = torch.tensor([enc_t, dec_t, t_e2e_enc, t_e2e_dec, t_wall], dtype=torch.float64, device=dev)
     sums = torch.tensor([tsv_bytes, zdw_bytes, float(d2h_enc), float(d2h_dec), float(launches),
-                         float(sum(host_lens[:len(e2e_dec_blocks)]))], dtype=torch.float64, device=dev)
+                         float(sum(host_lens[:len(e2e_dec_blocks)]) * reps)], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
@@ -727,8 +802,14 @@ def run_cuda(args):
                        "roofline": roof(kt_dec, "decode")},
             "roofline": roof(kt_enc, "encode"),
             "e2e": {"value": tot_tsv / t_e2e_enc / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(tot_tsv),
-                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "cpu_affinity": affinity, "lanes": args.e2e_lanes, "pcie_copy_gbs": pcie,
-                    "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_blocks), "pinned_decode_input": bool(dec_pinned) and not dec_keep,
+                    "d2h_bytes_per_step": int(d2h_enc_all), "pinned_host_input": pinned, "cpu_affinity": affinity, "lanes": args.e2e_lanes,
+                    "pcie_copy_gbs": pcie,
+                    # all ranks copying at once: what the host side of the box delivers; the e2e legs as a fraction of it
+                    # (encode moves its bytes host -> device, decode device -> host)
+                    "link_concurrent_gbs": {"h2d": link_h2d, "d2h": link_d2h},
+                    "frac_of_link": (tot_tsv / t_e2e_enc / 1e9) / link_h2d if link_h2d else None,
+                    "decode_frac_of_link": (e2e_dec_tsv / t_e2e_dec / 1e9) / link_d2h if link_d2h else None,
+                    "decode_value": e2e_dec_tsv / t_e2e_dec / 1e9, "decode_blocks_timed": len(e2e_dec_items), "pinned_decode_input": bool(dec_pinned) and not dec_keep,
                     "decode_d2h_bytes": int(d2h_dec_all)},
             "gpu_launches": int(launches_all),
             "parity": parity,
@@ -736,6 +817,11 @@ def run_cuda(args):
             "tsv_bytes": int(tot_tsv), "zdw_bytes": int(tot_zdw),
             "wall_s_timed_region": t_wall,
         }
+        if world == 1 and not args.no_configs:
+            try:
+                line["configs"] = other_configs(torch, dev, local)
+            except Exception as ex:  # noqa: BLE001
+                line["configs"] = {"error": f"{type(ex).__name__}: {ex}"}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline_sample(synth, args.cpu_rows)
             line["cpu_baseline"] = cb if cb else {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference",
@@ -840,6 +926,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")
     ap.add_argument("--ref-procs", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5 timings of the N=1 line")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison with oracle/_ref (diagnostic runs only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
