@@ -13,6 +13,7 @@
  */
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 typedef struct {
@@ -146,4 +147,79 @@ size_t synth_block(void* h, uint64_t seed, uint64_t block, uint32_t nrows, uint8
   free(cur);
   free(pop);
   return w;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Config C5: high-cardinality text.  Row i: i+1, 'K' + hex(sha256(str(i))), 'V' + the same hex reversed,
+ * 'W' + (i mod 97) - byte for byte what tests/c5_check.py:make_rows builds in Python, fast enough for 5 x 10^7 rows.
+ * --------------------------------------------------------------------------------------------------------------- */
+static uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+static void sha256_short(const unsigned char* msg, size_t len, unsigned char out[32]) { /* len < 56: one block */
+  static const uint32_t K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+  unsigned char blk[64];
+  memset(blk, 0, sizeof(blk));
+  memcpy(blk, msg, len);
+  blk[len] = 0x80;
+  const uint64_t bits = (uint64_t)len * 8;
+  for (int k = 0; k < 8; ++k) blk[63 - k] = (unsigned char)(bits >> (8 * k));
+  uint32_t w[64];
+  for (int t = 0; t < 16; ++t)
+    w[t] = ((uint32_t)blk[4 * t] << 24) | ((uint32_t)blk[4 * t + 1] << 16) | ((uint32_t)blk[4 * t + 2] << 8) | blk[4 * t + 3];
+  for (int t = 16; t < 64; ++t) {
+    const uint32_t s0 = rotr32(w[t - 15], 7) ^ rotr32(w[t - 15], 18) ^ (w[t - 15] >> 3);
+    const uint32_t s1 = rotr32(w[t - 2], 17) ^ rotr32(w[t - 2], 19) ^ (w[t - 2] >> 10);
+    w[t] = w[t - 16] + s0 + w[t - 7] + s1;
+  }
+  uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+  for (int t = 0; t < 64; ++t) {
+    const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25), ch = (e & f) ^ (~e & g);
+    const uint32_t t1 = hh + S1 + ch + K[t] + w[t];
+    const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22), maj = (a & b) ^ (a & c) ^ (b & c);
+    const uint32_t t2 = S0 + maj;
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  for (int k = 0; k < 8; ++k)
+    for (int j = 0; j < 4; ++j) out[4 * k + j] = (unsigned char)(h[k] >> (24 - 8 * j));
+}
+
+/* rows first .. first + count - 1 into out; returns the bytes written, 0 if they do not fit cap */
+size_t c5_rows(uint64_t first, uint64_t count, char* out, size_t cap) {
+  static const char HEX[] = "0123456789abcdef";
+  size_t at = 0;
+  for (uint64_t i = first; i < first + count; ++i) {
+    if (at + 200 > cap) return 0;
+    char num[24];
+    const int nl = snprintf(num, sizeof(num), "%llu", (unsigned long long)i);
+    unsigned char dig[32];
+    sha256_short((const unsigned char*)num, (size_t)nl, dig);
+    char hex[64];
+    for (int k = 0; k < 32; ++k) {
+      hex[2 * k] = HEX[dig[k] >> 4];
+      hex[2 * k + 1] = HEX[dig[k] & 15];
+    }
+    at += (size_t)snprintf(out + at, 24, "%llu", (unsigned long long)(i + 1));
+    out[at++] = '\t';
+    out[at++] = 'K';
+    memcpy(out + at, hex, 64);
+    at += 64;
+    out[at++] = '\t';
+    out[at++] = 'V';
+    for (int k = 0; k < 64; ++k) out[at + k] = hex[63 - k];
+    at += 64;
+    out[at++] = '\t';
+    out[at++] = 'W';
+    at += (size_t)snprintf(out + at, 8, "%u", (unsigned)(i % 97));
+    out[at++] = '\n';
+  }
+  return at;
 }

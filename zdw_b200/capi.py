@@ -74,6 +74,13 @@ class _RowsOut(C.Structure):
 _lib = None
 
 
+def _copy_out(ptr: int, n: int) -> bytes:
+    """n bytes at a raw host pointer (ctypes.string_at takes a C int: it fails beyond 2 GiB)."""
+    if not n:
+        return b""
+    return bytes((C.c_uint8 * n).from_address(ptr))
+
+
 def load_library():
     """Loads libzdw_b200.so; raises ImportError if it has not been built (no fallback)."""
     global _lib
@@ -217,7 +224,7 @@ class Context:
             raise e
         data = None
         if not output_on_device:
-            data = C.string_at(out.bytes, out.len) if out.len else b""
+            data = _copy_out(out.bytes, out.len)
         return EncodedBlock(data, int(out.bytes or 0), out.len, out.nrows, out.longest_line, out.tsv_consumed,
                             out.rows_in_buffer, out.ncols_used, out.dict_entries, out.dict_bytes, out.dict_index_size)
 
@@ -253,7 +260,7 @@ class Context:
         tsv = None
         offs = None
         if not output_on_device:
-            tsv = C.string_at(out.tsv, out.len) if out.len else b""
+            tsv = _copy_out(out.tsv, out.len)
             if want_row_offsets and out.row_off:
                 arr = (C.c_uint64 * (out.nrows + 1)).from_address(out.row_off)
                 offs = list(arr)

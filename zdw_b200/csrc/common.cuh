@@ -552,6 +552,36 @@ __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
   return v;
 }
 
+// ---- bulk asynchronous copies (TMA, 1-D) global -> shared with an mbarrier that counts the bytes that have landed.
+// One lane arms the barrier with the byte count and issues the copy; every consumer waits for the barrier's phase.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_LOOP:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra WAIT_DONE;\n"
+    "bra WAIT_LOOP;\n"
+    "WAIT_DONE:\n"
+    "}\n" ::"r"(smem_u32(bar)),
+    "r"(parity)
+    : "memory");
+}
+// orders the generic-proxy accesses of this thread before later async-proxy (bulk copy) accesses to shared memory
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // per-byte equality mask of a 32-bit word against a replicated byte: bit 7 of each byte lane set
 __device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t rep) {
   uint32_t x = w ^ rep;

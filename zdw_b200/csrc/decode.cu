@@ -1595,7 +1595,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
         return ZDWB_OK;
       }
     }
-    const uint32_t S = (nstrips + 255) / 256;
+    const uint32_t S = std::max<uint32_t>((nstrips + 255) / 256, 4);  // (the scan over segments is a serial loop: at least 4 per segment)
     const uint32_t nseg = (nstrips + S - 1) / S;
     ZDWB_TRY(seg_val.alloc(ctx, (size_t)nseg * U * 8));
     ZDWB_TRY(seg_has.alloc(ctx, (size_t)nseg * U));

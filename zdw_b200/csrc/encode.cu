@@ -1036,43 +1036,78 @@ struct D1Args {
 };
 
 // Row census of the delta path: per tile the number of row terminators, the last row break and the last row start.
-// Only newlines (and a backslash in front of one) matter, so the pass runs at the speed of the read.
+// Only newlines (and a backslash in front of one) matter, so the pass runs at the speed of the read: every warp streams
+// its tile through a two-stage ring in shared memory, filled by 1-D bulk copies (TMA, cp.async.bulk + mbarrier) that run
+// two chunks ahead of the lanes' 16-byte shared-memory loads.
+constexpr uint32_t CEN_CHUNK = 2048;  // bytes per bulk copy (four warp steps)
 __global__ void __launch_bounds__(ENC_THREADS)
     k_row_census(const uint8_t* __restrict__ buf, uint64_t n, int64_t lo, uint32_t ntiles, uint32_t tile_bytes, TileAgg* __restrict__ agg) {
-  const uint32_t tile = blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+  __shared__ __align__(128) uint8_t ring[ENC_WARPS][2][CEN_CHUNK];
+  __shared__ __align__(8) uint64_t bars[ENC_WARPS][2];
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
+  }
+  fence_proxy_async();
+  __syncthreads();
+  const uint32_t tile = blockIdx.x * ENC_WARPS + warp;
   if (tile >= ntiles) return;
-  const unsigned lane = lane_id();
   const int64_t t0 = lo + (int64_t)tile * tile_bytes, limit = (int64_t)n;
+  // chunks of the tile that hold bytes of the buffer; a chunk's copy ends at the 16-byte boundary behind the last byte
+  const int64_t tile_stop = t0 + (int64_t)tile_bytes < limit ? t0 + (int64_t)tile_bytes : limit;
+  const uint32_t nchunks = tile_stop > t0 ? (uint32_t)((tile_stop - t0 + CEN_CHUNK - 1) / CEN_CHUNK) : 0u;
+  auto issue = [&](uint32_t c) {  // lane 0 only
+    const int64_t at = t0 + (int64_t)c * CEN_CHUNK;
+    const int64_t left = limit - at;
+    const uint32_t bytes = left >= (int64_t)CEN_CHUNK ? CEN_CHUNK : (uint32_t)((left + 15) & ~(int64_t)15);
+    mbar_expect_tx(&bars[warp][c & 1u], bytes);
+    bulk_load(ring[warp][c & 1u], buf + at, bytes, &bars[warp][c & 1u]);
+  };
+  if (lane == 0) {
+    if (nchunks > 0) issue(0);
+    if (nchunks > 1) issue(1);
+  }
   uint32_t c_nl = t0 <= 0 ? 1u : (is_unescaped_newline(buf, t0 - 1) ? 1u : 0u);
   uint32_t rows = 0;
   int32_t last_r = -1, last_s = -1;
-  for (uint32_t s = 0; s < tile_bytes; s += STEP) {
-    const int64_t p0 = t0 + s + 16 * (int64_t)lane;
-    uint32_t nl = 0, in = 0;
-    if (p0 < limit && p0 + 16 > 0) {
-      const uint4 v = ldg_stream_u4(buf + p0);
-      const int64_t ia = p0 < 0 ? -p0 : 0;
-      const int64_t ib = p0 + 16 > limit ? limit - p0 : 16;
-      in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
-      if (chunk_has(v, '\n')) {
-        nl = chunk_mask(v, '\n') & in;
-        uint32_t m = nl;
-        while (m) {  // escape parity (getnextrow.cpp:44-53): rare, walked byte by byte
-          const int i = __ffs(m) - 1;
-          m &= m - 1;
-          if (odd_backslashes_before(buf, p0 + i)) nl &= ~(1u << i);
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    mbar_wait(&bars[warp][c & 1u], (c >> 1) & 1u);
+    const uint8_t* stage = ring[warp][c & 1u];
+    for (uint32_t q = 0; q < CEN_CHUNK; q += STEP) {
+      const uint32_t s = c * CEN_CHUNK + q;
+      const int64_t p0 = t0 + s + 16 * (int64_t)lane;
+      uint32_t nl = 0, in = 0;
+      if (p0 < limit && p0 + 16 > 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + q + 16u * lane);
+        const int64_t ia = p0 < 0 ? -p0 : 0;
+        const int64_t ib = p0 + 16 > limit ? limit - p0 : 16;
+        in = ((1u << ib) - 1u) & ~((1u << ia) - 1u);
+        if (chunk_has(v, '\n')) {
+          nl = chunk_mask(v, '\n') & in;
+          uint32_t m = nl;
+          while (m) {  // escape parity (getnextrow.cpp:44-53): rare, walked byte by byte
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            if (odd_backslashes_before(buf, p0 + i)) nl &= ~(1u << i);
+          }
         }
       }
+      uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
+      if (lane == 0) prevnl = c_nl;
+      uint32_t after_nl = ((nl << 1) | prevnl) & 0xffffu;
+      if (p0 <= 0 && p0 + 16 > 0) after_nl |= 1u << (-p0);
+      const uint32_t skip = nl & after_nl, term = nl & ~skip, rs = after_nl & ~nl & in;
+      rows += (uint32_t)__popc(term);
+      if (nl) last_r = (int32_t)(s + 16u * lane) + (31 - __clz(nl));
+      if (rs) last_s = (int32_t)(s + 16u * lane) + (31 - __clz(rs));
+      c_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
     }
-    uint32_t prevnl = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
-    if (lane == 0) prevnl = c_nl;
-    uint32_t after_nl = ((nl << 1) | prevnl) & 0xffffu;
-    if (p0 <= 0 && p0 + 16 > 0) after_nl |= 1u << (-p0);
-    const uint32_t skip = nl & after_nl, term = nl & ~skip, rs = after_nl & ~nl & in;
-    rows += (uint32_t)__popc(term);
-    if (nl) last_r = (int32_t)(s + 16u * lane) + (31 - __clz(nl));
-    if (rs) last_s = (int32_t)(s + 16u * lane) + (31 - __clz(rs));
-    c_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
+    __syncwarp();  // every lane has its bytes of the stage in registers: it can be filled again
+    if (lane == 0 && c + 2 < nchunks) {
+      fence_proxy_async();
+      issue(c + 2);
+    }
   }
   rows = __reduce_add_sync(0xffffffffu, rows);
   last_r = __reduce_max_sync(0xffffffffu, last_r);
@@ -2485,7 +2520,7 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
   bool delta = !probe && ctx->enc_delta != 0 && ncols <= DELTA_MAX_COLS && n >= 64 &&
                (ctx->enc_delta == 1 || (!ctx->delta_bailed && (ctx->last_row_bytes == 0 || ctx->last_row_bytes >= DELTA_MIN_ROW_BYTES)));
 
-  DevBuf agg, colset, colmin, colmax, slots, rec_col, rec_val, row_rec, row_cnt, chg_start, chg_len;
+  DevBuf agg, colset, colmin, colmax, slots, rec_col, rec_val, row_rec, row_cnt, chg_start, chg_len, csize, cbase, used_idx, used_cols;
   HashTable ht{nullptr, 0};
   uint32_t nrows = 0;
   bool is_last = false;
@@ -2584,6 +2619,10 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
     ZDWB_TRY(colset.alloc(ctx, (size_t)ncols * 4));
     ZDWB_TRY(colmin.alloc(ctx, (size_t)ncols * 8));
     ZDWB_TRY(colmax.alloc(ctx, (size_t)ncols * 8));
+    ZDWB_TRY(csize.alloc(ctx, ncols));
+    ZDWB_TRY(cbase.alloc(ctx, (size_t)ncols * 8));
+    ZDWB_TRY(used_idx.alloc(ctx, (size_t)ncols * 4));
+    ZDWB_TRY(used_cols.alloc(ctx, (size_t)ncols * 4));
     ne_total = hmeta->tot_ne;  // (general variant only: the delta census does not count fields)
     uint64_t rec_cap = 0;
     if (delta) {
@@ -2666,6 +2705,13 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
       } else {
         KernelScope _ks(ctx, "k_pass1");
         k_pass1<<<(p1_tiles + ENC_WARPS - 1) / ENC_WARPS, ENC_THREADS, 0, st>>>(A);
+      }
+      ZDWB_LAUNCH_CHECK(ctx);
+      {  // writeLookupColumnStats (ConvertToZDW.cpp:417-483) needs nothing from the host: it runs before the read-back
+        KernelScope _ks(ctx, "k_col_stats");
+        k_col_stats<<<1, ENC_THREADS, 0, st>>>(types_d.as<uint8_t>(), ncols, colset.as<uint32_t>(), colmin.as<unsigned long long>(),
+                                             colmax.as<unsigned long long>(), csize.as<uint8_t>(), cbase.as<unsigned long long>(),
+                                             used_idx.as<int32_t>(), used_cols.as<uint32_t>(), meta);
       }
       ZDWB_LAUNCH_CHECK(ctx);
       ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
@@ -2773,21 +2819,7 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
   max_line = std::max(max_line, spill_row_len);
   const uint32_t longest_field = longest_line_field(opts->prev_longest_line, max_line);
 
-  // ---- column statistics
-  DevBuf csize, cbase, used_idx, used_cols;
-  ZDWB_TRY(csize.alloc(ctx, ncols));
-  ZDWB_TRY(cbase.alloc(ctx, (size_t)ncols * 8));
-  ZDWB_TRY(used_idx.alloc(ctx, (size_t)ncols * 4));
-  ZDWB_TRY(used_cols.alloc(ctx, (size_t)ncols * 4));
-  {
-    KernelScope _ks(ctx, "k_col_stats");
-    k_col_stats<<<1, ENC_THREADS, 0, st>>>(types_d.as<uint8_t>(), ncols, colset.as<uint32_t>(), colmin.as<unsigned long long>(),
-                                         colmax.as<unsigned long long>(), csize.as<uint8_t>(), cbase.as<unsigned long long>(),
-                                         used_idx.as<int32_t>(), used_cols.as<uint32_t>(), meta);
-  }
-  ZDWB_LAUNCH_CHECK(ctx);
-  ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(hmeta, meta, sizeof(EncMeta), cudaMemcpyDeviceToHost, st));
-  ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  // ---- column statistics: k_col_stats ran right behind pass 1, its results came back with pass 1's (one round trip)
   const uint32_t U = hmeta->n_used, nflag = hmeta->nflag;
   const uint64_t rows_base = hmeta->rows_base;
 
@@ -2884,7 +2916,7 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
           k_p2d_summary<<<tiles2, ENC_THREADS, smem_sum, st>>>(A2, sval.as<unsigned long long>(), shas.as<uint8_t>());
         }
         ZDWB_LAUNCH_CHECK(ctx);
-        const uint32_t S = (tiles2 + 255) / 256;
+        const uint32_t S = std::max<uint32_t>((tiles2 + 255) / 256, 4);  // (the scan over segments is a serial loop: at least 4 per segment)
         const uint32_t nseg = (tiles2 + S - 1) / S;
         ZDWB_TRY(seg_val.alloc(ctx, (size_t)nseg * U * 8));
         ZDWB_TRY(seg_has.alloc(ctx, (size_t)nseg * U));
