@@ -86,18 +86,43 @@ __global__ void __launch_bounds__(DEC_THREADS)
   for (uint32_t i = threadIdx.x; i < 4 * P.W; i += DEC_THREADS) planes[i] = P.planes[i];
   __syncthreads();
   const uint32_t W = P.W;
-  for (uint32_t s = threadIdx.x; s < T; s += DEC_THREADS) {
-    const uint32_t a = s >> 2, sh = (s & 3u) * 8u;
-    uint32_t prev = words[a];
-    uint32_t acc = P.F;
-    for (uint32_t w = 0; w < W; ++w) {
-      const uint32_t nxt = words[a + w + 1];
-      const uint32_t word = __funnelshift_r(prev, nxt, sh);
-      prev = nxt;
-      acc += __popc(word & planes[w]) + 2u * __popc(word & planes[W + w]) + 4u * __popc(word & planes[2 * W + w]) +
-             8u * __popc(word & planes[3 * W + w]);
+  if (W <= 8) {
+    // up to 256 used columns: the bit planes stay in registers for all of the thread's positions
+    uint32_t pl[4][8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pl[k][w] = (uint32_t)w < W ? planes[k * W + w] : 0u;
     }
-    next[s] = s + acc;
+    for (uint32_t s = threadIdx.x; s < T; s += DEC_THREADS) {
+      const uint32_t a = s >> 2, sh = (s & 3u) * 8u;
+      uint32_t prev = words[a];
+      uint32_t acc = P.F;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        if ((uint32_t)w < W) {
+          const uint32_t nxt = words[a + w + 1];
+          const uint32_t word = __funnelshift_r(prev, nxt, sh);
+          prev = nxt;
+          acc += __popc(word & pl[0][w]) + 2u * __popc(word & pl[1][w]) + 4u * __popc(word & pl[2][w]) + 8u * __popc(word & pl[3][w]);
+        }
+      }
+      next[s] = s + acc;
+    }
+  } else {
+    for (uint32_t s = threadIdx.x; s < T; s += DEC_THREADS) {
+      const uint32_t a = s >> 2, sh = (s & 3u) * 8u;
+      uint32_t prev = words[a];
+      uint32_t acc = P.F;
+      for (uint32_t w = 0; w < W; ++w) {
+        const uint32_t nxt = words[a + w + 1];
+        const uint32_t word = __funnelshift_r(prev, nxt, sh);
+        prev = nxt;
+        acc += __popc(word & planes[w]) + 2u * __popc(word & planes[W + w]) + 4u * __popc(word & planes[2 * W + w]) +
+               8u * __popc(word & planes[3 * W + w]);
+      }
+      next[s] = s + acc;
+    }
   }
   __syncthreads();
   for (uint32_t e = threadIdx.x; e < P.M; e += DEC_THREADS) {
@@ -509,20 +534,26 @@ __device__ __forceinline__ void set_column(const DecParams& P, const WarpState& 
   }
 }
 
-// n bytes from the dictionary to a row by the 8 lanes of an octet, 4 bytes per lane per step
+// n bytes from the dictionary to a row by the 8 lanes of an octet: the destination's head up to its next 4-byte boundary
+// and its tail go byte by byte (lane 0 / lane 1), everything between as aligned words, one per lane and step, each put
+// together from two aligned source words
 __device__ __forceinline__ void octet_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t n, unsigned gl) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3u)) & 3u);
+  if (gl == 0) {
+    for (uint32_t k = 0; k < head; ++k) d[k] = __ldg(s + k);
+  }
+  const uint32_t nw = (n - head) >> 2, tail = (n - head) & 3u;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s + head);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
   const uint32_t sh = (uint32_t)(a & 3u) * 8u;
-  for (uint32_t k = gl * 4; k < n; k += 32) {
-    const uint32_t nb = n - k;
-    const uint32_t lo = __ldg(w + (k >> 2));
-    const uint32_t hi = (sh + min(nb, 4u) * 8u > 32u) ? __ldg(w + (k >> 2) + 1) : 0u;
-    const uint32_t x = __funnelshift_r(lo, hi, sh);
-    d[k] = (uint8_t)x;
-    if (nb > 1) d[k + 1] = (uint8_t)(x >> 8);
-    if (nb > 2) d[k + 2] = (uint8_t)(x >> 16);
-    if (nb > 3) d[k + 3] = (uint8_t)(x >> 24);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
+  for (uint32_t k = gl; k < nw; k += 8) {
+    const uint32_t lo = __ldg(w + k);
+    const uint32_t hi = sh ? __ldg(w + k + 1) : 0u;
+    dw[k] = __funnelshift_r(lo, hi, sh);
+  }
+  if (gl == 1) {
+    for (uint32_t k = 0; k < tail; ++k) d[head + 4u * nw + k] = __ldg(s + head + 4u * nw + k);
   }
 }
 
@@ -720,7 +751,7 @@ __global__ void __launch_bounds__(128, 10)
 // chunks that straddle a changed item go byte by byte.  The first row of a strip - and a row with more changes than
 // the warp's lists hold - is assembled in full from the column values the warp keeps.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t DLC = 128;  // changed items per row the delta path handles (more: the row is assembled in full)
+constexpr uint32_t DLC = 64;   // changed items per row the delta path handles (more: the row is assembled in full)
 
 struct DeltaLayout {   // byte offsets inside a warp's slice of dynamic shared memory
   uint32_t o_val, o_len, o_ioff, o_lcs, o_lce, o_lpe, o_lvoff, o_litem, o_lu, o_slow;
@@ -1535,7 +1566,7 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   const uint32_t GPW = 32 / G;
   // ---- the delta writer takes wide schemas whose output order follows the file order (so that the changed items of a
   // row come out of the flag walk in output order) and no running row number
-  bool use_delta = ctx->dec_delta != 0 && GL == 32 && FT.rownum_item == ITEM_ROWNUM && NI > 0 && NI < 65536 && U < 65536;
+  bool use_delta = ctx->dec_delta != 0 && GL == 32 && FT.rownum_item == ITEM_ROWNUM && NI > 0 && NI < 32768 && U < 65536;
   {
     int32_t last_item = -1;
     for (uint32_t u = 0; u < U && use_delta; ++u) {
