@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """golden_timing.py -- device-resident encode / decode times of the reference's own fixtures (configs C2 movie_tickets,
-C3 analytics-hits) with per-kernel CUDA-event times.  Prints one JSON line per fixture."""
+C3 analytics-hits) with per-kernel CUDA-event times.  Prints one JSON line per fixture.  Arguments: name=value tuning knobs."""
 from __future__ import annotations
 
 import json
@@ -21,6 +21,11 @@ def main():
     dev = torch.device("cuda", 0)
     ctx = Context(0)
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    tune = {}
+    for kv in sys.argv[1:]:  # name=value tuning knobs
+        k, v = kv.split("=")
+        ctx.set_tuning(k, int(v))
+        tune[k] = int(v)
     for name in ("movie_tickets", "analytics-hits"):
         g = ROOT / "tests" / "golden"
         tsv = lzma.decompress((g / f"{name}.sql.xz").read_bytes())
@@ -29,6 +34,8 @@ def main():
         t[:len(tsv)].copy_(torch.frombuffer(bytearray(tsv), dtype=torch.uint8))
         torch.cuda.synchronize()
         res = {"fixture": name, "tsv_bytes": len(tsv)}
+        if tune:
+            res["tune"] = tune
         for _ in range(2):
             blk = ctx.encode_block(sch.types, t.data_ptr(), len(tsv), input_on_device=True, output_on_device=True)
         z = torch.empty(blk.length + 64, dtype=torch.uint8, device=dev)

@@ -45,6 +45,7 @@ struct Ctx {
   unsigned long long last_unique = 0;  // dictionary size of the previous block (seeds the next hash set)
   long long enc_delta = -1;            // pass 1 variant: 1 = row-delta, 0 = general, -1 = by row width (encode.cu)
   long long enc_p2_rows = 0;           // rows per pass-2 tile (0 = automatic)
+  long long enc_dtile = 0;             // bytes per row-delta tile (0 = automatic; a power of two >= 2048)
   bool delta_bailed = false;           // a block of this context did not fit the row-delta pass: stop trying
   unsigned long long last_row_bytes = 0;  // mean row length of the previous block
   unsigned long long last_records = 0;    // records the previous block's row-delta pass 1 produced (sizes the next arrays)
@@ -537,6 +538,15 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
                : "l"(p));
   return r;
 }
+// 16-byte load of bytes that are read again soon (the row-delta pass compares every row with the one before it).
+// The no-allocate form above is treated as evict-first by L2 as well: with it 80 % of the TSV came from DRAM twice
+// (ncu: 905 MB read for a 504 MB block), the second time with DRAM latency in front of the compares.
+__device__ __forceinline__ uint4 ldg_keep_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
   uint64_t v;

@@ -98,6 +98,7 @@ int zdwb_ctx_set_tuning(zdwb_ctx* c, const char* name, long long value) {
     c->enc_delta = value;
     c->delta_bailed = false;
   } else if (!strcmp(name, "enc_p2_rows")) c->enc_p2_rows = value;
+  else if (!strcmp(name, "enc_dtile")) c->enc_dtile = value;
   else if (!strcmp(name, "kernel_timing")) c->timing = value != 0;
   else return ZDWB_ERR_BAD_ARG;
   return ZDWB_OK;

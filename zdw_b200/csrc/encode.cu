@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 4) k_pass1(const P1Args A) {
 // out of it without any search: the k-th field START (a content byte behind a boundary) pairs with the k-th CLOSING
 // delimiter behind a content byte, so both are dropped into per-row lists at their ordinals.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t DTILE = 32768;       // bytes of TSV whose row starts one warp owns
+constexpr uint32_t DTILE = 32768;       // bytes of TSV whose row starts one warp owns (small inputs: less, see the driver)
 constexpr uint32_t DSTEP = 1024;        // bytes per warp step: 32 lanes x 32 bytes
 constexpr uint32_t DCAP = 280;          // non-empty fields of a row a warp can hold (else: delta_bail)
 constexpr uint32_t DBW = 128;           // bitmap words per row: up to 4096 columns
@@ -1027,7 +1027,8 @@ struct D1Warp {
 
 struct D1Args {
   P1Args P;              // buf, n, lo, limit, ncols, types, trim, hash set, column statistics, rec_col / rec_val, meta
-  uint32_t ntiles;       // tiles of DTILE bytes
+  uint32_t ntiles;       // tiles of tile_bytes bytes
+  uint32_t tile_bytes;   // DTILE, or a smaller power of two when the input is too small to fill the GPU with DTILE tiles
   uint32_t nrows;        // rows of the block: the spilled row beyond it has records but no row entry
   uint32_t rec_cap;      // capacity of the record arrays
   uint32_t* row_cnt;     // [nrows] records of row r; they start at P.row_rec[r]
@@ -1451,9 +1452,9 @@ __global__ void __launch_bounds__(D1_THREADS, 8) k_pass1d(const D1Args A) {
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t tile = blockIdx.x * D1_WARPS + warp;
   if (tile >= A.ntiles) return;
-  const int64_t t0 = P.lo + (int64_t)tile * DTILE;
+  const int64_t t0 = P.lo + (int64_t)tile * A.tile_bytes;
   if (t0 >= P.limit) return;
-  const int64_t tile_end = t0 + DTILE;
+  const int64_t tile_end = t0 + A.tile_bytes;
   D1Warp& W = sw[warp];
   const uint32_t* wlast = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(P.buf + P.n - 1) & ~(uintptr_t)3);
   const TileAgg pre = P.pre[tile];
@@ -1506,8 +1507,9 @@ __global__ void __launch_bounds__(D1_THREADS, 8) k_pass1d(const D1Args A) {
       uint32_t nl = 0, bs = 0, in = 0;
       tab = 0;
       if (p0 < P.limit && p0 + 32 > scan_from) {
-        const uint4 v0 = ldg_stream_u4(P.buf + p0);
-        const uint4 v1 = p0 + 16 < P.limit ? ldg_stream_u4(P.buf + p0 + 16) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 v0 = ldg_keep_u4(P.buf + p0);
+        const uint4 v1 = p0 + 16 < P.limit ? ldg_keep_u4(P.buf + p0 + 16) : make_uint4(0u, 0u, 0u, 0u);
+        if (p0 + 2 * (int64_t)DSTEP < P.limit) prefetch_l2(P.buf + p0 + 2 * DSTEP);  // (measured: 0.983 -> 0.961 ms per C4 block)
         in = 0xffffffffu;
         if (sb < scan_from || sb + (int64_t)DSTEP > P.limit) {  // (warp-uniform: only the first and the last step)
           const int64_t ia = p0 < scan_from ? scan_from - p0 : 0;
@@ -2528,7 +2530,15 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
   uint64_t rows_total = 0, ne_total = 0;
   for (;;) {  // at most twice: the delta variant may hand the block over to the general one
     // ---- census: per-tile counts and their prefix
-    const uint32_t tile_bytes = delta ? DTILE : TILE;
+    // (delta: a warp walks its tile row by row, so a small input is cut into smaller tiles - down to 8 KiB - until there
+    // are about as many as warps fit on the GPU; every tile re-reads the row in front of it, which is why not smaller)
+    uint32_t tile_bytes = TILE;
+    if (delta) {
+      tile_bytes = DTILE;
+      while (tile_bytes > 8192 && ((uint64_t)(-lo) + n) / tile_bytes < (uint64_t)ctx->sm_count * 32) tile_bytes >>= 1;
+      if (ctx->enc_dtile >= 2048 && ctx->enc_dtile <= (1 << 20) && (ctx->enc_dtile & (ctx->enc_dtile - 1)) == 0)
+        tile_bytes = (uint32_t)ctx->enc_dtile;
+    }
     const uint64_t span = (uint64_t)(-lo) + n;
     const uint32_t ntiles = (uint32_t)((span + tile_bytes - 1) / tile_bytes);
     const uint32_t tile_ctas = (ntiles + ENC_WARPS - 1) / ENC_WARPS;
@@ -2686,6 +2696,7 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
         D1Args D;
         D.P = A;
         D.ntiles = p1_tiles;
+        D.tile_bytes = tile_bytes;
         D.nrows = nrows;
         D.rec_cap = (uint32_t)rec_cap;
         D.row_cnt = row_cnt.as<uint32_t>();

@@ -46,21 +46,23 @@ __global__ void k_make_keys(const uint8_t* __restrict__ base, const uint32_t* __
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;  // per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-constexpr int RS_WARP_ITEMS = RS_ITEMS * 32;
+// items per thread: 16 for large inputs (few tiles, small histograms), 4 below two million records - a C2-sized dictionary
+// (half a million strings) is otherwise 128 CTAs of 16 sequential steps each, on 148 SMs
+__host__ __device__ constexpr int rs_tile(int items) { return RS_THREADS * items; }
+inline int rs_items_for(uint32_t n) { return n < (1u << 21) ? 4 : 16; }
 
 __device__ __forceinline__ uint32_t rs_digit(const uint64_t* keys, const uint32_t* segs, uint32_t i, int pass) {
   return pass < 8 ? (uint32_t)((keys[i] >> (8 * pass)) & 255u) : ((segs[i] >> (8 * (pass - 8))) & 255u);
 }
 
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
     k_radix_hist(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs, uint32_t n, int pass,
                  uint32_t* __restrict__ hist, uint32_t ntiles) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t base = blockIdx.x * RS_TILE;
+  const uint32_t base = blockIdx.x * rs_tile(RS_ITEMS);
 #pragma unroll 4
   for (int k = 0; k < RS_ITEMS; ++k) {
     uint32_t i = base + k * RS_THREADS + threadIdx.x;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 
 // Stable scatter.  Warp w of the CTA owns the contiguous sub-range [tile + w*512, +512) and walks it in
 // 16 steps of 32 consecutive items, so the order (warp, step, lane) is the input order.
+template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
     k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs,
                     const uint32_t* __restrict__ vals, uint32_t n, int pass, const uint32_t* __restrict__ hist_scanned,
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(RS_THREADS)
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = lane; d < 256; d += 32) wc[warp][d] = 0;
   __syncwarp();
-  const uint32_t wbase = blockIdx.x * RS_TILE + warp * RS_WARP_ITEMS;
+  const uint32_t wbase = blockIdx.x * rs_tile(RS_ITEMS) + warp * (RS_ITEMS * 32);
   // sweep 1: per-warp digit counts
   for (int s = 0; s < RS_ITEMS; ++s) {
     uint32_t i = wbase + s * 32 + lane;
@@ -134,20 +137,28 @@ struct SortBufs {
 };
 
 // Sorts records [0,n) by digits `pass_list`; result ends up in b.{key,seg,val}[b.cur].
-int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, uint32_t* hist, uint32_t ntiles) {
+// (`hist` holds 256 counters for every tile of rs_tile(rs_items_for(n)) records)
+int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, uint32_t* hist) {
+  const int items = rs_items_for(n);
+  const uint32_t ntiles = (n + rs_tile(items) - 1) / rs_tile(items);
   for (int q = 0; q < npass; ++q) {
     const int pass = pass_list[q];
     const int s = b.cur, d = b.cur ^ 1;
     {
       KernelScope _ks(ctx, "k_radix_hist");
-      k_radix_hist<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
+      if (items == 4) k_radix_hist<4><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
+      else k_radix_hist<16><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
     }
     ZDWB_LAUNCH_CHECK(ctx);
     ZDWB_TRY(exclusive_scan_u32(ctx, hist, hist, (size_t)ntiles * 256, nullptr));
     {
       KernelScope _ks(ctx, "k_radix_scatter");
-      k_radix_scatter<<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
-                                                           b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
+      if (items == 4)
+        k_radix_scatter<4><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
+                                                                  b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
+      else
+        k_radix_scatter<16><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
+                                                                   b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
     }
     ZDWB_LAUNCH_CHECK(ctx);
     b.cur = d;
@@ -369,7 +380,9 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   }
 
   // ---- large path
-  const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
+  // refinement rounds sort m <= n records and may pick the smaller tile: size the histograms for the worst of the two
+  const uint32_t ntiles = std::max<uint32_t>((n + rs_tile(rs_items_for(n)) - 1) / rs_tile(rs_items_for(n)),
+                                             (std::min<uint32_t>(n, 1u << 21) + rs_tile(4) - 1) / rs_tile(4));
   DevBuf keyA, keyB, segA, segB, valA, valB, hist, head, unres, unres_scan, ids, pos, pos2, total;
   ZDWB_TRY(keyA.alloc(ctx, (size_t)n * 8));
   ZDWB_TRY(keyB.alloc(ctx, (size_t)n * 8));
@@ -398,7 +411,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   ZDWB_LAUNCH_CHECK(ctx);
   {
     const int passes[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-    ZDWB_TRY(radix_passes(ctx, b, n, passes, 8, hist.as<uint32_t>(), ntiles));
+    ZDWB_TRY(radix_passes(ctx, b, n, passes, 8, hist.as<uint32_t>()));
   }
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(order_out, b.val[b.cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
 
@@ -451,7 +464,6 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
       return ZDWB_ERR_CUDA;
     }
     const unsigned gm = (m + 255) / 256;
-    const uint32_t mt = (m + RS_TILE - 1) / RS_TILE;
     // records: key = next 8 bytes, seg = group id, val = string id
     b.seg[0] = segA.as<uint32_t>();
     b.seg[1] = segB.as<uint32_t>();
@@ -467,7 +479,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
     for (int p = 0; p < 8; ++p) passes[np++] = p;
     const uint32_t seg_bytes = bytes_needed((uint64_t)seg_max);
     for (uint32_t p = 0; p < seg_bytes; ++p) passes[np++] = 8 + (int)p;
-    ZDWB_TRY(radix_passes(ctx, b, m, passes, np, hist.as<uint32_t>(), mt));
+    ZDWB_TRY(radix_passes(ctx, b, m, passes, np, hist.as<uint32_t>()));
     // write the refined order back to the positions these records occupy
     {
       KernelScope _ks(ctx, "k_scatter_order");
