@@ -3,11 +3,13 @@
 //   ReadAheadInput vs the sequential window it replaced (fill to `cap` or end of stream, memmove on consume): same
 //   window bytes, length and end-of-stream flag at every step, for random consumption, random use of prefetch() and
 //   widen(), streams that end exactly on a window boundary, and a tee that must receive the stream once, in order.
+//   The same over a pipe with a slow producer, and close() with a read-ahead waiting on a pipe that stays silent.
 //   AsyncWriter: blocks arrive in order and complete.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <string>
@@ -168,6 +170,82 @@ static void writer_case(size_t nblocks) {
   CHECK(want == got, "writer: %zu bytes written, %zu expected", got.size(), want.size());
 }
 
+// a pipe with a producer that dawdles: read-ahead must deliver the stream unchanged while the producer runs on
+static void pipe_case(size_t total, size_t cap) {
+  int fds[2];
+  if (pipe(fds)) {
+    CHECK(false, "pipe");
+    return;
+  }
+  std::string bytes(total, 0);
+  for (size_t i = 0; i < total; ++i) bytes[i] = (char)(rnd() >> 56);
+  std::thread producer([&]() {
+    size_t at = 0;
+    while (at < total) {
+      const size_t n = std::min<size_t>(total - at, 1 + (at * 2654435761u) % 70000u);
+      const ssize_t w = write(fds[1], bytes.data() + at, n);
+      if (w <= 0) break;
+      at += (size_t)w;
+      if ((at >> 12) % 7 == 0) usleep(300);
+    }
+    close(fds[1]);
+  });
+  FILE* in = fdopen(fds[0], "r");
+  {
+    ReadAheadInput win;
+    CHECK(win.open(in, NULL, cap, malloc, free), "open failed");
+    size_t delivered = 0, steps = 0;
+    for (;;) {
+      win.fill();
+      CHECK(delivered + win.len() <= total && memcmp(bytes.data() + delivered, win.data(), win.len()) == 0,
+            "pipe: window is not the stream at %zu", delivered);
+      if (win.len() == 0 && win.eof()) break;
+      win.prefetch();
+      size_t n = win.len() - std::min<size_t>(win.len(), rnd() % (cap / 16 + 2));
+      if (n == 0) n = win.len();
+      win.consume(n);
+      delivered += n;
+      if (++steps > 100000) {
+        CHECK(false, "pipe: no progress");
+        break;
+      }
+    }
+    CHECK(delivered == total, "pipe: delivered %zu of %zu", delivered, total);
+  }
+  producer.join();
+  fclose(in);
+}
+
+// a read-ahead that waits for a producer which never writes again: close() must come back (the error paths of
+// convertDWfile -i rely on it)
+static void pipe_cancel_case() {
+  int fds[2];
+  if (pipe(fds)) {
+    CHECK(false, "pipe");
+    return;
+  }
+  const size_t cap = 4096;
+  std::string first(cap, 'x');
+  CHECK(write(fds[1], first.data(), cap) == (ssize_t)cap, "pipe write");
+  FILE* in = fdopen(fds[0], "r");
+  struct timespec t0, t1;
+  {
+    ReadAheadInput win;
+    CHECK(win.open(in, NULL, cap, malloc, free), "open failed");
+    win.fill();
+    CHECK(win.len() == cap && !win.eof(), "cancel: first window");
+    win.prefetch();  // nothing more will ever arrive, and the write end stays open
+    usleep(50000);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    win.close();
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+  }
+  const double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  CHECK(s < 2.0, "cancel: close() took %.2f s", s);
+  close(fds[1]);
+  fclose(in);
+}
+
 int main() {
   const size_t caps[] = {1, 2, 7, 8, 9, 64, 100, 1000, 4096, 65536, 1000003};
   int cases = 0;
@@ -183,6 +261,10 @@ int main() {
       }
     }
   }
+  pipe_case(0, 4096);
+  pipe_case(3000000, 65536);
+  pipe_case(1 << 20, 1 << 18);
+  pipe_cancel_case();
   writer_case(0);
   writer_case(1);
   writer_case(40);

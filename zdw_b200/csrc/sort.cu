@@ -55,36 +55,83 @@ __device__ __forceinline__ uint32_t rs_digit(const uint64_t* keys, const uint32_
   return pass < 8 ? (uint32_t)((keys[i] >> (8 * pass)) & 255u) : ((segs[i] >> (8 * (pass - 8))) & 255u);
 }
 
-template <int RS_ITEMS>
+// One launch per pass ("onesweep"): the digit histogram of the whole record set does not depend on the order of the
+// records, so the histograms of all passes of a round are taken in one go up front (k_radix_ghist); a pass's scatter
+// then needs, per tile and digit, only the count of that digit in the tiles in front of it - a decoupled look-back over
+// per-tile status words.  (The first version ran histogram + three scan launches + scatter per pass: 200 launches for
+// a C2-sized dictionary of half a million strings, and the launches were most of the time.)
+constexpr int RS_MAX_PASSES = 12;  // 8 key bytes + 4 segment bytes
+struct RadixPasses {
+  int n;
+  int pass[RS_MAX_PASSES];
+};
+struct RadixScratch {
+  uint32_t* ghist;             // [RS_MAX_PASSES][256] digit counts of the round's record set, per pass of the round
+  uint32_t* tickets;           // [RS_MAX_PASSES] tiles handed out so far, per pass of the round
+  unsigned long long* status;  // [ntiles][256] see os_pack; zeroed once per sort, told apart by the epoch afterwards
+  uint32_t epoch;              // passes run so far in this sort (never 0 in a status word)
+};
+constexpr size_t RS_SMALL_BYTES = (size_t)RS_MAX_PASSES * 256 * 4 + 64;  // ghist + tickets: zeroed every round
+
 __global__ void __launch_bounds__(RS_THREADS)
-    k_radix_hist(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs, uint32_t n, int pass,
-                 uint32_t* __restrict__ hist, uint32_t ntiles) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+    k_radix_ghist(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs, uint32_t n, const RadixPasses P,
+                  uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t h[RS_MAX_PASSES][256];
+  for (int j = threadIdx.x; j < RS_MAX_PASSES * 256; j += RS_THREADS) (&h[0][0])[j] = 0;
   __syncthreads();
-  const uint32_t base = blockIdx.x * rs_tile(RS_ITEMS);
-#pragma unroll 4
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    uint32_t i = base + k * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&h[rs_digit(keys, segs, i, pass)], 1u);
+  const uint32_t stride = gridDim.x * RS_THREADS;
+  const uint32_t rounds = (n + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; ++r) {  // (whole warps stay together for the vote below)
+    const uint32_t i = r * stride + blockIdx.x * RS_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    const uint64_t k = keys[i];
+    const uint32_t sg = segs ? segs[i] : 0u;
+    for (int q = 0; q < P.n; ++q) {
+      const int pass = P.pass[q];
+      const uint32_t d = pass < 8 ? (uint32_t)((k >> (8 * pass)) & 255u) : ((sg >> (8 * (pass - 8))) & 255u);
+      // padding bytes and the high bytes of group ids are the same digit for everyone: one add for the warp then
+      int same;
+      __match_all_sync(act, d, &same);
+      if (same) {
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) atomicAdd(&h[q][d], (uint32_t)__popc(act));
+      } else {
+        atomicAdd(&h[q][d], 1u);
+      }
+    }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+  for (int j = threadIdx.x; j < P.n * 256; j += RS_THREADS) {
+    const uint32_t c = (&h[0][0])[j];
+    if (c) atomicAdd(ghist + j, c);
+  }
 }
 
-// Stable scatter.  Warp w of the CTA owns the contiguous sub-range [tile + w*512, +512) and walks it in
-// 16 steps of 32 consecutive items, so the order (warp, step, lane) is the input order.
+// status word of (tile, digit): flag (bits 62-63: 1 = the tile's own count, 2 = count of this tile and all in front of
+// it) | epoch (bits 40-59) | count (bits 0-39)
+__device__ __forceinline__ unsigned long long os_pack(unsigned long long flag, uint32_t epoch, uint32_t count) {
+  return (flag << 62) | ((unsigned long long)epoch << 40) | (unsigned long long)count;
+}
+
+// Stable scatter of one pass.  Warp w of the CTA owns the contiguous sub-range [tile + w*32*ITEMS, +32*ITEMS) and walks
+// it in steps of 32 consecutive items, so the order (warp, step, lane) is the input order.  Tiles are taken in ticket
+// order: every tile in front of a running one is running or done, so the look-back cannot wait for a CTA that has not
+// started.
 template <int RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
-    k_radix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs,
-                    const uint32_t* __restrict__ vals, uint32_t n, int pass, const uint32_t* __restrict__ hist_scanned,
-                    uint32_t ntiles, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ segs_out,
-                    uint32_t* __restrict__ vals_out) {
+    k_radix_onesweep(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ segs, const uint32_t* __restrict__ vals,
+                     uint32_t n, int pass, int slot, uint32_t epoch, const uint32_t* __restrict__ ghist,
+                     uint32_t* __restrict__ tickets, unsigned long long* status, uint64_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ segs_out, uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t wc[RS_WARPS][256];
+  __shared__ uint32_t s_tile, s_warp[RS_WARPS];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tickets + slot, 1u);
   for (int d = lane; d < 256; d += 32) wc[warp][d] = 0;
-  __syncwarp();
-  const uint32_t wbase = blockIdx.x * rs_tile(RS_ITEMS) + warp * (RS_ITEMS * 32);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t wbase = tile * rs_tile(RS_ITEMS) + warp * (RS_ITEMS * 32);
   // sweep 1: per-warp digit counts
   for (int s = 0; s < RS_ITEMS; ++s) {
     uint32_t i = wbase + s * 32 + lane;
@@ -98,15 +145,47 @@ __global__ void __launch_bounds__(RS_THREADS)
     __syncwarp();
   }
   __syncthreads();
-  // per digit: global base of this tile, then exclusive over the warps of the CTA
   {
     const uint32_t d = threadIdx.x;
-    uint32_t run = hist_scanned[(size_t)d * ntiles + blockIdx.x];
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) t += wc[w][d];
+    // ---- records with digit d in the tiles in front of this one
+    volatile unsigned long long* st = status + (size_t)tile * 256 + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      *st = os_pack(2ull, epoch, t);
+    } else {
+      *st = os_pack(1ull, epoch, t);
+      const volatile unsigned long long* q = status + (size_t)(tile - 1) * 256 + d;
+      for (;;) {
+        const unsigned long long v = *q;
+        if ((uint32_t)((v >> 40) & 0xfffffu) != epoch || (v >> 62) == 0ull) continue;  // not published yet
+        excl += (uint32_t)(v & 0xffffffffffull);
+        if ((v >> 62) == 2ull) break;
+        q -= 256;  // (tile 0 always publishes an inclusive count: the walk ends there at the latest)
+      }
+      *st = os_pack(2ull, epoch, excl + t);
+    }
+    // ---- records with a smaller digit: exclusive scan of the pass's global histogram
+    const uint32_t g = ghist[slot * 256 + d];
+    uint32_t inc = g;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+    for (unsigned w = 0; w < warp; ++w) before += s_warp[w];
+    // ---- per digit: global base of this tile, then exclusive over the warps of the CTA
+    uint32_t run = before + inc - g + excl;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-      uint32_t t = wc[w][d];
+      uint32_t c = wc[w][d];
       wc[w][d] = run;
-      run += t;
+      run += c;
     }
   }
   __syncthreads();
@@ -136,29 +215,36 @@ struct SortBufs {
   int cur = 0;
 };
 
-// Sorts records [0,n) by digits `pass_list`; result ends up in b.{key,seg,val}[b.cur].
-// (`hist` holds 256 counters for every tile of rs_tile(rs_items_for(n)) records)
-int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, uint32_t* hist) {
+// Sorts records [0,n) by digits `pass_list` (least significant first); result ends up in b.{key,seg,val}[b.cur].
+int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, RadixScratch& R) {
   const int items = rs_items_for(n);
   const uint32_t ntiles = (n + rs_tile(items) - 1) / rs_tile(items);
+  if (npass > RS_MAX_PASSES || R.epoch + (uint32_t)npass >= (1u << 20)) {
+    ctx->err = "sort_strings: more radix passes than the status words can tell apart";
+    return ZDWB_ERR_UNSUPPORTED;
+  }
+  RadixPasses P;
+  P.n = npass;
+  for (int q = 0; q < npass; ++q) P.pass[q] = pass_list[q];
+  ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(R.ghist, 0, RS_SMALL_BYTES, ctx->stream));
+  {
+    KernelScope _ks(ctx, "k_radix_ghist");
+    const uint32_t grid = std::min<uint32_t>((n + RS_THREADS - 1) / RS_THREADS, (uint32_t)ctx->sm_count * 8);
+    k_radix_ghist<<<grid, RS_THREADS, 0, ctx->stream>>>(b.key[b.cur], b.seg[b.cur], n, P, R.ghist);
+  }
+  ZDWB_LAUNCH_CHECK(ctx);
   for (int q = 0; q < npass; ++q) {
     const int pass = pass_list[q];
     const int s = b.cur, d = b.cur ^ 1;
+    const uint32_t epoch = ++R.epoch;
     {
-      KernelScope _ks(ctx, "k_radix_hist");
-      if (items == 4) k_radix_hist<4><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
-      else k_radix_hist<16><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], n, pass, hist, ntiles);
-    }
-    ZDWB_LAUNCH_CHECK(ctx);
-    ZDWB_TRY(exclusive_scan_u32(ctx, hist, hist, (size_t)ntiles * 256, nullptr));
-    {
-      KernelScope _ks(ctx, "k_radix_scatter");
+      KernelScope _ks(ctx, "k_radix_onesweep");
       if (items == 4)
-        k_radix_scatter<4><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
-                                                                  b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
+        k_radix_onesweep<4><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, q, epoch, R.ghist, R.tickets,
+                                                                   R.status, b.key[d], b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
       else
-        k_radix_scatter<16><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, hist, ntiles, b.key[d],
-                                                                   b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
+        k_radix_onesweep<16><<<ntiles, RS_THREADS, 0, ctx->stream>>>(b.key[s], b.seg[s], b.val[s], n, pass, q, epoch, R.ghist, R.tickets,
+                                                                    R.status, b.key[d], b.seg[s] ? b.seg[d] : nullptr, b.val[d]);
     }
     ZDWB_LAUNCH_CHECK(ctx);
     b.cur = d;
@@ -230,12 +316,32 @@ __device__ __forceinline__ uint32_t load4_unaligned(const uint8_t* p) {
   return __funnelshift_r(lo, hi, sh);
 }
 
-// strcmp order of two strings that agree on their first `from` bytes: four bytes at a time, compared as big-endian
-// numbers (= unsigned byte order), then the tail; a proper prefix sorts first
+// strcmp order of two strings that agree on their first `from` bytes: sixteen bytes a round (the eight loads of a round
+// are in flight together - the compares of a tie group are a chain of dependent rounds, so the round count is what
+// counts), words compared as big-endian numbers (= unsigned byte order), then the tail; a proper prefix sorts first
 __device__ __forceinline__ bool str_less_from(const uint8_t* base, uint32_t sa, uint32_t la, uint32_t sb, uint32_t lb,
                                               uint32_t from) {
   const uint32_t m = la < lb ? la : lb;
   uint32_t i = from;
+  if (i + 16 <= m) {
+    const uintptr_t ua = reinterpret_cast<uintptr_t>(base + sa + i), ub = reinterpret_cast<uintptr_t>(base + sb + i);
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>(ua & ~(uintptr_t)3);
+    const uint32_t* wb = reinterpret_cast<const uint32_t*>(ub & ~(uintptr_t)3);
+    const uint32_t sha = (uint32_t)(ua & 3u) * 8u, shb = (uint32_t)(ub & 3u) * 8u;
+    // (only aligned words that hold one of the round's 16 bytes are read: five when the side is shifted, else four)
+    for (; i + 16 <= m; i += 16, wa += 4, wb += 4) {
+      const uint32_t a0 = __ldg(wa), a1 = __ldg(wa + 1), a2 = __ldg(wa + 2), a3 = __ldg(wa + 3), a4 = sha ? __ldg(wa + 4) : 0u;
+      const uint32_t b0 = __ldg(wb), b1 = __ldg(wb + 1), b2 = __ldg(wb + 2), b3 = __ldg(wb + 3), b4 = shb ? __ldg(wb + 4) : 0u;
+      const uint32_t x0 = __funnelshift_r(a0, a1, sha), y0 = __funnelshift_r(b0, b1, shb);
+      const uint32_t x1 = __funnelshift_r(a1, a2, sha), y1 = __funnelshift_r(b1, b2, shb);
+      const uint32_t x2 = __funnelshift_r(a2, a3, sha), y2 = __funnelshift_r(b2, b3, shb);
+      const uint32_t x3 = __funnelshift_r(a3, a4, sha), y3 = __funnelshift_r(b3, b4, shb);
+      if (x0 != y0) return __byte_perm(x0, 0, 0x0123) < __byte_perm(y0, 0, 0x0123);
+      if (x1 != y1) return __byte_perm(x1, 0, 0x0123) < __byte_perm(y1, 0, 0x0123);
+      if (x2 != y2) return __byte_perm(x2, 0, 0x0123) < __byte_perm(y2, 0, 0x0123);
+      if (x3 != y3) return __byte_perm(x3, 0, 0x0123) < __byte_perm(y3, 0, 0x0123);
+    }
+  }
   for (; i + 4 <= m; i += 4) {
     const uint32_t a = load4_unaligned(base + sa + i), b = load4_unaligned(base + sb + i);
     if (a != b) return __byte_perm(a, 0, 0x0123) < __byte_perm(b, 0, 0x0123);
@@ -301,18 +407,19 @@ __global__ void __launch_bounds__(RK_SORT_THREADS)
 
 // rank(i) += #{ j in tile : s_j < s_i }: lower bound of key_i among the tile's sorted keys; the strings that agree
 // with s_i on all 16 prefix bytes (a run right at the lower bound) are compared in memory.
-constexpr int RK_IPT = 4;  // strings per thread
+// strings per thread: 1 for small sets (a tie group is a serial chain of string compares: spread them), 4 for large
+// ones (every CTA first copies its tile of keys into shared memory)
 __global__ void __launch_bounds__(RK_THREADS)
     k_rank_count(const uint8_t* __restrict__ base, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
                  const ulonglong2* __restrict__ keys, const ulonglong2* __restrict__ skeys, const uint32_t* __restrict__ sidx,
-                 uint32_t n, uint32_t* __restrict__ rank) {
+                 uint32_t n, uint32_t ipt, uint32_t* __restrict__ rank) {
   __shared__ ulonglong2 sk[RK_JTILE];
   const uint32_t j0 = blockIdx.y * RK_JTILE, jn = min((uint32_t)RK_JTILE, n - j0);
   for (uint32_t t = threadIdx.x; t < jn; t += RK_THREADS) sk[t] = skeys[j0 + t];
   __syncthreads();
 #pragma unroll 1
-  for (int r = 0; r < RK_IPT; ++r) {
-    const uint32_t i = (blockIdx.x * RK_IPT + (uint32_t)r) * RK_THREADS + threadIdx.x;
+  for (uint32_t r = 0; r < ipt; ++r) {
+    const uint32_t i = (blockIdx.x * ipt + r) * RK_THREADS + threadIdx.x;
     if (i >= n) break;
     const ulonglong2 me = keys[i];
     uint32_t lo = 0, hi = jn;
@@ -367,8 +474,9 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
     ZDWB_LAUNCH_CHECK(ctx);
     {
       KernelScope _ks(ctx, "k_rank_count");
-      k_rank_count<<<dim3((gi + RK_IPT - 1) / RK_IPT, ntile), RK_THREADS, 0, st>>>(
-        base, starts, lens, keys.as<ulonglong2>(), skeys.as<ulonglong2>(), sidx.as<uint32_t>(), n, rank.as<uint32_t>());
+      const uint32_t ipt = n > 16384 ? 4 : 1;
+      k_rank_count<<<dim3((gi + ipt - 1) / ipt, ntile), RK_THREADS, 0, st>>>(
+        base, starts, lens, keys.as<ulonglong2>(), skeys.as<ulonglong2>(), sidx.as<uint32_t>(), n, ipt, rank.as<uint32_t>());
     }
     ZDWB_LAUNCH_CHECK(ctx);
     {
@@ -380,7 +488,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   }
 
   // ---- large path
-  // refinement rounds sort m <= n records and may pick the smaller tile: size the histograms for the worst of the two
+  // refinement rounds sort m <= n records and may pick the smaller tile: size the status words for the worst of the two
   const uint32_t ntiles = std::max<uint32_t>((n + rs_tile(rs_items_for(n)) - 1) / rs_tile(rs_items_for(n)),
                                              (std::min<uint32_t>(n, 1u << 21) + rs_tile(4) - 1) / rs_tile(4));
   DevBuf keyA, keyB, segA, segB, valA, valB, hist, head, unres, unres_scan, ids, pos, pos2, total;
@@ -388,7 +496,13 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   ZDWB_TRY(keyB.alloc(ctx, (size_t)n * 8));
   ZDWB_TRY(valA.alloc(ctx, (size_t)n * 4));
   ZDWB_TRY(valB.alloc(ctx, (size_t)n * 4));
-  ZDWB_TRY(hist.alloc(ctx, (size_t)ntiles * 256 * 4));
+  ZDWB_TRY(hist.alloc(ctx, RS_SMALL_BYTES + (size_t)ntiles * 256 * 8));
+  ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(hist.p, 0, RS_SMALL_BYTES + (size_t)ntiles * 256 * 8, st));
+  RadixScratch RSc;
+  RSc.ghist = hist.as<uint32_t>();
+  RSc.tickets = RSc.ghist + RS_MAX_PASSES * 256;
+  RSc.status = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(hist.p) + RS_SMALL_BYTES);
+  RSc.epoch = 0;
   ZDWB_TRY(head.alloc(ctx, (size_t)n * 4));
   ZDWB_TRY(unres.alloc(ctx, (size_t)n * 4));
   ZDWB_TRY(unres_scan.alloc(ctx, (size_t)n * 4));
@@ -411,7 +525,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   ZDWB_LAUNCH_CHECK(ctx);
   {
     const int passes[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-    ZDWB_TRY(radix_passes(ctx, b, n, passes, 8, hist.as<uint32_t>()));
+    ZDWB_TRY(radix_passes(ctx, b, n, passes, 8, RSc));
   }
   ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(order_out, b.val[b.cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
 
@@ -479,7 +593,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
     for (int p = 0; p < 8; ++p) passes[np++] = p;
     const uint32_t seg_bytes = bytes_needed((uint64_t)seg_max);
     for (uint32_t p = 0; p < seg_bytes; ++p) passes[np++] = 8 + (int)p;
-    ZDWB_TRY(radix_passes(ctx, b, m, passes, np, hist.as<uint32_t>()));
+    ZDWB_TRY(radix_passes(ctx, b, m, passes, np, RSc));
     // write the refined order back to the positions these records occupy
     {
       KernelScope _ks(ctx, "k_scatter_order");

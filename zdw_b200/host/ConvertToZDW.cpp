@@ -548,7 +548,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   AsyncWriter writer;
   size_t windowBytes = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
   bool oneWindow = false;
-  bool regularInput = false;  // reads of a regular file always come back; a pipe may keep a helper thread waiting for good
+  bool regularInput = false;  // (only a regular file can be cut into windows up front and dealt to encode workers)
   if (!bStreamingInput) {
     struct stat st;
     regularInput = fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode);
@@ -645,9 +645,10 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     } else if (eo.max_rows == 0) {
       eo.heap_blocks = heapBlocks;  // the reference's own cut (a window in which heap block K does not open is widened below)
     }
-    // a block cut by the window (not by a row count) uses the window up to its last row break: read ahead.  (Not from
-    // a pipe: its producer runs on anyway, and an error path must not wait for a read that may never return.)
-    if (eo.max_rows == 0 && eo.heap_blocks == 0 && regularInput) win.prefetch();
+    // a block cut by the window (not by a row count) uses the window up to its last row break: read ahead - from a
+    // pipe (-i) as well, so that its producer keeps running while the GPU encodes (the helper polls: an error path
+    // never waits for a read that does not return)
+    if (eo.max_rows == 0 && eo.heap_blocks == 0) win.prefetch();
     zdwb_block_out blk;
     const int rc = zdwb_encode_block(gpu.get(), &sch, win.data(), win.len(), &eo, &blk);
     if (rc == ZDWB_OK && planned && !win.eof() && blk.rows_in_buffer <= eo.max_rows) {

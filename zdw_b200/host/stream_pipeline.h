@@ -18,7 +18,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <errno.h>
+#include <poll.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -35,7 +40,7 @@ class ReadAheadInput {
   typedef void (*FreeFn)(void*);
 
   ReadAheadInput() : alloc_(NULL), free_(NULL), in_(NULL), tee_(NULL), cap_(0), gap_(0), streamEof_(false), pending_(false),
-                     aheadLen_(0), aheadEof_(false), aheadFailed_(false) {}
+                     stop_(false), aheadLen_(0), aheadEof_(false), aheadFailed_(false) {}
   ~ReadAheadInput() { close(); }
 
   // `windowBytes` = the most the caller takes per block; buffers are allocated with `alloc` on first use
@@ -51,7 +56,9 @@ class ReadAheadInput {
   }
 
   void close() {
+    stop_ = true;  // a read-ahead that waits for a pipe gives up (its bytes are not wanted any more)
     joinReader();
+    stop_ = false;
     if (free_) {
       if (cur_.buf) free_(cur_.buf);
       if (next_.buf) free_(next_.buf);
@@ -69,7 +76,7 @@ class ReadAheadInput {
       memmove(cur_.buf, cur_.buf + cur_.start, cur_.len);
       cur_.start = 0;
     }
-    cur_.len += readInto(cur_.buf + cur_.start + cur_.len, cap_ - cur_.len, streamEof_);
+    cur_.len += readInto(cur_.buf + cur_.start + cur_.len, cap_ - cur_.len, streamEof_, false);
   }
 
   char* data() const { return cur_.buf + cur_.start; }
@@ -93,7 +100,7 @@ class ReadAheadInput {
         aheadFailed_ = true;  // no second buffer: the caller carries on sequentially
         return;
       }
-      aheadLen_ = readInto(next_.buf + gap_, cap_ - gap_, aheadEof_);
+      aheadLen_ = readInto(next_.buf + gap_, cap_ - gap_, aheadEof_, true);
     });
   }
 
@@ -146,17 +153,31 @@ class ReadAheadInput {
     return true;
   }
 
-  // reads until `want` bytes arrived or a read comes back empty (then eof = true); everything read goes to the tee
-  size_t readInto(char* dst, size_t want, bool& eof) {
+  // reads until `want` bytes arrived or a read comes back empty (then eof = true); everything read goes to the tee.
+  // Reads the descriptor directly (nobody else reads this stream, so stdio's buffer stays empty): the helper thread
+  // can then wait for a pipe with poll() and notice close() within a tenth of a second instead of sitting in a read
+  // that may never return.
+  size_t readInto(char* dst, size_t want, bool& eof, bool helper) {
+    const int fd = fileno(in_);
     size_t got = 0;
     while (got < want) {
-      const size_t n = fread(dst + got, 1, want - got, in_);
-      if (n == 0) {
+      if (helper) {
+        if (stop_) break;
+        struct pollfd pf;
+        pf.fd = fd;
+        pf.events = POLLIN;
+        pf.revents = 0;
+        const int pr = poll(&pf, 1, 100);
+        if (pr == 0 || (pr < 0 && errno == EINTR)) continue;
+      }
+      const ssize_t n = read(fd, dst + got, std::min<size_t>(want - got, (size_t)1 << 30));
+      if (n < 0 && errno == EINTR) continue;
+      if (n <= 0) {
         eof = true;
         break;
       }
-      if (tee_) fwrite(dst + got, 1, n, tee_);
-      got += n;
+      if (tee_) fwrite(dst + got, 1, (size_t)n, tee_);
+      got += (size_t)n;
     }
     return got;
   }
@@ -205,6 +226,7 @@ class ReadAheadInput {
   Buf cur_, next_;
   bool streamEof_;
   bool pending_;
+  std::atomic<bool> stop_;
   std::thread reader_;
   size_t aheadLen_;
   bool aheadEof_, aheadFailed_;
