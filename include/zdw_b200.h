@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ZDWB_ABI_VERSION 3
+#define ZDWB_ABI_VERSION 4
 
 /* status codes (mapped to the reference's ERR_CODE enums by the host classes) */
 enum {
@@ -214,6 +214,20 @@ int zdwb_decode_block(zdwb_ctx* ctx, const zdwb_schema* schema, const void* zdw,
 /* ---- pinned host staging (used by the host classes and the end-to-end bench) ------------------ */
 void* zdwb_host_alloc(size_t bytes);   /* cudaHostAlloc'd (pinned, usable from every device) memory, NULL on failure */
 void zdwb_host_free(void* p);
+
+/* ---- file descriptor <-> device (ABI 4) ---------------------------------------------------------
+ * What the host tools use instead of window-sized host buffers: the reference reads its input with fgets
+ * (getnextrow.cpp:26-84) and writes rows through BufferedOutput (BufferedOutput.cpp:239-260); here a window of the
+ * input file goes straight to the device and the decoded rows of a block straight to the output file, in 8 MiB chunks
+ * through a pinned ring owned by the context, the copy of one chunk under the read / write of the next.
+ *   zdwb_fd_to_device: `len` bytes of fd from `offset` (pread; offset < 0: read() at the descriptor's position) into a
+ *     device buffer of the context; *dev stays valid until the next zdwb_fd_to_device call on it.  Encode it with
+ *     zdwb_encode_opts.input_on_device = 1.
+ *   zdwb_device_to_fd: `len` device bytes (e.g. zdwb_rows_out.tsv of a call with output_on_device = 1) to fd at `offset`
+ *     (pwrite; offset < 0: write()).  Returns when everything is written.
+ * ZDWB_ERR_BAD_ARG with zdwb_last_error() set when the descriptor fails or ends early. */
+int zdwb_fd_to_device(zdwb_ctx* ctx, int fd, long long offset, size_t len, const void** dev);
+int zdwb_device_to_fd(zdwb_ctx* ctx, const void* dev, size_t len, int fd, long long offset);
 
 #ifdef __cplusplus
 }

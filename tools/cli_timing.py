@@ -56,6 +56,8 @@ def main():
     ap.add_argument("--no-reference", action="store_true")
     ap.add_argument("--gpus", default="", help="comma separated list of --gpus values to time, e.g. 1,2,4,8 (default: the tools' default)")
     ap.add_argument("--lanes", type=int, default=0, help="--lanes-per-gpu for our tools (0 = their default)")
+    ap.add_argument("--stream", action="store_true",
+                    help="also time `gzip -dc x.sql.gz | convertDWfile -i x.sql` (streaming input), with and without the read-ahead")
     args = ap.parse_args()
 
     synth = bench.Synth()
@@ -94,6 +96,37 @@ def main():
                               "encode_gbs": tsv_bytes / t_enc / 1e9, "decode_gbs": tsv_bytes / t_dec / 1e9,
                               "round_trip_identical": same}), flush=True)
             shutil.rmtree(out, ignore_errors=True)
+
+        # ---- streaming input: the producer (gzip -dc) runs beside the encoder only if somebody keeps reading the pipe
+        if args.stream:
+            sd = work / "stream"
+            sd.mkdir()
+            gz = shutil.which("gzip")  # the real one: env_for("cat") puts a pass-through `gzip` first on the tools' PATH
+            subprocess.run(f"{gz} -1 -c {src} > {sd / 'x.sql.gz'}", shell=True, check=True)
+            shutil.copy(work / "x.desc.sql", sd / "x.desc.sql")
+            env = env_for("cat")
+            os.symlink(src, sd / "x.sql")
+            timed([str(BIN / "convertDWfile"), "-q", *extra, "x.sql"], sd, env)  # the file-input result to compare with
+            os.rename(sd / "x.zdw.gz", sd / "file.zdw.gz")
+            os.unlink(sd / "x.sql")
+            t0 = time.perf_counter()
+            subprocess.run(f"{gz} -dc {sd / 'x.sql.gz'} > /dev/null", shell=True, check=True)
+            t_producer = time.perf_counter() - t0
+            for label, extra_env in (("read-ahead", {}), ("sequential", {"ZDW_NO_READAHEAD": "1"})):
+                for f in sd.glob("x.zdw*"):
+                    f.unlink()
+                e2 = dict(env)
+                e2.update(extra_env)
+                t0 = time.perf_counter()
+                p = subprocess.run(f"{gz} -dc x.sql.gz | {BIN / 'convertDWfile'} -q -i {' '.join(extra)} x.sql", shell=True, cwd=sd, env=e2,
+                                   capture_output=True)
+                dt = time.perf_counter() - t0
+                if p.returncode != 0:
+                    raise RuntimeError(f"streaming convertDWfile failed ({p.returncode}): {p.stderr[-400:].decode('latin1')}")
+                same = subprocess.run(["cmp", "-s", str(sd / "x.zdw.gz"), str(sd / "file.zdw.gz")]).returncode == 0
+                print(json.dumps({"tool": "zdw_b200", "mode": "gzip -dc | convertDWfile -i", "input": label, "tsv_bytes": tsv_bytes,
+                                  "encode_s": round(dt, 3), "producer_alone_s": round(t_producer, 3),
+                                  "encode_gbs": tsv_bytes / dt / 1e9, "same_zdw_as_file_input": same}), flush=True)
 
         # ---- the reference on the first block of the same file (single-threaded; the whole file would take minutes)
         if not args.no_reference and bench.have_ref():

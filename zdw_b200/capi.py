@@ -18,7 +18,7 @@ STATUS_NAMES = {0: "OK", 1: "ERR_CUDA", 2: "ERR_OOM", 3: "ERR_WRONG_COLUMNS", 4:
 EXPORTED_SYMBOLS = [
     "zdwb_abi_version", "zdwb_device_count", "zdwb_ctx_create", "zdwb_ctx_destroy", "zdwb_last_error", "zdwb_ctx_set_stream",
     "zdwb_ctx_set_tuning", "zdwb_ctx_kernel_launches", "zdwb_ctx_kernel_times", "zdwb_encode_block", "zdwb_decode_block", "zdwb_host_alloc",
-    "zdwb_host_free",
+    "zdwb_host_free", "zdwb_fd_to_device", "zdwb_device_to_fd",
 ]
 
 
@@ -112,6 +112,8 @@ def load_library():
     L.zdwb_host_alloc.restype = C.c_void_p
     L.zdwb_host_free.argtypes = [C.c_void_p]
     L.zdwb_host_free.restype = None
+    L.zdwb_fd_to_device.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.zdwb_device_to_fd.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_longlong]
     _lib = L
     return L
 
@@ -199,6 +201,21 @@ class Context:
             name, cnt, ms = line.split("\t")
             out[name] = (int(cnt), float(ms))
         return out
+
+    # ------------------------------------------------------------------ file descriptor <-> device
+    def fd_to_device(self, fd: int, offset: int, n: int) -> int:
+        """`n` bytes of fd from `offset` (< 0: read() at its position) to a device buffer of the context; returns its address."""
+        dev = C.c_void_p()
+        rc = self._L.zdwb_fd_to_device(self._h, fd, offset, n, C.byref(dev))
+        if rc:
+            raise ZdwError(rc, self.last_error())
+        return int(dev.value or 0)
+
+    def device_to_fd(self, dev_ptr: int, n: int, fd: int, offset: int):
+        """`n` device bytes to fd at `offset` (< 0: write() at its position)."""
+        rc = self._L.zdwb_device_to_fd(self._h, C.c_void_p(dev_ptr), n, fd, offset)
+        if rc:
+            raise ZdwError(rc, self.last_error())
 
     # ------------------------------------------------------------------ encode
     def encode_block(self, types, tsv, n: int | None = None, *, trim=False, input_on_device=False,

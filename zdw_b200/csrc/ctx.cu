@@ -1,4 +1,7 @@
 // ctx.cu -- C ABI entry points of libzdw_b200 (see include/zdw_b200.h).
+#include <errno.h>
+#include <unistd.h>
+
 #include <map>
 #include <new>
 
@@ -70,8 +73,63 @@ void zdwb_ctx_destroy(zdwb_ctx* c) {
   if (c->out_host2) cudaFreeHost(c->out_host2);
   if (c->meta_host) cudaFreeHost(c->meta_host);
   if (c->stage_host) cudaFreeHost(c->stage_host);
+  zdwb::ring_destroy(c);
+  if (c->fd_dev) cudaFree(c->fd_dev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
+}
+
+// ---- file descriptor <-> device, through the pinned ring ----------------------------------------------------------
+int zdwb_fd_to_device(zdwb_ctx* c, int fd, long long offset, size_t len, const void** dev) {
+  if (!c || !dev || fd < 0) return ZDWB_ERR_BAD_ARG;
+  *dev = nullptr;
+  c->err.clear();
+  if (cudaSetDevice(c->device) != cudaSuccess) return ZDWB_ERR_NO_DEVICE;
+  if (c->fd_dev_cap < len + 64) {
+    ZDWB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->fd_dev) cudaFree(c->fd_dev);
+    c->fd_dev = nullptr;
+    c->fd_dev_cap = 0;
+    const size_t cap = len + len / 8 + 64;  // headroom: the windows of a file vary a little
+    ZDWB_CUDA_TRY(c, cudaMalloc(&c->fd_dev, cap));
+    c->fd_dev_cap = cap;
+  }
+  const int rc = zdwb::ring_h2d(c, c->fd_dev, len, [fd, offset, c](void* dst, size_t off, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+      const ssize_t r = offset >= 0 ? pread(fd, static_cast<char*>(dst) + got, n - got, (off_t)((size_t)offset + off + got))
+                                    : read(fd, static_cast<char*>(dst) + got, n - got);
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) {
+        c->err = r == 0 ? "fd_to_device: the input ended early" : std::string("fd_to_device: read failed: ") + strerror(errno);
+        return false;
+      }
+      got += (size_t)r;
+    }
+    return true;
+  });
+  if (rc != ZDWB_OK) return rc;
+  *dev = c->fd_dev;
+  return ZDWB_OK;
+}
+
+int zdwb_device_to_fd(zdwb_ctx* c, const void* dev, size_t len, int fd, long long offset) {
+  if (!c || (!dev && len) || fd < 0) return ZDWB_ERR_BAD_ARG;
+  c->err.clear();
+  if (cudaSetDevice(c->device) != cudaSuccess) return ZDWB_ERR_NO_DEVICE;
+  return zdwb::ring_d2h(c, dev, len, [fd, offset, c](const uint8_t* src, size_t off, size_t n) {
+    size_t put = 0;
+    while (put < n) {
+      const ssize_t w = offset >= 0 ? pwrite(fd, src + put, n - put, (off_t)((size_t)offset + off + put)) : write(fd, src + put, n - put);
+      if (w < 0 && errno == EINTR) continue;
+      if (w <= 0) {
+        c->err = std::string("device_to_fd: write failed: ") + strerror(errno);
+        return false;
+      }
+      put += (size_t)w;
+    }
+    return true;
+  });
 }
 
 const char* zdwb_last_error(const zdwb_ctx* c) { return c ? c->err.c_str() : "null context"; }

@@ -1293,7 +1293,15 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
   } else {
     const uint64_t need = rows_base + win;
     ZDWB_TRY(blk_dev.alloc(ctx, need + 64));
-    ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(blk_dev.p, src, need, cudaMemcpyHostToDevice, st));
+    if (need >= ((uint64_t)32 << 20) && is_pageable_host(src)) {  // (see encode_block_impl: pageable memory goes through the pinned ring)
+      const uint8_t* from = src;
+      ZDWB_TRY(ring_h2d(ctx, blk_dev.p, (size_t)need, [from](void* dst, size_t off, size_t k) {
+        memcpy(dst, from + off, k);
+        return true;
+      }));
+    } else {
+      ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(blk_dev.p, src, need, cudaMemcpyHostToDevice, st));
+    }
     blk = blk_dev.as<uint8_t>();
   }
   const uint64_t dev_avail = in_dev ? avail : rows_base + win;
@@ -1812,7 +1820,14 @@ int decode_block_impl(Ctx* ctx, const zdwb_schema* schema, const void* zdw, size
       ctx->out_host_cap = cap;
     }
   }
-  if (ctx->copy_gate && out_len >= COPY_GATE_MIN) {
+  if (!ctx->out_host_pinned && out_len >= ((size_t)32 << 20)) {
+    // a plain host buffer: through the pinned ring, chunk by chunk (the driver's own staging is several times slower)
+    uint8_t* dst = static_cast<uint8_t*>(ctx->out_host);
+    ZDWB_TRY(ring_d2h(ctx, ctx->out_dev, out_len, [dst](const uint8_t* src, size_t off, size_t k) {
+      memcpy(dst + off, src, k);
+      return true;
+    }));
+  } else if (ctx->copy_gate && out_len >= COPY_GATE_MIN) {
     ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));  // the rows are written: now wait for the link, not with it
     std::lock_guard<std::mutex> turn(copy_gate(ctx->device, 1));
     ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->out_host, ctx->out_dev, out_len, cudaMemcpyDeviceToHost, st));

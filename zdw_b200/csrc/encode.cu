@@ -2488,7 +2488,14 @@ static int encode_block_run(Ctx* ctx, const zdwb_schema* schema, const void* tsv
     buf = static_cast<const uint8_t*>(tsv);
   } else {
     ZDWB_TRY(tsv_dev.alloc(ctx, n + 64));
-    if (ctx->copy_gate && n >= COPY_GATE_MIN) {
+    if (n >= ((size_t)32 << 20) && is_pageable_host(tsv)) {
+      // pageable caller memory: through the pinned ring, chunk by chunk (the driver's own staging is several times slower)
+      const uint8_t* src = static_cast<const uint8_t*>(tsv);
+      ZDWB_TRY(ring_h2d(ctx, tsv_dev.p, n, [src](void* dst, size_t off, size_t k) {
+        memcpy(dst, src + off, k);
+        return true;
+      }));
+    } else if (ctx->copy_gate && n >= COPY_GATE_MIN) {
       std::lock_guard<std::mutex> turn(copy_gate(ctx->device, 0));
       ZDWB_CUDA_TRY(ctx, cudaMemcpyAsync(tsv_dev.p, tsv, n, cudaMemcpyHostToDevice, st));
       ZDWB_CUDA_TRY(ctx, cudaStreamSynchronize(st));

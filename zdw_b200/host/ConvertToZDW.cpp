@@ -315,8 +315,6 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
     statusOutput(ERROR, "%s: a single row exceeds %zu bytes (or the input could not be read)\n", exeName, (size_t)MAX_WINDOW_BYTES);
     return UNKNOWN_ERROR;
   }
-  size_t maxLen = 0;
-  for (size_t k = 0; k < wins.size(); ++k) maxLen = std::max(maxLen, wins[k].len);
   const double tStart = nowSeconds();
   if (hostTiming()) fprintf(stderr, "[zdw host] %zu windows planned (window %zu bytes)\n", wins.size(), cap);
 
@@ -340,45 +338,37 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
   const bool trim = bTrimTrailingSpaces;
   auto work = [&](int device) {
     GpuSession session;
-    char* buf = NULL;
-    bool pinned = false;
     std::string fatal;
     int fatalRc = ZDWB_OK;
     const double tw0 = nowSeconds();
-    double tOpen = 0, tAlloc = 0, tRead = 0, tEnc = 0, tCopy = 0;
-    // Pinning a window-sized buffer takes about as long as four copies out of pageable memory (measured: 0.45 s per
-    // GiB, and the driver serialises it with every other context's calls): only worth it for a worker that will see
-    // more than a few windows.  A plain buffer also needs no CUDA: the first window is read while the context comes up.
-    pinned = wins.size() > 4 * workers.size();
-    bool opened = false;
-    if (pinned) {
-      opened = session.open(device);
-      tOpen = nowSeconds() - tw0;
-      const double ta = nowSeconds();
-      if (opened) buf = static_cast<char*>(zdwb_host_alloc(maxLen + 64));
-      tAlloc = nowSeconds() - ta;
-    } else {
-      session.prefetch(device);
-      buf = static_cast<char*>(malloc(maxLen + 64));
-    }
-    if (!buf && (opened || !pinned)) {
-      fatal = "window allocation failed";
-      fatalRc = ZDWB_ERR_OOM;
-    }
-    bool sessionReady = pinned;
+    double tOpen = 0, tRead = 0, tEnc = 0;
+    // The first window of a worker is read into plain memory while its CUDA context comes up (about a second, and plain
+    // memory needs no CUDA); every later one goes from the file straight to the device, 8 MiB at a time through the
+    // context's pinned ring (zdwb_fd_to_device) - no window-sized host buffer, pinned (0.45 s per GiB to allocate) or
+    // pageable (2.5 GB/s through the driver's staging).
+    session.prefetch(device);
+    char* buf = NULL;
+    bool opened = false, sessionReady = false;
     for (;;) {
       const size_t k = next.fetch_add(1);
       if (k >= wins.size()) break;
       results.waitTurn(k, ahead);
       EncodedBlock r;
-      size_t preRead = 0;
-      if (!sessionReady && fatalRc == ZDWB_OK && !cancel) {  // the read of the first window overlaps the CUDA start-up
-        const FileWindow& w = wins[k];
+      const FileWindow& w = wins[k];
+      const bool first = !sessionReady;
+      size_t got = 0;
+      if (first && !cancel) {
+        buf = static_cast<char*>(malloc(w.len + 64));
+        if (!buf) {
+          fatal = "window allocation failed";
+          fatalRc = ZDWB_ERR_OOM;
+        }
         const double tr = nowSeconds();
-        while (preRead < w.len) {
-          const ssize_t n = pread(fd, buf + preRead, w.len - preRead, (off_t)(w.offset + preRead));
+        while (buf && got < w.len) {
+          const ssize_t n = pread(fd, buf + got, w.len - got, (off_t)(w.offset + got));
+          if (n < 0 && errno == EINTR) continue;
           if (n <= 0) break;
-          preRead += (size_t)n;
+          got += (size_t)n;
         }
         tRead += nowSeconds() - tr;
       }
@@ -399,15 +389,6 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
       } else if (cancel) {
         r.skipped = true;
       } else {
-        const FileWindow& w = wins[k];
-        size_t got = preRead;
-        const double tr = nowSeconds();
-        while (got < w.len) {
-          const ssize_t n = pread(fd, buf + got, w.len - got, (off_t)(w.offset + got));
-          if (n <= 0) break;
-          got += (size_t)n;
-        }
-        tRead += nowSeconds() - tr;
         zdwb_encode_opts eo;
         memset(&eo, 0, sizeof(eo));
         eo.trim_trailing_spaces = trim ? 1 : 0;
@@ -415,13 +396,22 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
         zdwb_block_out blk;
         memset(&blk, 0, sizeof(blk));
         const double te = nowSeconds();
-        if (got != w.len) {
-          r.rc = ZDWB_ERR_BAD_ARG;
-          r.err = "short read of the input file";
+        if (first) {
+          if (got != w.len) {
+            r.rc = ZDWB_ERR_BAD_ARG;
+            r.err = "short read of the input file";
+          } else {
+            r.rc = zdwb_encode_block(session.get(), &sch, buf, w.len, &eo, &blk);
+          }
         } else {
-          r.rc = zdwb_encode_block(session.get(), &sch, buf, w.len, &eo, &blk);
-          if (r.rc != ZDWB_OK) r.err = zdwb_last_error(session.get());
+          const void* dev = NULL;
+          r.rc = zdwb_fd_to_device(session.get(), fd, (long long)w.offset, w.len, &dev);
+          if (r.rc == ZDWB_OK) {
+            eo.input_on_device = 1;
+            r.rc = zdwb_encode_block(session.get(), &sch, dev, w.len, &eo, &blk);
+          }
         }
+        if (r.rc != ZDWB_OK && r.err.empty()) r.err = zdwb_last_error(session.get());
         tEnc += nowSeconds() - te;
         r.badRow = blk.bad_row;
         if (r.rc == ZDWB_OK && blk.nrows && w.more && blk.tsv_consumed != w.consumed) {
@@ -440,15 +430,15 @@ ConvertToZDW::ERR_CODE ConvertToZDW::encodeWindowsParallel(FILE* in, size_t wind
           cancel = true;
         }
       }
+      if (buf) {  // (only the first window used it)
+        free(buf);
+        buf = NULL;
+      }
       results.put(k, std::move(r));
     }
-    const double tf = nowSeconds();
-    if (buf && pinned) zdwb_host_free(buf);
-    else free(buf);
-    (void)tCopy;
     if (hostTiming())
-      fprintf(stderr, "[zdw host] encode worker on device %d: open %.3f s, pinned alloc %.3f s, read %.3f s, encode %.3f s, free %.3f s, total %.3f s\n",
-              device, tOpen, tAlloc, tRead, tEnc, nowSeconds() - tf, nowSeconds() - tw0);
+      fprintf(stderr, "[zdw host] encode worker on device %d: open %.3f s, first read %.3f s, upload + encode %.3f s, total %.3f s\n",
+              device, tOpen, tRead, tEnc, nowSeconds() - tw0);
   };
   vector<std::thread> threads;
   for (size_t w = 0; w < workers.size(); ++w) threads.push_back(std::thread(work, workers[w]));
@@ -546,6 +536,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   // a longer one goes through two pinned buffers: while the GPU encodes one window a helper thread reads the next.
   ReadAheadInput win;
   AsyncWriter writer;
+  const bool noReadAhead = getenv("ZDW_NO_READAHEAD") != NULL;  // measurement aid (tools/cli_timing.py --stream): read, then encode
   size_t windowBytes = std::min(std::max(blockBytes, (size_t)1 << 16), MAX_WINDOW_BYTES);
   bool oneWindow = false;
   bool regularInput = false;  // (only a regular file can be cut into windows up front and dealt to encode workers)
@@ -648,7 +639,7 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
     // a block cut by the window (not by a row count) uses the window up to its last row break: read ahead - from a
     // pipe (-i) as well, so that its producer keeps running while the GPU encodes (the helper polls: an error path
     // never waits for a read that does not return)
-    if (eo.max_rows == 0 && eo.heap_blocks == 0) win.prefetch();
+    if (eo.max_rows == 0 && eo.heap_blocks == 0 && !noReadAhead) win.prefetch();
     zdwb_block_out blk;
     const int rc = zdwb_encode_block(gpu.get(), &sch, win.data(), win.len(), &eo, &blk);
     if (rc == ZDWB_OK && planned && !win.eof() && blk.rows_in_buffer <= eo.max_rows) {

@@ -630,7 +630,7 @@ ERR_CODE UnconvertFromZDW_Base::peekBlock(BlockInfo& info) {
 
 int UnconvertFromZDW_Base::decodeBytes(GpuSession& g, const void* data, size_t avail, bool atEnd, unsigned long long firstRow,
                                        unsigned char separator, bool wantRowOffsets, bool validateOnly, bool wantFlagCounts,
-                                       bool skimOnly, zdwb_rows_out* out) const {
+                                       bool skimOnly, zdwb_rows_out* out, bool outputOnDevice) const {
   zdwb_schema sch;
   sch.ncols = numColumnsInExportFile;
   sch.types = columnType.data();
@@ -643,6 +643,7 @@ int UnconvertFromZDW_Base::decodeBytes(GpuSession& g, const void* data, size_t a
   o.validate_only = validateOnly ? 1 : 0;
   o.want_flag_counts = wantFlagCounts ? 1 : 0;
   o.skim_only = skimOnly ? 1 : 0;
+  o.output_on_device = outputOnDevice ? 1 : 0;
   o.first_row_number = firstRow;
   vector<int32_t> map32;
   zdwb_fill fill;
@@ -808,6 +809,24 @@ class OrderedSink {
     }
     return ok;
   }
+  // a regular file: the place of block `seq` (prefix + rows, `bytes` in all) - the caller writes there itself (the rows
+  // go from the device to the file through zdwb_device_to_fd).  false once anything failed.
+  bool seekable() const { return seekable_; }
+  int fd() const { return fd_; }
+  bool claim(size_t seq, size_t bytes, uint64_t* at) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
+    *at = base_ + total_;
+    total_ += bytes;
+    ++nextSeq_;
+    cv_.notify_all();
+    return !failed_;
+  }
+  void fail() {
+    std::lock_guard<std::mutex> g(m_);
+    failed_ = true;
+  }
+  bool writePrefix(const string& prefix, uint64_t at) { return writeAt(prefix.data(), prefix.size(), at); }
   // a block that produced nothing (its worker failed): later blocks must not wait for it for ever
   // (nothing behind it is written either: the output ends where the reference's would, in front of the bad block)
   void skip(size_t seq) {
@@ -897,9 +916,22 @@ ERR_CODE UnconvertFromZDW<T>::decodeBlocksFanOut(T& sink) {
       } else if (firstError.load() == OK) {  // (after a failure nothing more is written)
         zdwb_rows_out rows;
         memset(&rows, 0, sizeof(rows));
+        // a regular output file: the rows stay on the device and go to their place in the file through the context's
+        // pinned ring (no block-sized host buffer in between); a pipe / stdout: to the host, written in turn
+        const bool direct = ordered.seekable();
         const int zrc = this->decodeBytes(session, job.bytes.data(), job.bytes.size(), true, job.firstRow, '\t', false, false, false,
-                                          false, &rows);
-        if (zrc == ZDWB_OK) {
+                                          false, &rows, direct);
+        if (zrc == ZDWB_OK && direct) {
+          handedOver = true;
+          uint64_t at = 0;
+          bool ok = ordered.claim(job.seq, job.prefix.size() + (size_t)rows.len, &at);
+          ok = ok && ordered.writePrefix(job.prefix, at) &&
+               zdwb_device_to_fd(session.get(), rows.tsv, (size_t)rows.len, ordered.fd(), (long long)(at + job.prefix.size())) == ZDWB_OK;
+          if (!ok) {
+            ordered.fail();
+            rc = FILE_CREATION_ERR;
+          }
+        } else if (zrc == ZDWB_OK) {
           handedOver = true;
           if (!ordered.deliver(job.seq, job.prefix, rows.tsv, rows.len)) rc = FILE_CREATION_ERR;
         } else {

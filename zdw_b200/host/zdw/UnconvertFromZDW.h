@@ -193,7 +193,8 @@ class UnconvertFromZDW_Base {
   // the same on explicit bytes (a complete block when atEnd): what the decode workers call.  Reads only members that
   // do not change after readHeader(); error texts go to *errText instead of the status callback.
   int decodeBytes(GpuSession& g, const void* data, size_t avail, bool atEnd, unsigned long long firstRow, unsigned char separator,
-                  bool wantRowOffsets, bool validateOnly, bool wantFlagCounts, bool skimOnly, zdwb_rows_out* out) const;
+                  bool wantRowOffsets, bool validateOnly, bool wantFlagCounts, bool skimOnly, zdwb_rows_out* out,
+                  bool outputOnDevice = false) const;
   std::string getBlockHeaderString(const BlockInfo& info) const;
 
   ERR_CODE outputDescToFile(const std::vector<std::string>& names, const std::string& outputDir, const char* filestub,
