@@ -39,6 +39,31 @@ def test_c5_decode_through_unconvert_api(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("plan", [[(1000, 0), (3000, 0), (9000, 0), (27000, 0)],    # every block longer than the one before: the
+                                  [(30000, 0), (6000, 0), (3000, 0), (500, 0)],     # helper's buffer is too short / too long
+                                  [(1, 0), (1, 0), (20000, 0), (1, 0)]])
+@pytest.mark.parametrize("ahead", [True, False])
+def test_unconvert_api_decode_ahead(tmp_path, plan, ahead):
+    """getRow over blocks of very different sizes: the block decoded ahead on the helper thread (or, when the helper had
+    buffered too little of it, decoded again the ordinary way) gives the rows the one-thread loop gives."""
+    import os
+    sys.path.insert(0, str(ROOT / "tests"))
+    import c5_check
+    import oracle as O
+    tsv = c5_check.make_rows(50000)
+    z = O.encode(O.parse_desc(c5_check.DESC), tsv, plan=plan, rows_per_block=10000)
+    assert z.rc == 0 and z.nblocks >= 5
+    (tmp_path / "c5.zdw").write_bytes(z.data)
+    env = dict(os.environ)
+    if not ahead:
+        env["ZDW_NO_DECODE_AHEAD"] = "1"
+    p = subprocess.run([str(ROOT / "zdw_b200" / "bin" / "test_unconvert_api"), "c5.zdw"], cwd=tmp_path, capture_output=True, timeout=300,
+                       env=env)
+    assert p.returncode == 0, p.stderr[-500:]
+    assert p.stdout == tsv
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["test", "movie_tickets", "analytics-hits"])
 def test_api_rowloop_twins_agree_on_goldens(tmp_path, name):
     """The getRow loop (tests/api_rowloop.cpp) built against our host classes and against the unmodified reference

@@ -1131,14 +1131,47 @@ template class UnconvertFromZDWToFile<BufferedOrderedOutput>;
 UnconvertFromZDWToMemory::UnconvertFromZDWToMemory(const string& fileName, const bool useInternalBuffer, const bool showStatus,
                                                    const bool quiet, const bool testOnly, const bool descOnly)
     : UnconvertFromZDW<BufferedOutputInMem>(fileName, showStatus, quiet, testOnly, descOnly), bUseInternalBuffer(useInternalBuffer),
-      blockOpen(false), neededBufferSize(0), slab(NULL), slabRowOff(NULL), currentRowLength(0) {
+      blockOpen(false), neededBufferSize(0), slab(NULL), slabRowOff(NULL), currentRowLength(0),
+      bDecodeAhead(getenv("ZDW_NO_DECODE_AHEAD") == NULL), slabSession(1), aheadPending(false), aheadRc(-1) {
   statusOutput = defaultStatusOutputCallback;
+  memset(&aheadRows, 0, sizeof(aheadRows));
 }
 
-UnconvertFromZDWToMemory::~UnconvertFromZDWToMemory() {}
+UnconvertFromZDWToMemory::~UnconvertFromZDWToMemory() { joinDecodeAhead(); }
+
+// The current block has just been decoded and its bytes consumed: `input` stands at the next block.  The helper buffers
+// about as many bytes as the last block took and decodes them in the other context; what it finds is adopted by the next
+// handleZDWParseBlockHeader if it is a complete block, and decoded again the ordinary way if not (a longer block).
+void UnconvertFromZDWToMemory::startDecodeAhead() {
+  if (!bDecodeAhead || aheadPending || isLastBlock()) return;
+  const unsigned long long firstRow = rowsBeforeBlock + numLines + 1;
+  const size_t want = lastBlockBytes ? lastBlockBytes + lastBlockBytes / 4 + 4096 : ((size_t)1 << 20);
+  const int device = gpuList.empty() ? gpuDevice : gpuList[0];
+  GpuSession* g = slabSession == 0 ? &gpu2 : &gpu;
+  aheadPending = true;
+  aheadRc = -1;
+  aheadThread = std::thread([this, g, firstRow, want, device]() {
+    try {
+      input->ensure(want);
+      if (input->available() < 10 || !g->open(device)) return;
+      memset(&aheadRows, 0, sizeof(aheadRows));
+      aheadRc = decodeBytes(*g, input->data(), input->available(), input->sourceEnded(), firstRow, '\0', true, false, false, false,
+                            &aheadRows);
+    } catch (...) {
+      aheadRc = -1;  // (out of memory while buffering: the ordinary path reports it)
+    }
+  });
+}
+
+void UnconvertFromZDWToMemory::joinDecodeAhead() {
+  if (aheadThread.joinable()) aheadThread.join();
+}
 
 // Decodes the next block in one go (NUL-separated fields, row offsets) and keeps it for getRow to hand out.
 ERR_CODE UnconvertFromZDWToMemory::handleZDWParseBlockHeader() {
+  joinDecodeAhead();
+  const bool ahead = aheadPending && aheadRc == ZDWB_OK;
+  aheadPending = false;
   BlockInfo info;
   ERR_CODE rc = peekBlock(info);
   if (rc != OK) return rc;
@@ -1149,13 +1182,22 @@ ERR_CODE UnconvertFromZDWToMemory::handleZDWParseBlockHeader() {
                               pendingHeaderLine.empty() ? (size_t)0 : pendingHeaderLine.size() + 1);
   zdwb_rows_out rows;
   memset(&rows, 0, sizeof(rows));
-  rc = decodeBlock(info, '\0', true, false, false, &rows);
-  if (rc != OK) return rc;
+  if (ahead && aheadRows.nrows == info.numLines) {
+    rows = aheadRows;  // decoded while the caller walked the block before
+    slabSession ^= 1;
+    if (rows.consumed) lastBlockBytes = (size_t)rows.consumed;
+  } else {
+    // (the first block, a block longer than the helper buffered, or decode-ahead switched off)
+    rc = decodeBlock(info, '\0', true, false, false, &rows, slabSession == 0 ? &gpu2 : &gpu);
+    if (rc != OK) return rc;
+    slabSession ^= 1;
+  }
   slab = reinterpret_cast<const char*>(rows.tsv);
   slabRowOff = rows.row_off;
   input->consume((size_t)rows.consumed);
   blockOpen = true;
   setState(ZDW_OUTPUT_BLOCK_HEADER);
+  startDecodeAhead();
   return OK;
 }
 

@@ -306,6 +306,10 @@ class UnconvertFromZDWToMemory : public UnconvertFromZDW<BufferedOutputInMem> {
   ERR_CODE getRow(const char** outColumns);
   ERR_CODE getRow(char** buffer, size_t* size, const char** outColumns, size_t& numColumns);
   ERR_CODE getNumOutputColumns(size_t& num);
+  // While the caller walks the rows of a block, the next block is read and decoded on a helper thread in a second GPU
+  // context (on by default; off: one thread, one context, like the reference's one-thread loop).  Call before the
+  // first getRow.
+  void setDecodeAhead(bool on) { bDecodeAhead = on; }
   size_t getCurrentRowLength();
   // valid after getNumOutputColumns or getRow
   ULONG getLineLength() { return this->exportFileLineLength + this->virtualLineLength; }
@@ -327,6 +331,17 @@ class UnconvertFromZDWToMemory : public UnconvertFromZDW<BufferedOutputInMem> {
   const uint64_t* slabRowOff;
   size_t currentRowLength;
   std::vector<char> internalRow;
+  // decode-ahead (see setDecodeAhead): the block behind the current one, decoded in the context the current block does
+  // not live in.  The helper only runs between two handleZDWParseBlockHeader calls; everything that touches `input`
+  // joins it first.
+  void startDecodeAhead();
+  void joinDecodeAhead();
+  bool bDecodeAhead;
+  int slabSession;           // 0: the current block's rows live in `gpu`, 1: in `gpu2`
+  std::thread aheadThread;
+  bool aheadPending;
+  int aheadRc;               // ZDWB_* of the helper's decode (-1: it did not get that far)
+  zdwb_rows_out aheadRows;
 };
 
 }  // namespace zdw
