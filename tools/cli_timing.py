@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--no-reference", action="store_true")
     ap.add_argument("--gpus", default="", help="comma separated list of --gpus values to time, e.g. 1,2,4,8 (default: the tools' default)")
     ap.add_argument("--lanes", type=int, default=0, help="--lanes-per-gpu for our tools (0 = their default)")
+    ap.add_argument("--stream-only", action="store_true", help="only the --stream leg")
     ap.add_argument("--stream", action="store_true",
                     help="also time `gzip -dc x.sql.gz | convertDWfile -i x.sql` (streaming input), with and without the read-ahead")
     args = ap.parse_args()
@@ -78,7 +79,7 @@ def main():
         extra = [f"--block-bytes={args.block_bytes}"] if args.block_bytes else []
 
         runs = [(comp, g) for comp in args.compressors.split(",") if comp for g in (args.gpus.split(",") if args.gpus else [""])]
-        for comp, g in runs:
+        for comp, g in ([] if args.stream_only else runs):
             extra_g = ([f"--gpus={g}"] if g else []) + ([f"--lanes-per-gpu={args.lanes}"] if args.lanes else [])
             env = env_for(comp)
             for f in work.glob("x.zdw*"):
@@ -98,7 +99,7 @@ def main():
             shutil.rmtree(out, ignore_errors=True)
 
         # ---- streaming input: the producer (gzip -dc) runs beside the encoder only if somebody keeps reading the pipe
-        if args.stream:
+        if args.stream or args.stream_only:
             sd = work / "stream"
             sd.mkdir()
             gz = shutil.which("gzip")  # the real one: env_for("cat") puts a pass-through `gzip` first on the tools' PATH
@@ -112,6 +113,9 @@ def main():
             t0 = time.perf_counter()
             subprocess.run(f"{gz} -dc {sd / 'x.sql.gz'} > /dev/null", shell=True, check=True)
             t_producer = time.perf_counter() - t0
+            t0 = time.perf_counter()  # ... and through a pipe into a reader that does nothing else (what -i can reach at best)
+            subprocess.run(f"{gz} -dc {sd / 'x.sql.gz'} | cat > /dev/null", shell=True, check=True)
+            t_piped = time.perf_counter() - t0
             for label, extra_env in (("read-ahead", {}), ("sequential", {"ZDW_NO_READAHEAD": "1"})):
                 for f in sd.glob("x.zdw*"):
                     f.unlink()
@@ -125,11 +129,11 @@ def main():
                     raise RuntimeError(f"streaming convertDWfile failed ({p.returncode}): {p.stderr[-400:].decode('latin1')}")
                 same = subprocess.run(["cmp", "-s", str(sd / "x.zdw.gz"), str(sd / "file.zdw.gz")]).returncode == 0
                 print(json.dumps({"tool": "zdw_b200", "mode": "gzip -dc | convertDWfile -i", "input": label, "tsv_bytes": tsv_bytes,
-                                  "encode_s": round(dt, 3), "producer_alone_s": round(t_producer, 3),
+                                  "encode_s": round(dt, 3), "producer_alone_s": round(t_producer, 3), "producer_into_cat_s": round(t_piped, 3),
                                   "encode_gbs": tsv_bytes / dt / 1e9, "same_zdw_as_file_input": same}), flush=True)
 
         # ---- the reference on the first block of the same file (single-threaded; the whole file would take minutes)
-        if not args.no_reference and bench.have_ref():
+        if not args.no_reference and not args.stream_only and bench.have_ref():
             rd = work / "ref"
             rd.mkdir()
             with open(src, "rb") as f, open(rd / "x.sql", "wb") as g:

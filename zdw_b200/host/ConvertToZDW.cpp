@@ -54,11 +54,9 @@ double nowSeconds() {
   return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
-// the window's buffers: pinned memory of the C ABI (copies at the rate of the link) ...
-void* pinnedAlloc(size_t n) { return zdwb_host_alloc(n); }
-void pinnedFree(void* p) { zdwb_host_free(p); }
-// ... or plain memory for an input that fits one window: pinning a buffer costs about as much as copying out of it
-// unpinned once, and plain memory can be filled while CUDA is still starting up
+// the window's buffers: plain memory.  Pinning a window-sized buffer costs about as much as copying out of it unpinned
+// once did (0.45 s per GiB) and needs the CUDA context; plain memory can be filled while CUDA is still starting up, and the
+// library moves it to the device through its own small pinned ring
 void* plainAlloc(size_t n) { return malloc(n); }
 void plainFree(void* p) { free(p); }
 
@@ -533,7 +531,8 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
   }
 
   // The input window.  A regular file that fits one window is read into plain memory while the CUDA context comes up;
-  // a longer one goes through two pinned buffers: while the GPU encodes one window a helper thread reads the next.
+  // a longer one that is not dealt to encode workers (and a pipe) goes through two window buffers: while the GPU encodes
+  // one window a helper thread reads the next.
   ReadAheadInput win;
   AsyncWriter writer;
   const bool noReadAhead = getenv("ZDW_NO_READAHEAD") != NULL;  // measurement aid (tools/cli_timing.py --stream): read, then encode
@@ -561,6 +560,20 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       if (!win.widen(windowBytes)) return OUT_OF_MEMORY;
     }
   }
+  // Several windows, one after the other (a pipe, or one worker): plain memory as well - the library moves it to the
+  // device through its pinned ring at nearly the speed of a pinned window, a window-sized pinned buffer takes 0.45 s per
+  // GiB to allocate, and above all plain memory needs no CUDA: the first window is read (the producer of a pipe keeps
+  // running) while the context comes up.
+  if (!parallel && !oneWindow) {
+    if (!win.open(in, NULL, windowBytes, plainAlloc, plainFree)) {
+      if (tee) {
+        pclose(tee);
+        unlink(teeName.c_str());
+      }
+      return OUT_OF_MEMORY;
+    }
+    win.fill();
+  }
   if (!parallel && !gpu.open(gpuDevice)) {
     statusOutput(ERROR, "%s: no usable CUDA device (%s); this build has no CPU path\n", exeName, gpu.lastError().c_str());
     if (tee) {
@@ -568,13 +581,6 @@ ConvertToZDW::ERR_CODE ConvertToZDW::processFile(FILE* in, const char* filestub,
       unlink(teeName.c_str());
     }
     return UNKNOWN_ERROR;
-  }
-  if (!parallel && !oneWindow && !win.open(in, NULL, windowBytes, pinnedAlloc, pinnedFree)) {
-    if (tee) {
-      pclose(tee);
-      unlink(teeName.c_str());
-    }
-    return OUT_OF_MEMORY;
   }
 
   string cmd = compressorCommand();
