@@ -658,6 +658,10 @@ def run_cuda(args):
     if args.copy_gate is not None:  # A/B of the library's copy gate (default: on)
         for c in lanes:
             c.set_tuning("copy_gate", args.copy_gate)
+    for kv in args.e2e_tune:  # A/B of any other knob of the library in the e2e leg (diagnostic)
+        k, v = kv.split("=")
+        for c in lanes:
+            c.set_tuning(k, int(v))
     pool = ThreadPoolExecutor(max_workers=len(lanes))
 
     def _run_lanes(fn, items):
@@ -922,6 +926,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=4, help="contexts (host thread + stream) that share the rank's blocks in the device-resident leg")
     ap.add_argument("--e2e-lanes", type=int, default=3, help="contexts (host thread + stream) that overlap copies and kernels in the e2e leg")
     ap.add_argument("--copy-gate", type=int, default=None, help="0 / 1: large copies of the e2e contexts take turns (library default: 1)")
+    ap.add_argument("--e2e-tune", action="append", default=[], help="name=value tuning knob for the e2e contexts (diagnostic A/B)")
     ap.add_argument("--cpu-rows", type=int, default=131072, help="rows of the bounded cpu_baseline sample")
     ap.add_argument("--ref-rows", type=int, default=32768, help="rows per process per step of --impl reference")
     ap.add_argument("--ref-procs", type=int, default=32)

@@ -40,6 +40,7 @@ struct Ctx {
   long long copy_gate = 1;           // large H2D / D2H copies of different contexts take turns (0 = off)
   long long dec_emit_words = 1;      // the row writer stores cached texts as aligned words (k_dec_rows<.., true>; measured: 0.98 -> 0.90 ms)
   long long dec_delta = 1;           // wide schemas: rows are assembled from the row before (k_dec_write_delta)
+  long long dec_readback_kernel = 1; // small decode results reach the host through a kernel's stores, not the copy engine (decode.cu)
   long long dec_tile_bytes = 8192;   // row-stream bytes per CTA in the decoder's row-boundary discovery
   unsigned long long last_out_per_row = 0;  // decoded bytes per row of the previous block (sizes the next output)
   unsigned long long last_unique = 0;  // dictionary size of the previous block (seeds the next hash set)

@@ -51,7 +51,8 @@ int zdwb_ctx_create(int device, size_t workspace_hint, zdwb_ctx** out) {
     return ZDWB_ERR_CUDA;
   }
   c->stream = c->own_stream;
-  if (cudaHostAlloc(&c->meta_host, 4096, cudaHostAllocDefault) != cudaSuccess) {
+  // (mapped: kernels store small results straight into it, decode.cu k_readback)
+  if (cudaHostAlloc(&c->meta_host, 4096, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
     cudaStreamDestroy(c->own_stream);
     delete c;
     return ZDWB_ERR_OOM;
@@ -150,6 +151,7 @@ int zdwb_ctx_set_tuning(zdwb_ctx* c, const char* name, long long value) {
   else if (!strcmp(name, "copy_gate")) c->copy_gate = value;
   else if (!strcmp(name, "dec_emit_words")) c->dec_emit_words = value;
   else if (!strcmp(name, "dec_delta")) c->dec_delta = value;
+  else if (!strcmp(name, "dec_readback_kernel")) c->dec_readback_kernel = value;
   else if (!strcmp(name, "dec_strip_rows")) c->dec_strip_rows = value;
   else if (!strcmp(name, "dec_group_lanes")) c->dec_group_lanes = value;
   else if (!strcmp(name, "enc_delta")) {
