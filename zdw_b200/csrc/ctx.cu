@@ -95,7 +95,9 @@ int zdwb_fd_to_device(zdwb_ctx* c, int fd, long long offset, size_t len, const v
     ZDWB_CUDA_TRY(c, cudaMalloc(&c->fd_dev, cap));
     c->fd_dev_cap = cap;
   }
-  const int rc = zdwb::ring_h2d(c, c->fd_dev, len, [fd, offset, c](void* dst, size_t off, size_t n) {
+  int rc;
+  try {
+  rc = zdwb::ring_h2d(c, c->fd_dev, len, [fd, offset, c](void* dst, size_t off, size_t n) {
     size_t got = 0;
     while (got < n) {
       const ssize_t r = offset >= 0 ? pread(fd, static_cast<char*>(dst) + got, n - got, (off_t)((size_t)offset + off + got))
@@ -109,6 +111,10 @@ int zdwb_fd_to_device(zdwb_ctx* c, int fd, long long offset, size_t len, const v
     }
     return true;
   });
+  } catch (...) {  // (nothing of the host side's C++ may leave through the C ABI)
+    c->err = "zdwb_fd_to_device: out of host memory";
+    return ZDWB_ERR_OOM;
+  }
   if (rc != ZDWB_OK) return rc;
   *dev = c->fd_dev;
   return ZDWB_OK;
@@ -118,6 +124,7 @@ int zdwb_device_to_fd(zdwb_ctx* c, const void* dev, size_t len, int fd, long lon
   if (!c || (!dev && len) || fd < 0) return ZDWB_ERR_BAD_ARG;
   c->err.clear();
   if (cudaSetDevice(c->device) != cudaSuccess) return ZDWB_ERR_NO_DEVICE;
+  try {
   return zdwb::ring_d2h(c, dev, len, [fd, offset, c](const uint8_t* src, size_t off, size_t n) {
     size_t put = 0;
     while (put < n) {
@@ -131,6 +138,10 @@ int zdwb_device_to_fd(zdwb_ctx* c, const void* dev, size_t len, int fd, long lon
     }
     return true;
   });
+  } catch (...) {
+    c->err = "zdwb_device_to_fd: out of host memory";
+    return ZDWB_ERR_OOM;
+  }
 }
 
 const char* zdwb_last_error(const zdwb_ctx* c) { return c ? c->err.c_str() : "null context"; }

@@ -69,6 +69,7 @@ struct RadixScratch {
   uint32_t* ghist;             // [RS_MAX_PASSES][256] digit counts of the round's record set, per pass of the round
   uint32_t* tickets;           // [RS_MAX_PASSES] tiles handed out so far, per pass of the round
   unsigned long long* status;  // [ntiles][256] see os_pack; zeroed once per sort, told apart by the epoch afterwards
+  size_t status_bytes;
   uint32_t epoch;              // passes run so far in this sort (never 0 in a status word)
 };
 constexpr size_t RS_SMALL_BYTES = (size_t)RS_MAX_PASSES * 256 * 4 + 64;  // ghist + tickets: zeroed every round
@@ -219,9 +220,13 @@ struct SortBufs {
 int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, RadixScratch& R) {
   const int items = rs_items_for(n);
   const uint32_t ntiles = (n + rs_tile(items) - 1) / rs_tile(items);
-  if (npass > RS_MAX_PASSES || R.epoch + (uint32_t)npass >= (1u << 20)) {
-    ctx->err = "sort_strings: more radix passes than the status words can tell apart";
+  if (npass > RS_MAX_PASSES) {
+    ctx->err = "sort_strings: too many radix passes in one round";
     return ZDWB_ERR_UNSUPPORTED;
+  }
+  if (R.epoch + (uint32_t)npass >= (1u << 20)) {  // (a million passes: megabyte-long strings that tie) the epochs start over
+    ZDWB_CUDA_TRY(ctx, cudaMemsetAsync(R.status, 0, R.status_bytes, ctx->stream));
+    R.epoch = 0;
   }
   RadixPasses P;
   P.n = npass;
@@ -502,6 +507,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
   RSc.ghist = hist.as<uint32_t>();
   RSc.tickets = RSc.ghist + RS_MAX_PASSES * 256;
   RSc.status = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(hist.p) + RS_SMALL_BYTES);
+  RSc.status_bytes = (size_t)ntiles * 256 * 8;
   RSc.epoch = 0;
   ZDWB_TRY(head.alloc(ctx, (size_t)n * 4));
   ZDWB_TRY(unres.alloc(ctx, (size_t)n * 4));

@@ -941,11 +941,11 @@ ERR_CODE UnconvertFromZDW<T>::decodeBlocksFanOut(T& sink) {
           if (workerErr.empty()) workerErr = zdwb_last_error(session.get());
         }
       }
-      if (!handedOver) ordered.skip(job.seq);
-      if (rc != OK) {
+      if (rc != OK) {  // (before the sink moves on: a later block that finds the sink failed must not report first)
         int expected = OK;
         firstError.compare_exchange_strong(expected, (int)rc);
       }
+      if (!handedOver) ordered.skip(job.seq);
     }
   };
   vector<std::thread> threads;
