@@ -1,11 +1,13 @@
 // block_pipeline_test.cpp -- the host-side window cuts of the multi-GPU encoder (zdw_b200/host/block_pipeline.h) against a
-// plain sequential walk over the same bytes, and the ordered hand-over of results that finish out of order.
+// plain sequential walk over the same bytes, the ordered hand-over of results that finish out of order, and the sink that
+// puts decoded blocks out in file order (pipe: in turn; regular file: claimed places written side by side).
 // CPU only (g++), no CUDA.  Prints "<n> mismatches".
 #include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include <atomic>
+#include <chrono>
 #include <random>
 #include <string>
 #include <thread>
@@ -123,6 +125,105 @@ int main() {
     if (maxLead.load() > ahead + 4) {  // (taken is updated a moment after take() returns)
       ++bad;
       printf("lead %zu\n", maxLead.load());
+    }
+  }
+  // ---- OrderedSink: blocks decoded by several workers in any order leave in file order
+  for (int mode = 0; mode < 2; ++mode) {  // 0: a regular file (claim a place, write side by side), 1: a pipe (written in turn)
+    for (int round = 0; round < 20; ++round) {
+      const size_t nblocks = 1 + rng() % 40;
+      const size_t skipAt = (round % 5 == 4) ? rng() % nblocks : nblocks;  // one worker "fails": nothing behind it counts
+      std::vector<std::string> prefix(nblocks), rows(nblocks);
+      std::string want = "HEAD";
+      for (size_t k = 0; k < nblocks; ++k) {
+        if (rng() % 3 == 0) prefix[k] = "#header of block " + std::to_string(k) + "\n";
+        rows[k].assign(rng() % 5000, (char)('a' + k % 26));
+        rows[k] += "\n";
+        if (k < skipAt) want += prefix[k] + rows[k];
+      }
+      FILE* f = NULL;
+      int pfd[2] = {-1, -1};
+      std::string got;
+      std::thread drain;
+      char oname[] = "/tmp/zdw_os_XXXXXX";
+      if (mode == 0) {
+        const int ofd = mkstemp(oname);
+        f = fdopen(ofd, "w+");
+      } else {
+        if (pipe(pfd)) return 2;
+        f = fdopen(pfd[1], "w");
+        drain = std::thread([&]() {
+          char buf[4096];
+          ssize_t n;
+          while ((n = read(pfd[0], buf, sizeof(buf))) > 0) got.append(buf, (size_t)n);
+        });
+      }
+      fputs("HEAD", f);  // what was written in front of the blocks stays in front
+      bool finished = false;
+      {
+        OrderedSink sink(f);
+        if (sink.seekable() != (mode == 0)) {
+          ++bad;
+          printf("seekable() wrong in mode %d\n", mode);
+        }
+        std::atomic<size_t> next(0);
+        std::vector<std::thread> th;
+        for (int w = 0; w < 5; ++w) {
+          th.push_back(std::thread([&]() {
+            std::mt19937_64 r2(next.load() * 7919u + 17u);
+            for (;;) {
+              const size_t k = next.fetch_add(1);
+              if (k >= nblocks) break;
+              if (r2() % 3 == 0) std::this_thread::sleep_for(std::chrono::microseconds(r2() % 300));
+              if (k == skipAt) {
+                sink.skip(k);
+              } else if (sink.seekable() && (k & 1)) {  // the direct path of the decode workers: claim, then write on their own
+                uint64_t at = 0;
+                const bool ok = sink.claim(k, prefix[k].size() + rows[k].size(), &at);
+                if (ok) {
+                  sink.writePrefix(prefix[k], at);
+                  if (pwrite(sink.fd(), rows[k].data(), rows[k].size(), (off_t)(at + prefix[k].size())) != (ssize_t)rows[k].size()) sink.fail();
+                }
+              } else {
+                sink.deliver(k, prefix[k], rows[k].data(), rows[k].size());
+              }
+            }
+          }));
+        }
+        for (auto& t : th) t.join();
+        finished = sink.finish();
+      }
+      if (finished != (skipAt == nblocks)) {
+        ++bad;
+        printf("finish() = %d with skipAt %zu of %zu (mode %d)\n", (int)finished, skipAt, nblocks, mode);
+      }
+      if (mode == 0) {
+        fputs("TAIL", f);  // the FILE* stands behind the rows afterwards
+        fflush(f);
+        const long size = lseek(fileno(f), 0, SEEK_END);
+        got.resize((size_t)size);
+        if (pread(fileno(f), &got[0], got.size(), 0) != (ssize_t)got.size()) return 2;
+        fclose(f);
+        unlink(oname);
+        // (behind a failed block a regular file may hold later blocks' bytes at their offsets: only the front counts)
+        if (skipAt == nblocks) {
+          want += "TAIL";
+          if (got != want) {
+            ++bad;
+            printf("file sink: %zu bytes, expected %zu (round %d)\n", got.size(), want.size(), round);
+          }
+        } else if (got.compare(0, want.size(), want) != 0) {
+          ++bad;
+          printf("file sink: front differs after a failed block (round %d)\n", round);
+        }
+      } else {
+        fclose(f);
+        drain.join();
+        close(pfd[0]);
+        if (got != want) {
+          ++bad;
+          printf("pipe sink: %zu bytes, expected %zu (round %d, skipAt %zu of %zu)\n", got.size(), want.size(), round, skipAt, nblocks);
+        }
+      }
     }
   }
   printf("%d mismatches\n", bad);

@@ -1,5 +1,6 @@
 // UnconvertFromZDW.cpp -- see zdw/UnconvertFromZDW.h.  Reference behaviour cited as cplusplus/UnconvertFromZDW.cpp:<line>.
 #include "zdw/UnconvertFromZDW.h"
+#include "block_pipeline.h"
 
 #include <assert.h>
 #include <stdlib.h>
@@ -770,100 +771,6 @@ ERR_CODE UnconvertFromZDW<T>::parseNextBlock(T& sink) {
 // FILE* for pipes, or side by side with pwrite() at the block's offset when the sink is a regular file (a block's offset
 // is known as soon as the blocks in front of it have been decoded, not written).
 namespace {
-
-class OrderedSink {
- public:
-  explicit OrderedSink(FILE* f) : fp_(f), fd_(fileno(f)), seekable_(false), base_(0), nextSeq_(0), total_(0), failed_(false) {
-    struct stat st;
-    fflush(fp_);
-    if (fstat(fd_, &st) == 0 && S_ISREG(st.st_mode)) {
-      const off_t at = lseek(fd_, 0, SEEK_CUR);
-      if (at >= 0) {
-        seekable_ = true;
-        base_ = (uint64_t)at;
-      }
-    }
-  }
-  // rows of block `seq` (with the optional line that precedes them); returns false once anything failed to be written
-  bool deliver(size_t seq, const string& prefix, const void* rows, size_t len) {
-    std::unique_lock<std::mutex> lk(m_);
-    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
-    bool ok = !failed_;
-    if (!seekable_) {
-      if (ok && !prefix.empty()) ok = fwrite(prefix.data(), 1, prefix.size(), fp_) == prefix.size();
-      if (ok && len) ok = fwrite(rows, 1, len, fp_) == len;
-      if (!ok) failed_ = true;
-      ++nextSeq_;
-      cv_.notify_all();
-      return ok;
-    }
-    const uint64_t at = base_ + total_;
-    total_ += prefix.size() + len;
-    ++nextSeq_;  // the next block may take its offset: the writes themselves run side by side
-    cv_.notify_all();
-    lk.unlock();
-    ok = ok && writeAt(prefix.data(), prefix.size(), at) && writeAt(rows, len, at + prefix.size());
-    if (!ok) {
-      std::lock_guard<std::mutex> g(m_);
-      failed_ = true;
-    }
-    return ok;
-  }
-  // a regular file: the place of block `seq` (prefix + rows, `bytes` in all) - the caller writes there itself (the rows
-  // go from the device to the file through zdwb_device_to_fd).  false once anything failed.
-  bool seekable() const { return seekable_; }
-  int fd() const { return fd_; }
-  bool claim(size_t seq, size_t bytes, uint64_t* at) {
-    std::unique_lock<std::mutex> lk(m_);
-    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
-    *at = base_ + total_;
-    total_ += bytes;
-    ++nextSeq_;
-    cv_.notify_all();
-    return !failed_;
-  }
-  void fail() {
-    std::lock_guard<std::mutex> g(m_);
-    failed_ = true;
-  }
-  bool writePrefix(const string& prefix, uint64_t at) { return writeAt(prefix.data(), prefix.size(), at); }
-  // a block that produced nothing (its worker failed): later blocks must not wait for it for ever
-  // (nothing behind it is written either: the output ends where the reference's would, in front of the bad block)
-  void skip(size_t seq) {
-    std::unique_lock<std::mutex> lk(m_);
-    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
-    failed_ = true;
-    ++nextSeq_;
-    cv_.notify_all();
-  }
-  // after every worker is done: leaves the FILE* positioned behind the rows
-  bool finish() {
-    if (seekable_ && lseek(fd_, (off_t)(base_ + total_), SEEK_SET) < 0) return false;
-    return !failed_;
-  }
-
- private:
-  bool writeAt(const void* p, size_t n, uint64_t at) {
-    const char* c = static_cast<const char*>(p);
-    while (n) {
-      const ssize_t w = pwrite(fd_, c, n, (off_t)at);
-      if (w <= 0) return false;
-      c += w;
-      n -= (size_t)w;
-      at += (uint64_t)w;
-    }
-    return true;
-  }
-  FILE* fp_;
-  int fd_;
-  bool seekable_;
-  uint64_t base_;
-  std::mutex m_;
-  std::condition_variable cv_;
-  size_t nextSeq_;
-  uint64_t total_;
-  bool failed_;
-};
 
 struct DecodeJob {
   size_t seq;

@@ -13,12 +13,15 @@
 #define ZDWB_HOST_BLOCK_PIPELINE_H
 
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
+#include <string>
 #include <vector>
 
 namespace adobe {
@@ -145,6 +148,105 @@ class OrderedResults {
   std::vector<char> ready_;
   size_t retired_;
 };
+
+// Rows of decoded blocks leave in file order although their workers finish in any order (UnconvertFromZDW.cpp,
+// decodeBlocksFanOut): through the FILE* for pipes / stdout; when the sink is a regular file a block only CLAIMS its
+// place in turn (its offset is known once the blocks in front have been decoded, not written) and is written there side
+// by side with the others (pwrite, or zdwb_device_to_fd straight from the device).
+class OrderedSink {
+ public:
+  explicit OrderedSink(FILE* f) : fp_(f), fd_(fileno(f)), seekable_(false), base_(0), nextSeq_(0), total_(0), failed_(false) {
+    struct stat st;
+    fflush(fp_);
+    if (fstat(fd_, &st) == 0 && S_ISREG(st.st_mode)) {
+      const off_t at = lseek(fd_, 0, SEEK_CUR);
+      if (at >= 0) {
+        seekable_ = true;
+        base_ = (uint64_t)at;
+      }
+    }
+  }
+  // rows of block `seq` (with the optional line that precedes them); returns false once anything failed to be written
+  bool deliver(size_t seq, const std::string& prefix, const void* rows, size_t len) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
+    bool ok = !failed_;
+    if (!seekable_) {
+      if (ok && !prefix.empty()) ok = fwrite(prefix.data(), 1, prefix.size(), fp_) == prefix.size();
+      if (ok && len) ok = fwrite(rows, 1, len, fp_) == len;
+      if (!ok) failed_ = true;
+      ++nextSeq_;
+      cv_.notify_all();
+      return ok;
+    }
+    const uint64_t at = base_ + total_;
+    total_ += prefix.size() + len;
+    ++nextSeq_;  // the next block may take its offset: the writes themselves run side by side
+    cv_.notify_all();
+    lk.unlock();
+    ok = ok && writeAt(prefix.data(), prefix.size(), at) && writeAt(rows, len, at + prefix.size());
+    if (!ok) {
+      std::lock_guard<std::mutex> g(m_);
+      failed_ = true;
+    }
+    return ok;
+  }
+  // a regular file: the place of block `seq` (prefix + rows, `bytes` in all) - the caller writes there itself (the rows
+  // go from the device to the file through zdwb_device_to_fd).  false once anything failed.
+  bool seekable() const { return seekable_; }
+  int fd() const { return fd_; }
+  bool claim(size_t seq, size_t bytes, uint64_t* at) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
+    *at = base_ + total_;
+    total_ += bytes;
+    ++nextSeq_;
+    cv_.notify_all();
+    return !failed_;
+  }
+  void fail() {
+    std::lock_guard<std::mutex> g(m_);
+    failed_ = true;
+  }
+  bool writePrefix(const std::string& prefix, uint64_t at) { return writeAt(prefix.data(), prefix.size(), at); }
+  // a block that produced nothing (its worker failed): later blocks must not wait for it for ever
+  // (nothing behind it is written either: the output ends where the reference's would, in front of the bad block)
+  void skip(size_t seq) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&]() { return nextSeq_ == seq; });
+    failed_ = true;
+    ++nextSeq_;
+    cv_.notify_all();
+  }
+  // after every worker is done: leaves the FILE* positioned behind the rows
+  bool finish() {
+    if (seekable_ && lseek(fd_, (off_t)(base_ + total_), SEEK_SET) < 0) return false;
+    return !failed_;
+  }
+
+ private:
+  bool writeAt(const void* p, size_t n, uint64_t at) {
+    const char* c = static_cast<const char*>(p);
+    while (n) {
+      const ssize_t w = pwrite(fd_, c, n, (off_t)at);
+      if (w <= 0) return false;
+      c += w;
+      n -= (size_t)w;
+      at += (uint64_t)w;
+    }
+    return true;
+  }
+  FILE* fp_;
+  int fd_;
+  bool seekable_;
+  uint64_t base_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  size_t nextSeq_;
+  uint64_t total_;
+  bool failed_;
+};
+
 
 }  // namespace zdw
 }  // namespace adobe
