@@ -198,6 +198,22 @@ def _cases():
             cur[6] = b"%d" % rng.randrange(-1000, 1000)
         rs.append(list(cur))
     add("mixed_3000", desc(cols), rows(rs))
+
+    # d14: strings that agree on long prefixes (URLs do): the dictionary order is decided 15 .. 130 bytes into the strings,
+    # by a proper-prefix relation, by a high or low byte right behind the common part - the sort's prefix keys tie and its
+    # in-memory compares (16 bytes a round, then words, then bytes) decide.  ~2 500 strings: several sort tiles.
+    strings = []
+    for k, L in enumerate((15, 16, 17, 19, 31, 32, 33, 47, 48, 49, 63, 64, 65, 100, 130)):
+        stem = (b"http://www.example.com/%02d/" % k + b"path/" * 30)[:L]
+        assert len(stem) == L
+        for tail in (b"", b"a", b"b", b"\x01", b"\xff", b"aa", b"ab", b"a\x01", b"a" * 15, b"a" * 16, b"a" * 17, b"b" * 3 + b"\x7f",
+                     b"\x80", b"\xfe\xff", b"zzzzzzz"):
+            strings.append(stem + tail)
+        for j in range(150):
+            strings.append(stem + b"%c%05d" % (65 + j % 26, (j * 7919) % 100000))
+    rng14 = random.Random(14)
+    rng14.shuffle(strings)
+    add("d14_long_common_prefixes", d1c, rows([[x] for x in strings]))
     return out
 
 
