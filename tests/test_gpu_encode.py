@@ -58,31 +58,38 @@ def test_golden_configs(ctx, name):
     assert got == want, G.first_diff(got, want)
 
 
+@pytest.mark.parametrize("items", [4, 16])
 @pytest.mark.parametrize("name", ["analytics-hits", "movie_tickets"])
-def test_golden_radix_sort_path(ctx, name):
-    """Force the large-dictionary (radix + refinement) sort and a tiny first hash set."""
+def test_golden_radix_sort_path(ctx, name, items):
+    """Force the large-dictionary (radix + refinement) sort - with either tile size of its passes (the library picks 16
+    records per thread from two million records on) - and a tiny first hash set."""
     sch = O.parse_desc(O.golden(f"{name}.desc.sql"))
     tsv = O.golden(f"{name}.sql")
     want = O.golden_to_v11(O.golden(f"{name}.zdw"))
     ctx.set_tuning("small_sort_max", 0)
+    ctx.set_tuning("sort_radix_items", items)
     ctx.set_tuning("ht_initial_log2", 10)
     try:
         got = G.encode_file_with_product(ctx, sch, tsv)
     finally:
         ctx.set_tuning("small_sort_max", 65536)
+        ctx.set_tuning("sort_radix_items", 0)
         ctx.set_tuning("ht_initial_log2", 20)
     assert got == want, G.first_diff(got, want)
 
 
-def test_corpus_radix_sort_path(ctx):
+@pytest.mark.parametrize("items", [4, 16])
+def test_corpus_radix_sort_path(ctx, items):
     ctx.set_tuning("small_sort_max", 0)
+    ctx.set_tuning("sort_radix_items", items)
     ctx.set_tuning("ht_initial_log2", 10)
     try:
         for case in FAST:
-            if case[0].startswith(("d7", "d9", "mixed", "d1_", "d8_used25")):
+            if case[0].startswith(("d7", "d9", "d14", "mixed", "d1_", "d8_used25")):
                 _check_case(ctx, case)
     finally:
         ctx.set_tuning("small_sort_max", 65536)
+        ctx.set_tuning("sort_radix_items", 0)
         ctx.set_tuning("ht_initial_log2", 20)
 
 

@@ -34,6 +34,7 @@ struct Ctx {
   int sm_count = 148;
   // tuning knobs
   long long small_sort_max = 65536;  // dictionaries up to this many entries are ranked by tile sort + binary search
+  long long sort_radix_items = 0;    // records per thread in the radix passes: 4 or 16 (0 = by the number of records)
   long long ht_initial_log2 = 20;    // first-try size of the string hash set (grown x8 on overflow)
   long long dec_group_lanes = 0;     // lanes per strip in the row kernels: 8, 16, 32 (0 = by schema width)
   long long dec_strip_rows = 0;      // rows per strip of the row kernels (0 = automatic)

@@ -157,6 +157,7 @@ int zdwb_ctx_set_stream(zdwb_ctx* c, void* cuda_stream) {
 int zdwb_ctx_set_tuning(zdwb_ctx* c, const char* name, long long value) {
   if (!c || !name) return ZDWB_ERR_BAD_ARG;
   if (!strcmp(name, "small_sort_max")) c->small_sort_max = value;
+  else if (!strcmp(name, "sort_radix_items")) c->sort_radix_items = value;
   else if (!strcmp(name, "ht_initial_log2")) c->ht_initial_log2 = value;
   else if (!strcmp(name, "dec_tile_bytes")) c->dec_tile_bytes = value;
   else if (!strcmp(name, "copy_gate")) c->copy_gate = value;

@@ -49,7 +49,10 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 // items per thread: 16 for large inputs (few tiles, small histograms), 4 below two million records - a C2-sized dictionary
 // (half a million strings) is otherwise 128 CTAs of 16 sequential steps each, on 148 SMs
 __host__ __device__ constexpr int rs_tile(int items) { return RS_THREADS * items; }
-inline int rs_items_for(uint32_t n) { return n < (1u << 21) ? 4 : 16; }
+inline int rs_items_for(const Ctx* ctx, uint32_t n) {
+  if (ctx->sort_radix_items == 4 || ctx->sort_radix_items == 16) return (int)ctx->sort_radix_items;  // (tests force either)
+  return n < (1u << 21) ? 4 : 16;
+}
 
 __device__ __forceinline__ uint32_t rs_digit(const uint64_t* keys, const uint32_t* segs, uint32_t i, int pass) {
   return pass < 8 ? (uint32_t)((keys[i] >> (8 * pass)) & 255u) : ((segs[i] >> (8 * (pass - 8))) & 255u);
@@ -218,7 +221,7 @@ struct SortBufs {
 
 // Sorts records [0,n) by digits `pass_list` (least significant first); result ends up in b.{key,seg,val}[b.cur].
 int radix_passes(Ctx* ctx, SortBufs& b, uint32_t n, const int* pass_list, int npass, RadixScratch& R) {
-  const int items = rs_items_for(n);
+  const int items = rs_items_for(ctx, n);
   const uint32_t ntiles = (n + rs_tile(items) - 1) / rs_tile(items);
   if (npass > RS_MAX_PASSES) {
     ctx->err = "sort_strings: too many radix passes in one round";
@@ -494,7 +497,7 @@ int sort_strings(Ctx* ctx, const uint8_t* base, const uint32_t* starts, const ui
 
   // ---- large path
   // refinement rounds sort m <= n records and may pick the smaller tile: size the status words for the worst of the two
-  const uint32_t ntiles = std::max<uint32_t>((n + rs_tile(rs_items_for(n)) - 1) / rs_tile(rs_items_for(n)),
+  const uint32_t ntiles = std::max<uint32_t>((n + rs_tile(rs_items_for(ctx, n)) - 1) / rs_tile(rs_items_for(ctx, n)),
                                              (std::min<uint32_t>(n, 1u << 21) + rs_tile(4) - 1) / rs_tile(4));
   DevBuf keyA, keyB, segA, segB, valA, valB, hist, head, unres, unres_scan, ids, pos, pos2, total;
   ZDWB_TRY(keyA.alloc(ctx, (size_t)n * 8));
