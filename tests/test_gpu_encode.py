@@ -203,6 +203,31 @@ def test_pass1_variants_forced(ctx, variant, p2_rows):
         ctx.set_tuning("enc_p2_rows", 0)
 
 
+@pytest.mark.parametrize("tile", [2048, 4096, 16384, 65536])
+def test_row_delta_tile_sizes(ctx, tile):
+    """The row-delta pass cuts small inputs into smaller tiles (8 KiB .. 32 KiB by input size, `enc_dtile` forces one):
+    rows that start in one tile and end tiles later, reference rows far in front of a tile, tiles without a row start."""
+    ctx.set_tuning("enc_delta", 1)
+    ctx.set_tuning("enc_dtile", tile)
+    try:
+        for case in CASES:
+            if case[0].startswith(("d1_", "d2_", "d3_", "d4_", "d7", "d8_used25", "d11", "mixed", "trim")):
+                _check_case(ctx, case)
+        sch = O.parse_desc(O.golden("analytics-hits.desc.sql"))
+        want = O.golden_to_v11(O.golden("analytics-hits.zdw"))
+        got = G.encode_file_with_product(ctx, sch, O.golden("analytics-hits.sql"))
+        assert got == want, G.first_diff(got, want)
+        case = next(c for c in CASES if c[0] == "mixed_3000")
+        sch = O.parse_desc(case[1])
+        for plan in ([(1000, 3), (500, 1)], [(7, 8)]):
+            want = O.encode(sch, case[2], plan=plan).data
+            got = G.encode_file_with_product(ctx, sch, case[2], plan=plan)
+            assert got == want, f"plan {plan}: {G.first_diff(got, want)}"
+    finally:
+        ctx.set_tuning("enc_delta", -1)
+        ctx.set_tuning("enc_dtile", 0)
+
+
 def test_row_delta_falls_back_when_a_row_does_not_fit(ctx):
     """A row with more non-empty fields than a warp's lists hold (and one longer than 64 KiB): the row-delta pass gives
     the block back and the general pass encodes it - same bytes either way."""
