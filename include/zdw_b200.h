@@ -73,14 +73,18 @@ const char* zdwb_last_error(const zdwb_ctx* ctx);
  * harness time the kernels with events recorded on its own stream. */
 int zdwb_ctx_set_stream(zdwb_ctx* ctx, void* cuda_stream);
 
-/* Tuning / test knobs (name = value).  Known names: "small_sort_max" (largest dictionary ranked by the tile-sort
- * path instead of the radix sort), "ht_initial_log2" (first-try size of the string hash set), "dec_tile_bytes"
- * (row-stream bytes per CTA in the decoder's row-boundary discovery), "dec_strip_rows" (rows per strip of the
- * decoder's row kernels, 0 = automatic), "dec_group_lanes" (lanes per row in those kernels: 8, 16, 32, 0 = by schema
- * width), "copy_gate" (0/1, default 1: host<->device copies of 8 MiB and more take turns with those of the
- * process's other contexts on the same device instead of sharing the link), "dec_emit_words" (0/1, default 0:
- * experimental store pattern of the decoder's row writer, not yet measured), "kernel_timing" (0/1).  Returns
- * ZDWB_ERR_BAD_ARG for unknown names. */
+/* Tuning / test knobs (name = value); every default is what the measurements in DESIGN.md picked.  Encode:
+ * "enc_delta" (pass-1 variant: 1 = row-delta, 0 = general, -1 = by row width), "enc_dtile" (bytes per row-delta tile, a
+ * power of two >= 2048; 0 = by input size), "enc_p2_rows" (rows per pass-2 tile, 0 = automatic), "small_sort_max"
+ * (largest dictionary ranked by the tile-sort path instead of the radix sort), "sort_radix_items" (records per thread
+ * in the radix passes: 4 or 16, 0 = by size), "ht_initial_log2" (first-try size of the string hash set).  Decode:
+ * "dec_delta" (0/1: rows of wide schemas are assembled from the row before), "dec_strip_rows" (rows per strip of the row
+ * kernels, 0 = automatic), "dec_group_lanes" (lanes per row in the narrow-schema kernels: 8, 16, 32, 0 = by schema
+ * width), "dec_emit_words" (0/1: cached texts leave as aligned words), "dec_tile_bytes" (row-stream bytes per CTA in the
+ * row-boundary discovery), "dec_readback_kernel" (0/1: small results reach the host through a kernel's stores into
+ * mapped memory instead of the copy engine).  Both: "copy_gate" (0/1, default 1: host<->device copies of 8 MiB and more
+ * take turns with those of the process's other contexts on the same device instead of sharing the link),
+ * "kernel_timing" (0/1).  Returns ZDWB_ERR_BAD_ARG for unknown names. */
 int zdwb_ctx_set_tuning(zdwb_ctx* ctx, const char* name, long long value);
 
 /* Number of kernels this context has launched so far (bench.py reports the delta as gpu_launches). */
